@@ -1,0 +1,152 @@
+/* include/mifgpu.h -- C ABI of libmifgpu, the B200 (sm_100a) implementation of the projection-method
+ * time step of FattiMei/mpi-incompressible-fluid.
+ *
+ * The reference has no FFI layer: its boundary is a set of C++ free functions in namespace mif that take
+ * references to reference-defined classes.  This header is what a thin C++
+ * forwarding layer with the reference's own class and function names binds to (that layer lives in
+ * mpi-incompressible-fluid_b200/host/).  Each entry point names the reference
+ * interface it replaces (paths relative to the reference repository root).
+ *
+ * Conventions: extern "C"; plain pointers and sizes only; every function that can fail returns 0 on
+ * success or a negative mifgpu_status, and mifgpu_last_error() gives the message of the last failure on
+ * the calling thread; all host pointers are caller-owned; one host thread per context; host arrays use
+ * exactly the reference's ghosted, x-fastest layout  idx = i + j*sx + k*sx*sy  (include/Tensor.h:232-238)
+ * with the extents of src/StaggeredTensor.cpp:5-9.  There is no CPU fallback: without a CUDA device every
+ * compute entry point fails with MIFGPU_ERR_CUDA.
+ */
+#ifndef MIFGPU_H
+#define MIFGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIFGPU_ABI_VERSION 1
+
+typedef enum mifgpu_status {
+  MIFGPU_OK = 0,
+  MIFGPU_ERR_INVALID = -1,     /* bad argument (the reference would assert, src/Constants.cpp:104-119) */
+  MIFGPU_ERR_CUDA = -2,        /* CUDA runtime failure or no device */
+  MIFGPU_ERR_UNSUPPORTED = -3, /* valid reference configuration that this build does not cover yet */
+  MIFGPU_ERR_COMM = -4         /* multi-GPU communication failure */
+} mifgpu_status;
+
+/* include/StaggeredTensor.h:13-15 (enum StaggeringDirection {x, y, z, none}) */
+typedef enum mifgpu_staggering {
+  MIFGPU_STAGGER_X = 0, /* u */
+  MIFGPU_STAGGER_Y = 1, /* v */
+  MIFGPU_STAGGER_Z = 2, /* w */
+  MIFGPU_STAGGER_NONE = 3 /* pressure */
+} mifgpu_staggering;
+
+/* The 16 constructor arguments of mif::Constants (include/Constants.h:86-90, src/Constants.cpp:58-62),
+ * plus the CUDA device ordinal.  All derived quantities are recomputed by the library with the same
+ * formulas (src/Constants.cpp:63-101). */
+typedef struct mifgpu_params {
+  uint64_t Nx_global, Ny_global, Nz_global; /* pressure POINTS per direction, walls included */
+  double x_size, y_size_global, z_size_global;
+  double min_x_global, min_y_global, min_z_global;
+  double Re;
+  double final_time;
+  uint32_t num_time_steps; /* dt = final_time / num_time_steps */
+  int32_t Py, Pz, rank;    /* pencil decomposition: rank = y_rank*Pz + z_rank */
+  int32_t periodic_bc[3];
+  int32_t device;          /* CUDA device ordinal for this rank */
+} mifgpu_params;
+
+typedef struct mifgpu_ctx mifgpu_ctx;       /* replaces Constants + PressureSolverStructures */
+typedef struct mifgpu_tensor mifgpu_tensor; /* device-resident StaggeredTensor */
+
+/* Analytic boundary / forcing data evaluated on the device.  The reference passes std::function
+ * bundles (include/VectorFunction.h:16-54) that are evaluated point by point inside
+ * VelocityTensor::apply_bc (src/VelocityTensor.cpp:36-218); a device cannot call them, so the known
+ * analytic families are enumerated and anything else goes through the host-callback kind. */
+typedef enum mifgpu_bc_kind {
+  MIFGPU_BC_TEST_CASE_1 = 1,     /* include/TestCaseBoundaries.h:17-35  (v = 1 on the face x = 1)    */
+  MIFGPU_BC_TEST_CASE_2 = 2,     /* include/TestCaseBoundaries.h:38-56  (v = 1 on the face x = -0.5) */
+  MIFGPU_BC_ETHIER_STEINMAN = 3, /* generators/manufsol.py:31-72 (u_exact, v_exact, w_exact, dp_d*_exact) */
+  MIFGPU_BC_HOST_CALLBACK = 4    /* any other TimeVectorFunction: faces filled on the host */
+} mifgpu_bc_kind;
+
+/* Host callback for MIFGPU_BC_HOST_CALLBACK.  The library asks for ONE face of ONE component at one
+ * time; the callee writes the final boundary values (i.e. what src/VelocityTensor.cpp:36-218 would
+ * store, including the half-cell extrapolation of the wall-normal component) into `values`, a dense
+ * 2-D array over the FULL extent of that tensor on that face, first listed index fastest:
+ *   face 0,1 (z-, z+): values[i + j*sx]     face 2,3 (y-, y+): values[i + k*sx]
+ *   face 4,5 (x-, x+): values[j + k*sy]
+ * `which` is 0 for the velocity itself and 1 for the pressure-gradient data g used by the
+ * non-homogeneous Neumann variant (src/PressureEquation.cpp:10-56; time is then t_new, time_prev t_old
+ * and the callee returns g(t_new) - g(t_old) at unstaggered pressure points of the face). */
+typedef void (*mifgpu_face_callback)(void *user, int which, double time, double time_prev, int component,
+                                     int face, double *values);
+
+typedef struct mifgpu_bc {
+  int32_t kind; /* mifgpu_bc_kind */
+  double Re;    /* the reference's global `Reynolds` read by the generated exact solutions */
+  mifgpu_face_callback callback;
+  void *user;
+} mifgpu_bc;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+
+/* Constants::Constants (src/Constants.cpp:58-120) + PressureSolverStructures::PressureSolverStructures
+ * (src/PressureSolverStructures.cpp:13-70): geometry, decomposition, transform plans, eigenvalues. */
+int mifgpu_create(const mifgpu_params *params, mifgpu_ctx **ctx);
+void mifgpu_destroy(mifgpu_ctx *ctx);
+const char *mifgpu_last_error(void);
+int mifgpu_abi_version(void);
+
+/* Local extents {sx, sy, sz} of a tensor with the given staggering on this rank
+ * (src/StaggeredTensor.cpp:5-9 with src/Constants.cpp:80-85). */
+int mifgpu_tensor_extents(const mifgpu_ctx *ctx, int staggering, uint64_t extents[3]);
+
+/* ---- tensors ------------------------------------------------------------------------------------ */
+
+/* StaggeredTensor::StaggeredTensor (src/StaggeredTensor.cpp:5-36); zero-initialised like std::vector. */
+int mifgpu_tensor_create(mifgpu_ctx *ctx, int staggering, mifgpu_tensor **tensor);
+void mifgpu_tensor_destroy(mifgpu_tensor *tensor);
+/* Host <-> device copies of a whole tensor in the reference layout (Tensor::raw_data(), include/Tensor.h:118). */
+int mifgpu_tensor_upload(mifgpu_tensor *tensor, const double *host);
+int mifgpu_tensor_download(const mifgpu_tensor *tensor, double *host);
+/* Tensor::swap_data (include/Tensor.h:108-110) as used by VelocityTensor::swap_data (src/VelocityTensor.cpp:13-27). */
+int mifgpu_tensor_swap(mifgpu_tensor *a, mifgpu_tensor *b);
+
+/* ---- the hot path ------------------------------------------------------------------------------- */
+
+/* mif::timestep / mif::timestep_nhn (include/Timestep.h:16-27, src/Timestep.cpp:97-156): one
+ * three-stage projection step.  velocity, velocity_buffer, velocity_buffer_2 are {u, v, w} triples.
+ * On return `velocity` and `pressure` hold the new solution; the other tensors hold the same scratch
+ * contents the reference leaves in them.  nhn != 0 selects timestep_nhn (pressure-gradient data from
+ * bc->callback with which = 1, or the Ethier-Steinman gradient). */
+int mifgpu_timestep(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], mifgpu_tensor *const velocity_buffer[3],
+                    mifgpu_tensor *const velocity_buffer_2[3], const mifgpu_bc *bc, double t_n,
+                    mifgpu_tensor *pressure, mifgpu_tensor *pressure_buffer, int nhn);
+
+/* VelocityTensor::apply_bc (src/VelocityTensor.cpp:36-233) at one fixed time. */
+int mifgpu_apply_bc(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], const mifgpu_bc *bc, double time);
+
+/* mif::solve_pressure_equation_homogeneous_periodic / _non_homogeneous_neumann
+ * (include/PressureEquation.h:10-21, src/PressureEquation.cpp:266-286): pressure <- solution of
+ * lap(p) = div(velocity)/dt.  nhn_bc may be NULL (homogeneous / periodic); otherwise its callback is
+ * asked for the Neumann data with which = 1, time = nhn_time, time_prev = nhn_time (the caller's
+ * callback returns g at nhn_time when both are equal). */
+int mifgpu_solve_pressure(mifgpu_ctx *ctx, mifgpu_tensor *pressure, mifgpu_tensor *const velocity[3], double dt,
+                          const mifgpu_bc *nhn_bc, double nhn_time);
+
+/* Blocks until all work queued by this context has finished (cudaStreamSynchronize). */
+int mifgpu_synchronize(mifgpu_ctx *ctx);
+
+/* The CUDA stream (cudaStream_t) the context launches on, for callers that time with CUDA events. */
+void *mifgpu_stream(mifgpu_ctx *ctx);
+
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t mifgpu_launch_count(const mifgpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* MIFGPU_H */

@@ -1,0 +1,423 @@
+// mif_api.cu -- the C ABI of libmifgpu (include/mifgpu.h): context, tensors and the orchestration of one
+// projection time step (src/Timestep.cpp:97-156) on one CUDA stream.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mifgpu.h"
+#include "mif_kernels.h"
+
+using namespace mifgpu;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t err__ = (expr);                                                                   \
+    if (err__ != cudaSuccess)                                                                     \
+      return fail(MIFGPU_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+
+}  // namespace
+
+struct mifgpu_ctx {
+  mifgpu_params params;
+  Geom g;
+  int n_points[3];
+  cudaStream_t stream = nullptr;
+  PoissonPlan *plan = nullptr;
+  uint64_t launches = 0;
+  // host-callback boundary faces: pinned staging + device copies, [which][component][face]
+  double *face_host[2][3][6] = {};
+  double *face_dev[2][3][6] = {};
+};
+
+struct mifgpu_tensor {
+  mifgpu_ctx *ctx;
+  int staggering;
+  double *data;
+};
+
+namespace {
+
+// Derived constants, same formulas as src/Constants.cpp:63-101.
+int build_geometry(const mifgpu_params &p, Geom &g, int n_points[3]) {
+  if (p.Nx_global < 2 || p.Ny_global < 2 || p.Nz_global < 2) return fail(MIFGPU_ERR_INVALID, "grid needs >= 2 points per direction");
+  if (p.num_time_steps == 0 || !(p.final_time > 0)) return fail(MIFGPU_ERR_INVALID, "num_time_steps and final_time must be positive");
+  if (p.Py < 1 || p.Pz < 1) return fail(MIFGPU_ERR_INVALID, "Py and Pz must be >= 1");
+  if (p.rank < 0 || p.rank >= p.Py * p.Pz) return fail(MIFGPU_ERR_INVALID, "rank outside [0, Py*Pz)");
+  const bool per[3] = {p.periodic_bc[0] != 0, p.periodic_bc[1] != 0, p.periodic_bc[2] != 0};
+  const int Py = p.Py, Pz = p.Pz, rank = p.rank;
+  const int y_rank = rank / Pz, z_rank = rank % Pz;
+  const size_t ny_pts = p.Ny_global - per[1], nz_pts = p.Nz_global - per[2];
+  const size_t Ny_owner = ny_pts / Py + ((size_t)y_rank < ny_pts % Py ? 1 : 0);
+  const size_t Nz_owner = nz_pts / Pz + ((size_t)z_rank < nz_pts % Pz ? 1 : 0);
+  const size_t Nx = per[0] ? p.Nx_global + 1 : p.Nx_global;
+  const size_t Ny = (Py == 1) ? (per[1] ? p.Ny_global + 1 : p.Ny_global)
+                              : (((y_rank == Py - 1 && !per[1]) || (y_rank == 0 && !per[1])) ? Ny_owner + 1 : Ny_owner + 2);
+  const size_t Nz = (Pz == 1) ? (per[2] ? p.Nz_global + 1 : p.Nz_global)
+                              : (((z_rank == Pz - 1 && !per[2]) || (z_rank == 0 && !per[2])) ? Nz_owner + 1 : Nz_owner + 2);
+  const size_t Nx_st = per[0] ? Nx : Nx + 1;
+  const size_t Ny_st = (y_rank == Py - 1) ? Ny + 1 : Ny;
+  const size_t Nz_st = (z_rank == Pz - 1) ? Nz + 1 : Nz;
+  if (Nx_st > (1u << 30) || Ny_st > (1u << 30) || Nz_st > (1u << 30)) return fail(MIFGPU_ERR_INVALID, "extent too large");
+
+  g.Nx = (int)Nx; g.Ny = (int)Ny; g.Nz = (int)Nz;
+  g.sx[0] = (int)Nx_st; g.sy[0] = (int)Ny;    g.sz[0] = (int)Nz;
+  g.sx[1] = (int)Nx;    g.sy[1] = (int)Ny_st; g.sz[1] = (int)Nz;
+  g.sx[2] = (int)Nx;    g.sy[2] = (int)Ny;    g.sz[2] = (int)Nz_st;
+  g.sx[3] = (int)Nx;    g.sy[3] = (int)Ny;    g.sz[3] = (int)Nz;
+  g.PX = (int)((Nx_st + 15) / 16 * 16);
+  g.PY = (int)Ny_st;
+  g.PZ = (int)Nz_st;
+  g.plane = (long long)g.PX * g.PY;
+  g.volume = g.plane * g.PZ;
+  for (int d = 0; d < 3; d++) g.periodic[d] = per[d];
+  g.base_i = per[0] ? -1 : 0;
+  g.base_j = (int)(ny_pts / Py * y_rank + std::min((size_t)y_rank, ny_pts % Py)) - ((y_rank > 0 || per[1]) ? 1 : 0);
+  g.base_k = (int)(nz_pts / Pz * z_rank + std::min((size_t)z_rank, nz_pts % Pz)) - ((z_rank > 0 || per[2]) ? 1 : 0);
+  g.prev_y = (y_rank == 0) ? ((Py > 1 && per[1]) ? rank + (Py - 1) * Pz : -1) : rank - Pz;
+  g.next_y = (y_rank == Py - 1) ? ((Py > 1 && per[1]) ? rank - (Py - 1) * Pz : -1) : rank + Pz;
+  g.prev_z = (z_rank == 0) ? ((Pz > 1 && per[2]) ? rank + Pz - 1 : -1) : rank - 1;
+  g.next_z = (z_rank == Pz - 1) ? ((Pz > 1 && per[2]) ? rank - (Pz - 1) : -1) : rank + 1;
+  // owner ranges of pressure points (include/StaggeredTensorMacros.h:41-83)
+  g.own_lo[0] = per[0] ? 1 : 0;
+  g.own_hi[0] = per[0] ? g.Nx - 1 : g.Nx;
+  g.own_lo[1] = (g.prev_y != -1 || per[1]) ? 1 : 0;
+  g.own_hi[1] = (g.next_y != -1 || per[1]) ? g.Ny - 1 : g.Ny;
+  g.own_lo[2] = (g.prev_z != -1 || per[2]) ? 1 : 0;
+  g.own_hi[2] = (g.next_z != -1 || per[2]) ? g.Nz - 1 : g.Nz;
+
+  g.min_x = p.min_x_global; g.min_y = p.min_y_global; g.min_z = p.min_z_global;
+  const size_t Nx_domains = p.Nx_global - 1, Ny_domains = p.Ny_global - 1, Nz_domains = p.Nz_global - 1;
+  g.dt = p.final_time / p.num_time_steps;
+  g.dx = p.x_size / Nx_domains; g.dy = p.y_size_global / Ny_domains; g.dz = p.z_size_global / Nz_domains;
+  g.one_over_2_dx = 1 / (2 * g.dx); g.one_over_2_dy = 1 / (2 * g.dy); g.one_over_2_dz = 1 / (2 * g.dz);
+  g.one_over_8_dx = 1 / (8 * g.dx); g.one_over_8_dy = 1 / (8 * g.dy); g.one_over_8_dz = 1 / (8 * g.dz);
+  g.one_over_dx2_Re = 1 / (p.Re * g.dx * g.dx);
+  g.one_over_dy2_Re = 1 / (p.Re * g.dy * g.dy);
+  g.one_over_dz2_Re = 1 / (p.Re * g.dz * g.dz);
+  g.dx_over_2 = g.dx / 2; g.dy_over_2 = g.dy / 2; g.dz_over_2 = g.dz / 2;
+  g.one_over_dx = 1 / g.dx; g.one_over_dy = 1 / g.dy; g.one_over_dz = 1 / g.dz;
+  n_points[0] = (int)(p.Nx_global - per[0]);
+  n_points[1] = (int)ny_pts;
+  n_points[2] = (int)nz_pts;
+  return MIFGPU_OK;
+}
+
+Vec3 vec3(mifgpu_tensor *const t[3]) { return Vec3{{t[0]->data, t[1]->data, t[2]->data}}; }
+CVec3 cvec3(mifgpu_tensor *const t[3]) { return CVec3{{t[0]->data, t[1]->data, t[2]->data}}; }
+
+int check_triple(const mifgpu_ctx *ctx, mifgpu_tensor *const t[3], const char *name) {
+  if (!t) return fail(MIFGPU_ERR_INVALID, "%s is NULL", name);
+  for (int c = 0; c < 3; c++) {
+    if (!t[c]) return fail(MIFGPU_ERR_INVALID, "%s[%d] is NULL", name, c);
+    if (t[c]->ctx != ctx) return fail(MIFGPU_ERR_INVALID, "%s[%d] belongs to another context", name, c);
+    if (t[c]->staggering != c) return fail(MIFGPU_ERR_INVALID, "%s[%d] has staggering %d", name, c, t[c]->staggering);
+  }
+  return MIFGPU_OK;
+}
+
+int check_scalar(const mifgpu_ctx *ctx, const mifgpu_tensor *t, const char *name) {
+  if (!t) return fail(MIFGPU_ERR_INVALID, "%s is NULL", name);
+  if (t->ctx != ctx) return fail(MIFGPU_ERR_INVALID, "%s belongs to another context", name);
+  if (t->staggering != MIFGPU_STAGGER_NONE) return fail(MIFGPU_ERR_INVALID, "%s must be unstaggered", name);
+  return MIFGPU_OK;
+}
+
+bool face_is_active(const Geom &g, int face) {
+  switch (face) {
+    case 0: return g.prev_z == -1 && !g.periodic[2];
+    case 1: return g.next_z == -1 && !g.periodic[2];
+    case 2: return g.prev_y == -1 && !g.periodic[1];
+    case 3: return g.next_y == -1 && !g.periodic[1];
+    default: return !g.periodic[0];
+  }
+}
+
+// Fill the device face tables through the host callback.  which = 0: velocity faces of the three
+// components; which = 1: Neumann data on the faces of the pressure tensor (component = normal direction).
+int fill_face_tables(mifgpu_ctx *ctx, const mifgpu_bc *bc, int which, double time, double time_prev, BcDev &dev) {
+  if (!bc->callback) return fail(MIFGPU_ERR_INVALID, "boundary data needs a host callback but bc->callback is NULL");
+  const Geom &g = ctx->g;
+  for (int comp = 0; comp < 3; comp++) {
+    for (int face = 0; face < 6; face++) {
+      dev.tables[comp][face] = nullptr;
+      const int dir = 2 - face / 2;
+      if (which == 1 && comp != dir) continue;
+      if (which == 0 && !face_is_active(g, face)) continue;
+      const int t = (which == 1) ? 3 : comp;
+      const size_t na = (dir == 0) ? g.sy[t] : g.sx[t], nb = (dir == 2) ? g.sy[t] : g.sz[t];
+      const size_t bytes = na * nb * sizeof(double);
+      if (!ctx->face_host[which][comp][face]) {
+        CUDA_TRY(cudaMallocHost(&ctx->face_host[which][comp][face], bytes));
+        CUDA_TRY(cudaMalloc(&ctx->face_dev[which][comp][face], bytes));
+      }
+      // The previous asynchronous copy out of this staging buffer must have finished before it is refilled.
+      CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      bc->callback(bc->user, which, time, time_prev, comp, face, ctx->face_host[which][comp][face]);
+      CUDA_TRY(cudaMemcpyAsync(ctx->face_dev[which][comp][face], ctx->face_host[which][comp][face], bytes,
+                               cudaMemcpyHostToDevice, ctx->stream));
+      dev.tables[comp][face] = ctx->face_dev[which][comp][face];
+    }
+  }
+  return MIFGPU_OK;
+}
+
+int do_apply_bc(mifgpu_ctx *ctx, mifgpu_tensor *const vel[3], const mifgpu_bc *bc, double time) {
+  BcDev dev;
+  std::memset(&dev, 0, sizeof(dev));
+  dev.kind = bc->kind;
+  dev.time = time;
+  dev.Re = bc->Re;
+  if (bc->kind == MIFGPU_BC_HOST_CALLBACK) {
+    const int rc = fill_face_tables(ctx, bc, 0, time, time, dev);
+    if (rc) return rc;
+  } else if (bc->kind != MIFGPU_BC_TEST_CASE_1 && bc->kind != MIFGPU_BC_TEST_CASE_2 &&
+             bc->kind != MIFGPU_BC_ETHIER_STEINMAN) {
+    return fail(MIFGPU_ERR_INVALID, "unknown boundary kind %d", bc->kind);
+  }
+  launch_apply_bc(ctx->stream, ctx->g, vec3(vel), dev, &ctx->launches);
+  return MIFGPU_OK;
+}
+
+// solve_pressure_equation_homogeneous_periodic / _non_homogeneous_neumann (src/PressureEquation.cpp:266-286).
+int do_solve(mifgpu_ctx *ctx, mifgpu_tensor *dp, mifgpu_tensor *const vel[3], double dt, const mifgpu_bc *nhn_bc,
+             double t_new, double t_prev) {
+  launch_divergence(ctx->stream, ctx->g, cvec3(vel), 0.0, dt, dp->data, &ctx->launches);
+  if (nhn_bc) {
+    const Geom &g = ctx->g;
+    if (g.periodic[0] || g.periodic[1] || g.periodic[2])
+      return fail(MIFGPU_ERR_INVALID, "non-homogeneous Neumann data needs all directions non-periodic");
+    BcDev dev;
+    std::memset(&dev, 0, sizeof(dev));
+    const int rc = fill_face_tables(ctx, nhn_bc, 1, t_new, t_prev, dev);
+    if (rc) return rc;
+    launch_nhn_rhs(ctx->stream, g, dp->data, dev, &ctx->launches);
+  }
+  launch_poisson(ctx->stream, ctx->g, ctx->plan, dp->data, &ctx->launches);
+  launch_periodic(ctx->stream, ctx->g, dp->data, 3, &ctx->launches);  // copy_to_staggered, src/PressureTensor.cpp:21-34
+  return MIFGPU_OK;
+}
+
+int check_launch(mifgpu_ctx *ctx) {
+  (void)ctx;
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(MIFGPU_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
+  return MIFGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mifgpu_abi_version(void) { return MIFGPU_ABI_VERSION; }
+
+const char *mifgpu_last_error(void) { return g_last_error.c_str(); }
+
+int mifgpu_create(const mifgpu_params *params, mifgpu_ctx **out) {
+  if (!params || !out) return fail(MIFGPU_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  Geom g;
+  std::memset(&g, 0, sizeof(g));
+  int n_points[3];
+  int rc = build_geometry(*params, g, n_points);
+  if (rc) return rc;
+  if (params->Py * params->Pz != 1)
+    return fail(MIFGPU_ERR_UNSUPPORTED, "multi-rank decomposition (Py*Pz = %d) is not available in this build",
+                params->Py * params->Pz);
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return fail(MIFGPU_ERR_CUDA, "no CUDA device available (libmifgpu has no CPU fallback)");
+  if (params->device < 0 || params->device >= count) return fail(MIFGPU_ERR_INVALID, "device %d out of range", params->device);
+  CUDA_TRY(cudaSetDevice(params->device));
+  mifgpu_ctx *ctx = new mifgpu_ctx();
+  ctx->params = *params;
+  ctx->g = g;
+  for (int d = 0; d < 3; d++) ctx->n_points[d] = n_points[d];
+  cudaError_t err = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (err != cudaSuccess) {
+    delete ctx;
+    return fail(MIFGPU_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(err));
+  }
+  const int per[3] = {g.periodic[0], g.periodic[1], g.periodic[2]};
+  const double h[3] = {g.dx, g.dy, g.dz};
+  const int n_global[3] = {(int)params->Nx_global, (int)params->Ny_global, (int)params->Nz_global};
+  ctx->plan = poisson_plan_create(g, n_points, per, h, n_global);
+  err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) {
+    mifgpu_destroy(ctx);
+    return fail(MIFGPU_ERR_CUDA, "plan creation failed: %s", cudaGetErrorString(err));
+  }
+  *out = ctx;
+  return MIFGPU_OK;
+}
+
+void mifgpu_destroy(mifgpu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->params.device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (int w = 0; w < 2; w++)
+    for (int c = 0; c < 3; c++)
+      for (int f = 0; f < 6; f++) {
+        if (ctx->face_host[w][c][f]) cudaFreeHost(ctx->face_host[w][c][f]);
+        if (ctx->face_dev[w][c][f]) cudaFree(ctx->face_dev[w][c][f]);
+      }
+  poisson_plan_destroy(ctx->plan);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int mifgpu_tensor_extents(const mifgpu_ctx *ctx, int staggering, uint64_t extents[3]) {
+  if (!ctx || !extents || staggering < 0 || staggering > 3) return fail(MIFGPU_ERR_INVALID, "bad argument");
+  extents[0] = ctx->g.sx[staggering];
+  extents[1] = ctx->g.sy[staggering];
+  extents[2] = ctx->g.sz[staggering];
+  return MIFGPU_OK;
+}
+
+int mifgpu_tensor_create(mifgpu_ctx *ctx, int staggering, mifgpu_tensor **out) {
+  if (!ctx || !out || staggering < 0 || staggering > 3) return fail(MIFGPU_ERR_INVALID, "bad argument");
+  *out = nullptr;
+  CUDA_TRY(cudaSetDevice(ctx->params.device));
+  double *data = nullptr;
+  const size_t bytes = (size_t)ctx->g.volume * sizeof(double);
+  CUDA_TRY(cudaMalloc(&data, bytes));
+  cudaError_t err = cudaMemsetAsync(data, 0, bytes, ctx->stream);
+  if (err != cudaSuccess) {
+    cudaFree(data);
+    return fail(MIFGPU_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(err));
+  }
+  mifgpu_tensor *t = new mifgpu_tensor();
+  t->ctx = ctx;
+  t->staggering = staggering;
+  t->data = data;
+  *out = t;
+  return MIFGPU_OK;
+}
+
+void mifgpu_tensor_destroy(mifgpu_tensor *t) {
+  if (!t) return;
+  cudaSetDevice(t->ctx->params.device);
+  cudaStreamSynchronize(t->ctx->stream);
+  cudaFree(t->data);
+  delete t;
+}
+
+static int copy_tensor(const mifgpu_tensor *t, double *host, bool to_device) {
+  if (!t || !host) return fail(MIFGPU_ERR_INVALID, "NULL argument");
+  mifgpu_ctx *ctx = t->ctx;
+  const Geom &g = ctx->g;
+  CUDA_TRY(cudaSetDevice(ctx->params.device));
+  const int s = t->staggering;
+  cudaMemcpy3DParms parms;
+  std::memset(&parms, 0, sizeof(parms));
+  const cudaPitchedPtr host_ptr = make_cudaPitchedPtr(host, (size_t)g.sx[s] * sizeof(double), g.sx[s], g.sy[s]);
+  const cudaPitchedPtr dev_ptr = make_cudaPitchedPtr(t->data, (size_t)g.PX * sizeof(double), g.PX, g.PY);
+  parms.srcPtr = to_device ? host_ptr : dev_ptr;
+  parms.dstPtr = to_device ? dev_ptr : host_ptr;
+  parms.extent = make_cudaExtent((size_t)g.sx[s] * sizeof(double), g.sy[s], g.sz[s]);
+  parms.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  CUDA_TRY(cudaMemcpy3DAsync(&parms, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MIFGPU_OK;
+}
+
+int mifgpu_tensor_upload(mifgpu_tensor *t, const double *host) { return copy_tensor(t, const_cast<double *>(host), true); }
+int mifgpu_tensor_download(const mifgpu_tensor *t, double *host) { return copy_tensor(t, host, false); }
+
+int mifgpu_tensor_swap(mifgpu_tensor *a, mifgpu_tensor *b) {
+  if (!a || !b || a->ctx != b->ctx || a->staggering != b->staggering) return fail(MIFGPU_ERR_INVALID, "tensors are not swappable");
+  std::swap(a->data, b->data);
+  return MIFGPU_OK;
+}
+
+int mifgpu_apply_bc(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], const mifgpu_bc *bc, double time) {
+  if (!ctx || !bc) return fail(MIFGPU_ERR_INVALID, "NULL argument");
+  int rc = check_triple(ctx, velocity, "velocity");
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(ctx->params.device));
+  rc = do_apply_bc(ctx, velocity, bc, time);
+  if (rc) return rc;
+  return check_launch(ctx);
+}
+
+int mifgpu_solve_pressure(mifgpu_ctx *ctx, mifgpu_tensor *pressure, mifgpu_tensor *const velocity[3], double dt,
+                          const mifgpu_bc *nhn_bc, double nhn_time) {
+  if (!ctx) return fail(MIFGPU_ERR_INVALID, "NULL context");
+  int rc = check_triple(ctx, velocity, "velocity");
+  if (rc) return rc;
+  rc = check_scalar(ctx, pressure, "pressure");
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(ctx->params.device));
+  rc = do_solve(ctx, pressure, velocity, dt, nhn_bc, nhn_time, nhn_time);
+  if (rc) return rc;
+  return check_launch(ctx);
+}
+
+int mifgpu_timestep(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], mifgpu_tensor *const velocity_buffer[3],
+                    mifgpu_tensor *const velocity_buffer_2[3], const mifgpu_bc *bc, double t_n, mifgpu_tensor *pressure,
+                    mifgpu_tensor *pressure_buffer, int nhn) {
+  if (!ctx || !bc) return fail(MIFGPU_ERR_INVALID, "NULL argument");
+  int rc;
+  if ((rc = check_triple(ctx, velocity, "velocity"))) return rc;
+  if ((rc = check_triple(ctx, velocity_buffer, "velocity_buffer"))) return rc;
+  if ((rc = check_triple(ctx, velocity_buffer_2, "velocity_buffer_2"))) return rc;
+  if ((rc = check_scalar(ctx, pressure, "pressure"))) return rc;
+  if ((rc = check_scalar(ctx, pressure_buffer, "pressure_buffer"))) return rc;
+  CUDA_TRY(cudaSetDevice(ctx->params.device));
+  const Geom &g = ctx->g;
+  cudaStream_t s = ctx->stream;
+  // Stage times, src/Timestep.cpp:98-105.
+  const double dt_1 = 64.0 / 120.0 * g.dt, time_1 = t_n + dt_1;
+  const double dt_2 = 16.0 / 120.0 * g.dt, time_2 = time_1 + dt_2;
+  const double dt_3 = 40.0 / 120.0 * g.dt, final_time = t_n + g.dt;
+  const mifgpu_bc *nhn_bc = nhn ? bc : nullptr;
+
+  // Stage 1 (src/Timestep.cpp:107-117).
+  launch_stage(s, g, 1, cvec3(velocity), pressure->data, vec3(velocity_buffer), vec3(velocity_buffer_2), &ctx->launches);
+  if ((rc = do_apply_bc(ctx, velocity_buffer, bc, time_1))) return rc;
+  if ((rc = do_solve(ctx, pressure_buffer, velocity_buffer, dt_1, nhn_bc, time_1, t_n))) return rc;
+  launch_correct(s, g, vec3(velocity_buffer), pressure->data, pressure_buffer->data, dt_1, &ctx->launches);
+
+  // Stage 2 (src/Timestep.cpp:119-129).
+  launch_stage(s, g, 2, cvec3(velocity_buffer), pressure->data, vec3(velocity_buffer_2), vec3(velocity), &ctx->launches);
+  if ((rc = do_apply_bc(ctx, velocity_buffer_2, bc, time_2))) return rc;
+  if ((rc = do_solve(ctx, pressure_buffer, velocity_buffer_2, dt_2, nhn_bc, time_2, time_1))) return rc;
+  launch_correct(s, g, vec3(velocity_buffer_2), pressure->data, pressure_buffer->data, dt_2, &ctx->launches);
+
+  // Stage 3 (src/Timestep.cpp:131-141).
+  launch_stage(s, g, 3, cvec3(velocity_buffer_2), pressure->data, vec3(velocity), vec3(velocity), &ctx->launches);
+  if ((rc = do_apply_bc(ctx, velocity, bc, final_time))) return rc;
+  if ((rc = do_solve(ctx, pressure_buffer, velocity, dt_3, nhn_bc, final_time, time_2))) return rc;
+  launch_correct(s, g, vec3(velocity), pressure->data, pressure_buffer->data, dt_3, &ctx->launches);
+  return check_launch(ctx);
+}
+
+int mifgpu_synchronize(mifgpu_ctx *ctx) {
+  if (!ctx) return fail(MIFGPU_ERR_INVALID, "NULL context");
+  CUDA_TRY(cudaSetDevice(ctx->params.device));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MIFGPU_OK;
+}
+
+void *mifgpu_stream(mifgpu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+uint64_t mifgpu_launch_count(const mifgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

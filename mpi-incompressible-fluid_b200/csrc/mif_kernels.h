@@ -1,0 +1,49 @@
+// mif_kernels.h -- host-callable launchers of the libmifgpu kernels (definitions in mif_stencil.cu and
+// mif_poisson.cu).  Everything here is internal to the library; the public surface is include/mifgpu.h.
+#pragma once
+
+#include "mif_common.cuh"
+
+namespace mifgpu {
+
+struct Vec3 {
+  double *c[3];
+};
+struct CVec3 {
+  const double *c[3];
+};
+
+// ---- mif_stencil.cu ------------------------------------------------------------------------------
+
+// RK stage kernels (src/Timestep.cpp:10-54).  stage = 1 (Y2), 2 (Y3), 3 (U*).
+//   stage 1: in = velocity,          a = velocity_buffer (write Y2),           b = velocity_buffer_2 (write R1)
+//   stage 2: in = velocity_buffer,   a = velocity_buffer_2 (read R1, write Y3), b = velocity (write a2*R2)
+//   stage 3: in = velocity_buffer_2, a = velocity (read a2*R2, write U*),       b unused
+void launch_stage(cudaStream_t stream, const Geom &g, int stage, CVec3 in, const double *pressure, Vec3 a, Vec3 b,
+                  uint64_t *launches);
+
+// Dirichlet faces of all three components (src/VelocityTensor.cpp:36-218), then the single-rank
+// periodic ghost copies (src/StaggeredTensor.cpp:221-257).
+void launch_apply_bc(cudaStream_t stream, const Geom &g, Vec3 vel, const BcDev &bc, uint64_t *launches);
+void launch_periodic(cudaStream_t stream, const Geom &g, double *field, int comp, uint64_t *launches);
+
+// rhs = div(velocity)/dt on owner points (src/PressureEquation.cpp:59-61, include/VelocityDivergence.h:9-20).
+void launch_divergence(cudaStream_t stream, const Geom &g, CVec3 vel, double inv_dt_unused, double dt, double *rhs,
+                       uint64_t *launches);
+// rhs(face) +-= 2 g / h on the six faces (src/PressureEquation.cpp:10-56); tables as in BcDev.
+void launch_nhn_rhs(cudaStream_t stream, const Geom &g, double *rhs, const BcDev &bc, uint64_t *launches);
+
+// p += dp on all points and vel -= dt_s * grad(dp) on interior points (src/Timestep.cpp:66-81).
+void launch_correct(cudaStream_t stream, const Geom &g, Vec3 vel, double *pressure, const double *dp, double dt_s,
+                    uint64_t *launches);
+
+// ---- mif_poisson.cu ------------------------------------------------------------------------------
+
+struct PoissonPlan;  // transform tables + eigenvalues for one context
+PoissonPlan *poisson_plan_create(const Geom &g, const int n_points[3], const int periodic[3], const double h[3],
+                                 const int n_global[3]);
+void poisson_plan_destroy(PoissonPlan *plan);
+// In-place spectral solve on the owner region of `field` (src/PressureEquation.cpp:65-264).
+void launch_poisson(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *field, uint64_t *launches);
+
+}  // namespace mifgpu

@@ -1,0 +1,500 @@
+// mif_poisson.cu -- spectral pressure Poisson solve on the device (sm_100a, FP64), replacing
+// mif::solve_pressure_equation (src/PressureEquation.cpp:65-264), the FFTW plans of
+// PressureSolverStructures (src/PressureSolverStructures.cpp:23-41) and the 2Decomp pencil transposes
+// (deps/2Decomp_C/Transpose*.cpp), which on one GPU become strided tile accesses: every sweep reads a
+// tile of L lines straight out of the x-fastest array into shared memory, transforms them there and
+// writes them back in place, so no global transpose and no eigenvalue array exist.
+//
+// Transforms (FFTW definitions, see oracle/fft_cpu.h):
+//   non-periodic direction: FFTW_REDFT00 (DCT-I) on N_global points, forward and inverse
+//   periodic direction:     FFTW_R2HC forward / FFTW_HC2R inverse on N_global-1 points
+// each reduced to ONE complex DFT per line (length N-1 for DCT-I, n/2 for even-length real FFTs, n for
+// odd), executed as a power-of-two shared-memory FFT or, for other lengths, Bluestein's chirp-z on a
+// power-of-two FFT.  The sweep along z does forward transform, division by the eigenvalues
+// (src/PressureEquation.cpp:158-163), inverse transform and normalisation in one kernel.
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+#include "mif_kernels.h"
+
+namespace mifgpu {
+
+namespace {
+
+const double kPi = 3.14159265358979323846264338327950288;
+
+struct DirPlanDev {
+  int periodic;   // 0: DCT-I, 1: halfcomplex real FFT
+  int n;          // real points per line
+  int m;          // complex DFT length
+  int P, logP;    // executed power-of-two FFT size
+  int bluestein;  // m is not a power of two
+  const double2 *tw;      // P/2: exp(-2 pi i q / P)
+  const double2 *chirp;   // m:   exp(-i pi j^2 / m)                         (Bluestein)
+  const double2 *filt;    // P:   FFT_P(wrapped conj chirp) / P, bit-reversed (Bluestein)
+  const double2 *unpack;  // (cos, sin)(pi k / m) for DCT-I, (cos, sin)(2 pi k / n) for real FFTs
+  const double *lambda;   // n eigenvalues of the 1-D second difference in FFTW output order
+  double inv_norm;        // 1 / (2 (N_global - 1)) or 1 / (N_global - 1)
+};
+
+struct SweepJob {
+  DirPlanDev plan;
+  int dir;             // 0 = x, 1 = y, 2 = z
+  int L;               // lines per CTA
+  int n_tile_lines;    // number of lines along the tiled dimension
+  long long lstride;   // element offset between consecutive lines of a tile
+  long long estride;   // element offset between consecutive points of a line
+  int r_pitch;         // shared-memory pitch of one real line
+  int mode;            // 0 forward, 1 inverse (+normalise), 2 forward * eigen, inverse (+normalise)
+  const double *lam_a, *lam_b;  // eigenvalues of the two other directions (mode 2)
+  int lam_a_lo, lam_b_lo;       // owner offsets of those directions
+};
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cmul_conj(double2 a, double2 b) {  // a * conj(b)
+  return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+
+// Radix-2 decimation-in-frequency passes: natural order in, bit-reversed order out.
+__device__ void fft_dif(double2 *W, int L, int P, int logP, const double2 *__restrict__ tw, bool conj_tw) {
+  const int halfP = P >> 1;
+  for (int s = logP - 1; s >= 0; s--) {
+    const int half = 1 << s;
+    const int tstride = halfP >> s;
+    for (int item = threadIdx.x; item < L * halfP; item += blockDim.x) {
+      const int l = item / halfP, bfly = item - l * halfP;
+      const int k = bfly & (half - 1);
+      const int i0 = ((bfly >> s) << (s + 1)) + k;
+      double2 *w = W + (size_t)l * P;
+      const double2 a = w[i0], b = w[i0 + half];
+      double2 t = __ldg(&tw[k * tstride]);
+      if (conj_tw) t.y = -t.y;
+      w[i0] = make_double2(a.x + b.x, a.y + b.y);
+      w[i0 + half] = cmul(make_double2(a.x - b.x, a.y - b.y), t);
+    }
+    __syncthreads();
+  }
+}
+
+// Radix-2 decimation-in-time passes: bit-reversed order in, natural order out.
+__device__ void fft_dit(double2 *W, int L, int P, int logP, const double2 *__restrict__ tw, bool conj_tw) {
+  const int halfP = P >> 1;
+  for (int s = 0; s < logP; s++) {
+    const int half = 1 << s;
+    const int tstride = halfP >> s;
+    for (int item = threadIdx.x; item < L * halfP; item += blockDim.x) {
+      const int l = item / halfP, bfly = item - l * halfP;
+      const int k = bfly & (half - 1);
+      const int i0 = ((bfly >> s) << (s + 1)) + k;
+      double2 *w = W + (size_t)l * P;
+      double2 t = __ldg(&tw[k * tstride]);
+      if (conj_tw) t.y = -t.y;
+      const double2 a = w[i0], b = cmul(w[i0 + half], t);
+      w[i0] = make_double2(a.x + b.x, a.y + b.y);
+      w[i0 + half] = make_double2(a.x - b.x, a.y - b.y);
+    }
+    __syncthreads();
+  }
+}
+
+// Complex DFT of length m of every line of the tile.  Input: W[l][0..m) in natural order.
+// Output: element k of the spectrum is at W[l][spec_pos(k)].  inverse = unnormalised exp(+...).
+__device__ void cdft_tile(double2 *W, int L, const DirPlanDev &pl, bool inverse) {
+  const int P = pl.P, m = pl.m;
+  if (!pl.bluestein) {
+    fft_dif(W, L, P, pl.logP, pl.tw, inverse);
+    return;
+  }
+  // Bluestein: X_k = w_k sum_j (x_j w_j) conj(w_{k-j}), w_j = exp(-i pi j^2/m); the inverse transform is
+  // conj(DFT(conj x)).
+  for (int item = threadIdx.x; item < L * P; item += blockDim.x) {
+    const int l = item / P, j = item - l * P;
+    double2 *w = W + (size_t)l * P;
+    if (j < m) {
+      double2 x = w[j];
+      if (inverse) x.y = -x.y;
+      w[j] = cmul(x, __ldg(&pl.chirp[j]));
+    } else {
+      w[j] = make_double2(0.0, 0.0);
+    }
+  }
+  __syncthreads();
+  fft_dif(W, L, P, pl.logP, pl.tw, false);
+  for (int item = threadIdx.x; item < L * P; item += blockDim.x) {
+    const int l = item / P, j = item - l * P;
+    double2 *w = W + (size_t)l * P;
+    w[j] = cmul(w[j], __ldg(&pl.filt[j]));
+  }
+  __syncthreads();
+  fft_dit(W, L, P, pl.logP, pl.tw, true);
+  for (int item = threadIdx.x; item < L * m; item += blockDim.x) {
+    const int l = item / m, k = item - l * m;
+    double2 *w = W + (size_t)l * P;
+    double2 x = cmul(w[k], __ldg(&pl.chirp[k]));
+    if (inverse) x.y = -x.y;
+    w[k] = x;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int spec_pos(const DirPlanDev &pl, int k) {
+  if (pl.bluestein) return k;
+  return pl.logP == 0 ? 0 : (int)(__brev((unsigned)k) >> (32 - pl.logP));
+}
+
+// Forward real transform of every line: R (n reals, natural order) -> R (FFTW output order).
+__device__ void real_forward(double *R, double2 *W, int L, int r_pitch, const DirPlanDev &pl) {
+  const int n = pl.n, m = pl.m, P = pl.P;
+  // pack
+  for (int item = threadIdx.x; item < L * m; item += blockDim.x) {
+    const int l = item / m, j = item - l * m;
+    const double *r = R + (size_t)l * r_pitch;
+    double2 c;
+    if (!pl.periodic) {
+      const int q0 = 2 * j, q1 = 2 * j + 1;  // even extension of period 2m
+      c = make_double2(r[q0 <= m ? q0 : 2 * m - q0], r[q1 <= m ? q1 : 2 * m - q1]);
+    } else if ((n & 1) == 0) {
+      c = make_double2(r[2 * j], r[2 * j + 1]);
+    } else {
+      c = make_double2(r[j], 0.0);
+    }
+    W[(size_t)l * P + j] = c;
+  }
+  __syncthreads();
+  cdft_tile(W, L, pl, false);
+  // unpack
+  if (!pl.periodic) {
+    for (int item = threadIdx.x; item < L * n; item += blockDim.x) {
+      const int l = item / n, k = item - l * n;
+      const double2 *w = W + (size_t)l * P;
+      const int k0 = (k == m) ? 0 : k, k1 = (k == 0) ? 0 : m - k;
+      const double2 A = w[spec_pos(pl, k0)], B = w[spec_pos(pl, k1)];
+      const double2 cs = __ldg(&pl.unpack[k]);
+      R[(size_t)l * r_pitch + k] = 0.5 * ((A.x + B.x) + cs.x * (A.y + B.y) - cs.y * (A.x - B.x));
+    }
+  } else if ((n & 1) == 0) {
+    const int h = m;
+    for (int item = threadIdx.x; item < L * (h + 1); item += blockDim.x) {
+      const int l = item / (h + 1), k = item - l * (h + 1);
+      const double2 *w = W + (size_t)l * P;
+      const int k0 = (k == h) ? 0 : k, k1 = (k == 0) ? 0 : h - k;
+      const double2 A = w[spec_pos(pl, k0)], B = w[spec_pos(pl, k1)];
+      const double2 cs = __ldg(&pl.unpack[k]);
+      double *r = R + (size_t)l * r_pitch;
+      r[k] = 0.5 * ((A.x + B.x) + cs.x * (A.y + B.y) - cs.y * (A.x - B.x));
+      if (k > 0 && k < h) r[n - k] = 0.5 * ((A.y - B.y) - cs.x * (A.x - B.x) - cs.y * (A.y + B.y));
+    }
+  } else {
+    const int h = n / 2;
+    for (int item = threadIdx.x; item < L * (h + 1); item += blockDim.x) {
+      const int l = item / (h + 1), k = item - l * (h + 1);
+      const double2 A = W[(size_t)l * P + spec_pos(pl, k)];
+      double *r = R + (size_t)l * r_pitch;
+      r[k] = A.x;
+      if (k > 0) r[n - k] = A.y;
+    }
+  }
+  __syncthreads();
+}
+
+// Inverse real transform of every line (unnormalised): for DCT-I the same transform, for periodic
+// directions FFTW_HC2R.  R (FFTW order) -> R (natural order).
+__device__ void real_inverse(double *R, double2 *W, int L, int r_pitch, const DirPlanDev &pl) {
+  if (!pl.periodic) {
+    real_forward(R, W, L, r_pitch, pl);
+    return;
+  }
+  const int n = pl.n, m = pl.m, P = pl.P;
+  if ((n & 1) == 0) {
+    const int h = m;
+    for (int item = threadIdx.x; item < L * h; item += blockDim.x) {
+      const int l = item / h, k = item - l * h;
+      const double *r = R + (size_t)l * r_pitch;
+      const int kk = h - k;
+      const double xr = r[k], xi = (k == 0) ? 0.0 : r[n - k];
+      const double yr = r[kk], yi = (kk == h) ? 0.0 : r[n - kk];
+      const double pr = xr + yr, pi = xi - yi, dr = xr - yr, di = xi + yi;
+      const double2 cs = __ldg(&pl.unpack[k]);
+      W[(size_t)l * P + k] = make_double2(pr - cs.y * dr - cs.x * di, pi + cs.x * dr - cs.y * di);
+    }
+    __syncthreads();
+    cdft_tile(W, L, pl, true);
+    for (int item = threadIdx.x; item < L * h; item += blockDim.x) {
+      const int l = item / h, j = item - l * h;
+      const double2 A = W[(size_t)l * P + spec_pos(pl, j)];
+      double *r = R + (size_t)l * r_pitch;
+      r[2 * j] = A.x;
+      r[2 * j + 1] = A.y;
+    }
+  } else {
+    const int h = n / 2;
+    for (int item = threadIdx.x; item < L * (h + 1); item += blockDim.x) {
+      const int l = item / (h + 1), k = item - l * (h + 1);
+      const double *r = R + (size_t)l * r_pitch;
+      double2 *w = W + (size_t)l * P;
+      if (k == 0) {
+        w[0] = make_double2(r[0], 0.0);
+      } else {
+        w[k] = make_double2(r[k], r[n - k]);
+        w[n - k] = make_double2(r[k], -r[n - k]);
+      }
+    }
+    __syncthreads();
+    cdft_tile(W, L, pl, true);
+    for (int item = threadIdx.x; item < L * n; item += blockDim.x) {
+      const int l = item / n, j = item - l * n;
+      R[(size_t)l * r_pitch + j] = W[(size_t)l * P + spec_pos(pl, j)].x;
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) sweep_kernel(const SweepJob job, double *__restrict__ field, long long origin,
+                                                    long long tile_stride, long long outer_stride) {
+  extern __shared__ double2 smem2[];
+  const DirPlanDev &pl = job.plan;
+  const int L = job.L, n = pl.n, r_pitch = job.r_pitch;
+  double2 *W = smem2;
+  double *R = reinterpret_cast<double *>(W + (size_t)L * pl.P);
+  const int first_line = blockIdx.x * L;
+  const int lines = min(L, job.n_tile_lines - first_line);
+  double *base = field + origin + (long long)first_line * tile_stride + (long long)blockIdx.y * outer_stride;
+
+  // load: element-fastest when points of a line are contiguous (x sweeps), line-fastest otherwise
+  if (job.estride == 1) {
+    for (int item = threadIdx.x; item < L * n; item += blockDim.x) {
+      const int l = item / n, e = item - l * n;
+      R[(size_t)l * r_pitch + e] = (l < lines) ? base[(long long)l * job.lstride + e] : 0.0;
+    }
+  } else {
+    for (int item = threadIdx.x; item < L * n; item += blockDim.x) {
+      const int e = item / L, l = item - e * L;
+      R[(size_t)l * r_pitch + e] = (l < lines) ? base[(long long)l * job.lstride + (long long)e * job.estride] : 0.0;
+    }
+  }
+  __syncthreads();
+
+  if (job.mode == 0 || job.mode == 2) real_forward(R, W, L, r_pitch, pl);
+  if (job.mode == 2) {
+    // pressure_hat *= 1 / (lambda_x + lambda_y + lambda_z); mode (0,0,0) := 0  (src/PressureEquation.cpp:158-163,
+    // table of src/PressureSolverStructures.cpp:52-69).  For the z sweep a tile line is x index
+    // first_line + l and blockIdx.y is the y index.
+    const double lam_y = job.lam_b[blockIdx.y];
+    for (int item = threadIdx.x; item < L * n; item += blockDim.x) {
+      const int l = item / n, e = item - l * n;
+      if (l < lines) {
+        const int ix = first_line + l;
+        const double lam_x = job.lam_a[ix];
+        double scale = 1.0 / (lam_x + lam_y + pl.lambda[e]);
+        if (ix == 0 && blockIdx.y == 0 && e == 0) scale = 0.0;
+        R[(size_t)l * r_pitch + e] *= scale;
+      }
+    }
+    __syncthreads();
+  }
+  if (job.mode == 1 || job.mode == 2) {
+    real_inverse(R, W, L, r_pitch, pl);
+    for (int item = threadIdx.x; item < L * n; item += blockDim.x) {
+      const int l = item / n, e = item - l * n;
+      R[(size_t)l * r_pitch + e] *= pl.inv_norm;
+    }
+    __syncthreads();
+  }
+
+  if (job.estride == 1) {
+    for (int item = threadIdx.x; item < L * n; item += blockDim.x) {
+      const int l = item / n, e = item - l * n;
+      if (l < lines) base[(long long)l * job.lstride + e] = R[(size_t)l * r_pitch + e];
+    }
+  } else {
+    for (int item = threadIdx.x; item < L * n; item += blockDim.x) {
+      const int e = item / L, l = item - e * L;
+      if (l < lines) base[(long long)l * job.lstride + (long long)e * job.estride] = R[(size_t)l * r_pitch + e];
+    }
+  }
+}
+
+template <typename T>
+T *to_device(const std::vector<T> &host) {
+  if (host.empty()) return nullptr;
+  T *dev = nullptr;
+  cudaMalloc(&dev, host.size() * sizeof(T));
+  cudaMemcpy(dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return dev;
+}
+
+// exp(-2 pi i num / den) with the argument reduced in integers.
+double2 unit_root(long long num, long long den) {
+  num %= den;
+  const double a = -2.0 * kPi * (double)num / (double)den;
+  return make_double2(std::cos(a), std::sin(a));
+}
+
+void host_fft_pow2(std::vector<double2> &z, bool inverse) {  // small recursive helper for plan tables
+  const size_t n = z.size();
+  if (n <= 1) return;
+  std::vector<double2> even(n / 2), odd(n / 2);
+  for (size_t i = 0; i < n / 2; i++) {
+    even[i] = z[2 * i];
+    odd[i] = z[2 * i + 1];
+  }
+  host_fft_pow2(even, inverse);
+  host_fft_pow2(odd, inverse);
+  for (size_t k = 0; k < n / 2; k++) {
+    double2 t = unit_root((long long)k, (long long)n);
+    if (inverse) t.y = -t.y;
+    const double2 o = make_double2(odd[k].x * t.x - odd[k].y * t.y, odd[k].x * t.y + odd[k].y * t.x);
+    z[k] = make_double2(even[k].x + o.x, even[k].y + o.y);
+    z[k + n / 2] = make_double2(even[k].x - o.x, even[k].y - o.y);
+  }
+}
+
+}  // namespace
+
+struct PoissonPlan {
+  DirPlanDev dir[3];
+  int L[3];
+  size_t smem[3];
+  std::vector<void *> allocations;
+};
+
+PoissonPlan *poisson_plan_create(const Geom &g, const int n_points[3], const int periodic[3], const double h[3],
+                                 const int n_global[3]) {
+  (void)g;
+  PoissonPlan *plan = new PoissonPlan();
+  for (int d = 0; d < 3; d++) {
+    DirPlanDev &pl = plan->dir[d];
+    const int n = n_points[d];
+    pl.periodic = periodic[d];
+    pl.n = n;
+    pl.m = !periodic[d] ? n - 1 : ((n % 2 == 0) ? n / 2 : n);
+    if (pl.m < 1) pl.m = 1;
+    const bool pow2 = (pl.m & (pl.m - 1)) == 0;
+    pl.bluestein = !pow2;
+    int P = 1;
+    if (pow2) P = pl.m;
+    else while (P < 2 * pl.m - 1) P <<= 1;
+    pl.P = P;
+    pl.logP = 0;
+    while ((1 << pl.logP) < P) pl.logP++;
+
+    std::vector<double2> tw(std::max(P / 2, 1));
+    for (int q = 0; q < P / 2; q++) tw[q] = unit_root(q, P);
+    pl.tw = to_device(tw);
+    plan->allocations.push_back((void *)pl.tw);
+
+    pl.chirp = nullptr;
+    pl.filt = nullptr;
+    if (pl.bluestein) {
+      const int m = pl.m;
+      std::vector<double2> chirp(m), filt(P, make_double2(0.0, 0.0));
+      for (int j = 0; j < m; j++) chirp[j] = unit_root(((long long)j * j) % (2LL * m), 2LL * m);
+      for (int j = 0; j < m; j++) {
+        filt[j] = make_double2(chirp[j].x, -chirp[j].y);
+        if (j > 0) filt[P - j] = filt[j];
+      }
+      host_fft_pow2(filt, false);
+      std::vector<double2> filt_br(P);
+      for (int i = 0; i < P; i++) {
+        unsigned r = 0;
+        for (int b = 0; b < pl.logP; b++)
+          if (i & (1 << b)) r |= 1u << (pl.logP - 1 - b);
+        filt_br[i] = make_double2(filt[r].x / P, filt[r].y / P);
+      }
+      pl.chirp = to_device(chirp);
+      pl.filt = to_device(filt_br);
+      plan->allocations.push_back((void *)pl.chirp);
+      plan->allocations.push_back((void *)pl.filt);
+    }
+
+    // unpack twiddles: DCT-I exp(-i pi k / m), k <= m; real FFT exp(-2 pi i k / n), k <= n/2 (stored as cos, sin)
+    std::vector<double2> unpack;
+    if (!periodic[d]) {
+      unpack.resize(n);
+      for (int k = 0; k < n; k++) {
+        const double2 r = unit_root(k, 2LL * std::max(pl.m, 1));
+        unpack[k] = make_double2(r.x, -r.y);
+      }
+    } else {
+      unpack.resize(n / 2 + 1);
+      for (int k = 0; k <= n / 2; k++) {
+        const double2 r = unit_root(k, n);
+        unpack[k] = make_double2(r.x, -r.y);
+      }
+    }
+    pl.unpack = to_device(unpack);
+    plan->allocations.push_back((void *)pl.unpack);
+
+    // eigenvalues, formulas and evaluation order of src/PressureSolverStructures.cpp:5-11
+    std::vector<double> lambda(n);
+    for (int k = 0; k < n; k++) {
+      if (periodic[d]) lambda[k] = 2.0 * (std::cos(2.0 * M_PI * k / n) - 1.0) / (h[d] * h[d]);
+      else lambda[k] = 2.0 * (std::cos(M_PI * k / (n - 1)) - 1.0) / (h[d] * h[d]);
+    }
+    pl.lambda = to_device(lambda);
+    plan->allocations.push_back((void *)pl.lambda);
+    // src/PressureEquation.cpp:167,200,234: N_domains_global * (periodic ? 1 : 2)
+    pl.inv_norm = 1.0 / ((double)(n_global[d] - 1) * (periodic[d] ? 1.0 : 2.0));
+
+    // lines per CTA: the largest power of two <= 8 that fits a ~100 KB shared-memory budget (two CTAs per SM)
+    const size_t per_line = (size_t)P * sizeof(double2) + (size_t)(n | 1) * sizeof(double);
+    int L = 8;
+    while (L > 1 && per_line * L > 100 * 1024) L >>= 1;
+    plan->L[d] = L;
+    plan->smem[d] = per_line * L;
+  }
+  return plan;
+}
+
+void poisson_plan_destroy(PoissonPlan *plan) {
+  if (!plan) return;
+  for (void *p : plan->allocations) cudaFree(p);
+  delete plan;
+}
+
+void launch_poisson(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *field, uint64_t *launches) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  const int nx = g.own_hi[0] - g.own_lo[0], ny = g.own_hi[1] - g.own_lo[1], nz = g.own_hi[2] - g.own_lo[2];
+  const long long origin = gidx(g, g.own_lo[0], g.own_lo[1], g.own_lo[2]);
+  auto run = [&](int d, int mode) {
+    SweepJob job;
+    job.plan = plan->dir[d];
+    job.dir = d;
+    job.L = plan->L[d];
+    job.r_pitch = plan->dir[d].n | 1;
+    job.mode = mode;
+    job.lam_a = plan->dir[0].lambda;
+    job.lam_b = plan->dir[1].lambda;
+    job.lam_a_lo = 0;
+    job.lam_b_lo = 0;
+    long long tile_stride, outer_stride;
+    int outer;
+    if (d == 0) {  // lines along x, tile over y, outer z
+      job.n_tile_lines = ny; job.lstride = g.PX; job.estride = 1;
+      tile_stride = g.PX; outer_stride = g.plane; outer = nz;
+    } else if (d == 1) {  // lines along y, tile over x, outer z
+      job.n_tile_lines = nx; job.lstride = 1; job.estride = g.PX;
+      tile_stride = 1; outer_stride = g.plane; outer = nz;
+    } else {  // lines along z, tile over x, outer y
+      job.n_tile_lines = nx; job.lstride = 1; job.estride = g.plane;
+      tile_stride = 1; outer_stride = g.PX; outer = ny;
+    }
+    const dim3 grid((job.n_tile_lines + job.L - 1) / job.L, outer, 1);
+    sweep_kernel<<<grid, 256, plan->smem[d], stream>>>(job, field, origin, tile_stride, outer_stride);
+    ++*launches;
+  };
+  run(0, 0);  // forward x   (src/PressureEquation.cpp:79-101)
+  run(1, 0);  // forward y   (:106-128)
+  run(2, 2);  // forward z, eigenvalues, inverse z (:133-195)
+  run(1, 1);  // inverse y   (:200-229)
+  run(0, 1);  // inverse x   (:234-263)
+}
+
+}  // namespace mifgpu

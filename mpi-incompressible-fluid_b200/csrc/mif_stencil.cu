@@ -1,0 +1,416 @@
+// mif_stencil.cu -- stencil-type kernels of the projection step (sm_100a, FP64):
+//   RK stage kernels      src/Timestep.cpp:10-54 + include/MomentumEquation.h:42-255 + include/PressureGradient.h:9-24
+//   Dirichlet faces       src/VelocityTensor.cpp:36-218
+//   periodic ghost copies src/StaggeredTensor.cpp:221-257
+//   divergence rhs        src/PressureEquation.cpp:59-61 + include/VelocityDivergence.h:9-20
+//   p += dp, u -= dt grad(dp)   src/Timestep.cpp:66-81
+// All fields use the uniform padded layout of mif_common.cuh, so one linear index addresses every array.
+#include <math_constants.h>
+
+#include "../../include/mifgpu.h"
+#include "mif_kernels.h"
+
+namespace mifgpu {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// RK stage kernel.  One thread per grid index (i, j, k); the three components share their loads
+// (9 u + 9 v + 9 w + 4 p values) and each component is stored only where (i, j, k) is interior to it
+// (STAGGERED_TENSOR_ITERATE_OVER_ALL_POINTS with include_border = false, include/StaggeredTensorMacros.h:6-37).
+// ------------------------------------------------------------------------------------------------
+template <int STAGE>
+__global__ void __launch_bounds__(256)
+stage_kernel(const Geom g, const double *__restrict__ in_u, const double *__restrict__ in_v,
+             const double *__restrict__ in_w, const double *__restrict__ p, double *__restrict__ a_u,
+             double *__restrict__ a_v, double *__restrict__ a_w, double *__restrict__ b_u, double *__restrict__ b_v,
+             double *__restrict__ b_w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  const bool in_i_u = i <= g.sx[0] - 2, in_i_o = i <= g.Nx - 2;  // v, w and p share the unstaggered x extent
+  if (!in_i_u && !in_i_o) return;
+  const bool in_j_v = j <= g.sy[1] - 2, in_j_o = j <= g.Ny - 2;
+  if (!in_j_v && !in_j_o) return;
+  const bool in_k_w = k <= g.sz[2] - 2, in_k_o = k <= g.Nz - 2;
+  const bool do_u = in_i_u && in_j_o && in_k_o;
+  const bool do_v = in_i_o && in_j_v && in_k_o;
+  const bool do_w = in_i_o && in_j_o && in_k_w;
+  if (!do_u && !do_v && !do_w) return;
+
+  const long long c = gidx(g, i, j, k);
+  const long long sj = g.PX, sk = g.plane;
+
+  // Neighbourhood (names: m = minus, p = plus along x/y/z).
+  const double u_c = in_u[c], u_xm = in_u[c - 1], u_xp = in_u[c + 1];
+  const double u_ym = in_u[c - sj], u_yp = in_u[c + sj], u_zm = in_u[c - sk], u_zp = in_u[c + sk];
+  const double u_xp_ym = in_u[c + 1 - sj], u_xp_zm = in_u[c + 1 - sk];
+  const double v_c = in_v[c], v_xm = in_v[c - 1], v_xp = in_v[c + 1];
+  const double v_ym = in_v[c - sj], v_yp = in_v[c + sj], v_zm = in_v[c - sk], v_zp = in_v[c + sk];
+  const double v_xm_yp = in_v[c - 1 + sj], v_yp_zm = in_v[c + sj - sk];
+  const double w_c = in_w[c], w_xm = in_w[c - 1], w_xp = in_w[c + 1];
+  const double w_ym = in_w[c - sj], w_yp = in_w[c + sj], w_zm = in_w[c - sk], w_zp = in_w[c + sk];
+  const double w_xm_zp = in_w[c - 1 + sk], w_ym_zp = in_w[c - sj + sk];
+  const double p_c = p[c], p_xm = p[c - 1], p_ym = p[c - sj], p_zm = p[c - sk];
+
+  const double dt = g.dt;
+  double a1, a2, a3, b;
+  if (STAGE == 1) {
+    a1 = 64.0 / 120.0 * dt;
+    a2 = 0.0;
+    a3 = 0.0;
+    b = a1;
+  } else if (STAGE == 2) {
+    a1 = -34.0 / 120.0 * dt;
+    a2 = 50.0 / 120.0 * dt;
+    a3 = 0.0;
+    b = a1 + a2;
+  } else {
+    a1 = 0.0;
+    a2 = -50.0 / 120.0 * dt;
+    a3 = 90.0 / 120.0 * dt;
+    b = a2 + a3;
+  }
+  (void)a1;
+  (void)a2;
+  (void)a3;
+
+  if (do_u) {
+    // include/MomentumEquation.h:50-96
+    const double convection = -u_c * (u_xp - u_xm) * g.one_over_2_dx -
+                              (v_yp + v_c + v_xm_yp + v_xm) * (u_yp - u_ym) * g.one_over_8_dy -
+                              (w_zp + w_c + w_xm_zp + w_xm) * (u_zp - u_zm) * g.one_over_8_dz;
+    const double diffusion = (u_xp - 2 * u_c + u_xm) * g.one_over_dx2_Re + (u_yp - 2 * u_c + u_ym) * g.one_over_dy2_Re +
+                             (u_zp - 2 * u_c + u_zm) * g.one_over_dz2_Re;
+    const double rhs = convection + diffusion;
+    const double p_grad = (p_c - p_xm) * g.one_over_dx;  // include/PressureGradient.h:9-12
+    if (STAGE == 1) {
+      a_u[c] = u_c + a1 * rhs - b * p_grad;  // src/Timestep.cpp:18
+      b_u[c] = rhs;                          // src/Timestep.cpp:19
+    } else if (STAGE == 2) {
+      const double rhs_1 = a_u[c];
+      const double rhs_2_scaled = a2 * rhs;
+      a_u[c] = u_c + a1 * rhs_1 + rhs_2_scaled - b * p_grad;  // src/Timestep.cpp:35-36
+      b_u[c] = rhs_2_scaled;                                  // src/Timestep.cpp:37
+    } else {
+      const double rhs_2_scaled = -a_u[c];
+      a_u[c] = u_c + rhs_2_scaled + a3 * rhs - b * p_grad;  // src/Timestep.cpp:51-52
+    }
+  }
+  if (do_v) {
+    // include/MomentumEquation.h:126-165
+    const double convection = -(u_xp + u_c + u_xp_ym + u_ym) * (v_xp - v_xm) * g.one_over_8_dx -
+                              v_c * (v_yp - v_ym) * g.one_over_2_dy -
+                              (w_zp + w_c + w_ym_zp + w_ym) * (v_zp - v_zm) * g.one_over_8_dz;
+    const double diffusion = (v_xp - 2 * v_c + v_xm) * g.one_over_dx2_Re + (v_yp - 2 * v_c + v_ym) * g.one_over_dy2_Re +
+                             (v_zp - 2 * v_c + v_zm) * g.one_over_dz2_Re;
+    const double rhs = convection + diffusion;
+    const double p_grad = (p_c - p_ym) * g.one_over_dy;  // include/PressureGradient.h:15-18
+    if (STAGE == 1) {
+      a_v[c] = v_c + a1 * rhs - b * p_grad;
+      b_v[c] = rhs;
+    } else if (STAGE == 2) {
+      const double rhs_1 = a_v[c];
+      const double rhs_2_scaled = a2 * rhs;
+      a_v[c] = v_c + a1 * rhs_1 + rhs_2_scaled - b * p_grad;
+      b_v[c] = rhs_2_scaled;
+    } else {
+      const double rhs_2_scaled = -a_v[c];
+      a_v[c] = v_c + rhs_2_scaled + a3 * rhs - b * p_grad;
+    }
+  }
+  if (do_w) {
+    // include/MomentumEquation.h:196-236
+    const double convection = -(u_xp + u_c + u_xp_zm + u_zm) * (w_xp - w_xm) * g.one_over_8_dx -
+                              (v_yp + v_c + v_yp_zm + v_zm) * (w_yp - w_ym) * g.one_over_8_dy -
+                              w_c * (w_zp - w_zm) * g.one_over_2_dz;
+    const double diffusion = (w_xp - 2 * w_c + w_xm) * g.one_over_dx2_Re + (w_yp - 2 * w_c + w_ym) * g.one_over_dy2_Re +
+                             (w_zp - 2 * w_c + w_zm) * g.one_over_dz2_Re;
+    const double rhs = convection + diffusion;
+    const double p_grad = (p_c - p_zm) * g.one_over_dz;  // include/PressureGradient.h:21-24
+    if (STAGE == 1) {
+      a_w[c] = w_c + a1 * rhs - b * p_grad;
+      b_w[c] = rhs;
+    } else if (STAGE == 2) {
+      const double rhs_1 = a_w[c];
+      const double rhs_2_scaled = a2 * rhs;
+      a_w[c] = w_c + a1 * rhs_1 + rhs_2_scaled - b * p_grad;
+      b_w[c] = rhs_2_scaled;
+    } else {
+      const double rhs_2_scaled = -a_w[c];
+      a_w[c] = w_c + rhs_2_scaled + a3 * rhs - b * p_grad;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Analytic boundary data on the device.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double exact_velocity(int kind, int comp, double t, double x, double y, double z,
+                                                 double Re) {
+  if (kind == MIFGPU_BC_ETHIER_STEINMAN) {
+    // generators/manufsol.py:31-57 with a = pi/4, d = pi/2.
+    const double a = CUDART_PI / 4.0, d = CUDART_PI / 2.0;
+    const double decay = exp(-d * d * t / Re);
+    if (comp == 0) return -a * (exp(a * x) * sin(a * y + d * z) + exp(a * z) * cos(a * x + d * y)) * decay;
+    if (comp == 1) return -a * (exp(a * y) * sin(a * z + d * x) + exp(a * x) * cos(a * y + d * z)) * decay;
+    return -a * (exp(a * z) * sin(a * x + d * y) + exp(a * y) * cos(a * z + d * x)) * decay;
+  }
+  // include/TestCaseBoundaries.h:17-56: only v is non-zero, and only on one x face.
+  if (comp != 1) return 0.0;
+  const double face = (kind == MIFGPU_BC_TEST_CASE_1) ? 1.0 : -0.5;
+  const double precision = 1e-12;
+  return (x < face + precision && x > face - precision) ? 1.0 : 0.0;
+}
+
+// f_c evaluated at the staggered coordinate of component `at` index (i, j, k)
+// (evaluate_function_at_index, include/VelocityTensor.h:16-22,40-46,64-70) or, with at = 3, at the
+// unstaggered pressure point (include/StaggeredTensor.h:113-119).
+__device__ __forceinline__ double eval_at(const Geom &g, const BcDev &bc, int f_comp, int at, int i, int j, int k) {
+  double x = g.min_x + g.dx * (g.base_i + i);
+  double y = g.min_y + g.dy * (g.base_j + j);
+  double z = g.min_z + g.dz * (g.base_k + k);
+  if (at == 0) x -= g.dx_over_2;
+  if (at == 1) y -= g.dy_over_2;
+  if (at == 2) z -= g.dz_over_2;
+  return exact_velocity(bc.kind, f_comp, bc.time, x, y, z, bc.Re);
+}
+
+__device__ __forceinline__ bool face_active(const Geom &g, int face) {
+  switch (face) {
+    case 0: return g.prev_z == -1 && !g.periodic[2];
+    case 1: return g.next_z == -1 && !g.periodic[2];
+    case 2: return g.prev_y == -1 && !g.periodic[1];
+    case 3: return g.next_y == -1 && !g.periodic[1];
+    default: return !g.periodic[0];
+  }
+}
+
+// One thread per (component, face, point of the face).  The reference writes the faces in the order
+// z-, z+, y-, y+, x-, x+ over the full 2-D extent of each tensor, so on edges and corners the last face
+// wins (src/VelocityTensor.cpp:47-217); here a thread simply does not write where a later active face
+// owns the point, which gives the same final state without ordering launches.
+__global__ void __launch_bounds__(256) bc_face_kernel(const Geom g, double *u, double *v, double *w, const BcDev bc) {
+  const int comp = blockIdx.y / 6, face = blockIdx.y % 6;
+  if (!face_active(g, face)) return;
+  const int sx = g.sx[comp], sy = g.sy[comp], sz = g.sz[comp];
+  const int dir = 2 - face / 2;  // normal direction of the face: z, z, y, y, x, x
+  const int na = (dir == 0) ? sy : sx;
+  const int nb = (dir == 2) ? sy : sz;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)na * nb) return;
+  const int a = (int)(t % na), b2 = (int)(t / na);
+  const bool upper = face & 1;
+  int i, j, k;
+  if (dir == 2) {
+    i = a; j = b2; k = upper ? sz - 1 : 0;
+  } else if (dir == 1) {
+    i = a; k = b2; j = upper ? sy - 1 : 0;
+  } else {
+    j = a; k = b2; i = upper ? sx - 1 : 0;
+  }
+  // Later faces that also contain this point take precedence.
+  for (int later = face + 1; later < 6; later++) {
+    if (!face_active(g, later)) continue;
+    bool on;
+    switch (later) {
+      case 1: on = (k == sz - 1); break;
+      case 2: on = (j == 0); break;
+      case 3: on = (j == sy - 1); break;
+      case 4: on = (i == 0); break;
+      default: on = (i == sx - 1); break;
+    }
+    if (on) return;
+  }
+  double value;
+  if (bc.kind == MIFGPU_BC_HOST_CALLBACK) {
+    value = bc.tables[comp][face][t];
+  } else if (comp == dir) {
+    // Wall-normal component: value on the wall plus half a cell of -(tangential divergence) of the
+    // analytic field (src/VelocityTensor.cpp:51-60,78-90,109-118,136-148,167-176,194-206).
+    // `q` is the unstaggered index of the wall along the normal direction.
+    if (dir == 2) {
+      const int q = upper ? g.Nz - 1 : 0;
+      const double at_wall = eval_at(g, bc, 2, 3, i, j, q);
+      const double du_dx = (eval_at(g, bc, 0, 0, i + 1, j, q) - eval_at(g, bc, 0, 0, i, j, q)) * g.one_over_dx;
+      const double dv_dy = (eval_at(g, bc, 1, 1, i, j + 1, q) - eval_at(g, bc, 1, 1, i, j, q)) * g.one_over_dy;
+      value = upper ? at_wall - g.dz_over_2 * (du_dx + dv_dy) : at_wall + g.dz_over_2 * (du_dx + dv_dy);
+    } else if (dir == 1) {
+      const int q = upper ? g.Ny - 1 : 0;
+      const double at_wall = eval_at(g, bc, 1, 3, i, q, k);
+      const double du_dx = (eval_at(g, bc, 0, 0, i + 1, q, k) - eval_at(g, bc, 0, 0, i, q, k)) * g.one_over_dx;
+      const double dw_dz = (eval_at(g, bc, 2, 2, i, q, k + 1) - eval_at(g, bc, 2, 2, i, q, k)) * g.one_over_dz;
+      value = upper ? at_wall - g.dy_over_2 * (du_dx + dw_dz) : at_wall + g.dy_over_2 * (du_dx + dw_dz);
+    } else {
+      const int q = upper ? g.Nx - 1 : 0;
+      const double at_wall = eval_at(g, bc, 0, 3, q, j, k);
+      const double dv_dy = (eval_at(g, bc, 1, 1, q, j + 1, k) - eval_at(g, bc, 1, 1, q, j, k)) * g.one_over_dy;
+      const double dw_dz = (eval_at(g, bc, 2, 2, q, j, k + 1) - eval_at(g, bc, 2, 2, q, j, k)) * g.one_over_dz;
+      value = upper ? at_wall - g.dx_over_2 * (dv_dy + dw_dz) : at_wall + g.dx_over_2 * (dv_dy + dw_dz);
+    }
+  } else {
+    // Tangential component: the analytic value at the staggered coordinate of the face point
+    // (src/VelocityTensor.cpp:66-67,96-98,124-125,154-156,182-183,212-214).
+    value = eval_at(g, bc, comp, comp, i, j, k);
+  }
+  double *field = comp == 0 ? u : (comp == 1 ? v : w);
+  field[gidx(g, i, j, k)] = value;
+}
+
+// ghost(0) <- slice(s-2), ghost(s-1) <- slice(1) along `dir` (src/StaggeredTensor.cpp:221-257).
+__global__ void __launch_bounds__(256) periodic_copy_kernel(const Geom g, double *field, int sx, int sy, int sz, int dir) {
+  const int na = (dir == 0) ? sy : sx;
+  const int nb = (dir == 2) ? sy : sz;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)na * nb) return;
+  const int a = (int)(t % na), b = (int)(t / na);
+  if (dir == 0) {
+    field[gidx(g, 0, a, b)] = field[gidx(g, sx - 2, a, b)];
+    field[gidx(g, sx - 1, a, b)] = field[gidx(g, 1, a, b)];
+  } else if (dir == 1) {
+    field[gidx(g, a, 0, b)] = field[gidx(g, a, sy - 2, b)];
+    field[gidx(g, a, sy - 1, b)] = field[gidx(g, a, 1, b)];
+  } else {
+    field[gidx(g, a, b, 0)] = field[gidx(g, a, b, sz - 2)];
+    field[gidx(g, a, b, sz - 1)] = field[gidx(g, a, b, 1)];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+divergence_kernel(const Geom g, const double *__restrict__ u, const double *__restrict__ v,
+                  const double *__restrict__ w, double dt, double *__restrict__ rhs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + g.own_lo[0];
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + g.own_lo[1];
+  const int k = blockIdx.z + g.own_lo[2];
+  if (i >= g.own_hi[0] || j >= g.own_hi[1]) return;
+  const long long c = gidx(g, i, j, k);
+  const double du_dx = (u[c + 1] - u[c]) * g.one_over_dx;
+  const double dv_dy = (v[c + g.PX] - v[c]) * g.one_over_dy;
+  const double dw_dz = (w[c + g.plane] - w[c]) * g.one_over_dz;
+  rhs[c] = (du_dx + dv_dy + dw_dz) / dt;
+}
+
+__global__ void __launch_bounds__(256)
+correct_kernel(const Geom g, double *__restrict__ u, double *__restrict__ v, double *__restrict__ w,
+               double *__restrict__ p, const double *__restrict__ dp, double dt_s) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i >= g.sx[0] || j >= g.sy[1]) return;
+  const long long c = gidx(g, i, j, k);
+  const bool in_p = i < g.Nx && j < g.Ny && k < g.Nz;
+  const double d_c = in_p ? dp[c] : 0.0;
+  if (in_p) p[c] += d_c;  // src/Timestep.cpp:79-81 (all points, ghosts included)
+  const bool int_i_o = i >= 1 && i <= g.Nx - 2, int_j_o = j >= 1 && j <= g.Ny - 2, int_k_o = k >= 1 && k <= g.Nz - 2;
+  // src/Timestep.cpp:66-72 (interior points of each component)
+  if (i >= 1 && i <= g.sx[0] - 2 && int_j_o && int_k_o) u[c] -= (d_c - dp[c - 1]) * g.one_over_dx * dt_s;
+  if (int_i_o && j >= 1 && j <= g.sy[1] - 2 && int_k_o) v[c] -= (d_c - dp[c - g.PX]) * g.one_over_dy * dt_s;
+  if (int_i_o && int_j_o && k >= 1 && k <= g.sz[2] - 2) w[c] -= (d_c - dp[c - g.plane]) * g.one_over_dz * dt_s;
+}
+
+// rhs(face) +-= 2 g_n / h with g given as host-filled face tables (src/PressureEquation.cpp:10-56).
+// The six faces are applied one launch at a time in the reference order because edge points receive
+// the contribution of every face they lie on.
+__global__ void __launch_bounds__(256) nhn_face_kernel(const Geom g, double *rhs, const double *table, int face) {
+  const int dir = 2 - face / 2;
+  const int na = (dir == 0) ? g.Ny : g.Nx;
+  const int nb = (dir == 2) ? g.Ny : g.Nz;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)na * nb) return;
+  const int a = (int)(t % na), b = (int)(t / na);
+  const bool upper = face & 1;
+  int i, j, k;
+  double scale;
+  if (dir == 2) {
+    i = a; j = b; k = upper ? g.Nz - 1 : 0; scale = 2.0 * g.one_over_dz;
+  } else if (dir == 1) {
+    i = a; k = b; j = upper ? g.Ny - 1 : 0; scale = 2.0 * g.one_over_dy;
+  } else {
+    j = a; k = b; i = upper ? g.Nx - 1 : 0; scale = 2.0 * g.one_over_dx;
+  }
+  const double term = table[t] * scale;
+  const long long c = gidx(g, i, j, k);
+  if (upper) rhs[c] -= term;
+  else rhs[c] += term;
+}
+
+inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace
+
+void launch_stage(cudaStream_t stream, const Geom &g, int stage, CVec3 in, const double *pressure, Vec3 a, Vec3 b,
+                  uint64_t *launches) {
+  const int ni = max(g.sx[0], g.Nx) - 2, nj = max(g.sy[1], g.Ny) - 2, nk = max(g.sz[2], g.Nz) - 2;
+  if (ni <= 0 || nj <= 0 || nk <= 0) return;
+  const dim3 block(64, 4, 1);
+  const dim3 grid(cdiv(ni, block.x), cdiv(nj, block.y), nk);
+  if (stage == 1)
+    stage_kernel<1><<<grid, block, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
+                                                b.c[1], b.c[2]);
+  else if (stage == 2)
+    stage_kernel<2><<<grid, block, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
+                                                b.c[1], b.c[2]);
+  else
+    stage_kernel<3><<<grid, block, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
+                                                b.c[1], b.c[2]);
+  ++*launches;
+}
+
+void launch_periodic(cudaStream_t stream, const Geom &g, double *field, int comp, uint64_t *launches) {
+  const int sx = g.sx[comp], sy = g.sy[comp], sz = g.sz[comp];
+  // x, then y, then z: later copies read the ghosts written by earlier ones (src/StaggeredTensor.cpp:224-256).
+  if (g.periodic[0]) {
+    periodic_copy_kernel<<<cdiv((long long)sy * sz, 256), 256, 0, stream>>>(g, field, sx, sy, sz, 0);
+    ++*launches;
+  }
+  if (g.periodic[1] && g.prev_y == -1) {  // periodic_bc[1] && Py == 1
+    periodic_copy_kernel<<<cdiv((long long)sx * sz, 256), 256, 0, stream>>>(g, field, sx, sy, sz, 1);
+    ++*launches;
+  }
+  if (g.periodic[2] && g.prev_z == -1) {  // periodic_bc[2] && Pz == 1
+    periodic_copy_kernel<<<cdiv((long long)sx * sy, 256), 256, 0, stream>>>(g, field, sx, sy, sz, 2);
+    ++*launches;
+  }
+}
+
+void launch_apply_bc(cudaStream_t stream, const Geom &g, Vec3 vel, const BcDev &bc, uint64_t *launches) {
+  long long max_area = 0;
+  for (int c = 0; c < 3; c++) {
+    const long long sx = g.sx[c], sy = g.sy[c], sz = g.sz[c];
+    max_area = max(max_area, max(sx * sy, max(sx * sz, sy * sz)));
+  }
+  if (!(g.periodic[0] && g.periodic[1] && g.periodic[2])) {
+    const dim3 grid(cdiv(max_area, 256), 18, 1);
+    bc_face_kernel<<<grid, 256, 0, stream>>>(g, vel.c[0], vel.c[1], vel.c[2], bc);
+    ++*launches;
+  }
+  for (int c = 0; c < 3; c++) launch_periodic(stream, g, vel.c[c], c, launches);
+}
+
+void launch_divergence(cudaStream_t stream, const Geom &g, CVec3 vel, double, double dt, double *rhs,
+                       uint64_t *launches) {
+  const int ni = g.own_hi[0] - g.own_lo[0], nj = g.own_hi[1] - g.own_lo[1], nk = g.own_hi[2] - g.own_lo[2];
+  const dim3 block(64, 4, 1);
+  const dim3 grid(cdiv(ni, block.x), cdiv(nj, block.y), nk);
+  divergence_kernel<<<grid, block, 0, stream>>>(g, vel.c[0], vel.c[1], vel.c[2], dt, rhs);
+  ++*launches;
+}
+
+void launch_nhn_rhs(cudaStream_t stream, const Geom &g, double *rhs, const BcDev &bc, uint64_t *launches) {
+  for (int face = 0; face < 6; face++) {
+    const int dir = 2 - face / 2;
+    const long long na = (dir == 0) ? g.Ny : g.Nx, nb = (dir == 2) ? g.Ny : g.Nz;
+    nhn_face_kernel<<<cdiv(na * nb, 256), 256, 0, stream>>>(g, rhs, bc.tables[dir][face], face);
+    ++*launches;
+  }
+}
+
+void launch_correct(cudaStream_t stream, const Geom &g, Vec3 vel, double *pressure, const double *dp, double dt_s,
+                    uint64_t *launches) {
+  const dim3 block(64, 4, 1);
+  const dim3 grid(cdiv(g.sx[0], block.x), cdiv(g.sy[1], block.y), g.sz[2]);
+  correct_kernel<<<grid, block, 0, stream>>>(g, vel.c[0], vel.c[1], vel.c[2], pressure, dp, dt_s);
+  ++*launches;
+}
+
+}  // namespace mifgpu

@@ -1,0 +1,109 @@
+#!/usr/bin/env python3
+"""oracle/make_golden.py -- TEST INFRASTRUCTURE ONLY.
+
+Generates the golden vectors under tests/golden/ by running the UNMODIFIED reference (oracle/_ref/,
+built by oracle/Makefile from /root/reference) in THIS container.  The GPU box has no /root/reference,
+so the vectors are committed; re-run this script (`python oracle/make_golden.py`) to regenerate them.
+
+  tests/golden/<case>.npz   raw FP64 fields dumped by oracle/_ref/ref_dump (reference layout,
+                            arrays shaped (sz, sy, sx)), plus the case parameters
+  tests/golden/norms.json   the numbers printed by the reference's own test mains
+                            (test/full_test.cpp:171-175, test/pressure_test_*.cpp:76-79, velocity tests)
+"""
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.path.join(HERE, "_ref")
+GOLDEN = os.path.join(HERE, "..", "tests", "golden")
+
+
+def run(cmd, np_ranks=1, cwd=None):
+    env = dict(os.environ, MIF_SHIM_NP=str(np_ranks), MIF_SHIM_ABORT_ON_STALL="1")
+    out = subprocess.run(cmd, env=env, cwd=cwd, check=True, capture_output=True, text=True, timeout=600)
+    return out.stdout
+
+
+def load_dump(outdir, rank=0):
+    fields = {}
+    with open(os.path.join(outdir, f"manifest_r{rank}.txt")) as f:
+        for line in f:
+            name, r, sx, sy, sz = line.split()
+            data = np.fromfile(os.path.join(outdir, f"{name}_r{r}.f64"), dtype=np.float64)
+            fields[name] = data.reshape(int(sz), int(sy), int(sx))
+    return fields
+
+
+def dump_case(name, args, meta, np_ranks=1):
+    tmp = tempfile.mkdtemp(prefix="mifgolden_")
+    try:
+        cmd = [os.path.join(REF, "ref_dump")] + [str(a).replace("{out}", tmp) for a in args]
+        stdout = run(cmd, np_ranks)
+        fields = load_dump(tmp)
+        meta = dict(meta, command="ref_dump " + " ".join(str(a) for a in args), stdout=stdout.strip())
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), meta=json.dumps(meta), **fields)
+        print(f"{name}: {len(fields)} arrays, stdout={stdout.strip()!r}")
+    finally:
+        shutil.rmtree(tmp)
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    if not os.path.exists(os.path.join(REF, "ref_dump")):
+        sys.exit("oracle/_ref/ref_dump missing: run `make -C oracle ref` first")
+
+    # --- raw-field cases --------------------------------------------------------------------------
+    full = dict(kind="full", x_size=1.0, y_size=1.0, z_size=2.0, min=[0.0, 0.0, -1.0], Re=1e3, final_time=1e-4,
+                periodic=[0, 0, 0], bc="ethier_steinman")
+    dump_case("full_16_2", ["full", 16, 2, 1, "{out}"], dict(full, N=[16, 16, 16], steps=2, nhn=0))
+    dump_case("full_17_1", ["full", 17, 1, 1, "{out}"], dict(full, N=[17, 17, 17], steps=1, nhn=0))
+    dump_case("full_12_1_nhn", ["full", 12, 1, 1, "{out}", "nhn"], dict(full, N=[12, 12, 12], steps=1, nhn=1))
+    lid1 = dict(kind="lid", x_size=1.0, y_size=1.0, z_size=2.0, min=[0.0, 0.0, -1.0], Re=1e3, periodic=[0, 0, 0],
+                bc="test_case_1")
+    dump_case("lid1_12x10x14_2", ["lid", 12, 10, 14, 1e-3, 2, 0, 1, "{out}"],
+              dict(lid1, N=[12, 10, 14], steps=2, dt=1e-3, final_time=2e-3))
+    lid2 = dict(kind="lid", x_size=1.0, y_size=1.0, z_size=1.0, min=[-0.5, -0.5, -0.5], Re=1e3, periodic=[0, 0, 1],
+                bc="test_case_2")
+    dump_case("lid2_10x12x9_2", ["lid", 10, 12, 9, 1e-3, 2, 1, 1, "{out}"],
+              dict(lid2, N=[10, 12, 9], steps=2, dt=1e-3, final_time=2e-3))
+    for kind, dims in (("hn", (8, 24, 40)), ("mixed", (8, 24, 40)), ("nhn", (8, 24, 40)), ("mixed", (9, 17, 17)),
+                       ("hn", (17, 9, 33)), ("mixed", (7, 6, 10))):
+        lo = -np.pi / 2 if kind == "nhn" else 0.0
+        ln = np.pi / 2 if kind == "nhn" else 2 * np.pi
+        meta = dict(kind="ptest", ptest=kind, N=list(dims), x_size=ln, y_size=ln, z_size=ln, min=[lo, lo, lo], Re=1.0,
+                    final_time=1.0, steps=1, periodic=[0, 0, int(kind == "mixed")], time=1.0)
+        dump_case(f"ptest_{kind}_{dims[0]}x{dims[1]}x{dims[2]}", ["ptest", kind, *dims, 1, "{out}"], meta)
+
+    # --- numbers printed by the reference's own tests ----------------------------------------------
+    norms = {}
+    tmp = tempfile.mkdtemp(prefix="mifgolden_")
+    try:
+        for n, steps in ((16, 1), (32, 2), (64, 4)):
+            out = run([os.path.join(REF, "full_test"), str(n), str(steps), "1"], cwd=tmp)
+            norms[f"full_test {n} {steps} 1"] = [float(x) for x in out.split()]
+        out = run([os.path.join(REF, "full_test"), "16", "1", "2"], np_ranks=4, cwd=tmp)
+        norms["full_test 16 1 2 (4 ranks)"] = [float(x) for x in out.split()]
+        for test in ("pressure_test_hn", "pressure_test_mixed", "pressure_test_nhn"):
+            for n in (8, 16, 32):
+                out = run([os.path.join(REF, test), str(n), "1"], cwd=tmp)
+                line = [l for l in out.splitlines() if l.startswith("Errors:")][0]
+                norms[f"{test} {n} 1"] = [float(x) for x in line.split()[1:]]
+        for test in ("velocity_test", "velocity_test_mixed"):
+            for n in (16, 32):
+                out = run([os.path.join(REF, test), str(n), str(n // 16), "1"], cwd=tmp)
+                norms[f"{test} {n} {n // 16} 1"] = [float(x) for x in out.split()[:3]]
+    finally:
+        shutil.rmtree(tmp)
+    with open(os.path.join(GOLDEN, "norms.json"), "w") as f:
+        json.dump(norms, f, indent=1, sort_keys=True)
+    print("norms.json:", len(norms), "entries")
+
+
+if __name__ == "__main__":
+    main()
