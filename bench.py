@@ -1,0 +1,319 @@
+#!/usr/bin/env python3
+"""bench.py -- FP64 cell-steps/s of the full projection time step (3 RK stages incl. 3 Poisson solves).
+
+Workload (BASELINE.json configs[2], SURVEY.md section 8d "config 3"): the reference's input/input.txt
+boundary-layer set-up (src/main.cpp:121-156, test case 1: domain [0,1]x[0,1]x[-1,1], Re = 1e3, v = 1 on
+the face x = 1, dt = 1e-3) scaled to 512^3 cells = 513^3 pressure points, one mif::timestep per "step".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size POINTS]      our arm (CUDA, through the C ABI)
+  python bench.py --impl reference ...                                     the reference's own CPU code
+
+One JSON line on stdout (rank 0).  Keys beyond the base contract:
+  roofline      dominant kernel: algorithmic bytes / CUDA-event time against MEASURED_PEAKS.json
+  cpu_baseline  oracle/_ref (the unmodified reference compiled against the MPI/FFT stand-ins) timed on
+                this box's host cores on a bounded sample
+  kernels       per-kernel-group milliseconds per step from the library's CUDA-event profile
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "FP64 cell-steps/s, full RK timestep incl. Poisson solve"
+UNIT = "cell-steps/s"
+# Canonical algorithmic traffic of one cell-step: 111 FP64 words.
+BYTES_PER_CELL_STEP = 888.0
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.device = device_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, sm_max, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            if len(row) < 9:
+                continue
+            try:
+                sm.append(float(row[1]))
+                sm_max = float(row[2])
+            except ValueError:
+                continue
+            for name, cell in zip(names, row[5:9]):
+                if cell.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": sm_max, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def host_core_count():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def rank_grid(cores):
+    ranks = 1
+    while ranks * 2 <= min(cores, 64):
+        ranks *= 2
+    py = 1
+    while py * py * 4 <= ranks:
+        py *= 2
+    return ranks, py, ranks // py
+
+
+def run_reference_sample(points, iters, warmup, cores=None):
+    """Times the unmodified reference (oracle/_ref/ref_bench) on the host cores; ranks are threads."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
+    if not os.path.exists(exe):
+        return None
+    ranks, py, pz = rank_grid(cores or host_core_count())
+    env = dict(os.environ, MIF_SHIM_NP=str(ranks))
+    out = subprocess.run([exe, "step", str(points), str(points), str(points), str(iters), str(warmup), str(pz)],
+                         env=env, capture_output=True, text=True, timeout=1800)
+    if out.returncode != 0:
+        return None
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    res["cores"] = ranks
+    return res
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    points = args.ref_size
+    t0 = time.time()
+    res = run_reference_sample(points, args.steps, args.warmup)
+    if res is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_bench is not built (make -C oracle ref)"}))
+        return 0
+    value = res["cell_iters_per_s"]
+    sample = (f"{points}^3 pressure points ({points - 1}^3 cells) of the same test-case-1 set-up, {args.steps} timed "
+              f"steps + {args.warmup} warm-up, {res['ranks']} ranks (Py={res['Py']}, Pz={res['Pz']}) as threads of one "
+              "process; reference stencils/transposes + in-repo FFT and MPI stand-ins (no FFTW/MPI in the image)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "full projection timestep, input.txt boundary-layer set-up (test case 1)",
+                   "points": [points] * 3, "timed_on": "host CPU", "wall_s": round(time.time() - t0, 1)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=513, help="pressure points per direction (513 = 512^3 cells)")
+    ap.add_argument("--ref-size", type=int, default=257, help="points per direction of the CPU reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import mif_b200 as mif
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    mif.lib()  # fails loudly if libmifgpu.so is missing
+
+    N = args.size
+    steps, warmup = args.steps, max(args.warmup, 3)
+    dt = 1e-3
+    total_steps = warmup + 2 * steps + 16
+    # src/main.cpp:121-131, test case 1.  Each rank of a multi-GPU launch currently runs an independent
+    # replica of the same problem (the multi-GPU domain decomposition is not in this build yet).
+    ctx = mif.Context(N, N, N, 1.0, 1.0, 2.0, 0.0, 0.0, -1.0, 1e3, dt * total_steps, total_steps, device=local_rank)
+    vel, vb, vb2 = ctx.velocity(), ctx.velocity(), ctx.velocity()
+    p, dp = ctx.tensor(mif.STAGGER_NONE), ctx.tensor(mif.STAGGER_NONE)
+    bc = ctx.make_bc(mif.BC_TEST_CASE_1, 1e3)
+    # velocity.set(exact(t=0), include_border=true) (src/main.cpp:144-146): v = 1 on the plane x = 1, else 0.
+    host = []
+    for t in vel + [p]:
+        sx, sy, sz = t.shape
+        arr = torch.zeros((sz, sy, sx), dtype=torch.float64).pin_memory()
+        host.append(arr)
+    host[1][:, :, N - 1] = 1.0
+    for t, arr in zip(vel + [p], host):
+        t.upload(arr.numpy())
+
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    cells = float(N - 1) ** 3
+    step_index = [0]
+
+    def one_step():
+        ctx.timestep(vel, vb, vb2, bc, step_index[0] * dt, p, dp)
+        step_index[0] += 1
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(warmup):
+        one_step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        one_step()
+    ev1.record(stream)
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop()
+    if world > 1:
+        tmax = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tmax.item())
+    value = world * cells * steps / (elapsed_ms * 1e-3)
+
+    # Per-kernel-group times (CUDA events on the launching stream) over the same number of steps.
+    ctx.profile_enable(True)
+    for _ in range(steps):
+        one_step()
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    kernels = {k: round(ms / steps, 4) for k, (ms, n) in prof.items() if n}
+    peak, peak_src = measured_peaks()
+    points = float(N) ** 3
+    # Dominant kernel = the Poisson sweep kernel (5 launches per solve, 15 per step).  Algorithmic bytes
+    # per launch: one read + one write of every pressure point = 16 B * N^3 (SURVEY.md section 8d:
+    # "Poisson 6 sweeps x (1R+1W)"; the fused z launch does the work of two sweeps with the same 16 B).
+    sweep_ms = sum(ms for k, (ms, n) in prof.items() if k.startswith("sweep_"))
+    sweep_launches = sum(n for k, (ms, n) in prof.items() if k.startswith("sweep_"))
+    per_launch_ms = sweep_ms / max(sweep_launches, 1)
+    achieved = 16.0 * points / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+    step_profile_ms = sum(ms for ms, n in prof.values()) / steps
+    roofline = {
+        "bound": "hbm", "kernel": "sweep_kernel (batched DCT-I / real-FFT lines, 15 launches per step)",
+        "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+        "traffic": None, "peak_source": peak_src, "avg_launch_ms": round(per_launch_ms, 4),
+        "share_of_step": round(sweep_ms / steps / step_profile_ms, 4) if step_profile_ms else None,
+        "whole_step": {"algorithmic_bytes_per_cell_step": BYTES_PER_CELL_STEP,
+                       "achieved_GBs": round(value / world * BYTES_PER_CELL_STEP / 1e9, 1),
+                       "frac": round(value / world * BYTES_PER_CELL_STEP / 1e9 / peak, 4)},
+    }
+
+    # End to end through the C ABI with HOST buffers: every step uploads u, v, w, p from pinned host memory,
+    # runs mifgpu_timestep and downloads u, v, w, p (host <-> device copies inside the timed region).
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(3, min(steps, 5))
+        field_bytes = sum(int(np.prod(t.shape)) * 8 for t in vel + [p])
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            for t, arr in zip(vel + [p], host):
+                t.upload(arr.numpy())
+            one_step()
+            for t, arr in zip(vel + [p], host):
+                t.download(arr.numpy())
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            tmax = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            e2e_s = float(tmax.item())
+        e2e = {"value": world * cells * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": field_bytes,
+               "d2h_bytes_per_step": field_bytes, "steps": e2e_steps,
+               "what": "per step: upload u,v,w,p from pinned host memory, mifgpu_timestep, download u,v,w,p"}
+
+    finite = bool(np.isfinite(vel[1].download()).all())
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        res = run_reference_sample(args.ref_size, 2, 1)
+        if res is not None:
+            cpu_baseline = {
+                "value": res["cell_iters_per_s"], "unit": UNIT, "cores": res["cores"], "kind": "reference",
+                "sample": (f"{args.ref_size}^3 points of the same set-up, 2 timed steps + 1 warm-up, {res['ranks']} ranks "
+                           f"(Py={res['Py']}, Pz={res['Pz']}) as threads; unmodified reference sources + in-repo FFT/MPI "
+                           "stand-ins (oracle/_ref)")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "full projection timestep, input.txt boundary-layer set-up (test case 1) at 512^3 cells"
+                       if N == 513 else f"full projection timestep, test case 1 at {N - 1}^3 cells",
+                       "points": [N, N, N], "dt": dt, "Re": 1e3,
+                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one per GPU)",
+                       "l2": "inputs larger than L2 (each field %.2f GB)" % (points * 8 / 1e9), "finite": finite},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "kernels": kernels, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -142,6 +142,14 @@ int mifgpu_synchronize(mifgpu_ctx *ctx);
 /* The CUDA stream (cudaStream_t) the context launches on, for callers that time with CUDA events. */
 void *mifgpu_stream(mifgpu_ctx *ctx);
 
+/* Optional per-kernel timing (no counterpart in the reference, whose only timers are MPI_Wtime around the
+ * time loop, test/full_test.cpp:116-138).  While enabled, every kernel group of the step is bracketed by
+ * CUDA events on the context's stream; mifgpu_profile_read synchronises, returns the number of
+ * categories (<= capacity) and fills, per category, a static name, the accumulated milliseconds and the
+ * number of timed groups since the previous read. */
+int mifgpu_profile_enable(mifgpu_ctx *ctx, int enable);
+int mifgpu_profile_read(mifgpu_ctx *ctx, int capacity, const char **names, double *milliseconds, uint64_t *counts);
+
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t mifgpu_launch_count(const mifgpu_ctx *ctx);
 

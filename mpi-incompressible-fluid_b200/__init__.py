@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "mifgpu_abi_version", "mifgpu_last_error", "mifgpu_create", "mifgpu_destroy", "mifgpu_tensor_extents",
     "mifgpu_tensor_create", "mifgpu_tensor_destroy", "mifgpu_tensor_upload", "mifgpu_tensor_download",
     "mifgpu_tensor_swap", "mifgpu_timestep", "mifgpu_apply_bc", "mifgpu_solve_pressure", "mifgpu_synchronize",
-    "mifgpu_stream", "mifgpu_launch_count",
+    "mifgpu_stream", "mifgpu_launch_count", "mifgpu_profile_enable", "mifgpu_profile_read",
 ]
 
 
@@ -101,6 +101,8 @@ def lib() -> ctypes.CDLL:
     l.mifgpu_stream.restype = c_void_p
     l.mifgpu_launch_count.argtypes = [c_void_p]
     l.mifgpu_launch_count.restype = c_uint64
+    l.mifgpu_profile_enable.argtypes = [c_void_p, c_int]
+    l.mifgpu_profile_read.argtypes = [c_void_p, c_int, POINTER(ctypes.c_char_p), POINTER(c_double), POINTER(c_uint64)]
     _lib = l
     return l
 
@@ -205,6 +207,20 @@ class Context:
 
     def synchronize(self) -> None:
         _check(lib().mifgpu_synchronize(self.handle))
+
+    def profile_enable(self, enable: bool) -> None:
+        _check(lib().mifgpu_profile_enable(self.handle, int(enable)))
+
+    def profile_read(self):
+        """{category: (milliseconds, timed kernel groups)} accumulated since the previous read."""
+        cap = 32
+        names = (ctypes.c_char_p * cap)()
+        ms = (c_double * cap)()
+        counts = (c_uint64 * cap)()
+        n = lib().mifgpu_profile_read(self.handle, cap, names, ms, counts)
+        if n < 0:
+            _check(n)
+        return {names[i].decode(): (float(ms[i]), int(counts[i])) for i in range(n)}
 
     @property
     def stream(self) -> int:

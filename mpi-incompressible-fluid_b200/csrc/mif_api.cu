@@ -35,6 +35,18 @@ int fail(int code, const char *fmt, ...) {
 
 }  // namespace
 
+enum ProfCategory {
+  PROF_STAGE1, PROF_STAGE2, PROF_STAGE3, PROF_BC, PROF_DIVERGENCE, PROF_NHN, PROF_SWEEP_X_FWD, PROF_SWEEP_Y_FWD,
+  PROF_SWEEP_Z, PROF_SWEEP_Y_INV, PROF_SWEEP_X_INV, PROF_PERIODIC, PROF_CORRECT, PROF_COUNT
+};
+const char *const kProfNames[PROF_COUNT] = {"stage1", "stage2", "stage3", "bc_faces", "divergence", "nhn_rhs",
+                                            "sweep_x_fwd", "sweep_y_fwd", "sweep_z_fused", "sweep_y_inv",
+                                            "sweep_x_inv", "periodic", "correct"};
+struct ProfRecord {
+  int category;
+  cudaEvent_t start, stop;
+};
+
 struct mifgpu_ctx {
   mifgpu_params params;
   Geom g;
@@ -42,6 +54,8 @@ struct mifgpu_ctx {
   cudaStream_t stream = nullptr;
   PoissonPlan *plan = nullptr;
   uint64_t launches = 0;
+  bool profiling = false;
+  std::vector<ProfRecord> prof_records;
   // host-callback boundary faces: pinned staging + device copies, [which][component][face]
   double *face_host[2][3][6] = {};
   double *face_dev[2][3][6] = {};
@@ -120,6 +134,25 @@ int build_geometry(const mifgpu_params &p, Geom &g, int n_points[3]) {
   return MIFGPU_OK;
 }
 
+// Optional per-kernel timing with CUDA events on the context's stream (mifgpu_profile_*).
+struct ProfScope {
+  mifgpu_ctx *ctx;
+  ProfRecord rec;
+  bool active;
+  ProfScope(mifgpu_ctx *c, int category) : ctx(c), active(c->profiling) {
+    if (!active) return;
+    rec.category = category;
+    cudaEventCreate(&rec.start);
+    cudaEventCreate(&rec.stop);
+    cudaEventRecord(rec.start, ctx->stream);
+  }
+  ~ProfScope() {
+    if (!active) return;
+    cudaEventRecord(rec.stop, ctx->stream);
+    ctx->prof_records.push_back(rec);
+  }
+};
+
 Vec3 vec3(mifgpu_tensor *const t[3]) { return Vec3{{t[0]->data, t[1]->data, t[2]->data}}; }
 CVec3 cvec3(mifgpu_tensor *const t[3]) { return CVec3{{t[0]->data, t[1]->data, t[2]->data}}; }
 
@@ -192,6 +225,7 @@ int do_apply_bc(mifgpu_ctx *ctx, mifgpu_tensor *const vel[3], const mifgpu_bc *b
              bc->kind != MIFGPU_BC_ETHIER_STEINMAN) {
     return fail(MIFGPU_ERR_INVALID, "unknown boundary kind %d", bc->kind);
   }
+  ProfScope prof(ctx, PROF_BC);
   launch_apply_bc(ctx->stream, ctx->g, vec3(vel), dev, &ctx->launches);
   return MIFGPU_OK;
 }
@@ -199,7 +233,10 @@ int do_apply_bc(mifgpu_ctx *ctx, mifgpu_tensor *const vel[3], const mifgpu_bc *b
 // solve_pressure_equation_homogeneous_periodic / _non_homogeneous_neumann (src/PressureEquation.cpp:266-286).
 int do_solve(mifgpu_ctx *ctx, mifgpu_tensor *dp, mifgpu_tensor *const vel[3], double dt, const mifgpu_bc *nhn_bc,
              double t_new, double t_prev) {
-  launch_divergence(ctx->stream, ctx->g, cvec3(vel), 0.0, dt, dp->data, &ctx->launches);
+  {
+    ProfScope prof(ctx, PROF_DIVERGENCE);
+    launch_divergence(ctx->stream, ctx->g, cvec3(vel), 0.0, dt, dp->data, &ctx->launches);
+  }
   if (nhn_bc) {
     const Geom &g = ctx->g;
     if (g.periodic[0] || g.periodic[1] || g.periodic[2])
@@ -208,10 +245,21 @@ int do_solve(mifgpu_ctx *ctx, mifgpu_tensor *dp, mifgpu_tensor *const vel[3], do
     std::memset(&dev, 0, sizeof(dev));
     const int rc = fill_face_tables(ctx, nhn_bc, 1, t_new, t_prev, dev);
     if (rc) return rc;
+    ProfScope prof(ctx, PROF_NHN);
     launch_nhn_rhs(ctx->stream, g, dp->data, dev, &ctx->launches);
   }
-  launch_poisson(ctx->stream, ctx->g, ctx->plan, dp->data, &ctx->launches);
-  launch_periodic(ctx->stream, ctx->g, dp->data, 3, &ctx->launches);  // copy_to_staggered, src/PressureTensor.cpp:21-34
+  // forward x, forward y, (forward z, eigenvalues, inverse z), inverse y, inverse x
+  // (src/PressureEquation.cpp:79-101, 106-128, 133-195, 200-229, 234-263)
+  static const int kSweeps[5][3] = {{0, 0, PROF_SWEEP_X_FWD}, {1, 0, PROF_SWEEP_Y_FWD}, {2, 2, PROF_SWEEP_Z},
+                                    {1, 1, PROF_SWEEP_Y_INV}, {0, 1, PROF_SWEEP_X_INV}};
+  for (const auto &sw : kSweeps) {
+    ProfScope prof(ctx, sw[2]);
+    launch_poisson_sweep(ctx->stream, ctx->g, ctx->plan, dp->data, sw[0], sw[1], &ctx->launches);
+  }
+  {
+    ProfScope prof(ctx, PROF_PERIODIC);
+    launch_periodic(ctx->stream, ctx->g, dp->data, 3, &ctx->launches);  // copy_to_staggered, src/PressureTensor.cpp:21-34
+  }
   return MIFGPU_OK;
 }
 
@@ -390,22 +438,40 @@ int mifgpu_timestep(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], mifgpu_te
   const mifgpu_bc *nhn_bc = nhn ? bc : nullptr;
 
   // Stage 1 (src/Timestep.cpp:107-117).
-  launch_stage(s, g, 1, cvec3(velocity), pressure->data, vec3(velocity_buffer), vec3(velocity_buffer_2), &ctx->launches);
+  {
+    ProfScope prof(ctx, PROF_STAGE1);
+    launch_stage(s, g, 1, cvec3(velocity), pressure->data, vec3(velocity_buffer), vec3(velocity_buffer_2), &ctx->launches);
+  }
   if ((rc = do_apply_bc(ctx, velocity_buffer, bc, time_1))) return rc;
   if ((rc = do_solve(ctx, pressure_buffer, velocity_buffer, dt_1, nhn_bc, time_1, t_n))) return rc;
-  launch_correct(s, g, vec3(velocity_buffer), pressure->data, pressure_buffer->data, dt_1, &ctx->launches);
+  {
+    ProfScope prof(ctx, PROF_CORRECT);
+    launch_correct(s, g, vec3(velocity_buffer), pressure->data, pressure_buffer->data, dt_1, &ctx->launches);
+  }
 
   // Stage 2 (src/Timestep.cpp:119-129).
-  launch_stage(s, g, 2, cvec3(velocity_buffer), pressure->data, vec3(velocity_buffer_2), vec3(velocity), &ctx->launches);
+  {
+    ProfScope prof(ctx, PROF_STAGE2);
+    launch_stage(s, g, 2, cvec3(velocity_buffer), pressure->data, vec3(velocity_buffer_2), vec3(velocity), &ctx->launches);
+  }
   if ((rc = do_apply_bc(ctx, velocity_buffer_2, bc, time_2))) return rc;
   if ((rc = do_solve(ctx, pressure_buffer, velocity_buffer_2, dt_2, nhn_bc, time_2, time_1))) return rc;
-  launch_correct(s, g, vec3(velocity_buffer_2), pressure->data, pressure_buffer->data, dt_2, &ctx->launches);
+  {
+    ProfScope prof(ctx, PROF_CORRECT);
+    launch_correct(s, g, vec3(velocity_buffer_2), pressure->data, pressure_buffer->data, dt_2, &ctx->launches);
+  }
 
   // Stage 3 (src/Timestep.cpp:131-141).
-  launch_stage(s, g, 3, cvec3(velocity_buffer_2), pressure->data, vec3(velocity), vec3(velocity), &ctx->launches);
+  {
+    ProfScope prof(ctx, PROF_STAGE3);
+    launch_stage(s, g, 3, cvec3(velocity_buffer_2), pressure->data, vec3(velocity), vec3(velocity), &ctx->launches);
+  }
   if ((rc = do_apply_bc(ctx, velocity, bc, final_time))) return rc;
   if ((rc = do_solve(ctx, pressure_buffer, velocity, dt_3, nhn_bc, final_time, time_2))) return rc;
-  launch_correct(s, g, vec3(velocity), pressure->data, pressure_buffer->data, dt_3, &ctx->launches);
+  {
+    ProfScope prof(ctx, PROF_CORRECT);
+    launch_correct(s, g, vec3(velocity), pressure->data, pressure_buffer->data, dt_3, &ctx->launches);
+  }
   return check_launch(ctx);
 }
 
@@ -414,6 +480,34 @@ int mifgpu_synchronize(mifgpu_ctx *ctx) {
   CUDA_TRY(cudaSetDevice(ctx->params.device));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return MIFGPU_OK;
+}
+
+int mifgpu_profile_enable(mifgpu_ctx *ctx, int enable) {
+  if (!ctx) return fail(MIFGPU_ERR_INVALID, "NULL context");
+  ctx->profiling = enable != 0;
+  return MIFGPU_OK;
+}
+
+int mifgpu_profile_read(mifgpu_ctx *ctx, int capacity, const char **names, double *milliseconds, uint64_t *counts) {
+  if (!ctx || !names || !milliseconds || !counts) return fail(MIFGPU_ERR_INVALID, "NULL argument");
+  if (capacity < PROF_COUNT) return fail(MIFGPU_ERR_INVALID, "capacity must be >= %d", (int)PROF_COUNT);
+  CUDA_TRY(cudaSetDevice(ctx->params.device));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  for (int c = 0; c < PROF_COUNT; c++) {
+    names[c] = kProfNames[c];
+    milliseconds[c] = 0.0;
+    counts[c] = 0;
+  }
+  for (ProfRecord &rec : ctx->prof_records) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, rec.start, rec.stop);
+    milliseconds[rec.category] += ms;
+    counts[rec.category] += 1;
+    cudaEventDestroy(rec.start);
+    cudaEventDestroy(rec.stop);
+  }
+  ctx->prof_records.clear();
+  return PROF_COUNT;
 }
 
 void *mifgpu_stream(mifgpu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }

@@ -43,7 +43,10 @@ struct PoissonPlan;  // transform tables + eigenvalues for one context
 PoissonPlan *poisson_plan_create(const Geom &g, const int n_points[3], const int periodic[3], const double h[3],
                                  const int n_global[3]);
 void poisson_plan_destroy(PoissonPlan *plan);
-// In-place spectral solve on the owner region of `field` (src/PressureEquation.cpp:65-264).
-void launch_poisson(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *field, uint64_t *launches);
+// One sweep of the in-place spectral solve on the owner region of `field` (src/PressureEquation.cpp:65-264):
+// dir = 0/1/2 (x/y/z); mode = 0 forward, 1 inverse + normalisation, 2 forward, eigenvalue division, inverse.
+// The solve is the sequence (0,0) (1,0) (2,2) (1,1) (0,1).
+void launch_poisson_sweep(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *field, int dir, int mode,
+                          uint64_t *launches);
 
 }  // namespace mifgpu

@@ -455,7 +455,8 @@ void poisson_plan_destroy(PoissonPlan *plan) {
   delete plan;
 }
 
-void launch_poisson(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *field, uint64_t *launches) {
+void launch_poisson_sweep(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *field, int d, int mode,
+                          uint64_t *launches) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -463,7 +464,7 @@ void launch_poisson(cudaStream_t stream, const Geom &g, PoissonPlan *plan, doubl
   }
   const int nx = g.own_hi[0] - g.own_lo[0], ny = g.own_hi[1] - g.own_lo[1], nz = g.own_hi[2] - g.own_lo[2];
   const long long origin = gidx(g, g.own_lo[0], g.own_lo[1], g.own_lo[2]);
-  auto run = [&](int d, int mode) {
+  {
     SweepJob job;
     job.plan = plan->dir[d];
     job.dir = d;
@@ -489,12 +490,7 @@ void launch_poisson(cudaStream_t stream, const Geom &g, PoissonPlan *plan, doubl
     const dim3 grid((job.n_tile_lines + job.L - 1) / job.L, outer, 1);
     sweep_kernel<<<grid, 256, plan->smem[d], stream>>>(job, field, origin, tile_stride, outer_stride);
     ++*launches;
-  };
-  run(0, 0);  // forward x   (src/PressureEquation.cpp:79-101)
-  run(1, 0);  // forward y   (:106-128)
-  run(2, 2);  // forward z, eigenvalues, inverse z (:133-195)
-  run(1, 1);  // inverse y   (:200-229)
-  run(0, 1);  // inverse x   (:234-263)
+  }
 }
 
 }  // namespace mifgpu
