@@ -78,8 +78,11 @@ typedef enum mifgpu_bc_kind {
  *   face 0,1 (z-, z+): values[i + j*sx]     face 2,3 (y-, y+): values[i + k*sx]
  *   face 4,5 (x-, x+): values[j + k*sy]
  * `which` is 0 for the velocity itself and 1 for the pressure-gradient data g used by the
- * non-homogeneous Neumann variant (src/PressureEquation.cpp:10-56; time is then t_new, time_prev t_old
- * and the callee returns g(t_new) - g(t_old) at unstaggered pressure points of the face). */
+ * non-homogeneous Neumann variant (src/PressureEquation.cpp:10-56), evaluated at the unstaggered pressure
+ * points of the face.  Inside mifgpu_timestep time = t_new and time_prev = t_old of the stage, and the
+ * callee must return exactly what the reference hands to the solver there, namely
+ * exact_pressure_gradient.get_difference_over_time(t_new, t_old) = g(t_old) - g(t_new)
+ * (src/Timestep.cpp:89-93 with src/VectorFunction.cpp:52-60: the difference is "second minus first"). */
 typedef void (*mifgpu_face_callback)(void *user, int which, double time, double time_prev, int component,
                                      int face, double *values);
 

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <vector>
 
+#include "mif_fft_fast.cuh"
 #include "mif_kernels.h"
 
 namespace mifgpu {
@@ -31,6 +32,7 @@ struct DirPlanDev {
   int P, logP;    // executed power-of-two FFT size
   int bluestein;  // m is not a power of two
   const double2 *tw;      // P/2: exp(-2 pi i q / P)
+  const double2 *tw_full; // P:   exp(-2 pi i q / P), all q (fast path)
   const double2 *chirp;   // m:   exp(-i pi j^2 / m)                         (Bluestein)
   const double2 *filt;    // P:   FFT_P(wrapped conj chirp) / P, bit-reversed (Bluestein)
   const double2 *unpack;  // (cos, sin)(pi k / m) for DCT-I, (cos, sin)(2 pi k / n) for real FFTs
@@ -317,6 +319,119 @@ __global__ void __launch_bounds__(256) sweep_kernel(const SweepJob job, double *
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fast path: DCT-I sweeps with N - 1 = M = 2^LOGM (64 <= M <= 1024), 8 lines per CTA, M threads.
+// ------------------------------------------------------------------------------------------------
+struct FastJob {
+  long long origin, lstride, estride, tile_stride, outer_stride;
+  int n_tile_lines;
+  int mode;  // 0 forward, 1 inverse (+normalise), 2 forward, eigenvalues, inverse (+normalise)
+  const double2 *tw, *cs;
+  const double *lam_x, *lam_y, *lam_z;
+  double inv_norm;
+};
+
+template <int LOGM, bool CONTIG>
+__global__ void __launch_bounds__(1 << LOGM, (LOGM <= 9 ? 2 : 1)) fast_dct_kernel(const FastJob job, double *__restrict__ field) {
+  using namespace fast;
+  constexpr int M = 1 << LOGM, T = M / 8, THREADS = M, NPTS = M + 1;
+  extern __shared__ double2 smem2[];
+  double2 *S = smem2;
+  double *Sd = reinterpret_cast<double *>(smem2);
+  const int tid = threadIdx.x, line = tid & 7, j = tid >> 3;
+  const int first_line = blockIdx.x * kLines;
+  const int lines = min(kLines, job.n_tile_lines - first_line);
+  double *base = field + job.origin + (long long)first_line * job.tile_stride + (long long)blockIdx.y * job.outer_stride;
+
+  // load and pack the even extension (each value goes to its slot and to the slot of its mirror image)
+  if (CONTIG) {
+    for (int idx = tid; idx < kLines * NPTS; idx += THREADS) {
+      const int l = idx / NPTS, e = idx - l * NPTS;
+      const double value = (l < lines) ? base[(long long)l * job.lstride + e] : 0.0;
+      put_packed(Sd, M, e, l, value);
+    }
+  } else {
+    for (int e = j; e < NPTS; e += T) {
+      const double value = (line < lines) ? base[(long long)line * job.lstride + (long long)e * job.estride] : 0.0;
+      put_packed(Sd, M, e, line, value);
+    }
+  }
+  __syncthreads();
+  fft_lines<LOGM>(S, line, j, job.tw);
+  double lo[4], hi[4], mid;
+  dct_unpack<LOGM>(S, line, j, job.cs, lo, hi, mid);
+
+  if (job.mode == 2) {
+    // pressure_hat *= 1 / (lambda_x + lambda_y + lambda_z); mode (0,0,0) := 0 (src/PressureEquation.cpp:158-163)
+    const int ix = min(first_line + line, job.n_tile_lines - 1);
+    const double lam_xy = job.lam_x[ix] + job.lam_y[blockIdx.y];
+    const bool origin_line = (first_line + line == 0) && (blockIdx.y == 0);
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      const int k = j + T * s;
+      const double scale_lo = (origin_line && k == 0) ? 0.0 : 1.0 / (lam_xy + job.lam_z[k]);
+      lo[s] *= scale_lo;
+      hi[s] *= 1.0 / (lam_xy + job.lam_z[M - k]);
+    }
+    mid *= 1.0 / (lam_xy + job.lam_z[M / 2]);
+    __syncthreads();  // everyone has finished reading the spectrum
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      const int k = j + T * s;
+      put_packed(Sd, M, k, line, lo[s]);
+      put_packed(Sd, M, M - k, line, hi[s]);
+    }
+    if (j == 0) put_packed(Sd, M, M / 2, line, mid);
+    __syncthreads();
+    fft_lines<LOGM>(S, line, j, job.tw);
+    dct_unpack<LOGM>(S, line, j, job.cs, lo, hi, mid);
+  }
+  const double scale = (job.mode == 0) ? 1.0 : job.inv_norm;
+
+  if (!CONTIG) {
+    if (line < lines) {
+      double *out = base + (long long)line * job.lstride;
+#pragma unroll
+      for (int s = 0; s < 4; s++) {
+        const int k = j + T * s;
+        out[(long long)k * job.estride] = lo[s] * scale;
+        out[(long long)(M - k) * job.estride] = hi[s] * scale;
+      }
+      if (j == 0) out[(long long)(M / 2) * job.estride] = mid * scale;
+    }
+  } else {
+    // transpose through shared memory so that the global stores run along the contiguous x lines
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      const int k = j + T * s;
+      Sd[k * kSlotPitch + line] = lo[s] * scale;
+      Sd[(M - k) * kSlotPitch + line] = hi[s] * scale;
+    }
+    if (j == 0) Sd[(M / 2) * kSlotPitch + line] = mid * scale;
+    __syncthreads();
+    for (int idx = tid; idx < kLines * NPTS; idx += THREADS) {
+      const int l = idx / NPTS, e = idx - l * NPTS;
+      if (l < lines) base[(long long)l * job.lstride + e] = Sd[e * kSlotPitch + l];
+    }
+  }
+}
+
+template <int LOGM>
+void launch_fast(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid, double *field) {
+  constexpr int M = 1 << LOGM;
+  const size_t smem = (size_t)M * fast::kSlotPitch * sizeof(double2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(fast_dct_kernel<LOGM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(fast_dct_kernel<LOGM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  if (contig) fast_dct_kernel<LOGM, true><<<grid, M, smem, stream>>>(job, field);
+  else fast_dct_kernel<LOGM, false><<<grid, M, smem, stream>>>(job, field);
+}
+
 template <typename T>
 T *to_device(const std::vector<T> &host) {
   if (host.empty()) return nullptr;
@@ -356,6 +471,7 @@ void host_fft_pow2(std::vector<double2> &z, bool inverse) {  // small recursive 
 
 struct PoissonPlan {
   DirPlanDev dir[3];
+  int fast_logm[3];  // > 0: DCT-I with N - 1 = 2^fast_logm handled by fast_dct_kernel
   int L[3];
   size_t smem[3];
   std::vector<void *> allocations;
@@ -385,6 +501,10 @@ PoissonPlan *poisson_plan_create(const Geom &g, const int n_points[3], const int
     for (int q = 0; q < P / 2; q++) tw[q] = unit_root(q, P);
     pl.tw = to_device(tw);
     plan->allocations.push_back((void *)pl.tw);
+    std::vector<double2> tw_full(P);
+    for (int q = 0; q < P; q++) tw_full[q] = unit_root(q, P);
+    pl.tw_full = to_device(tw_full);
+    plan->allocations.push_back((void *)pl.tw_full);
 
     pl.chirp = nullptr;
     pl.filt = nullptr;
@@ -439,6 +559,7 @@ PoissonPlan *poisson_plan_create(const Geom &g, const int n_points[3], const int
     // src/PressureEquation.cpp:167,200,234: N_domains_global * (periodic ? 1 : 2)
     pl.inv_norm = 1.0 / ((double)(n_global[d] - 1) * (periodic[d] ? 1.0 : 2.0));
 
+    plan->fast_logm[d] = (!periodic[d] && pow2 && pl.logP >= 6 && pl.logP <= 10) ? pl.logP : 0;
     // lines per CTA: the largest power of two <= 8 that fits a ~100 KB shared-memory budget (two CTAs per SM)
     const size_t per_line = (size_t)P * sizeof(double2) + (size_t)(n | 1) * sizeof(double);
     int L = 8;
@@ -486,6 +607,25 @@ void launch_poisson_sweep(cudaStream_t stream, const Geom &g, PoissonPlan *plan,
     } else {  // lines along z, tile over x, outer y
       job.n_tile_lines = nx; job.lstride = 1; job.estride = g.plane;
       tile_stride = 1; outer_stride = g.PX; outer = ny;
+    }
+    if (plan->fast_logm[d] > 0) {
+      FastJob fj;
+      fj.origin = origin; fj.lstride = job.lstride; fj.estride = job.estride;
+      fj.tile_stride = tile_stride; fj.outer_stride = outer_stride;
+      fj.n_tile_lines = job.n_tile_lines; fj.mode = mode;
+      fj.tw = plan->dir[d].tw_full; fj.cs = plan->dir[d].unpack;
+      fj.lam_x = plan->dir[0].lambda; fj.lam_y = plan->dir[1].lambda; fj.lam_z = plan->dir[2].lambda;
+      fj.inv_norm = plan->dir[d].inv_norm;
+      const dim3 fgrid((job.n_tile_lines + fast::kLines - 1) / fast::kLines, outer, 1);
+      switch (plan->fast_logm[d]) {
+        case 6: launch_fast<6>(stream, fj, d == 0, fgrid, field); break;
+        case 7: launch_fast<7>(stream, fj, d == 0, fgrid, field); break;
+        case 8: launch_fast<8>(stream, fj, d == 0, fgrid, field); break;
+        case 9: launch_fast<9>(stream, fj, d == 0, fgrid, field); break;
+        default: launch_fast<10>(stream, fj, d == 0, fgrid, field); break;
+      }
+      ++*launches;
+      return;
     }
     const dim3 grid((job.n_tile_lines + job.L - 1) / job.L, outer, 1);
     sweep_kernel<<<grid, 256, plan->smem[d], stream>>>(job, field, origin, tile_stride, outer_stride);

@@ -64,6 +64,9 @@ def main():
     dump_case("full_16_2", ["full", 16, 2, 1, "{out}"], dict(full, N=[16, 16, 16], steps=2, nhn=0))
     dump_case("full_17_1", ["full", 17, 1, 1, "{out}"], dict(full, N=[17, 17, 17], steps=1, nhn=0))
     dump_case("full_12_1_nhn", ["full", 12, 1, 1, "{out}", "nhn"], dict(full, N=[12, 12, 12], steps=1, nhn=1))
+    # power-of-two cell counts (N - 1 = 64, 128): these exercise the register-blocked DCT-I fast path
+    dump_case("full_65x17x9_1", ["full", 65, 1, 1, "{out}", "hn", 17, 9], dict(full, N=[65, 17, 9], steps=1, nhn=0))
+    dump_case("full_6x65x9_1", ["full", 6, 1, 1, "{out}", "hn", 65, 9], dict(full, N=[6, 65, 9], steps=1, nhn=0))
     lid1 = dict(kind="lid", x_size=1.0, y_size=1.0, z_size=2.0, min=[0.0, 0.0, -1.0], Re=1e3, periodic=[0, 0, 0],
                 bc="test_case_1")
     dump_case("lid1_12x10x14_2", ["lid", 12, 10, 14, 1e-3, 2, 0, 1, "{out}"],
@@ -73,7 +76,7 @@ def main():
     dump_case("lid2_10x12x9_2", ["lid", 10, 12, 9, 1e-3, 2, 1, 1, "{out}"],
               dict(lid2, N=[10, 12, 9], steps=2, dt=1e-3, final_time=2e-3))
     for kind, dims in (("hn", (8, 24, 40)), ("mixed", (8, 24, 40)), ("nhn", (8, 24, 40)), ("mixed", (9, 17, 17)),
-                       ("hn", (17, 9, 33)), ("mixed", (7, 6, 10))):
+                       ("hn", (17, 9, 33)), ("mixed", (7, 6, 10)), ("hn", (65, 9, 129)), ("mixed", (9, 65, 17))):
         lo = -np.pi / 2 if kind == "nhn" else 0.0
         ln = np.pi / 2 if kind == "nhn" else 2 * np.pi
         meta = dict(kind="ptest", ptest=kind, N=list(dims), x_size=ln, y_size=ln, z_size=ln, min=[lo, lo, lo], Re=1.0,

@@ -5,7 +5,7 @@
 // reference's own tests only print error norms (test/full_test.cpp:171-175), which are far too
 // coarse for a 1e-11 parity contract.  The set-ups replicate the reference's mains:
 //
-//   full  N steps Pz out [nhn]        test/full_test.cpp:36-76,118-126   (Ethier-Steinman, all walls)
+//   full  N steps Pz out [nhn|hn [Ny Nz]]  test/full_test.cpp:36-76,118-126 (Ethier-Steinman, all walls)
 //   lid   Nx Ny Nz dt steps tc2 Pz out  src/main.cpp:121-156               (test case 1 / 2)
 //   ptest kind Nx Ny Nz Pz out        test/pressure_test_{hn,mixed,nhn}.cpp:20-59 (any grid, kind = hn|mixed|nhn)
 //   vtest N steps Pz out [mixed]      test/velocity_test{,_mixed}.cpp
@@ -74,11 +74,13 @@ static int run_full(int argc, char **argv, int size) {
   const int Pz = std::atoi(argv[4]);
   g_out = argv[5];
   const bool nhn = argc > 6 && std::strcmp(argv[6], "nhn") == 0;
+  // optional anisotropic grid (same physics as test/full_test.cpp, which is cubic): ... [nhn|hn] Ny Nz
+  const size_t Ny = argc > 8 ? std::atol(argv[7]) : N, Nz = argc > 8 ? std::atol(argv[8]) : N;
   reset_manifest();
   const int Py = size / Pz;
   constexpr Real Re = 1e3;
   const std::array<bool, 3> periodic{false, false, false};
-  const Constants constants(N, N, N, 1.0, 1.0, 2.0, 0.0, 0.0, -1.0, Re, 1e-4, steps, Py, Pz, g_rank, periodic);
+  const Constants constants(N, Ny, Nz, 1.0, 1.0, 2.0, 0.0, 0.0, -1.0, Re, 1e-4, steps, Py, Pz, g_rank, periodic);
   PressureSolverStructures structures(constants);
   Reynolds = Re;
   VelocityTensor velocity(constants), velocity_buffer(constants), velocity_buffer_2(constants);

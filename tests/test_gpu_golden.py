@@ -52,7 +52,8 @@ def face_points(meta, face):
 
 
 @pytest.mark.parametrize("case", ["ptest_hn_8x24x40", "ptest_mixed_8x24x40", "ptest_nhn_8x24x40", "ptest_mixed_9x17x17",
-                                  "ptest_hn_17x9x33", "ptest_mixed_7x6x10"])
+                                  "ptest_hn_17x9x33", "ptest_mixed_7x6x10", "ptest_hn_65x9x129",
+                                  "ptest_mixed_9x65x17"])
 def test_pressure_solve_matches_reference(mif, case):
     meta, f = load_golden(case)
     ctx = make_ctx(mif, meta)
@@ -88,7 +89,8 @@ def es_gradient_functions(Re):
     return [sp.lambdify((t, x, y, z), sp.diff(p, v), "numpy") for v in (x, y, z)]
 
 
-@pytest.mark.parametrize("case", ["full_16_2", "full_17_1", "full_12_1_nhn", "lid1_12x10x14_2", "lid2_10x12x9_2"])
+@pytest.mark.parametrize("case", ["full_16_2", "full_17_1", "full_12_1_nhn", "lid1_12x10x14_2", "lid2_10x12x9_2",
+                                  "full_65x17x9_1", "full_6x65x9_1"])
 def test_timestep_matches_reference(mif, case):
     meta, f = load_golden(case)
     ctx = make_ctx(mif, meta)
@@ -107,14 +109,21 @@ def test_timestep_matches_reference(mif, case):
         def cb(which, time, time_prev, comp, face, values):
             assert which == 1
             x, y, z = face_points(meta, face)
-            values[...] = grads[comp](time, x, y, z) - grads[comp](time_prev, x, y, z)
+            # The reference passes exact_pressure_gradient.get_difference_over_time(new_time, prev_time)
+            # (src/Timestep.cpp:92), which evaluates f(prev_time) - f(new_time) (src/VectorFunction.cpp:52-60).
+            values[...] = grads[comp](time_prev, x, y, z) - grads[comp](time, x, y, z)
     bc = ctx.make_bc(kind, meta["Re"], cb)
     dt = meta["final_time"] / meta["steps"]
     for step in range(meta["steps"]):
         ctx.timestep(vel, vb, vb2, bc, step * dt, p, dp, nhn=nhn)
         ctx.synchronize()
+        # A velocity component that is identically zero in exact arithmetic (w in the z-periodic lid case) holds
+        # only rounding noise (max|w| ~ 1e-10, and two builds of the reference itself differ by 9e-11 of that), so
+        # a component is normalised by max(its own maximum, 1e-6 of the largest velocity component).
+        vmax = max(float(np.max(np.abs(f[f"{c}_s{step + 1}"]))) for c in "uvw")
         for t, name in zip(vel + [p], "uvwp"):
             ref = f[f"{name}_s{step + 1}"]
-            err = rel_linf(t.download(), ref)
+            floor = 1e-6 * vmax if name in "uvw" else 0.0
+            err = float(np.max(np.abs(t.download() - ref))) / max(float(np.max(np.abs(ref))), floor)
             assert err <= (TOL_NHN if nhn else TOL), (name, step + 1, err)
     ctx.close()
