@@ -1,0 +1,82 @@
+"""CPU: the plain-C restatement (oracle/mif_oracle.c) against raw fields of the UNMODIFIED reference
+(tests/golden/*.npz, written by oracle/make_golden.py) and against definition-level transforms."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import mif_oracle as mo  # noqa: E402
+
+KINDS = {"ethier_steinman": mo.BC_ETHIER_STEINMAN, "test_case_1": mo.BC_TEST_CASE_1, "test_case_2": mo.BC_TEST_CASE_2}
+
+
+def grid_from(meta):
+    N = meta["N"]
+    return mo.Grid(N[0], N[1], N[2], meta["x_size"], meta["y_size"], meta["z_size"], *meta["min"], meta["Re"],
+                   meta["final_time"], meta["steps"], periodic=[bool(p) for p in meta["periodic"]])
+
+
+def rel(a, b, floor=0.0):
+    return float(np.max(np.abs(a - b))) / max(float(np.max(np.abs(b))), floor)
+
+
+@pytest.mark.parametrize("case", ["full_16_2", "full_17_1", "full_12_1_nhn", "lid1_12x10x14_2", "lid2_10x12x9_2",
+                                  "full_65x17x9_1", "full_6x65x9_1"])
+@pytest.mark.parametrize("direct", [False, True])
+def test_timestep_restatement_matches_reference(case, direct):
+    meta, f = load_golden(case)
+    if direct and max(meta["N"]) > 20:
+        pytest.skip("O(n^2) transforms only on the small cases")
+    g = grid_from(meta)
+    vel = [f[c + "_s0"].copy() for c in "uvw"]
+    buf = [g.zeros(c) for c in range(3)]
+    buf2 = [g.zeros(c) for c in range(3)]
+    p, dp = f["p_s0"].copy(), g.zeros(3)
+    nhn = bool(meta.get("nhn", 0))
+    dt = meta["final_time"] / meta["steps"]
+    for step in range(meta["steps"]):
+        g.timestep(KINDS[meta["bc"]], step * dt, vel, buf, buf2, p, dp, nhn=nhn, direct=direct)
+        vmax = max(float(np.max(np.abs(f[f"{c}_s{step + 1}"]))) for c in "uvw")
+        for arr, name in zip(vel + [p], "uvwp"):
+            ref = f[f"{name}_s{step + 1}"]
+            err = rel(arr, ref, 1e-6 * vmax if name in "uvw" else 0.0)
+            # nhn: g(t_prev) - g(t_new) cancels to ~7 digits, see tests/test_gpu_golden.py
+            assert err <= (2e-9 if nhn else 1e-11), (name, step + 1, err)
+
+
+@pytest.mark.parametrize("case", ["ptest_hn_8x24x40", "ptest_mixed_8x24x40", "ptest_mixed_9x17x17", "ptest_hn_17x9x33",
+                                  "ptest_mixed_7x6x10", "ptest_hn_65x9x129", "ptest_mixed_9x65x17"])
+def test_pressure_solve_restatement_matches_reference(case):
+    meta, f = load_golden(case)
+    g = grid_from(meta)
+    p = g.solve_pressure(f["u_in"], f["v_in"], f["w_in"], g.dt)
+    assert rel(p, f["p_out"]) <= 1e-11
+
+
+def test_initial_condition_matches_reference():
+    meta, f = load_golden("full_16_2")
+    g = grid_from(meta)
+    for arr, name in zip(g.set_velocity(mo.BC_ETHIER_STEINMAN, 0.0), "uvw"):
+        assert rel(arr, f[name + "_s0"]) <= 1e-14
+
+
+def test_ethier_steinman_pressure_gradient_matches_sympy():
+    import sympy as sp
+    t, x, y, z = sp.symbols("t x y z")
+    a, d, Re = sp.pi / 4, sp.pi / 2, 1000
+    p = (-a * a / 2 * (sp.exp(2 * a * x) + sp.exp(2 * a * y) + sp.exp(2 * a * z)
+                       + 2 * sp.sin(a * x + d * y) * sp.cos(a * z + d * x) * sp.exp(a * (y + z))
+                       + 2 * sp.sin(a * y + d * z) * sp.cos(a * x + d * y) * sp.exp(a * (z + x))
+                       + 2 * sp.sin(a * z + d * x) * sp.cos(a * y + d * z) * sp.exp(a * (x + y)))
+         * sp.exp(-2 * d * d * t / Re))
+    rng = np.random.default_rng(7)
+    for comp, var in enumerate((x, y, z)):
+        fn = sp.lambdify((t, x, y, z), sp.diff(p, var), "math")
+        for _ in range(20):
+            tt, xx, yy, zz = rng.uniform(0, 1), rng.uniform(0, 1), rng.uniform(0, 1), rng.uniform(-1, 1)
+            got = mo.lib().mo_es_pressure_gradient(comp, tt, xx, yy, zz, 1000.0)
+            assert abs(got - fn(tt, xx, yy, zz)) <= 1e-13 * max(1.0, abs(got))
