@@ -1,0 +1,50 @@
+"""GPU: the C++ host layer (mpi-incompressible-fluid_b200/host, the reference's own class and function names over
+the C ABI) reproduces the numbers printed by the reference's own test programs (tests/golden/norms.json, written by
+oracle/make_golden.py from test/full_test.cpp and test/pressure_test_*.cpp of the unmodified reference)."""
+import json
+import os
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN_DIR, ROOT
+
+pytestmark = pytest.mark.gpu
+
+BIN = os.path.join(ROOT, "mpi-incompressible-fluid_b200", "host", "bin")
+NORMS = json.load(open(os.path.join(GOLDEN_DIR, "norms.json")))
+
+
+def run(exe, *args):
+    out = subprocess.run([os.path.join(BIN, exe), *map(str, args)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    return out.stdout
+
+
+def close(got, want):
+    # the reference prints 6 significant digits
+    return all(abs(g - w) <= 2e-5 * abs(w) for g, w in zip(got, want)) and len(got) == len(want)
+
+
+@pytest.mark.parametrize("n,steps", [(16, 1), (32, 2), (64, 4)])
+def test_full_test_prints_reference_numbers(n, steps):
+    got = [float(x) for x in run("full_test", n, steps).split()]
+    assert close(got, NORMS[f"full_test {n} {steps} 1"]), got
+
+
+@pytest.mark.parametrize("kind", ["hn", "mixed", "nhn"])
+@pytest.mark.parametrize("n", [8, 16, 32])
+def test_pressure_tests_print_reference_numbers(kind, n):
+    out = run("pressure_test", kind, n)
+    line = [l for l in out.splitlines() if l.startswith("Errors:")][0]
+    got = [float(x) for x in line.split()[1:]]
+    assert close(got, NORMS[f"pressure_test_{kind} {n} 1"]), got
+
+
+def test_full_test_convergence_order():
+    """Velocity converges with order ~2, pressure with order ~1.5 (analysis/plot_convergence.py:63-64,80-81)."""
+    import math
+    e16 = [float(x) for x in run("full_test", 16, 1).split()]
+    e32 = [float(x) for x in run("full_test", 32, 2).split()]
+    assert 1.8 <= math.log2(e16[1] / e32[1]) <= 2.7   # velocity L2
+    assert 1.1 <= math.log2(e16[4] / e32[4]) <= 2.2   # pressure L2
