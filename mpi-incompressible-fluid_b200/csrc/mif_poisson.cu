@@ -14,9 +14,11 @@
 // (src/PressureEquation.cpp:158-163), inverse transform and normalisation in one kernel.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "mif_fft_fast.cuh"
+#include "mif_fft_warp.cuh"
 #include "mif_kernels.h"
 
 namespace mifgpu {
@@ -432,6 +434,174 @@ void launch_fast(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid
   else fast_dct_kernel<LOGM, false><<<grid, M, smem, stream>>>(job, field);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Warp-per-line path: DCT-I sweeps with M = 2^LOGM, 256 <= M <= 1024 (see mif_fft_warp.cuh).
+// ------------------------------------------------------------------------------------------------
+template <int LOGM, bool CONTIG>
+__global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 : 2)) warp_dct_kernel(const FastJob job, double *__restrict__ field) {
+  using namespace warpfft;
+  using C = Cfg<LOGM>;
+  using L = LastPass<LOGM>;
+  constexpr int M = C::M, TL = C::TL, NPTS = M + 1, EPT = C::EPT, PAIRS = EPT / 2;
+  constexpr bool SHUFFLE = (C::WPL == 1);  // whole line in one warp: unpack with shuffles, spectrum stays in registers
+  extern __shared__ double2 smem2[];
+  double2 *T = smem2 + kLines * C::LINE_PITCH;  // twiddle tables behind the line regions
+  const int tid = threadIdx.x;
+  const int line = tid / TL, j = tid - line * TL;  // FFT mapping: a line is one warp (two for M = 1024)
+  double2 *S = smem2 + line * C::LINE_PITCH;
+  double *Sd = reinterpret_cast<double *>(S);
+  const int first_line = blockIdx.x * kLines;
+  const int lines = min(kLines, job.n_tile_lines - first_line);
+  double *base = field + job.origin + (long long)first_line * job.tile_stride + (long long)blockIdx.y * job.outer_stride;
+  double2 v[EPT];
+
+  load_twiddles<LOGM>(T, job.tw);
+  if (CONTIG) {
+    // x sweep: lane j loads its first-pass inputs c[j + s*TL] = (e[2q], e[2q+1]) straight from global memory;
+    // slots q >= M/2 are the mirror images (x[2M-2q], x[2M-2q-1]).  No shared-memory staging, no CTA barrier.
+    const double *src = base + (long long)line * job.lstride;
+    const bool live = line < lines;
+#pragma unroll
+    for (int s = 0; s < EPT; s++) {
+      const int q = j + s * TL;
+      if (!live) v[s] = make_double2(0.0, 0.0);
+      else if (s < EPT / 2) v[s] = *reinterpret_cast<const double2 *>(src + 2 * q);
+      else v[s] = make_double2(src[2 * M - 2 * q], src[2 * M - 2 * q - 1]);
+    }
+    __syncthreads();  // twiddle tables are in place
+  } else {
+    // y / z sweep: line-fastest mapping so that the 8 lines (consecutive x) form 64-byte segments.
+    const int l = tid & 7, q0 = tid >> 3;
+    constexpr int QSTEP = C::THREADS / 8, NIT = (NPTS + QSTEP - 1) / QSTEP;
+    double *dst = reinterpret_cast<double *>(smem2 + l * C::LINE_PITCH);
+    const double *src = base + (long long)l * job.lstride;
+    double vals[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int e = q0 + it * QSTEP;
+      vals[it] = (e < NPTS && l < lines) ? src[(long long)e * job.estride] : 0.0;
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int e = q0 + it * QSTEP;
+      if (e < NPTS) put_packed(dst, M, e, vals[it]);
+    }
+    __syncthreads();  // all lines and the twiddle tables are in place
+  }
+
+  double lo[PAIRS], hi[PAIRS], mid = 0.0, e_last = 0.0;
+  double spec[EPT];  // shuffle path: spec[u + G t] = E_k, k = j + 32 u + NS t
+  fft_line<LOGM, CONTIG, SHUFFLE>(S, T, j, line, v);
+  if constexpr (SHUFFLE) unpack_regs<LOGM>(v, j, job.cs, spec, e_last);
+  else unpack_line<LOGM>(S, j, job.cs, lo, hi, mid);
+
+  if (job.mode == 2) {
+    // pressure_hat *= 1 / (lambda_x + lambda_y + lambda_z); mode (0,0,0) := 0 (src/PressureEquation.cpp:158-163)
+    const int ix = min(first_line + line, job.n_tile_lines - 1);
+    const double lam_xy = job.lam_x[ix] + job.lam_y[blockIdx.y];
+    const bool origin_line = (first_line + line == 0) && (blockIdx.y == 0);
+    if constexpr (SHUFFLE) {
+#pragma unroll
+      for (int u = 0; u < L::G; u++)
+#pragma unroll
+        for (int t = 0; t < L::R; t++) {
+          const int k = j + 32 * u + L::NS * t;
+          spec[u + L::G * t] *= (origin_line && k == 0) ? 0.0 : 1.0 / (lam_xy + job.lam_z[k]);
+        }
+      e_last *= 1.0 / (lam_xy + job.lam_z[M]);
+      line_sync<C::WPL>(line);  // all lanes are done with the previous contents of the line region
+#pragma unroll
+      for (int u = 0; u < L::G; u++)
+#pragma unroll
+        for (int t = 0; t < L::R; t++) put_packed(Sd, M, j + 32 * u + L::NS * t, spec[u + L::G * t]);
+      if (j == 0) put_packed(Sd, M, M, e_last);
+      line_sync<C::WPL>(line);
+      fft_line<LOGM, false, true>(S, T, j, line, v);
+      unpack_regs<LOGM>(v, j, job.cs, spec, e_last);
+    } else {
+#pragma unroll
+      for (int s = 0; s < PAIRS; s++) {
+        const int k = j + TL * s;
+        lo[s] *= (origin_line && k == 0) ? 0.0 : 1.0 / (lam_xy + job.lam_z[k]);
+        hi[s] *= 1.0 / (lam_xy + job.lam_z[M - k]);
+      }
+      mid *= 1.0 / (lam_xy + job.lam_z[M / 2]);
+      line_sync<C::WPL>(line);  // the whole line has been unpacked into registers
+#pragma unroll
+      for (int s = 0; s < PAIRS; s++) {
+        const int k = j + TL * s;
+        put_packed(Sd, M, k, lo[s]);
+        put_packed(Sd, M, M - k, hi[s]);
+      }
+      if (j == 0) put_packed(Sd, M, M / 2, mid);
+      line_sync<C::WPL>(line);
+      fft_line<LOGM, false, false>(S, T, j, line, v);
+      unpack_line<LOGM>(S, j, job.cs, lo, hi, mid);
+    }
+  }
+  const double scale = (job.mode == 0) ? 1.0 : job.inv_norm;
+
+  if constexpr (CONTIG && SHUFFLE) {
+    // x sweep: for fixed (u, t) the 32 lanes hold 32 consecutive outputs -> coalesced stores from registers.
+    if (line < lines) {
+      double *out = base + (long long)line * job.lstride;
+#pragma unroll
+      for (int u = 0; u < L::G; u++)
+#pragma unroll
+        for (int t = 0; t < L::R; t++) out[j + 32 * u + L::NS * t] = spec[u + L::G * t] * scale;
+      if (j == 0) out[M] = e_last * scale;
+    }
+    return;
+  }
+  // Results go back through the line's own region as plain reals R[e], then out with coalesced stores.
+  line_sync<C::WPL>(line);
+  if constexpr (SHUFFLE) {
+#pragma unroll
+    for (int u = 0; u < L::G; u++)
+#pragma unroll
+      for (int t = 0; t < L::R; t++) Sd[j + 32 * u + L::NS * t] = spec[u + L::G * t] * scale;
+    if (j == 0) Sd[M] = e_last * scale;
+  } else {
+#pragma unroll
+    for (int s = 0; s < PAIRS; s++) {
+      const int k = j + TL * s;
+      Sd[k] = lo[s] * scale;
+      Sd[M - k] = hi[s] * scale;
+    }
+    if (j == 0) Sd[M / 2] = mid * scale;
+  }
+  if (CONTIG) {
+    line_sync<C::WPL>(line);
+    if (line < lines) {
+      double *out = base + (long long)line * job.lstride;
+      for (int e = j; e < NPTS; e += TL) out[e] = Sd[e];
+    }
+  } else {
+    __syncthreads();
+    const int l = tid & 7, q0 = tid >> 3;
+    constexpr int QSTEP = C::THREADS / 8;
+    if (l < lines) {
+      const double *srcl = reinterpret_cast<const double *>(smem2 + l * C::LINE_PITCH);
+      double *out = base + (long long)l * job.lstride;
+      for (int e = q0; e < NPTS; e += QSTEP) out[(long long)e * job.estride] = srcl[e];
+    }
+  }
+}
+
+template <int LOGM>
+void launch_warp(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid, double *field) {
+  using C = warpfft::Cfg<LOGM>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(warp_dct_kernel<LOGM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    cudaFuncSetAttribute(warp_dct_kernel<LOGM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    attr_set = true;
+  }
+  if (contig) warp_dct_kernel<LOGM, true><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
+  else warp_dct_kernel<LOGM, false><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
+}
+
 template <typename T>
 T *to_device(const std::vector<T> &host) {
   if (host.empty()) return nullptr;
@@ -617,12 +787,22 @@ void launch_poisson_sweep(cudaStream_t stream, const Geom &g, PoissonPlan *plan,
       fj.lam_x = plan->dir[0].lambda; fj.lam_y = plan->dir[1].lambda; fj.lam_z = plan->dir[2].lambda;
       fj.inv_norm = plan->dir[d].inv_norm;
       const dim3 fgrid((job.n_tile_lines + fast::kLines - 1) / fast::kLines, outer, 1);
+      static const bool use_cta_sync_variant = getenv("MIFGPU_FFT_CTA_SYNC") != nullptr;  // A/B switch for profiling
       switch (plan->fast_logm[d]) {
         case 6: launch_fast<6>(stream, fj, d == 0, fgrid, field); break;
         case 7: launch_fast<7>(stream, fj, d == 0, fgrid, field); break;
-        case 8: launch_fast<8>(stream, fj, d == 0, fgrid, field); break;
-        case 9: launch_fast<9>(stream, fj, d == 0, fgrid, field); break;
-        default: launch_fast<10>(stream, fj, d == 0, fgrid, field); break;
+        case 8:
+          if (use_cta_sync_variant) launch_fast<8>(stream, fj, d == 0, fgrid, field);
+          else launch_warp<8>(stream, fj, d == 0, fgrid, field);
+          break;
+        case 9:
+          if (use_cta_sync_variant) launch_fast<9>(stream, fj, d == 0, fgrid, field);
+          else launch_warp<9>(stream, fj, d == 0, fgrid, field);
+          break;
+        default:
+          if (use_cta_sync_variant) launch_fast<10>(stream, fj, d == 0, fgrid, field);
+          else launch_warp<10>(stream, fj, d == 0, fgrid, field);
+          break;
       }
       ++*launches;
       return;

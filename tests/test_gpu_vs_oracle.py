@@ -40,6 +40,14 @@ GRIDS = [
     ((8, 11, 9), (False, True, False)),        # periodic y
     ((9, 10, 12), (True, True, True)),         # fully periodic
     ((2, 5, 3), (False, False, False)),        # smallest legal extents
+    ((257, 6, 5), (False, False, False)),      # warp-per-line DCT path, M = 256, x sweep
+    ((5, 257, 6), (False, False, False)),      # ... y sweep
+    ((6, 5, 257), (False, False, False)),      # ... fused z sweep
+    ((513, 4, 9), (False, False, False)),      # M = 512
+    ((9, 513, 3), (False, False, False)),
+    ((11, 3, 513), (False, False, False)),
+    ((1025, 3, 4), (False, False, False)),     # M = 1024 (two warps per line)
+    ((10, 4, 1025), (False, False, False)),
 ]
 
 
@@ -58,7 +66,7 @@ def test_pressure_solve_random_velocity(mif, N, periodic):
     ctx.close()
 
 
-@pytest.mark.parametrize("N,periodic", GRIDS[:10])
+@pytest.mark.parametrize("N,periodic", GRIDS[:10] + GRIDS[11:17:2])
 @pytest.mark.parametrize("kind", ["ethier_steinman", "test_case_1", "test_case_2"])
 def test_timestep_random_state(mif, N, periodic, kind):
     ctx, grid = make_pair(mif, N, periodic)
