@@ -99,6 +99,21 @@ typedef struct mifgpu_bc {
  * (src/PressureSolverStructures.cpp:13-70): geometry, decomposition, transform plans, eigenvalues. */
 int mifgpu_create(const mifgpu_params *params, mifgpu_ctx **ctx);
 void mifgpu_destroy(mifgpu_ctx *ctx);
+
+/* Multi-GPU: one process (or thread) per GPU, rank = params->rank of params->Py * params->Pz ranks.  Replaces the
+ * MPI set-up of the reference (MPI_Init + the Cartesian communicators of deps/2Decomp_C/C2Decomp.cpp:34-62): rank 0
+ * calls mifgpu_comm_unique_id, the host program distributes the MIFGPU_UNIQUE_ID_BYTES bytes to all ranks by any
+ * means (MPI_Bcast, torch.distributed, a file), and every rank calls mifgpu_create_distributed collectively.
+ * Halos (src/StaggeredTensor.cpp:60-165) and pencil transposes (deps/2Decomp_C/Transpose*.cpp) then run inside the
+ * library over NCCL.  This build supports slab decompositions (Py = 1, Pz = number of GPUs). */
+#define MIFGPU_UNIQUE_ID_BYTES 128
+int mifgpu_comm_unique_id(void *unique_id);
+int mifgpu_create_distributed(const mifgpu_params *params, const void *unique_id, mifgpu_ctx **ctx);
+
+/* Host-only helper (no GPU needed): the block distribution used for both the z slabs and the y ranges of the z
+ * pencils, first[r] .. first[r+1] for r < parts, bigger blocks on the low ranks (src/Constants.cpp:78-79,
+ * deps/2Decomp_C/C2Decomp.cpp:273-324).  `first` has parts + 1 entries. */
+int mifgpu_slab_plan(uint64_t n_points, int32_t parts, int32_t *first);
 const char *mifgpu_last_error(void);
 int mifgpu_abi_version(void);
 

@@ -29,7 +29,8 @@ EXPORTED_SYMBOLS = [
     "mifgpu_abi_version", "mifgpu_last_error", "mifgpu_create", "mifgpu_destroy", "mifgpu_tensor_extents",
     "mifgpu_tensor_create", "mifgpu_tensor_destroy", "mifgpu_tensor_upload", "mifgpu_tensor_download",
     "mifgpu_tensor_swap", "mifgpu_timestep", "mifgpu_apply_bc", "mifgpu_solve_pressure", "mifgpu_synchronize",
-    "mifgpu_stream", "mifgpu_launch_count", "mifgpu_profile_enable", "mifgpu_profile_read",
+    "mifgpu_stream", "mifgpu_launch_count", "mifgpu_profile_enable", "mifgpu_profile_read", "mifgpu_comm_unique_id",
+    "mifgpu_create_distributed", "mifgpu_slab_plan",
 ]
 
 
@@ -85,6 +86,9 @@ def lib() -> ctypes.CDLL:
     l.mifgpu_create.argtypes = [POINTER(Params), POINTER(c_void_p)]
     l.mifgpu_destroy.argtypes = [c_void_p]
     l.mifgpu_destroy.restype = None
+    l.mifgpu_comm_unique_id.argtypes = [c_void_p]
+    l.mifgpu_create_distributed.argtypes = [POINTER(Params), c_void_p, POINTER(c_void_p)]
+    l.mifgpu_slab_plan.argtypes = [c_uint64, c_int32, POINTER(c_int32)]
     l.mifgpu_tensor_extents.argtypes = [c_void_p, c_int, POINTER(c_uint64)]
     l.mifgpu_tensor_create.argtypes = [c_void_p, c_int, POINTER(c_void_p)]
     l.mifgpu_tensor_destroy.argtypes = [c_void_p]
@@ -110,6 +114,23 @@ def lib() -> ctypes.CDLL:
 def _check(rc: int) -> None:
     if rc != 0:
         raise MifGpuError(f"libmifgpu error {rc}: {lib().mifgpu_last_error().decode()}")
+
+
+UNIQUE_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """Rank 0: a fresh communicator id to hand to every rank's Context(comm_id=...) (any transport will do)."""
+    buf = ctypes.create_string_buffer(UNIQUE_ID_BYTES)
+    _check(lib().mifgpu_comm_unique_id(buf))
+    return buf.raw
+
+
+def slab_plan(n_points: int, parts: int):
+    """first[r]..first[r+1]: block distribution of n_points over `parts` ranks (host-only, no GPU needed)."""
+    first = (c_int32 * (parts + 1))()
+    _check(lib().mifgpu_slab_plan(n_points, parts, first))
+    return [int(v) for v in first]
 
 
 class Tensor:
@@ -149,11 +170,17 @@ class Context:
 
     def __init__(self, Nx: int, Ny: int, Nz: int, x_size: float, y_size: float, z_size: float, min_x: float,
                  min_y: float, min_z: float, Re: float, final_time: float, num_time_steps: int, Py: int = 1,
-                 Pz: int = 1, rank: int = 0, periodic: Sequence[bool] = (False, False, False), device: int = 0):
+                 Pz: int = 1, rank: int = 0, periodic: Sequence[bool] = (False, False, False), device: int = 0,
+                 comm_id: Optional[bytes] = None):
         self.params = Params(Nx, Ny, Nz, x_size, y_size, z_size, min_x, min_y, min_z, Re, final_time,
                              num_time_steps, Py, Pz, rank, (c_int32 * 3)(*[int(b) for b in periodic]), device)
         handle = c_void_p()
-        _check(lib().mifgpu_create(ctypes.byref(self.params), ctypes.byref(handle)))
+        if comm_id is None:
+            _check(lib().mifgpu_create(ctypes.byref(self.params), ctypes.byref(handle)))
+        else:
+            if len(comm_id) != UNIQUE_ID_BYTES:
+                raise ValueError("comm_id must be the 128 bytes returned by comm_unique_id() on rank 0")
+            _check(lib().mifgpu_create_distributed(ctypes.byref(self.params), ctypes.c_char_p(comm_id), ctypes.byref(handle)))
         self.handle = handle
         self.dt = final_time / num_time_steps
         self._keepalive = []

@@ -1,5 +1,8 @@
 // mif_api.cu -- the C ABI of libmifgpu (include/mifgpu.h): context, tensors and the orchestration of one
 // projection time step (src/Timestep.cpp:97-156) on one CUDA stream.
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -26,6 +29,52 @@ int fail(int code, const char *fmt, ...) {
   return code;
 }
 
+// NCCL is bound at run time (dlopen) the first time a multi-GPU context is requested: single-GPU users need no NCCL
+// at all, and inside a process that already carries an NCCL (e.g. PyTorch's bundled one) that copy is reused
+// instead of a second libnccl.so.2 being forced into the process at load time.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi g_nccl;
+
+bool load_nccl() {
+  if (g_nccl.ok) return true;
+  void *handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+  if (!handle) {
+    g_last_error = std::string("cannot load libnccl.so.2: ") + dlerror();
+    return false;
+  }
+  auto sym = [&](const char *name) { return dlsym(handle, name); };
+  g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(sym("ncclGetUniqueId"));
+  g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(sym("ncclCommInitRank"));
+  g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(sym("ncclCommDestroy"));
+  g_nccl.GroupStart = reinterpret_cast<decltype(g_nccl.GroupStart)>(sym("ncclGroupStart"));
+  g_nccl.GroupEnd = reinterpret_cast<decltype(g_nccl.GroupEnd)>(sym("ncclGroupEnd"));
+  g_nccl.Send = reinterpret_cast<decltype(g_nccl.Send)>(sym("ncclSend"));
+  g_nccl.Recv = reinterpret_cast<decltype(g_nccl.Recv)>(sym("ncclRecv"));
+  g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(sym("ncclGetErrorString"));
+  g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.GroupStart && g_nccl.GroupEnd &&
+              g_nccl.Send && g_nccl.Recv && g_nccl.GetErrorString;
+  if (!g_nccl.ok) g_last_error = "libnccl.so.2 lacks a required symbol";
+  return g_nccl.ok;
+}
+
+#define NCCL_TRY(expr)                                                                            \
+  do {                                                                                            \
+    ncclResult_t err__ = (expr);                                                                  \
+    if (err__ != ncclSuccess)                                                                     \
+      return fail(MIFGPU_ERR_COMM, "%s failed: %s (%s:%d)", #expr, g_nccl.GetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+
 #define CUDA_TRY(expr)                                                                            \
   do {                                                                                            \
     cudaError_t err__ = (expr);                                                                   \
@@ -37,11 +86,12 @@ int fail(int code, const char *fmt, ...) {
 
 enum ProfCategory {
   PROF_STAGE1, PROF_STAGE2, PROF_STAGE3, PROF_BC, PROF_DIVERGENCE, PROF_NHN, PROF_SWEEP_X_FWD, PROF_SWEEP_Y_FWD,
-  PROF_SWEEP_Z, PROF_SWEEP_Y_INV, PROF_SWEEP_X_INV, PROF_PERIODIC, PROF_CORRECT, PROF_COUNT
+  PROF_SWEEP_Z, PROF_SWEEP_Y_INV, PROF_SWEEP_X_INV, PROF_PERIODIC, PROF_CORRECT, PROF_HALO, PROF_TRANSPOSE, PROF_COUNT
 };
 const char *const kProfNames[PROF_COUNT] = {"stage1", "stage2", "stage3", "bc_faces", "divergence", "nhn_rhs",
                                             "sweep_x_fwd", "sweep_y_fwd", "sweep_z_fused", "sweep_y_inv",
-                                            "sweep_x_inv", "periodic", "correct"};
+                                            "sweep_x_inv", "periodic", "correct", "halo_exchange",
+                                            "transpose_alltoall"};
 struct ProfRecord {
   int category;
   cudaEvent_t start, stop;
@@ -56,6 +106,14 @@ struct mifgpu_ctx {
   uint64_t launches = 0;
   bool profiling = false;
   std::vector<ProfRecord> prof_records;
+  // multi-GPU slab decomposition (Py = 1, Pz = nranks): NCCL communicator, y ranges of the z pencils, buffers
+  ncclComm_t comm = nullptr;
+  int nranks = 1;
+  std::vector<int> ylo;      // nranks + 1: y rows [ylo[r], ylo[r+1]) of the transform domain belong to rank r's z pencil
+  std::vector<int> zlo;      // nranks + 1: owner z points [zlo[r], zlo[r+1]) of rank r's slab
+  int *ylo_dev = nullptr;
+  double *xfer = nullptr;    // send / receive staging, one local owner volume
+  double *zbuf = nullptr;    // z pencil: zbuf[z][y_local][x]
   // host-callback boundary faces: pinned staging + device copies, [which][component][face]
   double *face_host[2][3][6] = {};
   double *face_dev[2][3][6] = {};
@@ -212,6 +270,59 @@ int fill_face_tables(mifgpu_ctx *ctx, const mifgpu_bc *bc, int which, double tim
   return MIFGPU_OK;
 }
 
+// 1-cell halo exchange in z of whole (padded) planes: plane 1 -> prev rank's last plane, plane sz-2 -> next rank's
+// plane 0 (src/StaggeredTensor.cpp:60-135; tags and Isend/Recv become one NCCL group).
+int exchange_z(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count) {
+  if (ctx->nranks == 1) return MIFGPU_OK;
+  const Geom &g = ctx->g;
+  ProfScope prof(ctx, PROF_HALO);
+  const size_t plane = (size_t)g.plane;
+  NCCL_TRY(g_nccl.GroupStart());
+  for (int t = 0; t < count; t++) {
+    double *data = tensors[t]->data;
+    const int sz = g.sz[tensors[t]->staggering];
+    if (g.prev_z != -1) {
+      NCCL_TRY(g_nccl.Send(data + plane, plane, ncclDouble, g.prev_z, ctx->comm, ctx->stream));
+      NCCL_TRY(g_nccl.Recv(data, plane, ncclDouble, g.prev_z, ctx->comm, ctx->stream));
+    }
+    if (g.next_z != -1) {
+      NCCL_TRY(g_nccl.Send(data + plane * (sz - 2), plane, ncclDouble, g.next_z, ctx->comm, ctx->stream));
+      NCCL_TRY(g_nccl.Recv(data + plane * (sz - 1), plane, ncclDouble, g.next_z, ctx->comm, ctx->stream));
+    }
+  }
+  NCCL_TRY(g_nccl.GroupEnd());
+  return MIFGPU_OK;
+}
+
+// Slab -> z pencil (forward = true) and back: the 2Decomp Y<->Z transposes (deps/2Decomp_C/TransposeY2Z.cpp:22-50,
+// TransposeZ2Y.cpp:18-46) as one grouped NCCL send/recv all-to-all.  Forward: pack rows per destination, receive
+// straight into zbuf (the planes of one source are contiguous there).  Backward: send straight out of zbuf,
+// receive into the staging buffer, unpack.
+int transpose_slab(mifgpu_ctx *ctx, double *field, bool forward) {
+  const Geom &g = ctx->g;
+  ProfScope prof(ctx, PROF_TRANSPOSE);
+  const int me = ctx->params.rank, P = ctx->nranks;
+  const long long nz_me = ctx->zlo[me + 1] - ctx->zlo[me], ny_me = ctx->ylo[me + 1] - ctx->ylo[me];
+  if (forward) launch_pack_slab(ctx->stream, g, field, ctx->xfer, ctx->ylo_dev, P, &ctx->launches);
+  NCCL_TRY(g_nccl.GroupStart());
+  for (int r = 0; r < P; r++) {
+    const long long ny_r = ctx->ylo[r + 1] - ctx->ylo[r], nz_r = ctx->zlo[r + 1] - ctx->zlo[r];
+    double *slab_block = ctx->xfer + nz_me * g.PX * ctx->ylo[r];            // [z_local][y in r's range][x]
+    double *pencil_block = ctx->zbuf + (long long)ctx->zlo[r] * ny_me * g.PX;  // planes z in r's slab
+    const size_t slab_count = (size_t)(nz_me * ny_r * g.PX), pencil_count = (size_t)(nz_r * ny_me * g.PX);
+    if (forward) {
+      NCCL_TRY(g_nccl.Send(slab_block, slab_count, ncclDouble, r, ctx->comm, ctx->stream));
+      NCCL_TRY(g_nccl.Recv(pencil_block, pencil_count, ncclDouble, r, ctx->comm, ctx->stream));
+    } else {
+      NCCL_TRY(g_nccl.Send(pencil_block, pencil_count, ncclDouble, r, ctx->comm, ctx->stream));
+      NCCL_TRY(g_nccl.Recv(slab_block, slab_count, ncclDouble, r, ctx->comm, ctx->stream));
+    }
+  }
+  NCCL_TRY(g_nccl.GroupEnd());
+  if (!forward) launch_unpack_slab(ctx->stream, g, field, ctx->xfer, ctx->ylo_dev, P, &ctx->launches);
+  return MIFGPU_OK;
+}
+
 int do_apply_bc(mifgpu_ctx *ctx, mifgpu_tensor *const vel[3], const mifgpu_bc *bc, double time) {
   BcDev dev;
   std::memset(&dev, 0, sizeof(dev));
@@ -225,9 +336,11 @@ int do_apply_bc(mifgpu_ctx *ctx, mifgpu_tensor *const vel[3], const mifgpu_bc *b
              bc->kind != MIFGPU_BC_ETHIER_STEINMAN) {
     return fail(MIFGPU_ERR_INVALID, "unknown boundary kind %d", bc->kind);
   }
-  ProfScope prof(ctx, PROF_BC);
-  launch_apply_bc(ctx->stream, ctx->g, vec3(vel), dev, &ctx->launches);
-  return MIFGPU_OK;
+  {
+    ProfScope prof(ctx, PROF_BC);
+    launch_apply_bc(ctx->stream, ctx->g, vec3(vel), dev, &ctx->launches);
+  }
+  return exchange_z(ctx, vel, 3);  // send_mpi_data / receive_mpi_data of the three components (src/VelocityTensor.cpp:225-232)
 }
 
 // solve_pressure_equation_homogeneous_periodic / _non_homogeneous_neumann (src/PressureEquation.cpp:266-286).
@@ -250,17 +363,34 @@ int do_solve(mifgpu_ctx *ctx, mifgpu_tensor *dp, mifgpu_tensor *const vel[3], do
   }
   // forward x, forward y, (forward z, eigenvalues, inverse z), inverse y, inverse x
   // (src/PressureEquation.cpp:79-101, 106-128, 133-195, 200-229, 234-263)
-  static const int kSweeps[5][3] = {{0, 0, PROF_SWEEP_X_FWD}, {1, 0, PROF_SWEEP_Y_FWD}, {2, 2, PROF_SWEEP_Z},
-                                    {1, 1, PROF_SWEEP_Y_INV}, {0, 1, PROF_SWEEP_X_INV}};
-  for (const auto &sw : kSweeps) {
-    ProfScope prof(ctx, sw[2]);
-    launch_poisson_sweep(ctx->stream, ctx->g, ctx->plan, dp->data, sw[0], sw[1], &ctx->launches);
+  auto sweep = [&](int dir, int mode, int category) {
+    ProfScope prof(ctx, category);
+    launch_poisson_sweep(ctx->stream, ctx->g, ctx->plan, dp->data, dir, mode, &ctx->launches);
+  };
+  sweep(0, 0, PROF_SWEEP_X_FWD);
+  sweep(1, 0, PROF_SWEEP_Y_FWD);
+  if (ctx->nranks == 1) {
+    sweep(2, 2, PROF_SWEEP_Z);
+  } else {
+    int rc = transpose_slab(ctx, dp->data, true);
+    if (rc) return rc;
+    {
+      ProfScope prof(ctx, PROF_SWEEP_Z);
+      const int me = ctx->params.rank;
+      launch_poisson_zpencil(ctx->stream, ctx->g, ctx->plan, ctx->zbuf, ctx->ylo[me + 1] - ctx->ylo[me], ctx->ylo[me],
+                             ctx->ylo[me] == 0, &ctx->launches);
+    }
+    rc = transpose_slab(ctx, dp->data, false);
+    if (rc) return rc;
   }
+  sweep(1, 1, PROF_SWEEP_Y_INV);
+  sweep(0, 1, PROF_SWEEP_X_INV);
   {
     ProfScope prof(ctx, PROF_PERIODIC);
     launch_periodic(ctx->stream, ctx->g, dp->data, 3, &ctx->launches);  // copy_to_staggered, src/PressureTensor.cpp:21-34
   }
-  return MIFGPU_OK;
+  mifgpu_tensor *one[1] = {dp};
+  return exchange_z(ctx, one, 1);  // other.send_mpi_data(base_tag) / receive_mpi_data (src/PressureTensor.cpp:30-33)
 }
 
 int check_launch(mifgpu_ctx *ctx) {
@@ -278,7 +408,31 @@ int mifgpu_abi_version(void) { return MIFGPU_ABI_VERSION; }
 
 const char *mifgpu_last_error(void) { return g_last_error.c_str(); }
 
+static int create_context(const mifgpu_params *params, const void *unique_id, mifgpu_ctx **out);
+
 int mifgpu_create(const mifgpu_params *params, mifgpu_ctx **out) {
+  if (params && params->Py * params->Pz != 1)
+    return fail(MIFGPU_ERR_INVALID, "Py*Pz = %d: use mifgpu_create_distributed with a communicator id", params->Py * params->Pz);
+  return create_context(params, nullptr, out);
+}
+
+int mifgpu_comm_unique_id(void *unique_id) {
+  if (!unique_id) return fail(MIFGPU_ERR_INVALID, "NULL argument");
+  static_assert(sizeof(ncclUniqueId) <= MIFGPU_UNIQUE_ID_BYTES, "unique id does not fit");
+  if (!load_nccl()) return MIFGPU_ERR_COMM;
+  ncclUniqueId id;
+  NCCL_TRY(g_nccl.GetUniqueId(&id));
+  std::memset(unique_id, 0, MIFGPU_UNIQUE_ID_BYTES);
+  std::memcpy(unique_id, &id, sizeof(id));
+  return MIFGPU_OK;
+}
+
+int mifgpu_create_distributed(const mifgpu_params *params, const void *unique_id, mifgpu_ctx **out) {
+  if (!unique_id) return fail(MIFGPU_ERR_INVALID, "NULL communicator id");
+  return create_context(params, unique_id, out);
+}
+
+static int create_context(const mifgpu_params *params, const void *unique_id, mifgpu_ctx **out) {
   if (!params || !out) return fail(MIFGPU_ERR_INVALID, "NULL argument");
   *out = nullptr;
   Geom g;
@@ -286,9 +440,11 @@ int mifgpu_create(const mifgpu_params *params, mifgpu_ctx **out) {
   int n_points[3];
   int rc = build_geometry(*params, g, n_points);
   if (rc) return rc;
-  if (params->Py * params->Pz != 1)
-    return fail(MIFGPU_ERR_UNSUPPORTED, "multi-rank decomposition (Py*Pz = %d) is not available in this build",
-                params->Py * params->Pz);
+  if (params->Py != 1)
+    return fail(MIFGPU_ERR_UNSUPPORTED, "only slab decompositions (Py = 1, Pz = number of GPUs) are available in this build, got Py = %d",
+                params->Py);
+  if (params->Pz > 1 && (params->Nz_global - (params->periodic_bc[2] ? 1 : 0)) / params->Pz < 2)
+    return fail(MIFGPU_ERR_INVALID, "fewer than 2 owner planes per rank");
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
     return fail(MIFGPU_ERR_CUDA, "no CUDA device available (libmifgpu has no CPU fallback)");
@@ -307,6 +463,38 @@ int mifgpu_create(const mifgpu_params *params, mifgpu_ctx **out) {
   const double h[3] = {g.dx, g.dy, g.dz};
   const int n_global[3] = {(int)params->Nx_global, (int)params->Ny_global, (int)params->Nz_global};
   ctx->plan = poisson_plan_create(g, n_points, per, h, n_global);
+  ctx->nranks = params->Pz;
+  if (ctx->nranks > 1) {
+    // MIF block distribution: the first (n mod P) ranks own one more point (src/Constants.cpp:78-79,
+    // deps/2Decomp_C/C2Decomp.cpp:273-324).
+    const int P = ctx->nranks;
+    ctx->ylo.assign(P + 1, 0);
+    ctx->zlo.assign(P + 1, 0);
+    for (int r = 0; r < P; r++) {
+      ctx->ylo[r + 1] = ctx->ylo[r] + n_points[1] / P + (r < n_points[1] % P ? 1 : 0);
+      ctx->zlo[r + 1] = ctx->zlo[r] + n_points[2] / P + (r < n_points[2] % P ? 1 : 0);
+    }
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id, sizeof(id));
+    if (!load_nccl()) {
+      mifgpu_destroy(ctx);
+      return MIFGPU_ERR_COMM;
+    }
+    ncclResult_t nerr = g_nccl.CommInitRank(&ctx->comm, P, id, params->rank);
+    if (nerr != ncclSuccess) {
+      mifgpu_destroy(ctx);
+      return fail(MIFGPU_ERR_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(nerr));
+    }
+    const int me = params->rank;
+    const size_t slab = (size_t)(ctx->zlo[me + 1] - ctx->zlo[me]) * n_points[1] * g.PX;
+    const size_t pencil = (size_t)n_points[2] * (ctx->ylo[me + 1] - ctx->ylo[me]) * g.PX;
+    if (cudaMalloc(&ctx->xfer, slab * sizeof(double)) != cudaSuccess || cudaMalloc(&ctx->zbuf, pencil * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&ctx->ylo_dev, (P + 1) * sizeof(int)) != cudaSuccess) {
+      mifgpu_destroy(ctx);
+      return fail(MIFGPU_ERR_CUDA, "allocating the transpose buffers failed");
+    }
+    cudaMemcpy(ctx->ylo_dev, ctx->ylo.data(), (P + 1) * sizeof(int), cudaMemcpyHostToDevice);
+  }
   err = cudaDeviceSynchronize();
   if (err != cudaSuccess) {
     mifgpu_destroy(ctx);
@@ -327,6 +515,10 @@ void mifgpu_destroy(mifgpu_ctx *ctx) {
         if (ctx->face_dev[w][c][f]) cudaFree(ctx->face_dev[w][c][f]);
       }
   poisson_plan_destroy(ctx->plan);
+  if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
+  if (ctx->xfer) cudaFree(ctx->xfer);
+  if (ctx->zbuf) cudaFree(ctx->zbuf);
+  if (ctx->ylo_dev) cudaFree(ctx->ylo_dev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -448,6 +640,7 @@ int mifgpu_timestep(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], mifgpu_te
     ProfScope prof(ctx, PROF_CORRECT);
     launch_correct(s, g, vec3(velocity_buffer), pressure->data, pressure_buffer->data, dt_1, &ctx->launches);
   }
+  if ((rc = exchange_z(ctx, velocity_buffer, 3))) return rc;  // src/Timestep.cpp:68-75
 
   // Stage 2 (src/Timestep.cpp:119-129).
   {
@@ -460,6 +653,7 @@ int mifgpu_timestep(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], mifgpu_te
     ProfScope prof(ctx, PROF_CORRECT);
     launch_correct(s, g, vec3(velocity_buffer_2), pressure->data, pressure_buffer->data, dt_2, &ctx->launches);
   }
+  if ((rc = exchange_z(ctx, velocity_buffer_2, 3))) return rc;  // src/Timestep.cpp:68-75
 
   // Stage 3 (src/Timestep.cpp:131-141).
   {
@@ -472,7 +666,15 @@ int mifgpu_timestep(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], mifgpu_te
     ProfScope prof(ctx, PROF_CORRECT);
     launch_correct(s, g, vec3(velocity), pressure->data, pressure_buffer->data, dt_3, &ctx->launches);
   }
+  if ((rc = exchange_z(ctx, velocity, 3))) return rc;  // src/Timestep.cpp:68-75
   return check_launch(ctx);
+}
+
+int mifgpu_slab_plan(uint64_t n_points, int32_t parts, int32_t *first) {
+  if (!first || parts < 1) return fail(MIFGPU_ERR_INVALID, "bad argument");
+  first[0] = 0;
+  for (int r = 0; r < parts; r++) first[r + 1] = first[r] + (int32_t)(n_points / parts) + ((uint64_t)r < n_points % parts ? 1 : 0);
+  return MIFGPU_OK;
 }
 
 int mifgpu_synchronize(mifgpu_ctx *ctx) {

@@ -48,5 +48,16 @@ void poisson_plan_destroy(PoissonPlan *plan);
 // The solve is the sequence (0,0) (1,0) (2,2) (1,1) (0,1).
 void launch_poisson_sweep(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *field, int dir, int mode,
                           uint64_t *launches);
+// The fused z sweep (mode 2) on a z pencil zbuf[z][y_local][x] (rows of g.PX doubles) that holds all z points of
+// the y rows [y_offset, y_offset + ny_local) of the transform domain (multi-GPU slab decomposition).
+void launch_poisson_zpencil(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *zbuf, int ny_local,
+                            int y_offset, bool has_origin, uint64_t *launches);
+
+// Slab <-> z-pencil repacking (mif_stencil.cu).  ylo[r], ylo[r+1] delimit the y rows of rank r; the send buffer is
+// ordered [dest][z_local][y in dest's range][x] with rows of g.PX doubles.
+void launch_pack_slab(cudaStream_t stream, const Geom &g, const double *field, double *send, const int *ylo_dev,
+                      int nranks, uint64_t *launches);
+void launch_unpack_slab(cudaStream_t stream, const Geom &g, double *field, const double *recv, const int *ylo_dev,
+                        int nranks, uint64_t *launches);
 
 }  // namespace mifgpu

@@ -52,7 +52,7 @@ struct SweepJob {
   int r_pitch;         // shared-memory pitch of one real line
   int mode;            // 0 forward, 1 inverse (+normalise), 2 forward * eigen, inverse (+normalise)
   const double *lam_a, *lam_b;  // eigenvalues of the two other directions (mode 2)
-  int lam_a_lo, lam_b_lo;       // owner offsets of those directions
+  bool has_origin;              // this launch holds the (0,0,0) mode at tile line 0, outer index 0
 };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) sweep_kernel(const SweepJob job, double *
         const int ix = first_line + l;
         const double lam_x = job.lam_a[ix];
         double scale = 1.0 / (lam_x + lam_y + pl.lambda[e]);
-        if (ix == 0 && blockIdx.y == 0 && e == 0) scale = 0.0;
+        if (job.has_origin && ix == 0 && blockIdx.y == 0 && e == 0) scale = 0.0;
         R[(size_t)l * r_pitch + e] *= scale;
       }
     }
@@ -332,6 +332,7 @@ struct FastJob {
   const double2 *tw, *cs;
   const double *lam_x, *lam_y, *lam_z;
   double inv_norm;
+  bool has_origin;  // the tile at (blockIdx.x, blockIdx.y) = (0, 0) contains the (0,0,0) mode
 };
 
 template <int LOGM, bool CONTIG>
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(1 << LOGM, (LOGM <= 9 ? 2 : 1)) fast_dct_kerne
     // pressure_hat *= 1 / (lambda_x + lambda_y + lambda_z); mode (0,0,0) := 0 (src/PressureEquation.cpp:158-163)
     const int ix = min(first_line + line, job.n_tile_lines - 1);
     const double lam_xy = job.lam_x[ix] + job.lam_y[blockIdx.y];
-    const bool origin_line = (first_line + line == 0) && (blockIdx.y == 0);
+    const bool origin_line = job.has_origin && (first_line + line == 0) && (blockIdx.y == 0);
 #pragma unroll
     for (int s = 0; s < 4; s++) {
       const int k = j + T * s;
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
     // pressure_hat *= 1 / (lambda_x + lambda_y + lambda_z); mode (0,0,0) := 0 (src/PressureEquation.cpp:158-163)
     const int ix = min(first_line + line, job.n_tile_lines - 1);
     const double lam_xy = job.lam_x[ix] + job.lam_y[blockIdx.y];
-    const bool origin_line = (first_line + line == 0) && (blockIdx.y == 0);
+    const bool origin_line = job.has_origin && (first_line + line == 0) && (blockIdx.y == 0);
     if constexpr (SHUFFLE) {
 #pragma unroll
       for (int u = 0; u < L::G; u++)
@@ -746,71 +747,110 @@ void poisson_plan_destroy(PoissonPlan *plan) {
   delete plan;
 }
 
-void launch_poisson_sweep(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *field, int d, int mode,
-                          uint64_t *launches) {
+namespace {
+
+// Where the lines of one sweep live: `origin` is the first point of the first line, consecutive points of a line
+// are `estride` apart, consecutive lines of a tile `lstride`, tiles `tile_stride`, outer index `outer_stride`.
+struct SweepLayout {
+  long long origin, lstride, estride, tile_stride, outer_stride;
+  int n_tile_lines, outer;
+  bool contig;       // estride == 1 (x sweeps)
+  int lam_y_offset;  // first global y index of outer index 0 (z sweeps on a y-distributed pencil)
+  bool has_origin;   // this rank holds the (0,0,0) mode
+};
+
+void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, int mode, const SweepLayout &lay,
+                  uint64_t *launches) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
-  const int nx = g.own_hi[0] - g.own_lo[0], ny = g.own_hi[1] - g.own_lo[1], nz = g.own_hi[2] - g.own_lo[2];
-  const long long origin = gidx(g, g.own_lo[0], g.own_lo[1], g.own_lo[2]);
-  {
-    SweepJob job;
-    job.plan = plan->dir[d];
-    job.dir = d;
-    job.L = plan->L[d];
-    job.r_pitch = plan->dir[d].n | 1;
-    job.mode = mode;
-    job.lam_a = plan->dir[0].lambda;
-    job.lam_b = plan->dir[1].lambda;
-    job.lam_a_lo = 0;
-    job.lam_b_lo = 0;
-    long long tile_stride, outer_stride;
-    int outer;
-    if (d == 0) {  // lines along x, tile over y, outer z
-      job.n_tile_lines = ny; job.lstride = g.PX; job.estride = 1;
-      tile_stride = g.PX; outer_stride = g.plane; outer = nz;
-    } else if (d == 1) {  // lines along y, tile over x, outer z
-      job.n_tile_lines = nx; job.lstride = 1; job.estride = g.PX;
-      tile_stride = 1; outer_stride = g.plane; outer = nz;
-    } else {  // lines along z, tile over x, outer y
-      job.n_tile_lines = nx; job.lstride = 1; job.estride = g.plane;
-      tile_stride = 1; outer_stride = g.PX; outer = ny;
+  if (plan->fast_logm[d] > 0) {
+    FastJob fj;
+    fj.origin = lay.origin; fj.lstride = lay.lstride; fj.estride = lay.estride;
+    fj.tile_stride = lay.tile_stride; fj.outer_stride = lay.outer_stride;
+    fj.n_tile_lines = lay.n_tile_lines; fj.mode = mode;
+    fj.tw = plan->dir[d].tw_full; fj.cs = plan->dir[d].unpack;
+    fj.lam_x = plan->dir[0].lambda; fj.lam_y = plan->dir[1].lambda + lay.lam_y_offset; fj.lam_z = plan->dir[2].lambda;
+    fj.inv_norm = plan->dir[d].inv_norm;
+    fj.has_origin = lay.has_origin;
+    const dim3 fgrid((lay.n_tile_lines + fast::kLines - 1) / fast::kLines, lay.outer, 1);
+    static const bool use_cta_sync_variant = getenv("MIFGPU_FFT_CTA_SYNC") != nullptr;  // A/B switch for profiling
+    switch (plan->fast_logm[d]) {
+      case 6: launch_fast<6>(stream, fj, lay.contig, fgrid, field); break;
+      case 7: launch_fast<7>(stream, fj, lay.contig, fgrid, field); break;
+      case 8:
+        if (use_cta_sync_variant) launch_fast<8>(stream, fj, lay.contig, fgrid, field);
+        else launch_warp<8>(stream, fj, lay.contig, fgrid, field);
+        break;
+      case 9:
+        if (use_cta_sync_variant) launch_fast<9>(stream, fj, lay.contig, fgrid, field);
+        else launch_warp<9>(stream, fj, lay.contig, fgrid, field);
+        break;
+      default:
+        if (use_cta_sync_variant) launch_fast<10>(stream, fj, lay.contig, fgrid, field);
+        else launch_warp<10>(stream, fj, lay.contig, fgrid, field);
+        break;
     }
-    if (plan->fast_logm[d] > 0) {
-      FastJob fj;
-      fj.origin = origin; fj.lstride = job.lstride; fj.estride = job.estride;
-      fj.tile_stride = tile_stride; fj.outer_stride = outer_stride;
-      fj.n_tile_lines = job.n_tile_lines; fj.mode = mode;
-      fj.tw = plan->dir[d].tw_full; fj.cs = plan->dir[d].unpack;
-      fj.lam_x = plan->dir[0].lambda; fj.lam_y = plan->dir[1].lambda; fj.lam_z = plan->dir[2].lambda;
-      fj.inv_norm = plan->dir[d].inv_norm;
-      const dim3 fgrid((job.n_tile_lines + fast::kLines - 1) / fast::kLines, outer, 1);
-      static const bool use_cta_sync_variant = getenv("MIFGPU_FFT_CTA_SYNC") != nullptr;  // A/B switch for profiling
-      switch (plan->fast_logm[d]) {
-        case 6: launch_fast<6>(stream, fj, d == 0, fgrid, field); break;
-        case 7: launch_fast<7>(stream, fj, d == 0, fgrid, field); break;
-        case 8:
-          if (use_cta_sync_variant) launch_fast<8>(stream, fj, d == 0, fgrid, field);
-          else launch_warp<8>(stream, fj, d == 0, fgrid, field);
-          break;
-        case 9:
-          if (use_cta_sync_variant) launch_fast<9>(stream, fj, d == 0, fgrid, field);
-          else launch_warp<9>(stream, fj, d == 0, fgrid, field);
-          break;
-        default:
-          if (use_cta_sync_variant) launch_fast<10>(stream, fj, d == 0, fgrid, field);
-          else launch_warp<10>(stream, fj, d == 0, fgrid, field);
-          break;
-      }
-      ++*launches;
-      return;
-    }
-    const dim3 grid((job.n_tile_lines + job.L - 1) / job.L, outer, 1);
-    sweep_kernel<<<grid, 256, plan->smem[d], stream>>>(job, field, origin, tile_stride, outer_stride);
     ++*launches;
+    return;
   }
+  SweepJob job;
+  job.plan = plan->dir[d];
+  job.dir = d;
+  job.L = plan->L[d];
+  job.r_pitch = plan->dir[d].n | 1;
+  job.mode = mode;
+  job.lam_a = plan->dir[0].lambda;
+  job.lam_b = plan->dir[1].lambda + lay.lam_y_offset;
+  job.has_origin = lay.has_origin;
+  job.n_tile_lines = lay.n_tile_lines;
+  job.lstride = lay.lstride;
+  job.estride = lay.estride;
+  const dim3 grid((job.n_tile_lines + job.L - 1) / job.L, lay.outer, 1);
+  sweep_kernel<<<grid, 256, plan->smem[d], stream>>>(job, field, lay.origin, lay.tile_stride, lay.outer_stride);
+  ++*launches;
+}
+
+}  // namespace
+
+void launch_poisson_sweep(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *field, int d, int mode,
+                          uint64_t *launches) {
+  const int nx = g.own_hi[0] - g.own_lo[0], ny = g.own_hi[1] - g.own_lo[1], nz = g.own_hi[2] - g.own_lo[2];
+  SweepLayout lay;
+  lay.origin = gidx(g, g.own_lo[0], g.own_lo[1], g.own_lo[2]);
+  lay.lam_y_offset = 0;
+  lay.has_origin = true;
+  lay.contig = (d == 0);
+  if (d == 0) {  // lines along x, tile over y, outer z
+    lay.n_tile_lines = ny; lay.lstride = g.PX; lay.estride = 1;
+    lay.tile_stride = g.PX; lay.outer_stride = g.plane; lay.outer = nz;
+  } else if (d == 1) {  // lines along y, tile over x, outer z
+    lay.n_tile_lines = nx; lay.lstride = 1; lay.estride = g.PX;
+    lay.tile_stride = 1; lay.outer_stride = g.plane; lay.outer = nz;
+  } else {  // lines along z, tile over x, outer y
+    lay.n_tile_lines = nx; lay.lstride = 1; lay.estride = g.plane;
+    lay.tile_stride = 1; lay.outer_stride = g.PX; lay.outer = ny;
+  }
+  launch_sweep(stream, plan, field, d, mode, lay, launches);
+}
+
+void launch_poisson_zpencil(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *zbuf, int ny_local,
+                            int y_offset, bool has_origin, uint64_t *launches) {
+  // zbuf[z][y_local][x]: x rows of PX doubles, ny_local rows per z plane, all N_z transform points.
+  SweepLayout lay;
+  lay.origin = g.own_lo[0];
+  lay.n_tile_lines = g.own_hi[0] - g.own_lo[0];
+  lay.lstride = 1;
+  lay.tile_stride = 1;
+  lay.estride = (long long)ny_local * g.PX;
+  lay.outer_stride = g.PX;
+  lay.outer = ny_local;
+  lay.contig = false;
+  lay.lam_y_offset = y_offset;
+  lay.has_origin = has_origin;
+  launch_sweep(stream, plan, zbuf, 2, 2, lay, launches);
 }
 
 }  // namespace mifgpu

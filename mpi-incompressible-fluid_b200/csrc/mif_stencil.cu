@@ -519,6 +519,25 @@ __global__ void __launch_bounds__(256) nhn_face_kernel(const Geom g, double *rhs
   else rhs[c] += term;
 }
 
+
+// Slab (all y, local z) <-> blocks per destination rank (its y rows, local z), whole padded x rows.
+template <bool PACK>
+__global__ void __launch_bounds__(256) slab_pack_kernel(const Geom g, double *field, double *buf, const int *__restrict__ ylo,
+                                                        int nranks) {
+  const int nz = g.own_hi[2] - g.own_lo[2];
+  const int y = blockIdx.y, zl = blockIdx.z;  // y: row index inside the owner region
+  int r = 0;
+  while (r + 1 < nranks && y >= ylo[r + 1]) r++;
+  const int ny_r = ylo[r + 1] - ylo[r];
+  const long long block = (long long)nz * g.PX * ylo[r];
+  double *row_buf = buf + block + ((long long)zl * ny_r + (y - ylo[r])) * g.PX;
+  double *row_field = field + gidx(g, 0, g.own_lo[1] + y, g.own_lo[2] + zl);
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < g.PX; x += gridDim.x * blockDim.x) {
+    if (PACK) row_buf[x] = row_field[x];
+    else row_field[x] = row_buf[x];
+  }
+}
+
 inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
 }  // namespace
@@ -614,6 +633,20 @@ void launch_nhn_rhs(cudaStream_t stream, const Geom &g, double *rhs, const BcDev
     nhn_face_kernel<<<cdiv(na * nb, 256), 256, 0, stream>>>(g, rhs, bc.tables[dir][face], face);
     ++*launches;
   }
+}
+
+void launch_pack_slab(cudaStream_t stream, const Geom &g, const double *field, double *send, const int *ylo_dev,
+                      int nranks, uint64_t *launches) {
+  const dim3 grid(cdiv(g.PX, 256), g.own_hi[1] - g.own_lo[1], g.own_hi[2] - g.own_lo[2]);
+  slab_pack_kernel<true><<<grid, 256, 0, stream>>>(g, const_cast<double *>(field), send, ylo_dev, nranks);
+  ++*launches;
+}
+
+void launch_unpack_slab(cudaStream_t stream, const Geom &g, double *field, const double *recv, const int *ylo_dev,
+                        int nranks, uint64_t *launches) {
+  const dim3 grid(cdiv(g.PX, 256), g.own_hi[1] - g.own_lo[1], g.own_hi[2] - g.own_lo[2]);
+  slab_pack_kernel<false><<<grid, 256, 0, stream>>>(g, field, const_cast<double *>(recv), ylo_dev, nranks);
+  ++*launches;
 }
 
 void launch_correct(cudaStream_t stream, const Geom &g, Vec3 vel, double *pressure, const double *dp, double dt_s,

@@ -1,0 +1,80 @@
+"""Worker of the multi-GPU tests: run under torchrun (one rank per GPU).  Each rank builds its slab of a golden
+case (tests/golden, dumped from the single-rank reference; all-Neumann results are decomposition independent), runs
+the time steps through the C ABI with Pz = world_size and compares its slab of the result with the golden fields.
+For the z-periodic case the goldens come from the reference run with the same number of ranks (rank-specific
+dumps), because periodic time stepping is decomposition dependent in the reference."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import mif_b200 as mif  # noqa: E402
+
+
+def local_slab(arr, klo, khi):
+    return np.ascontiguousarray(arr[klo:khi])
+
+
+def main():
+    case = sys.argv[1]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    dist.init_process_group("gloo")
+    torch.cuda.set_device(local_rank)
+    ids = [mif.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+
+    data = np.load(os.path.join(ROOT, "tests", "golden", case + ".npz"))
+    meta = json.loads(str(data["meta"]))
+    N = meta["N"]
+    periodic = [bool(p) for p in meta["periodic"]]
+    assert not periodic[2], "slab tests use the decomposition-independent (non-periodic z) goldens"
+    ctx = mif.Context(N[0], N[1], N[2], meta["x_size"], meta["y_size"], meta["z_size"], *meta["min"], meta["Re"],
+                      meta["final_time"], meta["steps"], Py=1, Pz=world, rank=rank, periodic=periodic,
+                      device=local_rank, comm_id=ids[0])
+    # z range of this rank's local arrays inside the global (single-rank) arrays: owner planes plus one ghost
+    # plane towards each neighbour (src/Constants.cpp:78-94); staggered w has one more plane on the last rank.
+    first = mif.slab_plan(N[2], world)
+    klo = first[rank] - (1 if rank > 0 else 0)
+    khi = first[rank + 1] + (1 if rank < world - 1 else 0)
+
+    def cut(name, arr):
+        extra = 1 if (name == "w" and rank == world - 1) else 0
+        return local_slab(arr, klo, khi + extra)
+
+    vel, vb, vb2 = ctx.velocity(), ctx.velocity(), ctx.velocity()
+    p, dp = ctx.tensor(mif.STAGGER_NONE), ctx.tensor(mif.STAGGER_NONE)
+    for t, name in zip(vel + [p], "uvwp"):
+        host = cut(name, data[name + "_s0"])
+        assert t.shape == host.shape[::-1], (name, t.shape, host.shape)
+        t.upload(host)
+    kind = {"ethier_steinman": mif.BC_ETHIER_STEINMAN, "test_case_1": mif.BC_TEST_CASE_1}[meta["bc"]]
+    bc = ctx.make_bc(kind, meta["Re"])
+    dt = meta["final_time"] / meta["steps"]
+    worst = 0.0
+    for step in range(meta["steps"]):
+        ctx.timestep(vel, vb, vb2, bc, step * dt, p, dp)
+        ctx.synchronize()
+        vmax = max(float(np.max(np.abs(data[f"{c}_s{step + 1}"]))) for c in "uvw")
+        for t, name in zip(vel + [p], "uvwp"):
+            ref_full = data[f"{name}_s{step + 1}"]
+            ref = cut(name, ref_full)
+            scale = max(float(np.max(np.abs(ref_full))), 1e-6 * vmax if name in "uvw" else 0.0)
+            err = float(np.max(np.abs(t.download() - ref))) / scale
+            worst = max(worst, err)
+    errs = [None] * world
+    dist.all_gather_object(errs, worst)
+    ctx.close()
+    if rank == 0:
+        print(json.dumps({"case": case, "world": world, "max_rel_err": max(errs)}))
+    dist.destroy_process_group()
+    return 0 if max(errs) <= 1e-11 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

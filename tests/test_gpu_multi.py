@@ -1,0 +1,30 @@
+"""GPU, >= 2 devices: the slab-decomposed path (NCCL halos + all-to-all transposes inside libmifgpu) reproduces the
+single-rank reference goldens on every rank's slab (tests/mp_worker.py under torchrun)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def device_count():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("case", ["full_16_2", "full_17_1", "lid1_12x10x14_2", "full_65x17x9_1", "full_6x65x9_1"])
+@pytest.mark.parametrize("world", [2, 4])
+def test_slab_decomposition_matches_single_rank_reference(case, world):
+    if device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29500 + world), os.path.join(ROOT, "tests", "mp_worker.py"), case]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line)["max_rel_err"] <= 1e-11
