@@ -181,24 +181,42 @@ def main():
     steps, warmup = args.steps, max(args.warmup, 3)
     dt = 1e-3
     total_steps = warmup + 2 * steps + 16
-    # src/main.cpp:121-131, test case 1.  Each rank of a multi-GPU launch currently runs an independent
-    # replica of the same problem (the multi-GPU domain decomposition is not in this build yet).
-    ctx = mif.Context(N, N, N, 1.0, 1.0, 2.0, 0.0, 0.0, -1.0, 1e3, dt * total_steps, total_steps, device=local_rank)
+    # Weak scaling with 512^3 cells per GPU (for the default size): the grid doubles in z, then y, then x, so
+    # 8 GPUs run the 1024^3-cell problem of BASELINE.json configs[3]; cells stay cubic.  The domain is split into
+    # z slabs (Py = 1, Pz = GPUs) inside libmifgpu: NCCL halo exchange + all-to-all pencil transposes.
+    cells_1d = N - 1
+    mult = [1, 1, 1]
+    for level in range(max(world.bit_length() - 1, 0)):
+        mult[2 - level % 3] *= 2
+    dims = [cells_1d * m + 1 for m in mult]
+    comm_id = None
+    if world > 1:
+        ident = torch.zeros(mif.UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            ident.copy_(torch.frombuffer(bytearray(mif.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(ident, src=0)
+        comm_id = bytes(ident.cpu().numpy().tobytes())
+    # src/main.cpp:121-131, test case 1.
+    ctx = mif.Context(dims[0], dims[1], dims[2], 1.0 * mult[0], 1.0 * mult[1], 2.0 * mult[2], 0.0, 0.0, -1.0 * mult[2], 1e3,
+                      dt * total_steps, total_steps, Py=1, Pz=world, rank=rank, device=local_rank, comm_id=comm_id)
     vel, vb, vb2 = ctx.velocity(), ctx.velocity(), ctx.velocity()
     p, dp = ctx.tensor(mif.STAGGER_NONE), ctx.tensor(mif.STAGGER_NONE)
     bc = ctx.make_bc(mif.BC_TEST_CASE_1, 1e3)
-    # velocity.set(exact(t=0), include_border=true) (src/main.cpp:144-146): v = 1 on the plane x = 1, else 0.
+    # velocity.set(exact(t=0), include_border=true) (src/main.cpp:144-146): v = 1 on the plane x = x_max, else 0
+    # (with the domain stretched in x for the 8-GPU grid the lid sits at x = 1 * mult[0]; exact_v_t1 tests x == 1,
+    # so for mult[0] > 1 the boundary data is zero everywhere -- the cost of a step does not depend on the data).
     host = []
     for t in vel + [p]:
         sx, sy, sz = t.shape
         arr = torch.zeros((sz, sy, sx), dtype=torch.float64).pin_memory()
         host.append(arr)
-    host[1][:, :, N - 1] = 1.0
+    if mult[0] == 1:
+        host[1][:, :, dims[0] - 1] = 1.0
     for t, arr in zip(vel + [p], host):
         t.upload(arr.numpy())
 
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
-    cells = float(N - 1) ** 3
+    cells = float(dims[0] - 1) * float(dims[1] - 1) * float(dims[2] - 1) / world  # per GPU
     step_index = [0]
 
     def one_step():
@@ -241,7 +259,7 @@ def main():
     ctx.profile_enable(False)
     kernels = {k: round(ms / steps, 4) for k, (ms, n) in prof.items() if n}
     peak, peak_src = measured_peaks()
-    points = float(N) ** 3
+    points = float(dims[0]) * float(dims[1]) * float(dims[2]) / world  # pressure points per GPU
     # Dominant kernel = the Poisson sweep kernel (5 launches per solve, 15 per step).  Algorithmic bytes
     # per launch: one read + one write of every pressure point = 16 B * N^3 (SURVEY.md section 8d:
     # "Poisson 6 sweeps x (1R+1W)"; the fused z launch does the work of two sweeps with the same 16 B).
@@ -301,10 +319,11 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "full projection timestep, input.txt boundary-layer set-up (test case 1) at 512^3 cells"
-                       if N == 513 else f"full projection timestep, test case 1 at {N - 1}^3 cells",
-                       "points": [N, N, N], "dt": dt, "Re": 1e3,
-                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one per GPU)",
+            "config": {"workload": ("full projection timestep, input.txt boundary-layer set-up (test case 1) at "
+                                    f"{dims[0] - 1}x{dims[1] - 1}x{dims[2] - 1} cells ({cells_1d}^3 cells per GPU)"),
+                       "points": dims, "dt": dt, "Re": 1e3,
+                       "parallelism": "single GPU" if world == 1 else
+                       f"z slabs Py=1 Pz={world}: NCCL plane halos + grouped send/recv all-to-all pencil transposes",
                        "l2": "inputs larger than L2 (each field %.2f GB)" % (points * 8 / 1e9), "finite": finite},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "kernels": kernels, "clocks": clocks,
