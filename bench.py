@@ -23,6 +23,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line (NCCL prints its version banner otherwise)
 sys.path.insert(0, ROOT)
 
 METRIC = "FP64 cell-steps/s, full RK timestep incl. Poisson solve"
@@ -53,7 +54,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None

@@ -19,7 +19,7 @@ from typing import Callable, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmifgpu.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("MIFGPU_LIB", "libmifgpu.so"))
 
 STAGGER_X, STAGGER_Y, STAGGER_Z, STAGGER_NONE = 0, 1, 2, 3
 BC_TEST_CASE_1, BC_TEST_CASE_2, BC_ETHIER_STEINMAN, BC_HOST_CALLBACK = 1, 2, 3, 4

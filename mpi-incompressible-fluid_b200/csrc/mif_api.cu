@@ -114,6 +114,8 @@ struct mifgpu_ctx {
   int *ylo_dev = nullptr;
   double *xfer = nullptr;    // send / receive staging, one local owner volume
   double *zbuf = nullptr;    // z pencil: zbuf[z][y_local][x]
+  double *staging = nullptr; // compact device copy of one tensor for host transfers
+  size_t staging_bytes = 0;
   // host-callback boundary faces: pinned staging + device copies, [which][component][face]
   double *face_host[2][3][6] = {};
   double *face_dev[2][3][6] = {};
@@ -346,7 +348,10 @@ int do_apply_bc(mifgpu_ctx *ctx, mifgpu_tensor *const vel[3], const mifgpu_bc *b
 // solve_pressure_equation_homogeneous_periodic / _non_homogeneous_neumann (src/PressureEquation.cpp:266-286).
 int do_solve(mifgpu_ctx *ctx, mifgpu_tensor *dp, mifgpu_tensor *const vel[3], double dt, const mifgpu_bc *nhn_bc,
              double t_new, double t_prev) {
-  {
+  // Without Neumann face terms the right-hand side is consumed only by the forward x sweep, which can compute it
+  // on the fly; otherwise it is materialised first (src/PressureEquation.cpp:59-61).
+  const bool fuse_rhs = !nhn_bc && poisson_can_fuse_divergence(ctx->plan);
+  if (!fuse_rhs) {
     ProfScope prof(ctx, PROF_DIVERGENCE);
     launch_divergence(ctx->stream, ctx->g, cvec3(vel), 0.0, dt, dp->data, &ctx->launches);
   }
@@ -367,7 +372,13 @@ int do_solve(mifgpu_ctx *ctx, mifgpu_tensor *dp, mifgpu_tensor *const vel[3], do
     ProfScope prof(ctx, category);
     launch_poisson_sweep(ctx->stream, ctx->g, ctx->plan, dp->data, dir, mode, &ctx->launches);
   };
-  sweep(0, 0, PROF_SWEEP_X_FWD);
+  if (fuse_rhs) {
+    ProfScope prof(ctx, PROF_SWEEP_X_FWD);
+    const double *velocity[3] = {vel[0]->data, vel[1]->data, vel[2]->data};
+    launch_poisson_sweep(ctx->stream, ctx->g, ctx->plan, dp->data, 0, 0, &ctx->launches, velocity, dt);
+  } else {
+    sweep(0, 0, PROF_SWEEP_X_FWD);
+  }
   sweep(1, 0, PROF_SWEEP_Y_FWD);
   if (ctx->nranks == 1) {
     sweep(2, 2, PROF_SWEEP_Z);
@@ -519,6 +530,7 @@ void mifgpu_destroy(mifgpu_ctx *ctx) {
   if (ctx->xfer) cudaFree(ctx->xfer);
   if (ctx->zbuf) cudaFree(ctx->zbuf);
   if (ctx->ylo_dev) cudaFree(ctx->ylo_dev);
+  if (ctx->staging) cudaFree(ctx->staging);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -559,21 +571,38 @@ void mifgpu_tensor_destroy(mifgpu_tensor *t) {
   delete t;
 }
 
+// Host (compact reference extents) <-> device (padded pitches).  The PCIe transfer is one contiguous copy to or
+// from a compact device staging buffer (row-pitched DMA over PCIe is several times slower); the re-pitching is a
+// device-to-device 3-D copy.
 static int copy_tensor(const mifgpu_tensor *t, double *host, bool to_device) {
   if (!t || !host) return fail(MIFGPU_ERR_INVALID, "NULL argument");
   mifgpu_ctx *ctx = t->ctx;
   const Geom &g = ctx->g;
   CUDA_TRY(cudaSetDevice(ctx->params.device));
   const int s = t->staggering;
+  const size_t bytes = (size_t)g.sx[s] * g.sy[s] * g.sz[s] * sizeof(double);
+  if (ctx->staging_bytes < bytes) {
+    if (ctx->staging) cudaFree(ctx->staging);
+    ctx->staging = nullptr;
+    ctx->staging_bytes = 0;
+    CUDA_TRY(cudaMalloc(&ctx->staging, bytes));
+    ctx->staging_bytes = bytes;
+  }
   cudaMemcpy3DParms parms;
   std::memset(&parms, 0, sizeof(parms));
-  const cudaPitchedPtr host_ptr = make_cudaPitchedPtr(host, (size_t)g.sx[s] * sizeof(double), g.sx[s], g.sy[s]);
-  const cudaPitchedPtr dev_ptr = make_cudaPitchedPtr(t->data, (size_t)g.PX * sizeof(double), g.PX, g.PY);
-  parms.srcPtr = to_device ? host_ptr : dev_ptr;
-  parms.dstPtr = to_device ? dev_ptr : host_ptr;
+  const cudaPitchedPtr compact = make_cudaPitchedPtr(ctx->staging, (size_t)g.sx[s] * sizeof(double), g.sx[s], g.sy[s]);
+  const cudaPitchedPtr padded = make_cudaPitchedPtr(t->data, (size_t)g.PX * sizeof(double), g.PX, g.PY);
+  parms.srcPtr = to_device ? compact : padded;
+  parms.dstPtr = to_device ? padded : compact;
   parms.extent = make_cudaExtent((size_t)g.sx[s] * sizeof(double), g.sy[s], g.sz[s]);
-  parms.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
-  CUDA_TRY(cudaMemcpy3DAsync(&parms, ctx->stream));
+  parms.kind = cudaMemcpyDeviceToDevice;
+  if (to_device) {
+    CUDA_TRY(cudaMemcpyAsync(ctx->staging, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpy3DAsync(&parms, ctx->stream));
+  } else {
+    CUDA_TRY(cudaMemcpy3DAsync(&parms, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(host, ctx->staging, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return MIFGPU_OK;
 }

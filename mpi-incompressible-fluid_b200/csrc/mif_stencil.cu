@@ -23,8 +23,11 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_l2(const double *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
+#ifndef MIFGPU_STAGE_MIN_BLOCKS
+#define MIFGPU_STAGE_MIN_BLOCKS 4
+#endif
 template <int STAGE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MIFGPU_STAGE_MIN_BLOCKS)
 stage_kernel(const Geom g, const double *__restrict__ in_u, const double *__restrict__ in_v,
              const double *__restrict__ in_w, const double *__restrict__ p, double *__restrict__ a_u,
              double *__restrict__ a_v, double *__restrict__ a_w, double *__restrict__ b_u, double *__restrict__ b_v,
