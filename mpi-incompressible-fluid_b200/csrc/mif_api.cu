@@ -40,6 +40,7 @@ struct NcclApi {
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
 };
@@ -61,9 +62,10 @@ bool load_nccl() {
   g_nccl.GroupEnd = reinterpret_cast<decltype(g_nccl.GroupEnd)>(sym("ncclGroupEnd"));
   g_nccl.Send = reinterpret_cast<decltype(g_nccl.Send)>(sym("ncclSend"));
   g_nccl.Recv = reinterpret_cast<decltype(g_nccl.Recv)>(sym("ncclRecv"));
+  g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(sym("ncclAllReduce"));
   g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(sym("ncclGetErrorString"));
   g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.GroupStart && g_nccl.GroupEnd &&
-              g_nccl.Send && g_nccl.Recv && g_nccl.GetErrorString;
+              g_nccl.Send && g_nccl.Recv && g_nccl.AllReduce && g_nccl.GetErrorString;
   if (!g_nccl.ok) g_last_error = "libnccl.so.2 lacks a required symbol";
   return g_nccl.ok;
 }
@@ -114,6 +116,11 @@ struct mifgpu_ctx {
   int *ylo_dev = nullptr;
   double *xfer = nullptr;    // send / receive staging, one local owner volume
   double *zbuf = nullptr;    // z pencil: zbuf[z][y_local][x]
+  // peer-memory transposes: zbuf / xfer of every rank mapped with CUDA IPC (index = rank; own entry = local pointer)
+  bool peer_mode = false;
+  double *zbuf_peer[8] = {};
+  double *xfer_peer[8] = {};
+  int *barrier_word = nullptr;
   double *staging = nullptr; // compact device copy of one tensor for host transfers
   size_t staging_bytes = 0;
   // host-callback boundary faces: pinned staging + device copies, [which][component][face]
@@ -296,6 +303,79 @@ int exchange_z(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count) {
   return MIFGPU_OK;
 }
 
+// Stream-ordered barrier across all ranks (a one-word NCCL all-reduce): every rank's preceding kernels -- including
+// their stores into peer memory -- have completed when it returns.
+int rank_barrier(mifgpu_ctx *ctx) {
+  NCCL_TRY(g_nccl.AllReduce(ctx->barrier_word, ctx->barrier_word + 1, 1, ncclInt, ncclSum, ctx->comm, ctx->stream));
+  return MIFGPU_OK;
+}
+
+// Map the pencil (zbuf) and slab staging (xfer) buffers of all ranks into this process: the IPC handles travel
+// through device buffers with one grouped NCCL exchange.
+int setup_peer_memory(mifgpu_ctx *ctx) {
+  const int P = ctx->nranks, me = ctx->params.rank;
+  struct Handles { cudaIpcMemHandle_t zbuf, xfer; };
+  std::vector<Handles> all(P);
+  CUDA_TRY(cudaIpcGetMemHandle(&all[me].zbuf, ctx->zbuf));
+  CUDA_TRY(cudaIpcGetMemHandle(&all[me].xfer, ctx->xfer));
+  Handles *dev = nullptr;
+  CUDA_TRY(cudaMalloc(&dev, sizeof(Handles) * P));
+  CUDA_TRY(cudaMemcpy(dev + me, &all[me], sizeof(Handles), cudaMemcpyHostToDevice));
+  NCCL_TRY(g_nccl.GroupStart());
+  for (int r = 0; r < P; r++) {
+    if (r == me) continue;
+    NCCL_TRY(g_nccl.Send(dev + me, sizeof(Handles), ncclChar, r, ctx->comm, ctx->stream));
+    NCCL_TRY(g_nccl.Recv(dev + r, sizeof(Handles), ncclChar, r, ctx->comm, ctx->stream));
+  }
+  NCCL_TRY(g_nccl.GroupEnd());
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(cudaMemcpy(all.data(), dev, sizeof(Handles) * P, cudaMemcpyDeviceToHost));
+  cudaFree(dev);
+  bool ok = true;
+  for (int r = 0; r < P; r++) {
+    if (r == me) {
+      ctx->zbuf_peer[r] = ctx->zbuf;
+      ctx->xfer_peer[r] = ctx->xfer;
+      continue;
+    }
+    void *pz = nullptr, *px = nullptr;
+    if (cudaIpcOpenMemHandle(&pz, all[r].zbuf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&px, all[r].xfer, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = false;
+      break;
+    }
+    ctx->zbuf_peer[r] = static_cast<double *>(pz);
+    ctx->xfer_peer[r] = static_cast<double *>(px);
+  }
+  // All ranks must agree, otherwise one side would wait at a barrier the other never reaches.
+  int flags[2] = {ok ? 0 : 1, 0};
+  CUDA_TRY(cudaMemcpy(ctx->barrier_word, flags, sizeof(flags), cudaMemcpyHostToDevice));
+  int rc = rank_barrier(ctx);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(cudaMemcpy(flags, ctx->barrier_word, sizeof(flags), cudaMemcpyDeviceToHost));
+  ctx->peer_mode = (flags[1] == 0);
+  flags[0] = 0;
+  CUDA_TRY(cudaMemcpy(ctx->barrier_word, flags, sizeof(int), cudaMemcpyHostToDevice));
+  return MIFGPU_OK;
+}
+
+PeerLayout peer_layout(const mifgpu_ctx *ctx) {
+  PeerLayout p;
+  p.rank = ctx->params.rank;
+  p.nranks = ctx->nranks;
+  for (int r = 0; r <= ctx->nranks; r++) {
+    p.ylo[r] = ctx->ylo[r];
+    p.zlo[r] = ctx->zlo[r];
+  }
+  for (int r = 0; r < ctx->nranks; r++) {
+    p.zbuf[r] = ctx->zbuf_peer[r];
+    p.xfer[r] = ctx->xfer_peer[r];
+  }
+  return p;
+}
+
 // Slab -> z pencil (forward = true) and back: the 2Decomp Y<->Z transposes (deps/2Decomp_C/TransposeY2Z.cpp:22-50,
 // TransposeZ2Y.cpp:18-46) as one grouped NCCL send/recv all-to-all.  Forward: pack rows per destination, receive
 // straight into zbuf (the planes of one source are contiguous there).  Backward: send straight out of zbuf,
@@ -372,6 +452,35 @@ int do_solve(mifgpu_ctx *ctx, mifgpu_tensor *dp, mifgpu_tensor *const vel[3], do
     ProfScope prof(ctx, category);
     launch_poisson_sweep(ctx->stream, ctx->g, ctx->plan, dp->data, dir, mode, &ctx->launches);
   };
+  if (ctx->nranks > 1 && ctx->peer_mode && poisson_peer_capable(ctx->plan)) {
+    // Transposes fused into the sweeps: the forward y sweep stores into the z pencils of the owning GPUs, the fused
+    // z sweep stores into their slab staging buffers, the inverse y sweep reads its staging buffer (NVLink peer
+    // stores; two stream-ordered rank barriers per solve).
+    const PeerLayout peer = peer_layout(ctx);
+    sweep(0, 0, PROF_SWEEP_X_FWD);
+    int rc;
+    {
+      ProfScope prof(ctx, PROF_SWEEP_Y_FWD);
+      launch_poisson_sweep_peer(ctx->stream, ctx->g, ctx->plan, dp->data, peer, 0, &ctx->launches);
+      if ((rc = rank_barrier(ctx))) return rc;
+    }
+    {
+      ProfScope prof(ctx, PROF_SWEEP_Z);
+      launch_poisson_sweep_peer(ctx->stream, ctx->g, ctx->plan, dp->data, peer, 1, &ctx->launches);
+      if ((rc = rank_barrier(ctx))) return rc;
+    }
+    {
+      ProfScope prof(ctx, PROF_SWEEP_Y_INV);
+      launch_poisson_sweep_peer(ctx->stream, ctx->g, ctx->plan, dp->data, peer, 2, &ctx->launches);
+    }
+    sweep(0, 1, PROF_SWEEP_X_INV);
+    {
+      ProfScope prof(ctx, PROF_PERIODIC);
+      launch_periodic(ctx->stream, ctx->g, dp->data, 3, &ctx->launches);
+    }
+    mifgpu_tensor *one_peer[1] = {dp};
+    return exchange_z(ctx, one_peer, 1);
+  }
   if (fuse_rhs) {
     ProfScope prof(ctx, PROF_SWEEP_X_FWD);
     const double *velocity[3] = {vel[0]->data, vel[1]->data, vel[2]->data};
@@ -505,6 +614,17 @@ static int create_context(const mifgpu_params *params, const void *unique_id, mi
       return fail(MIFGPU_ERR_CUDA, "allocating the transpose buffers failed");
     }
     cudaMemcpy(ctx->ylo_dev, ctx->ylo.data(), (P + 1) * sizeof(int), cudaMemcpyHostToDevice);
+    if (cudaMalloc(&ctx->barrier_word, 2 * sizeof(int)) != cudaSuccess || cudaMemset(ctx->barrier_word, 0, 2 * sizeof(int)) != cudaSuccess) {
+      mifgpu_destroy(ctx);
+      return fail(MIFGPU_ERR_CUDA, "allocating the barrier word failed");
+    }
+    if (P <= 8 && getenv("MIFGPU_NO_PEER") == nullptr) {
+      const int prc = setup_peer_memory(ctx);
+      if (prc) {
+        mifgpu_destroy(ctx);
+        return prc;
+      }
+    }
   }
   err = cudaDeviceSynchronize();
   if (err != cudaSuccess) {
@@ -526,11 +646,22 @@ void mifgpu_destroy(mifgpu_ctx *ctx) {
         if (ctx->face_dev[w][c][f]) cudaFree(ctx->face_dev[w][c][f]);
       }
   poisson_plan_destroy(ctx->plan);
-  if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
   if (ctx->xfer) cudaFree(ctx->xfer);
   if (ctx->zbuf) cudaFree(ctx->zbuf);
+  for (int r = 0; r < 8; r++) {
+    if (r == ctx->params.rank) continue;
+    if (ctx->zbuf_peer[r]) cudaIpcCloseMemHandle(ctx->zbuf_peer[r]);
+    if (ctx->xfer_peer[r]) cudaIpcCloseMemHandle(ctx->xfer_peer[r]);
+  }
+  if (ctx->peer_mode && ctx->comm && ctx->barrier_word) {
+    // nobody frees a buffer that another rank may still have mapped: destruction is collective
+    g_nccl.AllReduce(ctx->barrier_word, ctx->barrier_word + 1, 1, ncclInt, ncclSum, ctx->comm, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  if (ctx->barrier_word) cudaFree(ctx->barrier_word);
   if (ctx->ylo_dev) cudaFree(ctx->ylo_dev);
   if (ctx->staging) cudaFree(ctx->staging);
+  if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -56,6 +56,19 @@ bool poisson_can_fuse_divergence(const PoissonPlan *plan);
 void launch_poisson_zpencil(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *zbuf, int ny_local,
                             int y_offset, bool has_origin, uint64_t *launches);
 
+// Peer-memory variant of the slab <-> pencil exchange: zbuf[r] / xfer[r] are the pencil and slab staging buffers of
+// every rank, mapped into this process (CUDA IPC).  which = 0: forward y sweep whose results are stored straight into
+// the z pencils of the owning GPUs; 1: fused z sweep on the local pencil, results stored into the slab staging of
+// the owning GPUs; 2: inverse y sweep reading the local slab staging, writing `field`.
+struct PeerLayout {
+  int rank, nranks;
+  int ylo[9], zlo[9];
+  double *zbuf[8], *xfer[8];
+};
+bool poisson_peer_capable(const PoissonPlan *plan);
+void launch_poisson_sweep_peer(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *field, const PeerLayout &peer,
+                               int which, uint64_t *launches);
+
 // Slab <-> z-pencil repacking (mif_stencil.cu).  ylo[r], ylo[r+1] delimit the y rows of rank r; the send buffer is
 // ordered [dest][z_local][y in dest's range][x] with rows of g.PX doubles.
 void launch_pack_slab(cudaStream_t stream, const Geom &g, const double *field, double *send, const int *ylo_dev,

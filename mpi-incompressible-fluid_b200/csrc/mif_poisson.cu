@@ -325,7 +325,24 @@ __global__ void __launch_bounds__(256) sweep_kernel(const SweepJob job, double *
 // ------------------------------------------------------------------------------------------------
 // Fast path: DCT-I sweeps with N - 1 = M = 2^LOGM (64 <= M <= 1024), 8 lines per CTA, M threads.
 // ------------------------------------------------------------------------------------------------
+// Piecewise-strided addressing of a line for the multi-GPU sweeps: the points [lo[r], lo[r+1]) of every line live
+// in segment r (a block of a staging buffer, possibly in the memory of peer GPU r mapped over NVLink):
+//   address(e, outer, x) = base[r] + (e - lo[r]) * estride[r] + outer * outer_stride[r] + x.
+constexpr int kMaxRanks = 8;
+struct SegMap {
+  int n = 0;  // 0: plain strided addressing
+  int lo[kMaxRanks + 1];
+  double *base[kMaxRanks];
+  long long estride[kMaxRanks], outer_stride[kMaxRanks];
+};
+__device__ __forceinline__ double *seg_address(const SegMap &m, int e, int outer, int x) {
+  int r = 0;
+  while (r + 1 < m.n && e >= m.lo[r + 1]) r++;
+  return m.base[r] + (long long)(e - m.lo[r]) * m.estride[r] + (long long)outer * m.outer_stride[r] + x;
+}
+
 struct FastJob {
+  SegMap load_map, store_map;  // strided (y / z) sweeps of the warp-per-line kernel only
   long long origin, lstride, estride, tile_stride, outer_stride;
   int n_tile_lines;
   int mode;  // 0 forward, 1 inverse (+normalise), 2 forward, eigenvalues, inverse (+normalise)
@@ -513,7 +530,10 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
 #pragma unroll
     for (int it = 0; it < NIT; it++) {
       const int e = q0 + it * QSTEP;
-      vals[it] = (e < NPTS && l < lines) ? src[(long long)e * job.estride] : 0.0;
+      if (e < NPTS && l < lines)
+        vals[it] = job.load_map.n ? *seg_address(job.load_map, e, blockIdx.y, first_line + l) : src[(long long)e * job.estride];
+      else
+        vals[it] = 0.0;
     }
 #pragma unroll
     for (int it = 0; it < NIT; it++) {
@@ -618,7 +638,13 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
     if (l < lines) {
       const double *srcl = reinterpret_cast<const double *>(smem2 + l * C::LINE_PITCH);
       double *out = base + (long long)l * job.lstride;
-      for (int e = q0; e < NPTS; e += QSTEP) out[(long long)e * job.estride] = srcl[e];
+      if (job.store_map.n) {
+        // Fused transpose: the results go straight into the pencil / slab buffers of the owning GPUs (peer stores
+        // over NVLink for r != this rank), so no pack kernel and no separate all-to-all copy exist.
+        for (int e = q0; e < NPTS; e += QSTEP) *seg_address(job.store_map, e, blockIdx.y, first_line + l) = srcl[e];
+      } else {
+        for (int e = q0; e < NPTS; e += QSTEP) out[(long long)e * job.estride] = srcl[e];
+      }
     }
   }
 }
@@ -790,6 +816,7 @@ struct SweepLayout {
   bool contig;       // estride == 1 (x sweeps)
   int lam_y_offset;  // first global y index of outer index 0 (z sweeps on a y-distributed pencil)
   bool has_origin;   // this rank holds the (0,0,0) mode
+  SegMap load_map, store_map;
   const double *div_u = nullptr, *div_v = nullptr, *div_w = nullptr;  // fused right-hand side (forward x sweep only)
   double one_over_dx = 0, one_over_dy = 0, one_over_dz = 0, dt = 1;
   long long stride_y = 0, stride_z = 0;
@@ -811,6 +838,7 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
     fj.lam_x = plan->dir[0].lambda; fj.lam_y = plan->dir[1].lambda + lay.lam_y_offset; fj.lam_z = plan->dir[2].lambda;
     fj.inv_norm = plan->dir[d].inv_norm;
     fj.has_origin = lay.has_origin;
+    fj.load_map = lay.load_map; fj.store_map = lay.store_map;
     fj.div_u = lay.div_u; fj.div_v = lay.div_v; fj.div_w = lay.div_w;
     fj.one_over_dx = lay.one_over_dx; fj.one_over_dy = lay.one_over_dy; fj.one_over_dz = lay.one_over_dz;
     fj.dt = lay.dt; fj.stride_y = lay.stride_y; fj.stride_z = lay.stride_z;
@@ -885,6 +913,68 @@ void launch_poisson_sweep(cudaStream_t stream, const Geom &g, PoissonPlan *plan,
     lay.dt = dt; lay.stride_y = g.PX; lay.stride_z = g.plane;
   }
   launch_sweep(stream, plan, field, d, mode, lay, launches);
+}
+
+bool poisson_peer_capable(const PoissonPlan *plan) { return plan->fast_logm[1] >= 8 && plan->fast_logm[2] >= 8; }
+
+static void fill_map(SegMap &m, const PeerLayout &p, int which, int x_origin, const Geom &g) {
+  const int me = p.rank, P = p.nranks;
+  const long long nz_me = p.zlo[me + 1] - p.zlo[me], ny_me = p.ylo[me + 1] - p.ylo[me];
+  m.n = P;
+  for (int r = 0; r < P; r++) {
+    const long long ny_r = p.ylo[r + 1] - p.ylo[r], nz_r = p.zlo[r + 1] - p.zlo[r];
+    if (which == 0) {         // forward y sweep -> z pencils: segments are y ranges, outer index is the local z plane
+      m.lo[r] = p.ylo[r];
+      m.base[r] = p.zbuf[r] + (long long)p.zlo[me] * ny_r * g.PX + x_origin;
+      m.estride[r] = g.PX;
+      m.outer_stride[r] = ny_r * g.PX;
+    } else if (which == 1) {  // fused z sweep -> slab staging of the owners: segments are z ranges, outer is local y
+      m.lo[r] = p.zlo[r];
+      m.base[r] = p.xfer[r] + nz_r * g.PX * p.ylo[me] + x_origin;
+      m.estride[r] = ny_me * g.PX;
+      m.outer_stride[r] = g.PX;
+    } else {                  // inverse y sweep <- own slab staging: segments are the y ranges of the sources
+      m.lo[r] = p.ylo[r];
+      m.base[r] = p.xfer[me] + nz_me * g.PX * p.ylo[r] + x_origin;
+      m.estride[r] = g.PX;
+      m.outer_stride[r] = ny_r * g.PX;
+    }
+  }
+  m.lo[P] = (which == 1) ? p.zlo[P] : p.ylo[P];
+}
+
+void launch_poisson_sweep_peer(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *field, const PeerLayout &peer,
+                               int which, uint64_t *launches) {
+  const int me = peer.rank;
+  const int nx = g.own_hi[0] - g.own_lo[0], nz = g.own_hi[2] - g.own_lo[2];
+  SweepLayout lay;
+  lay.lam_y_offset = 0;
+  lay.has_origin = false;
+  lay.contig = false;
+  lay.n_tile_lines = nx;
+  lay.lstride = 1;
+  lay.tile_stride = 1;
+  if (which == 0 || which == 2) {
+    // y sweeps on the local slab: lines along y, tile over x, outer over the local owner z planes
+    lay.origin = gidx(g, g.own_lo[0], g.own_lo[1], g.own_lo[2]);
+    lay.estride = g.PX;
+    lay.outer_stride = g.plane;
+    lay.outer = nz;
+    if (which == 0) fill_map(lay.store_map, peer, 0, g.own_lo[0], g);
+    else fill_map(lay.load_map, peer, 2, g.own_lo[0], g);
+    launch_sweep(stream, plan, field, 1, which == 0 ? 0 : 1, lay, launches);
+  } else {
+    // fused z sweep on the local z pencil zbuf[z][y_local][x]
+    const int ny_local = peer.ylo[me + 1] - peer.ylo[me];
+    lay.origin = g.own_lo[0];
+    lay.estride = (long long)ny_local * g.PX;
+    lay.outer_stride = g.PX;
+    lay.outer = ny_local;
+    lay.lam_y_offset = peer.ylo[me];
+    lay.has_origin = peer.ylo[me] == 0;
+    fill_map(lay.store_map, peer, 1, g.own_lo[0], g);
+    launch_sweep(stream, plan, peer.zbuf[me], 2, 2, lay, launches);
+  }
 }
 
 void launch_poisson_zpencil(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *zbuf, int ny_local,

@@ -17,7 +17,8 @@ def device_count():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("case", ["full_16_2", "full_17_1", "lid1_12x10x14_2", "full_65x17x9_1", "full_6x65x9_1"])
+@pytest.mark.parametrize("case", ["full_16_2", "full_17_1", "lid1_12x10x14_2", "full_65x17x9_1", "full_6x65x9_1",
+                                  "es:9x257x257", "es:7x513x257"])
 @pytest.mark.parametrize("world", [2, 4])
 def test_slab_decomposition_matches_single_rank_reference(case, world):
     if device_count() < world:
@@ -28,3 +29,17 @@ def test_slab_decomposition_matches_single_rank_reference(case, world):
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     assert json.loads(line)["max_rel_err"] <= 1e-11
+
+
+@pytest.mark.parametrize("no_peer", ["", "1"])
+def test_peer_memory_and_nccl_transposes_agree(no_peer):
+    """The same case through the fused peer-store transposes (default) and through the NCCL all-to-all (MIFGPU_NO_PEER)."""
+    if device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ)
+    if no_peer:
+        env["MIFGPU_NO_PEER"] = "1"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "mp_worker.py"), "es:9x257x257"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
