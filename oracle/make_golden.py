@@ -83,6 +83,13 @@ def main():
                     final_time=1.0, steps=1, periodic=[0, 0, int(kind == "mixed")], time=1.0)
         dump_case(f"ptest_{kind}_{dims[0]}x{dims[1]}x{dims[2]}", ["ptest", kind, *dims, 1, "{out}"], meta)
 
+    # --- output files of the reference's writers (src/VTKDatExport.cpp) on analytically set fields ------------------
+    for periodic_z in (0, 1):
+        outdir = os.path.join(GOLDEN, f"export_{periodic_z}")
+        os.makedirs(outdir, exist_ok=True)
+        run([os.path.join(REF, "ref_dump"), "export", "8", str(periodic_z), outdir])
+        print("export", periodic_z, sorted(os.listdir(outdir)))
+
     # --- numbers printed by the reference's own tests ----------------------------------------------
     norms = {}
     tmp = tempfile.mkdtemp(prefix="mifgolden_")

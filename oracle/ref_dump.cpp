@@ -26,6 +26,7 @@
 #include "Norms.h"
 #include "PressureEquation.h"
 #include "TestCaseBoundaries.h"
+#include "VTKDatExport.h"
 #include "Timestep.h"
 
 // include/TimestepVelocity.h shares its include guard with include/Timestep.h (both use
@@ -201,6 +202,29 @@ static int run_vtest(int argc, char **argv, int size) {
   return 0;
 }
 
+// export N periodic_z out: the reference's output writers (src/VTKDatExport.cpp) on fields set analytically, the
+// counterpart of mpi-incompressible-fluid_b200/host/apps/export_test.cpp.
+static int run_export(int argc, char **argv) {
+  (void)argc;
+  const size_t N = std::atol(argv[2]);
+  const bool periodic_z = std::atoi(argv[3]) != 0;
+  const std::string out = argv[4];
+  const std::array<bool, 3> periodic{false, false, periodic_z};
+  const Constants constants(N, N + 2, N + 1, 1.0, 1.0, 2.0, -0.25, -0.5, -1.0, 1.0, 1.0, 1, 1, 1, 0, periodic);
+  VelocityTensor velocity(constants);
+  StaggeredTensor pressure(constants, StaggeringDirection::none);
+  velocity.u.set([](Real x, Real y, Real z) { return 0.5 * x + 0.25 * y * z - 2.0 * z; }, true);
+  velocity.v.set([](Real x, Real y, Real z) { return x * y - 0.125 * z + 1.0; }, true);
+  velocity.w.set([](Real x, Real y, Real z) { return 4.0 * x - y + 0.5 * z * z; }, true);
+  pressure.set([](Real x, Real y, Real z) { return x * x - 0.5 * y + 0.25 * z; }, true);
+  writeVTK(out + "/solution.vtk", velocity, pressure);
+  writeVTKFullMesh(out + "/full.vtk", velocity, pressure);
+  writeDat(out + "/profile_y.dat", velocity, pressure, 1, 0.25, 0.0, 0.0);
+  writeDat(out + "/profile_x.dat", velocity, pressure, 0, 0.0, 0.0, 0.0);
+  writeDat(out + "/profile_z.dat", velocity, pressure, 2, 0.25, 0.0, 0.0);
+  return 0;
+}
+
 int main(int argc, char *argv[]) {
   int size;
   MPI_Init(&argc, &argv);
@@ -216,6 +240,7 @@ int main(int argc, char *argv[]) {
   else if (mode == "lid" && argc >= 10) rc = run_lid(argc, argv, size);
   else if (mode == "ptest" && argc >= 8) rc = run_ptest(argc, argv, size);
   else if (mode == "vtest" && argc >= 6) rc = run_vtest(argc, argv, size);
+  else if (mode == "export" && argc >= 5) rc = run_export(argc, argv);
   else std::fprintf(stderr, "ref_dump: bad arguments\n");
   MPI_Finalize();
   return rc;
