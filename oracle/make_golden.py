@@ -90,6 +90,15 @@ def main():
         run([os.path.join(REF, "ref_dump"), "export", "8", str(periodic_z), outdir])
         print("export", periodic_z, sorted(os.listdir(outdir)))
 
+    # --- the reference driver end to end (src/main.cpp): input file -> solution.vtk + profile*.dat --------------------
+    for name, tc2 in (("mif_case1", "false"), ("mif_case2", "true")):
+        outdir = os.path.join(GOLDEN, name)
+        os.makedirs(outdir, exist_ok=True)
+        with open(os.path.join(outdir, "input.txt"), "w") as f:
+            f.write(f"Nt : 3\ndt : 1e-3\nNx : 17\nNy : 13\nNz : 15\nPy : 1\nPz : 1\ntest_case_2 : {tc2}")
+        run([os.path.join(REF, "mif"), "input.txt"], cwd=outdir)
+        print(name, sorted(os.listdir(outdir)))
+
     # --- numbers printed by the reference's own tests ----------------------------------------------
     norms = {}
     tmp = tempfile.mkdtemp(prefix="mifgolden_")

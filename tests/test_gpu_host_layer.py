@@ -48,3 +48,42 @@ def test_full_test_convergence_order():
     e32 = [float(x) for x in run("full_test", 32, 2).split()]
     assert 1.8 <= math.log2(e16[1] / e32[1]) <= 2.7   # velocity L2
     assert 1.1 <= math.log2(e16[4] / e32[4]) <= 2.2   # pressure L2
+
+
+@pytest.mark.parametrize("case", ["mif_case1", "mif_case2"])
+def test_mif_driver_writes_the_reference_outputs(case, tmp_path):
+    """`mif input.txt` (host/apps/mif.cpp, the port of src/main.cpp) against the files the reference driver wrote for the
+    same input (tests/golden/mif_case*/, oracle/make_golden.py): solution.vtk and the profiles, compared numerically."""
+    import re
+    import shutil
+
+    import numpy as np
+    golden = os.path.join(GOLDEN_DIR, case)
+    shutil.copy(os.path.join(golden, "input.txt"), tmp_path)
+    out = subprocess.run([os.path.join(BIN, "mif"), "input.txt"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+
+    def vtk_fields(path):
+        blob = open(path, "rb").read()
+        n = int(re.search(rb"POINTS (\d+) double\n", blob).group(1))
+        fields, off = {}, re.search(rb"POINTS \d+ double\n", blob).end()
+        fields["points"] = np.frombuffer(blob[off:off + 24 * n], dtype=">f8")
+        off += 24 * n
+        for name in "uvwp":
+            m = re.search(rb"SCALARS " + name.encode() + rb" double 1\nLOOKUP_TABLE default\n", blob[off:])
+            off += m.end()
+            fields[name] = np.frombuffer(blob[off:off + 8 * n], dtype=">f8")
+            off += 8 * n
+        return fields
+
+    ref, got = vtk_fields(os.path.join(golden, "solution.vtk")), vtk_fields(os.path.join(tmp_path, "solution.vtk"))
+    for key in ref:
+        assert ref[key].shape == got[key].shape
+        scale = max(float(np.max(np.abs(ref[key]))), 1e-6)
+        assert float(np.max(np.abs(ref[key] - got[key]))) <= 1e-10 * scale, key
+    profiles = [f for f in sorted(os.listdir(golden)) if f.startswith("profile")]
+    assert profiles and sorted(f for f in os.listdir(tmp_path) if f.startswith("profile")) == profiles
+    for name in profiles:
+        a, b = np.loadtxt(os.path.join(golden, name)), np.loadtxt(os.path.join(tmp_path, name))
+        assert a.shape == b.shape
+        assert np.allclose(a, b, rtol=1e-7, atol=1e-12), name
