@@ -147,11 +147,12 @@ struct LastPass {
 // Forward complex FFT of one line (padded, natural order in S); T = twiddle tables of load_twiddles.
 //   FROM_REGS: v[] already holds x[j + s*TL] (the first pass does not read shared memory);
 //   KEEP:      the spectrum stays in registers, element (u, t) of the last pass, v[u + G t] = X[j + TL u + NS t].
-template <int LOGM, bool FROM_REGS, bool KEEP>
+//   SKIP_FIRST: the first pass has already been done and its output stored (strided sweeps, first_pass_in_place).
+template <int LOGM, bool FROM_REGS, bool KEEP, bool SKIP_FIRST = false>
 __device__ __forceinline__ void fft_line(double2 *S, const double2 *T, int j, int line, double2 *v) {
   using C = Cfg<LOGM>;
   const double2 *T2 = T, *T3 = T + C::TW_PASS2, *T4 = T3 + C::TW_PASS3;
-  pass<LOGM, 8, 1, !FROM_REGS, true>(S, T, j, line, v);
+  if (!SKIP_FIRST) pass<LOGM, 8, 1, !FROM_REGS, true>(S, T, j, line, v);
   pass<LOGM, 8, 8>(S, T2, j, line, v);
   if (LOGM == 7) pass<LOGM, 2, 64, true, !KEEP>(S, T3, j, line, v);
   if (LOGM == 8) pass<LOGM, 4, 64, true, !KEEP>(S, T3, j, line, v);
@@ -159,6 +160,26 @@ __device__ __forceinline__ void fft_line(double2 *S, const double2 *T, int j, in
   if (LOGM == 10) {
     pass<LOGM, 8, 64>(S, T3, j, line, v);
     pass<LOGM, 2, 512, true, !KEEP>(S, T4, j, line, v);
+  }
+}
+
+// First radix-8 pass (no twiddles) on values v[s] = c[b + s*TL] that the caller loaded straight from global memory,
+// executed by the thread that loaded them -- in the strided sweeps that is thread (line l, butterfly index b) of the
+// line-fastest mapping, not a lane of the line's warp.  Stores the pass output into line l's region; the caller
+// separates this from the following passes with __syncthreads().
+template <int LOGM>
+__device__ __forceinline__ void first_pass_in_place(double2 *S_line, int b, double2 *v) {
+  using C = Cfg<LOGM>;
+  constexpr int TL = C::TL, G = C::EPT / 8;
+#pragma unroll
+  for (int u = 0; u < G; u++) {
+    double2 a[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) a[t] = v[u + G * t];
+    fast::dft8(a);
+    const int jj = b + u * TL;
+#pragma unroll
+    for (int t = 0; t < 8; t++) S_line[pad(jj * 8 + t)] = a[t];
   }
 }
 
@@ -170,9 +191,17 @@ template <int LOGM>
 __device__ __forceinline__ void unpack_regs(const double2 *v, int j, const double2 *__restrict__ cs, double *out,
                                             double &e_last) {
   using L = LastPass<LOGM>;
-  constexpr int R = L::R, NS = L::NS, G = L::G;
+  constexpr int R = L::R, G = L::G;
   static_assert(Cfg<LOGM>::WPL == 1, "shuffle unpack needs the whole line in one warp");
   const int src = (32 - j) & 31;
+  // cos / sin of pi t / 8, t = 0..7
+  constexpr double kRotCos[8] = {1.0, 0.92387953251128675613, 0.70710678118654752440, 0.38268343236508977173,
+                                 0.0, -0.38268343236508977173, -0.70710678118654752440, -0.92387953251128675613};
+  constexpr double kRotSin[8] = {0.0, 0.38268343236508977173, 0.70710678118654752440, 0.92387953251128675613,
+                                 1.0, 0.92387953251128675613, 0.70710678118654752440, 0.38268343236508977173};
+  double2 base_w[G];
+#pragma unroll
+  for (int u = 0; u < G; u++) base_w[u] = __ldg(&cs[j + 32 * u]);
 #pragma unroll
   for (int u = 0; u < G; u++)
 #pragma unroll
@@ -182,10 +211,13 @@ __device__ __forceinline__ void unpack_regs(const double2 *v, int j, const doubl
       // lane 0: k = 32 u + NS t.  u = 0: partner NS (R - t) in the same butterfly (t = 0 pairs with itself);
       // u >= 1: partner in butterfly G - u, output R - 1 - t.
       if (j == 0) B = (u == 0) ? v[G * ((R - t) % R)] : v[(G - u) + G * (R - 1 - t)];
-      const int k = j + 32 * u + NS * t;
+      // exp(i pi k / M) for k = k0 + NS t is exp(i pi k0 / M) times the constant exp(i pi t / R): one table load per
+      // butterfly instead of one per output (the loads go through the same L1/shared pipe that bounds this kernel).
       const double2 A = v[u + G * t];
-      const double2 w = __ldg(&cs[k]);
-      out[u + G * t] = 0.5 * ((A.x + B.x) + w.x * (A.y + B.y) - w.y * (A.x - B.x));
+      const double2 w0 = base_w[u];
+      const double cr = kRotCos[(8 / R) * t], sr = kRotSin[(8 / R) * t];
+      const double wx = w0.x * cr - w0.y * sr, wy = w0.x * sr + w0.y * cr;
+      out[u + G * t] = 0.5 * ((A.x + B.x) + wx * (A.y + B.y) - wy * (A.x - B.x));
     }
   e_last = v[0].x - v[0].y;  // E_M = Re C_0 - Im C_0 (meaningful in lane 0)
 }

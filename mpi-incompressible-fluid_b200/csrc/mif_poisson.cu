@@ -521,31 +521,32 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
     }
     __syncthreads();  // twiddle tables are in place
   } else {
-    // y / z sweep: line-fastest mapping so that the 8 lines (consecutive x) form 64-byte segments.
-    const int l = tid & 7, q0 = tid >> 3;
-    constexpr int QSTEP = C::THREADS / 8, NIT = (NPTS + QSTEP - 1) / QSTEP;
-    double *dst = reinterpret_cast<double *>(smem2 + l * C::LINE_PITCH);
+    // y / z sweep: line-fastest mapping (the 8 lines are 8 consecutive x, so every request is a set of 64-byte
+    // segments).  Thread (l, b) loads the inputs of the first-pass butterflies jj = b + u*TL of line l straight from
+    // global memory -- slots jj + (M/8) t, i.e. elements (2q, 2q+1) or their mirror images (2M-2q, 2M-2q-1) -- runs
+    // that pass in registers and stores its output into line l's region: the packed even extension never exists
+    // in shared memory.
+    const int l = tid & 7, b = tid >> 3;
+    const bool live = l < lines;
     const double *src = base + (long long)l * job.lstride;
-    double vals[NIT];
+    auto element = [&](int e) -> double {
+      if (!live) return 0.0;
+      return job.load_map.n ? *seg_address(job.load_map, e, blockIdx.y, first_line + l) : src[(long long)e * job.estride];
+    };
 #pragma unroll
-    for (int it = 0; it < NIT; it++) {
-      const int e = q0 + it * QSTEP;
-      if (e < NPTS && l < lines)
-        vals[it] = job.load_map.n ? *seg_address(job.load_map, e, blockIdx.y, first_line + l) : src[(long long)e * job.estride];
-      else
-        vals[it] = 0.0;
+    for (int s = 0; s < EPT; s++) {
+      const int q = b + s * TL;
+      if (s < EPT / 2) v[s] = make_double2(element(2 * q), element(2 * q + 1));
+      else v[s] = make_double2(element(2 * M - 2 * q), element(2 * M - 2 * q - 1));
     }
-#pragma unroll
-    for (int it = 0; it < NIT; it++) {
-      const int e = q0 + it * QSTEP;
-      if (e < NPTS) put_packed(dst, M, e, vals[it]);
-    }
+    first_pass_in_place<LOGM>(smem2 + l * C::LINE_PITCH, b, v);
     __syncthreads();  // all lines and the twiddle tables are in place
   }
 
   double lo[PAIRS], hi[PAIRS], mid = 0.0, e_last = 0.0;
   double spec[EPT];  // shuffle path: spec[u + G t] = E_k, k = j + 32 u + NS t
-  if (CONTIG && job.div_u == nullptr) fft_line<LOGM, true, SHUFFLE>(S, T, j, line, v);  // first pass from registers
+  if (!CONTIG) fft_line<LOGM, false, SHUFFLE, true>(S, T, j, line, v);                     // first pass already done
+  else if (job.div_u == nullptr) fft_line<LOGM, true, SHUFFLE>(S, T, j, line, v);       // first pass from registers
   else fft_line<LOGM, false, SHUFFLE>(S, T, j, line, v);
   if constexpr (SHUFFLE) unpack_regs<LOGM>(v, j, job.cs, spec, e_last);
   else unpack_line<LOGM>(S, j, job.cs, lo, hi, mid);
