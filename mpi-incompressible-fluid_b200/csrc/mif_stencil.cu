@@ -168,6 +168,129 @@ stage_kernel(const Geom g, const double *__restrict__ in_u, const double *__rest
 
 
 // ------------------------------------------------------------------------------------------------
+// RK stage kernel, z-marching: a thread owns a column (i, j) and walks kz planes, keeping the z neighbours of its
+// own point (and the diagonal neighbours that are in-plane neighbours one plane earlier or later) in registers, so
+// a plane costs 20 loads per point instead of 31 -- the kernel is bound by load-issue / L1 wavefronts and latency,
+// not by HBM traffic, which is already at the algorithmic minimum.  Arithmetic is identical to stage_kernel.
+// ------------------------------------------------------------------------------------------------
+template <int STAGE>
+__global__ void __launch_bounds__(256, 2)
+stage_kernel_march(const Geom g, const double *__restrict__ in_u, const double *__restrict__ in_v,
+                   const double *__restrict__ in_w, const double *__restrict__ p, double *__restrict__ a_u,
+                   double *__restrict__ a_v, double *__restrict__ a_w, double *__restrict__ b_u, double *__restrict__ b_v,
+                   double *__restrict__ b_w, int kz) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const bool in_i_u = i <= g.sx[0] - 2, in_i_o = i <= g.Nx - 2;
+  const bool in_j_v = j <= g.sy[1] - 2, in_j_o = j <= g.Ny - 2;
+  if ((!in_i_u && !in_i_o) || (!in_j_v && !in_j_o)) return;
+  const int nk = max(g.sz[2], g.Nz) - 2;
+  const int k_first = blockIdx.z * kz + 1, k_last = min(k_first + kz - 1, nk);
+  if (k_first > k_last) return;
+  const long long sj = g.PX, sk = g.plane;
+  const double dt = g.dt;
+  double a1 = 0.0, a2 = 0.0, a3 = 0.0, b;
+  if (STAGE == 1) { a1 = 64.0 / 120.0 * dt; b = a1; }
+  else if (STAGE == 2) { a1 = -34.0 / 120.0 * dt; a2 = 50.0 / 120.0 * dt; b = a1 + a2; }
+  else { a2 = -50.0 / 120.0 * dt; a3 = 90.0 / 120.0 * dt; b = a2 + a3; }
+  (void)a1; (void)a2; (void)a3;
+
+  long long c = gidx(g, i, j, k_first);
+  // rolling registers: values at plane k-1 and k of this column, and the neighbours that roll with the planes
+  double u_zm = in_u[c - sk], u_c = in_u[c], u_xp_zm = in_u[c + 1 - sk];
+  double v_zm = in_v[c - sk], v_c = in_v[c], v_yp_zm = in_v[c + sj - sk];
+  double w_zm = in_w[c - sk], w_c = in_w[c], w_xm = in_w[c - 1], w_ym = in_w[c - sj];
+  double p_zm = p[c - sk], p_c = p[c];
+
+  for (int k = k_first; k <= k_last; k++, c += sk) {
+    // one lane per 32-byte sector asks L2 for the plane after next
+    if ((threadIdx.x & 3) == 0 && k + 2 < g.PZ) {
+      prefetch_l2(in_u + c - 1 + 2 * sk);
+      prefetch_l2(in_v + c - 1 + 2 * sk);
+      prefetch_l2(in_w + c - 1 + 2 * sk);
+      prefetch_l2(p + c - 1 + 2 * sk);
+    }
+    const double u_xm = in_u[c - 1], u_xp = in_u[c + 1], u_ym = in_u[c - sj], u_yp = in_u[c + sj], u_xp_ym = in_u[c + 1 - sj];
+    const double v_xm = in_v[c - 1], v_xp = in_v[c + 1], v_ym = in_v[c - sj], v_yp = in_v[c + sj], v_xm_yp = in_v[c - 1 + sj];
+    const double w_xp = in_w[c + 1], w_yp = in_w[c + sj];
+    const double u_zp = in_u[c + sk], v_zp = in_v[c + sk];
+    const double w_zp = in_w[c + sk], w_xm_zp = in_w[c - 1 + sk], w_ym_zp = in_w[c - sj + sk];
+    const double p_xm = p[c - 1], p_ym = p[c - sj];
+    const double p_zp = (k < k_last) ? p[c + sk] : 0.0;
+
+    const bool in_k_w = k <= g.sz[2] - 2, in_k_o = k <= g.Nz - 2;
+    if (in_i_u && in_j_o && in_k_o) {
+      const double convection = -u_c * (u_xp - u_xm) * g.one_over_2_dx -
+                                (v_yp + v_c + v_xm_yp + v_xm) * (u_yp - u_ym) * g.one_over_8_dy -
+                                (w_zp + w_c + w_xm_zp + w_xm) * (u_zp - u_zm) * g.one_over_8_dz;
+      const double diffusion = (u_xp - 2 * u_c + u_xm) * g.one_over_dx2_Re + (u_yp - 2 * u_c + u_ym) * g.one_over_dy2_Re +
+                               (u_zp - 2 * u_c + u_zm) * g.one_over_dz2_Re;
+      const double rhs = convection + diffusion;
+      const double p_grad = (p_c - p_xm) * g.one_over_dx;
+      if (STAGE == 1) {
+        a_u[c] = u_c + a1 * rhs - b * p_grad;
+        b_u[c] = rhs;
+      } else if (STAGE == 2) {
+        const double rhs_1 = a_u[c];
+        const double rhs_2_scaled = a2 * rhs;
+        a_u[c] = u_c + a1 * rhs_1 + rhs_2_scaled - b * p_grad;
+        b_u[c] = rhs_2_scaled;
+      } else {
+        const double rhs_2_scaled = -a_u[c];
+        a_u[c] = u_c + rhs_2_scaled + a3 * rhs - b * p_grad;
+      }
+    }
+    if (in_i_o && in_j_v && in_k_o) {
+      const double convection = -(u_xp + u_c + u_xp_ym + u_ym) * (v_xp - v_xm) * g.one_over_8_dx -
+                                v_c * (v_yp - v_ym) * g.one_over_2_dy -
+                                (w_zp + w_c + w_ym_zp + w_ym) * (v_zp - v_zm) * g.one_over_8_dz;
+      const double diffusion = (v_xp - 2 * v_c + v_xm) * g.one_over_dx2_Re + (v_yp - 2 * v_c + v_ym) * g.one_over_dy2_Re +
+                               (v_zp - 2 * v_c + v_zm) * g.one_over_dz2_Re;
+      const double rhs = convection + diffusion;
+      const double p_grad = (p_c - p_ym) * g.one_over_dy;
+      if (STAGE == 1) {
+        a_v[c] = v_c + a1 * rhs - b * p_grad;
+        b_v[c] = rhs;
+      } else if (STAGE == 2) {
+        const double rhs_1 = a_v[c];
+        const double rhs_2_scaled = a2 * rhs;
+        a_v[c] = v_c + a1 * rhs_1 + rhs_2_scaled - b * p_grad;
+        b_v[c] = rhs_2_scaled;
+      } else {
+        const double rhs_2_scaled = -a_v[c];
+        a_v[c] = v_c + rhs_2_scaled + a3 * rhs - b * p_grad;
+      }
+    }
+    if (in_i_o && in_j_o && in_k_w) {
+      const double convection = -(u_xp + u_c + u_xp_zm + u_zm) * (w_xp - w_xm) * g.one_over_8_dx -
+                                (v_yp + v_c + v_yp_zm + v_zm) * (w_yp - w_ym) * g.one_over_8_dy -
+                                w_c * (w_zp - w_zm) * g.one_over_2_dz;
+      const double diffusion = (w_xp - 2 * w_c + w_xm) * g.one_over_dx2_Re + (w_yp - 2 * w_c + w_ym) * g.one_over_dy2_Re +
+                               (w_zp - 2 * w_c + w_zm) * g.one_over_dz2_Re;
+      const double rhs = convection + diffusion;
+      const double p_grad = (p_c - p_zm) * g.one_over_dz;
+      if (STAGE == 1) {
+        a_w[c] = w_c + a1 * rhs - b * p_grad;
+        b_w[c] = rhs;
+      } else if (STAGE == 2) {
+        const double rhs_1 = a_w[c];
+        const double rhs_2_scaled = a2 * rhs;
+        a_w[c] = w_c + a1 * rhs_1 + rhs_2_scaled - b * p_grad;
+        b_w[c] = rhs_2_scaled;
+      } else {
+        const double rhs_2_scaled = -a_w[c];
+        a_w[c] = w_c + rhs_2_scaled + a3 * rhs - b * p_grad;
+      }
+    }
+    // roll the column one plane up
+    u_zm = u_c; u_c = u_zp; u_xp_zm = u_xp;
+    v_zm = v_c; v_c = v_zp; v_yp_zm = v_yp;
+    w_zm = w_c; w_c = w_zp; w_xm = w_xm_zp; w_ym = w_ym_zp;
+    p_zm = p_c; p_c = p_zp;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // RK stage kernel, 2.5-D blocked: a CTA owns a 64 x 8 tile in (x, y) and marches along z, keeping a ring of
 // three z planes of u, v, w, p (each with a one-cell halo in x and y) in shared memory, so every input is
 // fetched from L2/HBM about once instead of once per z neighbour.  The plane two steps ahead is prefetched into
@@ -551,6 +674,22 @@ void launch_stage(cudaStream_t stream, const Geom &g, int stage, CVec3 in, const
   if (ni <= 0 || nj <= 0 || nk <= 0) return;
   static const bool use_tiled = getenv("MIFGPU_STAGE_TILED") != nullptr;  // A/B switch for profiling
   static const int prefetch_planes = getenv("MIFGPU_STAGE_PREFETCH") ? atoi(getenv("MIFGPU_STAGE_PREFETCH")) : 1;
+  static const int march_kz = getenv("MIFGPU_STAGE_MARCH") ? atoi(getenv("MIFGPU_STAGE_MARCH")) : 0;
+  if (march_kz > 0) {
+    const dim3 mblock(64, 4, 1);
+    const dim3 mgrid(cdiv(ni, mblock.x), cdiv(nj, mblock.y), cdiv(nk, march_kz));
+    if (stage == 1)
+      stage_kernel_march<1><<<mgrid, mblock, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
+                                                          b.c[1], b.c[2], march_kz);
+    else if (stage == 2)
+      stage_kernel_march<2><<<mgrid, mblock, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
+                                                          b.c[1], b.c[2], march_kz);
+    else
+      stage_kernel_march<3><<<mgrid, mblock, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
+                                                          b.c[1], b.c[2], march_kz);
+    ++*launches;
+    return;
+  }
   if (use_tiled) {
     const int kz = 64;  // planes marched by one CTA
     const dim3 tblock(kTX, kTY, 1);
