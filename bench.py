@@ -41,8 +41,10 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The sampler is started before the
+    warm-up (nvidia-smi needs up to a second to produce its first row, longer on an 8-GPU box) and only the rows
+    whose own timestamp falls inside [mark_begin(), mark_end()] are used."""
+    QUERY = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -50,6 +52,7 @@ class ClockSampler:
         self.device = device_index
         self.rows = []
         self.proc = None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
@@ -61,32 +64,59 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
+
+    @staticmethod
+    def _stamp(cell):
+        import datetime
+        try:
+            return datetime.datetime.strptime(cell, "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, sm_max, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
-            if len(row) < 9:
-                continue
-            try:
-                sm.append(float(row[1]))
-                sm_max = float(row[2])
-            except ValueError:
-                continue
-            for name, cell in zip(names, row[5:9]):
-                if cell.lower().startswith("active"):
-                    reasons.add(name)
+
+        def collect(inside_only):
+            sm, sm_max, reasons = [], None, set()
+            for arrival, row in self.rows:
+                if len(row) < 10:
+                    continue
+                stamp = self._stamp(row[0]) or arrival
+                if inside_only and self.t_begin is not None and not (self.t_begin <= stamp <= (self.t_end or 1e300)):
+                    continue
+                try:
+                    sm.append(float(row[2]))
+                    sm_max = float(row[3])
+                except ValueError:
+                    continue
+                for name, cell in zip(names, row[6:10]):
+                    if cell.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, sm_max, reasons
+
+        sm, sm_max, reasons = collect(True)
+        window = "timed region"
+        if not sm:  # the timed region was shorter than one sampling period: fall back to the whole run under load
+            sm, sm_max, reasons = collect(False)
+            window = "whole run (no sample fell inside the timed region)"
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": sm_max, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "reasons": sorted(reasons), "window": window}
 
 
 def host_core_count():
@@ -150,6 +180,74 @@ def reference_arm(args):
     return 0
 
 
+def poisson_workload(args):
+    """BASELINE.json configs[1]: solve_pressure_equation_homogeneous_periodic alone (test/pressure_test_mixed.cpp:
+    domain [0, 2 pi]^3, z periodic, dt = 1), here on a cubic 513^3-point grid with a seeded random velocity (the cost
+    of a solve does not depend on the data).  One "step" = divergence + 5 sweep launches + ghost refresh."""
+    import numpy as np
+    import torch
+
+    import mif_b200 as mif
+
+    torch.cuda.set_device(0)
+    mif.lib()
+    N = args.size
+    two_pi = 2.0 * 3.14159265358979323846
+    ctx = mif.Context(N, N, N, two_pi, two_pi, two_pi, 0.0, 0.0, 0.0, 1e3, 1.0, 1, periodic=(False, False, True))
+    vel = ctx.velocity()
+    rng = np.random.default_rng(1234)
+    for t in vel:
+        sx, sy, sz = t.shape
+        t.upload(rng.uniform(-1, 1, (sz, sy, sx)))
+    p = ctx.tensor(mif.STAGGER_NONE)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", 0))
+    steps, warmup = args.steps, max(args.warmup, 3)
+    for _ in range(warmup):
+        ctx.solve_pressure(p, vel, 1.0)
+    ctx.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.5)
+    sampler.mark_begin()
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        ctx.solve_pressure(p, vel, 1.0)
+    ev1.record(stream)
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    sampler.mark_end()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop()
+    ctx.profile_enable(True)
+    for _ in range(steps):
+        ctx.solve_pressure(p, vel, 1.0)
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    kernels = {k: round(v / steps, 4) for k, (v, n) in prof.items() if n}
+    cells = float(N - 1) ** 3
+    value = cells * steps / (ms * 1e-3)
+    peak, peak_src = measured_peaks()
+    # SURVEY.md section 8d: divergence 3R + 1W, six sweeps x (1R + 1W) = 16 FP64 words = 128 B per cell-solve
+    bytes_per_solve = 128.0
+    line = {
+        "metric": "FP64 cell-solves/s, spectral pressure Poisson solve alone", "value": value, "unit": "cell-solves/s",
+        "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"pressure_test_mixed-type Poisson solve, {N}^3 points, x/y Neumann (DCT-I), z periodic (real FFT)",
+                   "points": [N, N, N], "l2": "inputs larger than L2", "finite": bool(np.isfinite(p.download()).all())},
+        "roofline": {"bound": "hbm", "kernel": "whole solve (divergence + 5 sweep launches)",
+                     "achieved": round(value * bytes_per_solve / 1e9, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(value * bytes_per_solve / 1e9 / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_cell_solve": bytes_per_solve},
+        "gpu_launches": int(launches), "kernels": kernels, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -157,12 +255,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=513, help="pressure points per direction (513 = 512^3 cells)")
+    ap.add_argument("--dims", type=int, nargs=3, default=None, metavar=("NX", "NY", "NZ"),
+                    help="explicit pressure points per direction (kernel studies on non-cubic grids; single GPU only)")
     ap.add_argument("--ref-size", type=int, default=257, help="points per direction of the CPU reference sample")
+    ap.add_argument("--workload", default="timestep", choices=["timestep", "poisson"],
+                    help="timestep: the north-star metric (default); poisson: BASELINE.json configs[1], the pressure "
+                         "solve alone on a pressure_test_mixed-type grid (x, y Neumann / DCT-I, z periodic / real FFT)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
+    if args.workload == "poisson":
+        return poisson_workload(args)
 
     import numpy as np
     import torch
@@ -190,6 +295,11 @@ def main():
     for level in range(max(world.bit_length() - 1, 0)):
         mult[2 - level % 3] *= 2
     dims = [cells_1d * m + 1 for m in mult]
+    if args.dims is not None:
+        if world != 1:
+            raise SystemExit("--dims is a single-GPU option")
+        dims = list(args.dims)
+        mult = [(d - 1) / cells_1d for d in dims]
     comm_id = None
     if world > 1:
         ident = torch.zeros(mif.UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
@@ -230,12 +340,14 @@ def main():
         if world > 1:
             dist.barrier()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(warmup):
         one_step()
     barrier()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark_begin()
     launches0 = ctx.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -243,9 +355,10 @@ def main():
         one_step()
     ev1.record(stream)
     barrier()
+    sampler.mark_end()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         tmax = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -269,10 +382,20 @@ def main():
     per_launch_ms = sweep_ms / max(sweep_launches, 1)
     achieved = 16.0 * points / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
     step_profile_ms = sum(ms for ms, n in prof.values()) / steps
+    # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (513^3, one GPU only).
+    traffic, traffic_src = None, None
+    ncu_summary = os.path.join(ROOT, "profiles", "r01_ncu_full_step_kernels.json")
+    if world == 1 and dims == [513, 513, 513] and os.path.exists(ncu_summary):
+        with open(ncu_summary) as f:
+            rows = [r for r in json.load(f) if "dct_kernel" in r["kernel"]]
+        if rows:
+            traffic = round(sum(r["dram_read_GB"] + r["dram_write_GB"] for r in rows) / len(rows) * 1e9)
+            traffic_src = "profiles/r01_ncu_full_step_kernels.json (dram__bytes_read.sum + dram__bytes_write.sum, mean of %d sweep launches)" % len(rows)
     roofline = {
         "bound": "hbm", "kernel": "sweep_kernel (batched DCT-I / real-FFT lines, 15 launches per step)",
         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-        "traffic": None, "peak_source": peak_src, "avg_launch_ms": round(per_launch_ms, 4),
+        "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": 16.0 * points,
+        "peak_source": peak_src, "avg_launch_ms": round(per_launch_ms, 4),
         "share_of_step": round(sweep_ms / steps / step_profile_ms, 4) if step_profile_ms else None,
         "whole_step": {"algorithmic_bytes_per_cell_step": BYTES_PER_CELL_STEP,
                        "achieved_GBs": round(value / world * BYTES_PER_CELL_STEP / 1e9, 1),

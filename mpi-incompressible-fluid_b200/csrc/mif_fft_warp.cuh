@@ -53,12 +53,13 @@ __device__ __forceinline__ void line_sync(int line) {
 
 // Copy the twiddles the passes need into shared memory: T2[ti][k] = W_64^(k t), T3[ti][k] = W_(64 R3)^(k t)
 // with t = 1, 2, 4 (ti = 0, 1, 2), T4[k] = W_1024^k.  tw[q] = exp(-2 pi i q / M).
-template <int LOGM>
+// TW_STRIDE > 1: tw is the table of the TW_STRIDE times longer transform (tw[q * TW_STRIDE] = exp(-2 pi i q / M)).
+template <int LOGM, int TW_STRIDE = 1, int THREADS = Cfg<LOGM>::THREADS>
 __device__ __forceinline__ void load_twiddles(double2 *T, const double2 *__restrict__ tw) {
   using C = Cfg<LOGM>;
   constexpr int M = C::M;
   constexpr int R3 = (LOGM == 7) ? 2 : (LOGM == 8 ? 4 : 8);  // radix of the NS = 64 pass
-  for (int idx = threadIdx.x; idx < C::TW_TOTAL; idx += C::THREADS) {
+  for (int idx = threadIdx.x; idx < C::TW_TOTAL; idx += THREADS) {
     int q;
     if (idx < C::TW_PASS2) {
       const int ti = idx / 8, k = idx - ti * 8;
@@ -69,7 +70,7 @@ __device__ __forceinline__ void load_twiddles(double2 *T, const double2 *__restr
     } else {
       q = idx - C::TW_PASS2 - C::TW_PASS3;  // NS = 512, R = 2: W_1024^k
     }
-    T[idx] = __ldg(&tw[q & (M - 1)]);
+    T[idx] = __ldg(&tw[(q & (M - 1)) * TW_STRIDE]);
   }
 }
 
@@ -187,13 +188,21 @@ __device__ __forceinline__ void first_pass_in_place(double2 *S_line, int b, doub
 // Its partners C_{M-k} all live in lane 32 - j (butterfly G-1-u, output R-1-t), so one round of shuffles
 // replaces the shared-memory round trip; lane 0 is its own partner with a slightly different index map.
 // out[u + G t] = E_k for the same k; E_M is returned separately (valid in lane 0).
-template <int LOGM>
+//
+// SPLIT (lines of 2M + 1 points, mif_poisson.cu warp_dct_split_kernel): the warp holds one half of a radix-2
+// decimation-in-frequency split of the length-2M transform, C_{2k} (ODD = false) or C_{2k+1} (ODD = true), and
+// produces E_{2k} resp. E_{2k+1} of the long line.  cs is then the table of the long transform, (cos, sin)(pi q / 2M).
+// Even half: partners and angles are those of the short transform (cs[2k]).  Odd half: the partner of C_{2k+1} is
+// C_{2M-2k-1} = C_{2(M-1-k)+1}, i.e. index M-1-k, which lives in lane 31 - j (butterfly G-1-u, output R-1-t) with no
+// special case, and the angle is pi (2k+1) / 2M (cs[2k+1]).
+template <int LOGM, bool SPLIT = false, bool ODD = false>
 __device__ __forceinline__ void unpack_regs(const double2 *v, int j, const double2 *__restrict__ cs, double *out,
                                             double &e_last) {
   using L = LastPass<LOGM>;
   constexpr int R = L::R, G = L::G;
   static_assert(Cfg<LOGM>::WPL == 1, "shuffle unpack needs the whole line in one warp");
-  const int src = (32 - j) & 31;
+  static_assert(SPLIT || !ODD, "ODD only exists in the split scheme");
+  const int src = ODD ? 31 - j : (32 - j) & 31;
   // cos / sin of pi t / 8, t = 0..7
   constexpr double kRotCos[8] = {1.0, 0.92387953251128675613, 0.70710678118654752440, 0.38268343236508977173,
                                  0.0, -0.38268343236508977173, -0.70710678118654752440, -0.92387953251128675613};
@@ -201,7 +210,7 @@ __device__ __forceinline__ void unpack_regs(const double2 *v, int j, const doubl
                                  1.0, 0.92387953251128675613, 0.70710678118654752440, 0.38268343236508977173};
   double2 base_w[G];
 #pragma unroll
-  for (int u = 0; u < G; u++) base_w[u] = __ldg(&cs[j + 32 * u]);
+  for (int u = 0; u < G; u++) base_w[u] = __ldg(&cs[SPLIT ? 2 * (j + 32 * u) + (ODD ? 1 : 0) : j + 32 * u]);
 #pragma unroll
   for (int u = 0; u < G; u++)
 #pragma unroll
@@ -210,7 +219,7 @@ __device__ __forceinline__ void unpack_regs(const double2 *v, int j, const doubl
       double2 B = make_double2(__shfl_sync(0xffffffffu, mine.x, src), __shfl_sync(0xffffffffu, mine.y, src));
       // lane 0: k = 32 u + NS t.  u = 0: partner NS (R - t) in the same butterfly (t = 0 pairs with itself);
       // u >= 1: partner in butterfly G - u, output R - 1 - t.
-      if (j == 0) B = (u == 0) ? v[G * ((R - t) % R)] : v[(G - u) + G * (R - 1 - t)];
+      if (!ODD && j == 0) B = (u == 0) ? v[G * ((R - t) % R)] : v[(G - u) + G * (R - 1 - t)];
       // exp(i pi k / M) for k = k0 + NS t is exp(i pi k0 / M) times the constant exp(i pi t / R): one table load per
       // butterfly instead of one per output (the loads go through the same L1/shared pipe that bounds this kernel).
       const double2 A = v[u + G * t];
@@ -220,6 +229,89 @@ __device__ __forceinline__ void unpack_regs(const double2 *v, int j, const doubl
       out[u + G * t] = 0.5 * ((A.x + B.x) + wx * (A.y + B.y) - wy * (A.x - B.x));
     }
   e_last = v[0].x - v[0].y;  // E_M = Re C_0 - Im C_0 (meaningful in lane 0)
+}
+
+// cos / sin of pi t / 8, t = 0..7: exp(i pi k / M) for k = k0 + NS t is exp(i pi k0 / M) times exp(i pi t / R).
+__device__ __forceinline__ double2 rot8(int t) {
+  constexpr double kRotCos[8] = {1.0, 0.92387953251128675613, 0.70710678118654752440, 0.38268343236508977173,
+                                 0.0, -0.38268343236508977173, -0.70710678118654752440, -0.92387953251128675613};
+  constexpr double kRotSin[8] = {0.0, 0.38268343236508977173, 0.70710678118654752440, 0.92387953251128675613,
+                                 1.0, 0.92387953251128675613, 0.70710678118654752440, 0.38268343236508977173};
+  return make_double2(kRotCos[t], kRotSin[t]);
+}
+
+// Real FFT of n = 2M points (FFTW_R2HC) from the length-M complex FFT of the packed line c_q = x_{2q} + i x_{2q+1}:
+//   X_k = 1/2 [ (C_k + conj C_{M-k}) - i exp(-2 pi i k / n) (C_k - conj C_{M-k}) ],  k = 0 .. M  (C_M = C_0).
+// Same register / lane layout as unpack_regs: lane j holds C_k for k = j + 32 u + NS t and receives C_{M-k} from lane
+// 32 - j.  re/im[u + G t] = X_k; X_0 and X_M are real, X_M is returned in x_last (lane 0).  cs[k] = (cos, sin)(2 pi k / n).
+template <int LOGM>
+__device__ __forceinline__ void unpack_r2hc_regs(const double2 *v, int j, const double2 *__restrict__ cs, double *re,
+                                                 double *im, double &x_last) {
+  using L = LastPass<LOGM>;
+  constexpr int R = L::R, G = L::G;
+  static_assert(Cfg<LOGM>::WPL == 1, "shuffle unpack needs the whole line in one warp");
+  const int src = (32 - j) & 31;
+  double2 base_w[G];
+#pragma unroll
+  for (int u = 0; u < G; u++) base_w[u] = __ldg(&cs[j + 32 * u]);
+#pragma unroll
+  for (int u = 0; u < G; u++)
+#pragma unroll
+    for (int t = 0; t < R; t++) {
+      const double2 mine = v[(G - 1 - u) + G * (R - 1 - t)];
+      double2 B = make_double2(__shfl_sync(0xffffffffu, mine.x, src), __shfl_sync(0xffffffffu, mine.y, src));
+      if (j == 0) B = (u == 0) ? v[G * ((R - t) % R)] : v[(G - u) + G * (R - 1 - t)];
+      const double2 A = v[u + G * t];
+      const double2 w0 = base_w[u], r = rot8((8 / R) * t);
+      const double c = w0.x * r.x - w0.y * r.y, sn = w0.x * r.y + w0.y * r.x;
+      const double sum_r = A.x + B.x, dif_i = A.y - B.y, dif_r = A.x - B.x, sum_i = A.y + B.y;
+      re[u + G * t] = 0.5 * (sum_r + c * sum_i - sn * dif_r);
+      im[u + G * t] = 0.5 * (dif_i - c * dif_r - sn * sum_i);
+    }
+  x_last = v[0].x - v[0].y;  // X_M = Re C_0 - Im C_0 (meaningful in lane 0)
+}
+
+// Input of the inverse (FFTW_HC2R, unnormalised) as ONE complex FFT:  Z_k = (X_k + conj X_{M-k}) + i exp(+2 pi i k / n)
+// (X_k - conj X_{M-k}), z = inverse FFT_M(Z) = conj(FFT_M(conj Z)),  x_{2q} = Re z_q, x_{2q+1} = Im z_q.
+// Returns conj(Z_k) from X_k = (xr, xi), X_{M-k} = (yr, yi) and (c, sn) = (cos, sin)(2 pi k / n).
+__device__ __forceinline__ double2 hc2r_input(double xr, double xi, double yr, double yi, double c, double sn) {
+  const double pr = xr + yr, pi = xi - yi, dr = xr - yr, di = xi + yi;
+  return make_double2(pr - sn * dr - c * di, -(pi + c * dr - sn * di));
+}
+
+// The same from the registers left by unpack_r2hc_regs (after the eigenvalue scaling): the partners X_{M-k} come
+// from lane 32 - j again; the results are the first-pass inputs v[s] of the next transform because
+// k = j + 32 (u + G t) is exactly slot s = u + G t of lane j.
+template <int LOGM>
+__device__ __forceinline__ void pack_hc2r_regs(const double *re, const double *im, double x_last, int j,
+                                               const double2 *__restrict__ cs, double2 *v) {
+  using L = LastPass<LOGM>;
+  constexpr int R = L::R, G = L::G;
+  const int src = (32 - j) & 31;
+  double2 base_w[G];
+#pragma unroll
+  for (int u = 0; u < G; u++) base_w[u] = __ldg(&cs[j + 32 * u]);
+#pragma unroll
+  for (int u = 0; u < G; u++)
+#pragma unroll
+    for (int t = 0; t < R; t++) {
+      const int partner = (G - 1 - u) + G * (R - 1 - t);
+      double yr = __shfl_sync(0xffffffffu, re[partner], src), yi = __shfl_sync(0xffffffffu, im[partner], src);
+      if (j == 0) {
+        if (u == 0 && t == 0) {
+          yr = x_last;  // X_M
+          yi = 0.0;
+        } else {
+          const int own = (u == 0) ? G * (R - t) : (G - u) + G * (R - 1 - t);
+          yr = re[own];
+          yi = im[own];
+        }
+      }
+      const double2 w0 = base_w[u], r = rot8((8 / R) * t);
+      const double c = w0.x * r.x - w0.y * r.y, sn = w0.x * r.y + w0.y * r.x;
+      const double xi = (j == 0 && u == 0 && t == 0) ? 0.0 : im[u + G * t];
+      v[u + G * t] = hc2r_input(re[u + G * t], xi, yr, yi, c, sn);
+    }
 }
 
 // Store real element e (0 <= e <= M) of the even extension and its mirror image 2M - e into the packed line.

@@ -650,6 +650,347 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Periodic directions: FFTW_R2HC / FFTW_HC2R on n = 2M real points (M = 256 or 512) with the same warp-per-line
+// machinery -- the line is packed two reals per complex, transformed by ONE length-M complex FFT and unpacked to
+// FFTW's halfcomplex order r_0 .. r_{n/2}, i_{n/2-1} .. i_1 with shuffles.  The fused z sweep never leaves the
+// registers: unpack, eigenvalue scaling in halfcomplex order, repack (the unpacked index k = j + 32 (u + G t) is
+// the first-pass slot of the next transform), inverse FFT as conj(FFT(conj .)), normalisation.
+// ------------------------------------------------------------------------------------------------
+template <int LOGM, bool CONTIG>
+__global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, 2) warp_rfft_kernel(const FastJob job, double *__restrict__ field) {
+  using namespace warpfft;
+  using C = Cfg<LOGM>;
+  using L = LastPass<LOGM>;
+  constexpr int M = C::M, n = 2 * M, TL = C::TL, EPT = C::EPT;
+  static_assert(C::WPL == 1, "one warp per line");
+  extern __shared__ double2 smem2[];
+  double2 *T = smem2 + kLines * C::LINE_PITCH;
+  const int tid = threadIdx.x;
+  const int line = tid / TL, j = tid - line * TL;
+  double2 *S = smem2 + line * C::LINE_PITCH;
+  const int first_line = blockIdx.x * kLines;
+  const int lines = min(kLines, job.n_tile_lines - first_line);
+  double *base = field + job.origin + (long long)first_line * job.tile_stride + (long long)blockIdx.y * job.outer_stride;
+  double2 v[EPT];
+
+  load_twiddles<LOGM>(T, job.tw);
+  // loader thread: (line, j) along the line for x sweeps, line-fastest (l, b) for the strided sweeps
+  const int ll = CONTIG ? line : (tid & 7), lb = CONTIG ? j : (tid >> 3);
+  const bool live = ll < lines;
+  const double *src = base + (long long)ll * job.lstride;
+  auto element = [&](int e) -> double { return live ? src[(long long)e * job.estride] : 0.0; };
+  if (job.mode == 1) {
+    // halfcomplex input: X_k = (in[k], in[n-k]), partner X_{M-k} = (in[M-k], in[M+k]); X_0 and X_M are real
+#pragma unroll
+    for (int s = 0; s < EPT; s++) {
+      const int k = lb + 32 * s;
+      const double xr = element(k), yr = element(M - k);
+      const double xi = (k == 0) ? 0.0 : element(n - k), yi = (k == 0) ? 0.0 : element(M + k);
+      const double2 w = __ldg(&job.cs[k]);
+      v[s] = hc2r_input(xr, xi, yr, yi, w.x, w.y);
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < EPT; s++) {
+      const int q = lb + 32 * s;
+      v[s] = make_double2(element(2 * q), element(2 * q + 1));
+    }
+  }
+  if (CONTIG) {
+    __syncthreads();  // twiddle tables are in place
+    fft_line<LOGM, true, true>(S, T, j, line, v);
+  } else {
+    first_pass_in_place<LOGM>(smem2 + ll * C::LINE_PITCH, lb, v);
+    __syncthreads();
+    fft_line<LOGM, false, true, true>(S, T, j, line, v);
+  }
+
+  double re[EPT], im[EPT], x_last = 0.0;
+  if (job.mode != 1) {
+    unpack_r2hc_regs<LOGM>(v, j, job.cs, re, im, x_last);
+    if (job.mode == 2) {
+      // pressure_hat *= 1 / (lambda_x + lambda_y + lambda_z) in FFTW output order; mode (0,0,0) := 0
+      // (src/PressureEquation.cpp:158-163)
+      const int ix = min(first_line + line, job.n_tile_lines - 1);
+      const double lam_xy = job.lam_x[ix] + job.lam_y[blockIdx.y];
+      const bool origin_line = job.has_origin && (first_line + line == 0) && (blockIdx.y == 0);
+#pragma unroll
+      for (int u = 0; u < L::G; u++)
+#pragma unroll
+        for (int t = 0; t < L::R; t++) {
+          const int k = j + 32 * u + L::NS * t;
+          re[u + L::G * t] *= (origin_line && k == 0) ? 0.0 : 1.0 / (lam_xy + job.lam_z[k]);
+          if (k > 0) im[u + L::G * t] *= 1.0 / (lam_xy + job.lam_z[n - k]);
+        }
+      x_last *= 1.0 / (lam_xy + job.lam_z[M]);
+      pack_hc2r_regs<LOGM>(re, im, x_last, j, job.cs, v);
+      __syncwarp();
+      fft_line<LOGM, true, true>(S, T, j, line, v);
+    }
+  }
+
+  if (job.mode == 0) {
+    // halfcomplex output
+    if (CONTIG) {
+      if (line < lines) {
+        double *out = base + (long long)line * job.lstride;
+#pragma unroll
+        for (int u = 0; u < L::G; u++)
+#pragma unroll
+          for (int t = 0; t < L::R; t++) {
+            const int k = j + 32 * u + L::NS * t;
+            out[k] = re[u + L::G * t];
+            if (k > 0) out[n - k] = im[u + L::G * t];
+          }
+        if (j == 0) out[M] = x_last;
+      }
+      return;
+    }
+    double *Sd = reinterpret_cast<double *>(S);
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < L::G; u++)
+#pragma unroll
+      for (int t = 0; t < L::R; t++) {
+        const int k = j + 32 * u + L::NS * t;
+        Sd[k] = re[u + L::G * t];
+        if (k > 0) Sd[n - k] = im[u + L::G * t];
+      }
+    if (j == 0) Sd[M] = x_last;
+  } else {
+    // x_{2k} = Re z_k, x_{2k+1} = Im z_k with z = conj(FFT(conj Z)); normalised (src/PressureEquation.cpp:167-195)
+    const double scale = job.inv_norm;
+    if (CONTIG) {
+      if (line < lines) {
+        double *out = base + (long long)line * job.lstride;
+#pragma unroll
+        for (int s = 0; s < EPT; s++) {
+          const int k = j + 32 * s;
+          out[2 * k] = v[s].x * scale;
+          out[2 * k + 1] = -v[s].y * scale;
+        }
+      }
+      return;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < EPT; s++) S[j + 32 * s] = make_double2(v[s].x * scale, -v[s].y * scale);
+  }
+  // strided sweeps: the line's region now holds the n output reals; store them line-fastest
+  __syncthreads();
+  if (live) {
+    const double *srcl = reinterpret_cast<const double *>(smem2 + ll * C::LINE_PITCH);
+    double *out = base + (long long)ll * job.lstride;
+    for (int e = lb; e < n; e += C::THREADS / 8) out[(long long)e * job.estride] = srcl[e];
+  }
+}
+
+template <int LOGM>
+void launch_rfft(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid, double *field) {
+  using C = warpfft::Cfg<LOGM>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(warp_rfft_kernel<LOGM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    cudaFuncSetAttribute(warp_rfft_kernel<LOGM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    attr_set = true;
+  }
+  if (contig) warp_rfft_kernel<LOGM, true><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
+  else warp_rfft_kernel<LOGM, false><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Split path for lines of 1025 points (M = 1024): the length-1024 complex FFT is split by one radix-2
+// decimation-in-frequency step into two independent length-512 transforms,
+//     a_q = c_q + c_{q+512}  ->  C_{2k},        b_q = (c_q - c_{q+512}) W_1024^q  ->  C_{2k+1},      q, k < 512,
+// and each of them is run by ONE warp like a 513-point line of warp_dct_kernel<9>: radix-8 passes through the
+// warp's own shared-memory region with __syncwarp() only, spectrum kept in registers, DCT-I unpack by shuffles
+// (even half: the pairs of the short transform; odd half: C_{2k+1} pairs with C_{2(511-k)+1}).
+// Loading: thread jj (0..63) of a line owns first-pass butterfly jj of BOTH halves -- it loads the pairs
+// (c_q, c_{q+512}), q = jj + 64 t, t < 8, exactly once, forms a_q and b_q, runs the two radix-8 butterflies in
+// registers and stores them into the two regions.  For x sweeps thread jj is lane jj & 31 of the line's warp
+// jj >> 5 (coalesced along the line); for the strided sweeps it is thread (l, jj) of the line-fastest mapping.
+// The two warps of a line meet at a 64-thread named barrier after that first pass and where the 1025 results
+// are gathered (eigenvalue step of the fused z sweep, coalesced store).  The previous M = 1024 variant (two warps
+// sharing every pass through bar.sync and a shared-memory unpack, one 512-thread CTA per SM) stays available with
+// MIFGPU_FFT_NO_SPLIT=1.
+// ------------------------------------------------------------------------------------------------
+namespace split {
+constexpr int kFull = 1024;
+using C9 = warpfft::Cfg<9>;
+constexpr size_t smem_bytes(int lines) { return (size_t)(2 * lines * C9::LINE_PITCH + C9::TW_TOTAL) * sizeof(double2); }
+// exp(-2 pi i t / 16) = W_1024^(64 t), t < 8
+__device__ __forceinline__ double2 rot16(int t) {
+  constexpr double kCos[8] = {1.0, 0.92387953251128675613, 0.70710678118654752440, 0.38268343236508977173,
+                              0.0, -0.38268343236508977173, -0.70710678118654752440, -0.92387953251128675613};
+  constexpr double kSin[8] = {0.0, 0.38268343236508977173, 0.70710678118654752440, 0.92387953251128675613,
+                              1.0, 0.92387953251128675613, 0.70710678118654752440, 0.38268343236508977173};
+  return make_double2(kCos[t], -kSin[t]);
+}
+// 64-thread named barrier of one line's two warps.  Immediate barrier numbers: with a register operand ptxas
+// reserves all 16 hardware barriers for the CTA, which limits the CTAs per SM.
+__device__ __forceinline__ void pair_sync(int line) {
+  switch (line) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    case 3: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    case 4: asm volatile("bar.sync 5, 64;" ::: "memory"); break;
+    case 5: asm volatile("bar.sync 6, 64;" ::: "memory"); break;
+    case 6: asm volatile("bar.sync 7, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 8, 64;" ::: "memory"); break;
+  }
+}
+// First pass of both halves for butterfly jj: a[t], b[t] hold the pairs' sums / differences for q = jj + 64 t on
+// entry (differences not yet multiplied by W_1024^q); results go to slots 8 jj + t of the two regions.
+__device__ __forceinline__ void first_pass_both(double2 *even_region, double2 *odd_region, int jj, double2 wjj,
+                                                double2 *a, double2 *b) {
+#pragma unroll
+  for (int t = 0; t < 8; t++) b[t] = warpfft::cmul(b[t], warpfft::cmul(wjj, rot16(t)));
+  fast::dft8(a);
+  fast::dft8(b);
+#pragma unroll
+  for (int t = 0; t < 8; t++) {
+    even_region[warpfft::pad(jj * 8 + t)] = a[t];
+    odd_region[warpfft::pad(jj * 8 + t)] = b[t];
+  }
+}
+}  // namespace split
+
+// LINES lines per CTA (64 threads each): 8 lines fill the register file with ONE CTA per SM, whose 16 warps then load,
+// transform and store in lockstep; 4 lines give two independent CTAs per SM that overlap each other's phases.
+template <bool CONTIG, int LINES>
+__global__ void __launch_bounds__(64 * LINES, 8 / LINES) warp_dct_split_kernel(const FastJob job, double *__restrict__ field) {
+  using namespace warpfft;
+  using namespace split;
+  using L = LastPass<9>;
+  constexpr int EPT = C9::EPT, NPTS = kFull + 1, kThreads = 64 * LINES, kLines = LINES;
+  extern __shared__ double2 smem2[];
+  double2 *T = smem2 + 2 * kLines * C9::LINE_PITCH;
+  const int tid = threadIdx.x, warp = tid >> 5, j = tid & 31;
+  const int line = warp >> 1;
+  const bool odd = warp & 1;
+  double2 *S = smem2 + warp * C9::LINE_PITCH;                                        // this warp's FFT region
+  double *Rl = reinterpret_cast<double *>(smem2 + (2 * line) * C9::LINE_PITCH);      // the line's 1025 reals (aliases S of the even warp)
+  const int first_line = blockIdx.x * kLines;
+  const int lines = min(kLines, job.n_tile_lines - first_line);
+  double *base = field + job.origin + (long long)first_line * job.tile_stride + (long long)blockIdx.y * job.outer_stride;
+  double2 v[EPT];
+
+  load_twiddles<9, 2, kThreads>(T, job.tw);
+  {
+    // loader thread: butterfly jj of line ll
+    const int ll = CONTIG ? line : tid % LINES, jj = CONTIG ? (odd ? 32 : 0) + j : tid / LINES;
+    const bool live = ll < lines;
+    const double *src = base + (long long)ll * job.lstride;
+    auto element = [&](int e) -> double {
+      if (!live) return 0.0;
+      if (CONTIG) return src[e];
+      return job.load_map.n ? *seg_address(job.load_map, e, blockIdx.y, first_line + ll) : src[(long long)e * job.estride];
+    };
+    double2 *a = v, *b = v + 8;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      const int q = jj + 64 * t;
+      double2 lo;
+      if (CONTIG) lo = live ? *reinterpret_cast<const double2 *>(src + 2 * q) : make_double2(0.0, 0.0);
+      else lo = make_double2(element(2 * q), element(2 * q + 1));
+      const double2 hi = make_double2(element(kFull - 2 * q), element(kFull - 1 - 2 * q));
+      a[t] = cadd(lo, hi);
+      b[t] = csub(lo, hi);
+    }
+    first_pass_both(smem2 + (2 * ll) * C9::LINE_PITCH, smem2 + (2 * ll + 1) * C9::LINE_PITCH, jj, __ldg(&job.tw[jj]), a, b);
+  }
+  __syncthreads();  // first passes of all lines and the twiddle tables are in place
+  fft_line<9, false, true, true>(S, T, j, line, v);
+
+  double spec[EPT], e_last = 0.0;  // spec[u + G t] = E_(2k + odd), k = j + 32 u + 64 t
+  if (odd) unpack_regs<9, true, true>(v, j, job.cs, spec, e_last);
+  else unpack_regs<9, true, false>(v, j, job.cs, spec, e_last);
+
+  if (job.mode == 2) {
+    // pressure_hat *= 1 / (lambda_x + lambda_y + lambda_z); mode (0,0,0) := 0 (src/PressureEquation.cpp:158-163)
+    const int ix = min(first_line + line, job.n_tile_lines - 1);
+    const double lam_xy = job.lam_x[ix] + job.lam_y[blockIdx.y];
+    const bool origin_line = job.has_origin && (first_line + line == 0) && (blockIdx.y == 0);
+#pragma unroll
+    for (int u = 0; u < L::G; u++)
+#pragma unroll
+      for (int t = 0; t < L::R; t++) {
+        const int k = 2 * (j + 32 * u + L::NS * t) + (odd ? 1 : 0);
+        spec[u + L::G * t] *= (origin_line && k == 0) ? 0.0 : 1.0 / (lam_xy + job.lam_z[k]);
+      }
+    e_last *= 1.0 / (lam_xy + job.lam_z[kFull]);
+    pair_sync(line);  // both warps are done with their regions
+#pragma unroll
+    for (int u = 0; u < L::G; u++)
+#pragma unroll
+      for (int t = 0; t < L::R; t++) Rl[2 * (j + 32 * u + L::NS * t) + (odd ? 1 : 0)] = spec[u + L::G * t];
+    if (!odd && j == 0) Rl[kFull] = e_last;
+    pair_sync(line);
+    {
+      const int jj = (odd ? 32 : 0) + j;
+      double2 *a = v, *b = v + 8;
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        const int q = jj + 64 * t;
+        const double2 lo = *reinterpret_cast<const double2 *>(Rl + 2 * q);
+        const double2 hi = make_double2(Rl[kFull - 2 * q], Rl[kFull - 1 - 2 * q]);
+        a[t] = cadd(lo, hi);
+        b[t] = csub(lo, hi);
+      }
+      pair_sync(line);  // the whole line has been read before the regions (which alias it) are overwritten
+      first_pass_both(smem2 + (2 * line) * C9::LINE_PITCH, smem2 + (2 * line + 1) * C9::LINE_PITCH, jj, __ldg(&job.tw[jj]), a, b);
+    }
+    pair_sync(line);
+    fft_line<9, false, true, true>(S, T, j, line, v);
+    if (odd) unpack_regs<9, true, true>(v, j, job.cs, spec, e_last);
+    else unpack_regs<9, true, false>(v, j, job.cs, spec, e_last);
+  }
+  const double scale = (job.mode == 0) ? 1.0 : job.inv_norm;
+
+  // gather the line as plain reals, then coalesced stores
+  pair_sync(line);
+#pragma unroll
+  for (int u = 0; u < L::G; u++)
+#pragma unroll
+    for (int t = 0; t < L::R; t++) Rl[2 * (j + 32 * u + L::NS * t) + (odd ? 1 : 0)] = spec[u + L::G * t] * scale;
+  if (!odd && j == 0) Rl[kFull] = e_last * scale;
+  if (CONTIG) {
+    pair_sync(line);
+    if (line < lines) {
+      double *out = base + (long long)line * job.lstride;
+      for (int e = (odd ? 32 : 0) + j; e < NPTS; e += 64) out[e] = Rl[e];
+    }
+  } else {
+    __syncthreads();
+    const int l = tid % LINES, q0 = tid / LINES;
+    if (l < lines) {
+      const double *srcl = reinterpret_cast<const double *>(smem2 + (2 * l) * C9::LINE_PITCH);
+      double *out = base + (long long)l * job.lstride;
+      if (job.store_map.n) {
+        for (int e = q0; e < NPTS; e += 64) *seg_address(job.store_map, e, blockIdx.y, first_line + l) = srcl[e];
+      } else {
+        for (int e = q0; e < NPTS; e += 64) out[(long long)e * job.estride] = srcl[e];
+      }
+    }
+  }
+}
+
+template <int LINES>
+void launch_split(cudaStream_t stream, const FastJob &job, bool contig, int outer, double *field) {
+  static bool attr_set = false;
+  const size_t smem = split::smem_bytes(LINES);
+  if (!attr_set) {
+    cudaFuncSetAttribute(warp_dct_split_kernel<true, LINES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(warp_dct_split_kernel<false, LINES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  const dim3 grid((job.n_tile_lines + LINES - 1) / LINES, outer, 1);
+  if (contig) warp_dct_split_kernel<true, LINES><<<grid, 64 * LINES, smem, stream>>>(job, field);
+  else warp_dct_split_kernel<false, LINES><<<grid, 64 * LINES, smem, stream>>>(job, field);
+}
+
 template <int LOGM>
 void launch_warp(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid, double *field) {
   using C = warpfft::Cfg<LOGM>;
@@ -703,6 +1044,7 @@ void host_fft_pow2(std::vector<double2> &z, bool inverse) {  // small recursive 
 struct PoissonPlan {
   DirPlanDev dir[3];
   int fast_logm[3];  // > 0: DCT-I with N - 1 = 2^fast_logm handled by fast_dct_kernel
+  int rfft_logm[3];  // > 0: periodic direction with n / 2 = 2^rfft_logm handled by warp_rfft_kernel
   int L[3];
   size_t smem[3];
   std::vector<void *> allocations;
@@ -791,6 +1133,8 @@ PoissonPlan *poisson_plan_create(const Geom &g, const int n_points[3], const int
     pl.inv_norm = 1.0 / ((double)(n_global[d] - 1) * (periodic[d] ? 1.0 : 2.0));
 
     plan->fast_logm[d] = (!periodic[d] && pow2 && pl.logP >= 6 && pl.logP <= 10) ? pl.logP : 0;
+    static const bool no_rfft = getenv("MIFGPU_NO_WARP_RFFT") != nullptr;  // A/B switch for profiling
+    plan->rfft_logm[d] = (periodic[d] && n % 2 == 0 && pow2 && (pl.logP == 8 || pl.logP == 9) && !no_rfft) ? pl.logP : 0;
     // lines per CTA: the largest power of two <= 8 that fits a ~100 KB shared-memory budget (two CTAs per SM)
     const size_t per_line = (size_t)P * sizeof(double2) + (size_t)(n | 1) * sizeof(double);
     int L = 8;
@@ -830,7 +1174,7 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
     cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
-  if (plan->fast_logm[d] > 0) {
+  if (plan->fast_logm[d] > 0 || plan->rfft_logm[d] > 0) {
     FastJob fj;
     fj.origin = lay.origin; fj.lstride = lay.lstride; fj.estride = lay.estride;
     fj.tile_stride = lay.tile_stride; fj.outer_stride = lay.outer_stride;
@@ -845,6 +1189,12 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
     fj.dt = lay.dt; fj.stride_y = lay.stride_y; fj.stride_z = lay.stride_z;
     const dim3 fgrid((lay.n_tile_lines + fast::kLines - 1) / fast::kLines, lay.outer, 1);
     static const bool use_cta_sync_variant = getenv("MIFGPU_FFT_CTA_SYNC") != nullptr;  // A/B switch for profiling
+    if (plan->rfft_logm[d] > 0) {
+      if (plan->rfft_logm[d] == 8) launch_rfft<8>(stream, fj, lay.contig, fgrid, field);
+      else launch_rfft<9>(stream, fj, lay.contig, fgrid, field);
+      ++*launches;
+      return;
+    }
     switch (plan->fast_logm[d]) {
       case 6: launch_fast<6>(stream, fj, lay.contig, fgrid, field); break;
       case 7: launch_fast<7>(stream, fj, lay.contig, fgrid, field); break;
@@ -856,10 +1206,18 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
         if (use_cta_sync_variant) launch_fast<9>(stream, fj, lay.contig, fgrid, field);
         else launch_warp<9>(stream, fj, lay.contig, fgrid, field);
         break;
-      default:
+      default: {
+        static const bool use_two_warp_variant = getenv("MIFGPU_FFT_NO_SPLIT") != nullptr;  // A/B switch for profiling
         if (use_cta_sync_variant) launch_fast<10>(stream, fj, lay.contig, fgrid, field);
-        else launch_warp<10>(stream, fj, lay.contig, fgrid, field);
+        else if (use_two_warp_variant || fj.div_u != nullptr) launch_warp<10>(stream, fj, lay.contig, fgrid, field);
+        else {
+          static const int lines_contig = getenv("MIFGPU_SPLIT_LINES_X") ? atoi(getenv("MIFGPU_SPLIT_LINES_X")) : 4;
+          static const int lines_strided = getenv("MIFGPU_SPLIT_LINES_YZ") ? atoi(getenv("MIFGPU_SPLIT_LINES_YZ")) : 4;
+          if ((lay.contig ? lines_contig : lines_strided) == 8) launch_split<8>(stream, fj, lay.contig, lay.outer, field);
+          else launch_split<4>(stream, fj, lay.contig, lay.outer, field);
+        }
         break;
+      }
     }
     ++*launches;
     return;

@@ -31,10 +31,14 @@ __global__ void __launch_bounds__(256, MIFGPU_STAGE_MIN_BLOCKS)
 stage_kernel(const Geom g, const double *__restrict__ in_u, const double *__restrict__ in_v,
              const double *__restrict__ in_w, const double *__restrict__ p, double *__restrict__ a_u,
              double *__restrict__ a_v, double *__restrict__ a_w, double *__restrict__ b_u, double *__restrict__ b_v,
-             double *__restrict__ b_w, int prefetch_planes) {
+             double *__restrict__ b_w, int prefetch_planes, int nk, int chunk_blocks_y) {
+  // blockIdx.z = y_chunk * nk + (k - 1): CTAs are scheduled x fastest, then y, then z, so the grid is walked one
+  // y chunk at a time, plane after plane.  The z neighbours of a plane are then still in L2 when they are needed
+  // even when a whole plane set (3 planes x 7 arrays) would not fit -- at 1025^2-point planes that set is 179 MB.
+  const int y_chunk = blockIdx.z / nk;
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
-  const int k = blockIdx.z + 1;
+  const int j = (y_chunk * chunk_blocks_y + blockIdx.y) * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z - y_chunk * nk + 1;
   // Each thread brings only 4-7 unique values in from HBM (everything else hits L1/L2), so the demand loads alone
   // keep too few bytes in flight to cover the HBM latency.  The plane above (first touched by this plane's CTAs,
   // which run in plane order) is therefore requested into L2 right away, one lane per 32-byte sector; measured on
@@ -601,22 +605,52 @@ divergence_kernel(const Geom g, const double *__restrict__ u, const double *__re
   rhs[c] = (du_dx + dv_dy + dw_dz) / dt;
 }
 
+// Two x-adjacent points per thread with 128-bit accesses (rows start on 128-byte boundaries and PX is even, so the
+// pair (i, i+1), i even, is 16-byte aligned in every array); arithmetic per point as in the reference.
 __global__ void __launch_bounds__(256)
 correct_kernel(const Geom g, double *__restrict__ u, double *__restrict__ v, double *__restrict__ w,
                double *__restrict__ p, const double *__restrict__ dp, double dt_s) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   const int k = blockIdx.z;
   if (i >= g.sx[0] || j >= g.sy[1]) return;
   const long long c = gidx(g, i, j, k);
-  const bool in_p = i < g.Nx && j < g.Ny && k < g.Nz;
-  const double d_c = in_p ? dp[c] : 0.0;
-  if (in_p) p[c] += d_c;  // src/Timestep.cpp:79-81 (all points, ghosts included)
-  const bool int_i_o = i >= 1 && i <= g.Nx - 2, int_j_o = j >= 1 && j <= g.Ny - 2, int_k_o = k >= 1 && k <= g.Nz - 2;
+  const double2 raw = *reinterpret_cast<const double2 *>(dp + c);
+  const bool in_jk = j < g.Ny && k < g.Nz;
+  const bool in_p0 = in_jk && i < g.Nx, in_p1 = in_jk && i + 1 < g.Nx;
+  const double d0 = in_p0 ? raw.x : 0.0, d1 = in_p1 ? raw.y : 0.0;
+  if (in_p0) {  // src/Timestep.cpp:79-81 (all points, ghosts included)
+    double2 pv = *reinterpret_cast<double2 *>(p + c);
+    pv.x += d0;
+    if (in_p1) pv.y += d1;
+    *reinterpret_cast<double2 *>(p + c) = pv;
+  }
+  const bool int_j_o = j >= 1 && j <= g.Ny - 2, int_k_o = k >= 1 && k <= g.Nz - 2;
+  const bool int_i_o0 = i >= 1 && i <= g.Nx - 2, int_i_o1 = i + 1 <= g.Nx - 2;
   // src/Timestep.cpp:66-72 (interior points of each component)
-  if (i >= 1 && i <= g.sx[0] - 2 && int_j_o && int_k_o) u[c] -= (d_c - dp[c - 1]) * g.one_over_dx * dt_s;
-  if (int_i_o && j >= 1 && j <= g.sy[1] - 2 && int_k_o) v[c] -= (d_c - dp[c - g.PX]) * g.one_over_dy * dt_s;
-  if (int_i_o && int_j_o && k >= 1 && k <= g.sz[2] - 2) w[c] -= (d_c - dp[c - g.plane]) * g.one_over_dz * dt_s;
+  if (int_j_o && int_k_o) {
+    const bool do0 = i >= 1 && i <= g.sx[0] - 2, do1 = i + 1 <= g.sx[0] - 2;
+    if (do0 || do1) {
+      double2 uv = *reinterpret_cast<double2 *>(u + c);
+      if (do0) uv.x -= (d0 - dp[c - 1]) * g.one_over_dx * dt_s;
+      if (do1) uv.y -= (d1 - raw.x) * g.one_over_dx * dt_s;
+      *reinterpret_cast<double2 *>(u + c) = uv;
+    }
+  }
+  if ((int_i_o0 || int_i_o1) && j >= 1 && j <= g.sy[1] - 2 && int_k_o) {
+    const double2 low = *reinterpret_cast<const double2 *>(dp + c - g.PX);
+    double2 vv = *reinterpret_cast<double2 *>(v + c);
+    if (int_i_o0) vv.x -= (d0 - low.x) * g.one_over_dy * dt_s;
+    if (int_i_o1) vv.y -= (d1 - low.y) * g.one_over_dy * dt_s;
+    *reinterpret_cast<double2 *>(v + c) = vv;
+  }
+  if ((int_i_o0 || int_i_o1) && int_j_o && k >= 1 && k <= g.sz[2] - 2) {
+    const double2 low = *reinterpret_cast<const double2 *>(dp + c - g.plane);
+    double2 wv = *reinterpret_cast<double2 *>(w + c);
+    if (int_i_o0) wv.x -= (d0 - low.x) * g.one_over_dz * dt_s;
+    if (int_i_o1) wv.y -= (d1 - low.y) * g.one_over_dz * dt_s;
+    *reinterpret_cast<double2 *>(w + c) = wv;
+  }
 }
 
 // rhs(face) +-= 2 g_n / h with g given as host-filled face tables (src/PressureEquation.cpp:10-56).
@@ -715,16 +749,28 @@ void launch_stage(cudaStream_t stream, const Geom &g, int stage, CVec3 in, const
     return;
   }
   const dim3 block(64, 4, 1);
-  const dim3 grid(cdiv(ni, block.x), cdiv(nj, block.y), nk);
+  // y chunks of about 2.2 MB per array and plane (the plane size of the 513^3 case, where one launch reads every
+  // input exactly once from HBM); MIFGPU_STAGE_CHUNK_MB overrides.
+  static const double chunk_mb = getenv("MIFGPU_STAGE_CHUNK_MB") ? atof(getenv("MIFGPU_STAGE_CHUNK_MB")) : 2.2;
+  const int blocks_y = (int)cdiv(nj, block.y);
+  int chunk_blocks_y = (int)(chunk_mb * 1e6 / ((double)g.PX * sizeof(double) * block.y));
+  chunk_blocks_y = max(1, min(chunk_blocks_y, blocks_y));
+  int n_chunks = (int)cdiv(blocks_y, chunk_blocks_y);
+  while ((long long)n_chunks * nk > 65535 && chunk_blocks_y < blocks_y) {  // gridDim.z limit
+    chunk_blocks_y *= 2;
+    n_chunks = (int)cdiv(blocks_y, chunk_blocks_y);
+  }
+  chunk_blocks_y = (int)cdiv(blocks_y, n_chunks);  // equal chunks
+  const dim3 grid(cdiv(ni, block.x), chunk_blocks_y, nk * n_chunks);
   if (stage == 1)
     stage_kernel<1><<<grid, block, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
-                                                b.c[1], b.c[2], prefetch_planes);
+                                                b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y);
   else if (stage == 2)
     stage_kernel<2><<<grid, block, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
-                                                b.c[1], b.c[2], prefetch_planes);
+                                                b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y);
   else
     stage_kernel<3><<<grid, block, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
-                                                b.c[1], b.c[2], prefetch_planes);
+                                                b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y);
   ++*launches;
 }
 
@@ -794,7 +840,7 @@ void launch_unpack_slab(cudaStream_t stream, const Geom &g, double *field, const
 void launch_correct(cudaStream_t stream, const Geom &g, Vec3 vel, double *pressure, const double *dp, double dt_s,
                     uint64_t *launches) {
   const dim3 block(64, 4, 1);
-  const dim3 grid(cdiv(g.sx[0], block.x), cdiv(g.sy[1], block.y), g.sz[2]);
+  const dim3 grid(cdiv(g.sx[0], 2 * block.x), cdiv(g.sy[1], block.y), g.sz[2]);
   correct_kernel<<<grid, block, 0, stream>>>(g, vel.c[0], vel.c[1], vel.c[2], pressure, dp, dt_s);
   ++*launches;
 }

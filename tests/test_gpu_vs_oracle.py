@@ -46,8 +46,16 @@ GRIDS = [
     ((513, 4, 9), (False, False, False)),      # M = 512
     ((9, 513, 3), (False, False, False)),
     ((11, 3, 513), (False, False, False)),
-    ((1025, 3, 4), (False, False, False)),     # M = 1024 (two warps per line)
+    ((1025, 3, 4), (False, False, False)),     # M = 1024 (split into two 512-point halves, one warp each)
     ((10, 4, 1025), (False, False, False)),
+    ((9, 1025, 3), (False, False, False)),
+    ((20, 9, 513), (False, False, True)),      # periodic z, n = 512: warp real-FFT path (M = 256), fused z sweep
+    ((513, 5, 6), (True, False, False)),       # ... periodic x: R2HC / HC2R as separate x sweeps
+    ((6, 513, 5), (False, True, False)),       # ... periodic y
+    ((5, 4, 1025), (False, False, True)),      # n = 1024 (M = 512)
+    ((1025, 4, 5), (True, False, False)),
+    ((4, 1025, 5), (False, True, False)),
+    ((513, 513, 5), (True, True, False)),      # two periodic directions, full tiles
 ]
 
 
