@@ -350,12 +350,45 @@ struct FastJob {
   const double *lam_x, *lam_y, *lam_z;
   double inv_norm;
   bool has_origin;  // the tile at (blockIdx.x, blockIdx.y) = (0, 0) contains the (0,0,0) mode
+  int prefetch_ctas;  // L2 prefetch distance in CTAs of the launch order (0 = off), see prefetch_next_tile
   // Forward x sweep fused with the right-hand side (src/PressureEquation.cpp:59-61): when div_u != nullptr the
   // input line is not read from `field` but computed as div(u, v, w) / dt from the velocity (same linear index).
   const double *div_u, *div_v, *div_w;
   double one_over_dx, one_over_dy, one_over_dz, dt;
   long long stride_y, stride_z;
 };
+
+// Optional L2 prefetch (MIFGPU_SWEEP_PREFETCH=<CTAs>, off by default) of the tile that the CTA `job.prefetch_ctas`
+// positions further down the launch order will load (CTAs start in linear order, so with prefetch_ctas = resident
+// CTAs per GPU that tile is needed roughly when this CTA retires).  Motivation: each warp of the sweep kernels is a
+// serial load -> transform -> store chain and only 16 warps fit an SM, so about a fifth of the issue slots are lost
+// waiting for the first loads of a line (stall_long_sb in the ncu source view).  One request per 32-byte sector.
+// Measured: a net loss, see launch_sweep.
+__device__ __forceinline__ void prefetch_l2_sector(const double *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+template <bool CONTIG, int LINES, int THREADS>
+__device__ __forceinline__ void prefetch_next_tile(const FastJob &job, const double *field, int npts) {
+  if (job.prefetch_ctas <= 0 || job.load_map.n != 0 || job.div_u != nullptr) return;
+  const long long id = (long long)blockIdx.x + (long long)gridDim.x * blockIdx.y + job.prefetch_ctas;
+  const int by = (int)(id / gridDim.x), bx = (int)(id - (long long)by * gridDim.x);
+  if (by >= (int)gridDim.y) return;
+  const int first_line = bx * LINES;
+  const int lines = min(LINES, job.n_tile_lines - first_line);
+  const double *base = field + job.origin + (long long)first_line * job.tile_stride + (long long)by * job.outer_stride;
+  if (CONTIG) {
+    const int per_line = (npts + 3) / 4;  // sectors per line
+    for (int idx = threadIdx.x; idx < lines * per_line; idx += THREADS) {
+      const int l = idx / per_line, t = idx - l * per_line;
+      prefetch_l2_sector(base + (long long)l * job.lstride + 4 * t);
+    }
+  } else {
+    const int per_row = (lines + 3) / 4;  // sectors per row of `lines` consecutive x
+    for (int idx = threadIdx.x; idx < npts * per_row; idx += THREADS) {
+      const int e = idx / per_row, t = idx - e * per_row;
+      prefetch_l2_sector(base + (long long)e * job.estride + 4 * t);
+    }
+  }
+}
 
 template <int LOGM, bool CONTIG>
 __global__ void __launch_bounds__(1 << LOGM, (LOGM <= 9 ? 2 : 1)) fast_dct_kernel(const FastJob job, double *__restrict__ field) {
@@ -479,6 +512,7 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
   double *base = field + job.origin + (long long)first_line * job.tile_stride + (long long)blockIdx.y * job.outer_stride;
   double2 v[EPT];
 
+  prefetch_next_tile<CONTIG, kLines, C::THREADS>(job, field, NPTS);
   load_twiddles<LOGM>(T, job.tw);
   if (CONTIG) {
     // x sweep: lane j loads its first-pass inputs c[j + s*TL] = (e[2q], e[2q+1]) straight from global memory;
@@ -674,6 +708,7 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, 2) warp_rfft_kern
   double *base = field + job.origin + (long long)first_line * job.tile_stride + (long long)blockIdx.y * job.outer_stride;
   double2 v[EPT];
 
+  prefetch_next_tile<CONTIG, kLines, C::THREADS>(job, field, n);
   load_twiddles<LOGM>(T, job.tw);
   // loader thread: (line, j) along the line for x sweeps, line-fastest (l, b) for the strided sweeps
   const int ll = CONTIG ? line : (tid & 7), lb = CONTIG ? j : (tid >> 3);
@@ -877,6 +912,7 @@ __global__ void __launch_bounds__(64 * LINES, 8 / LINES) warp_dct_split_kernel(c
   double *base = field + job.origin + (long long)first_line * job.tile_stride + (long long)blockIdx.y * job.outer_stride;
   double2 v[EPT];
 
+  prefetch_next_tile<CONTIG, LINES, kThreads>(job, field, NPTS);
   load_twiddles<9, 2, kThreads>(T, job.tw);
   {
     // loader thread: butterfly jj of line ll
@@ -1183,6 +1219,11 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
     fj.lam_x = plan->dir[0].lambda; fj.lam_y = plan->dir[1].lambda + lay.lam_y_offset; fj.lam_z = plan->dir[2].lambda;
     fj.inv_norm = plan->dir[d].inv_norm;
     fj.has_origin = lay.has_origin;
+    // Off by default: measured on B200 at 513^3 with distances 148 / 296 / 592 the sweeps got 2-7 % SLOWER (x 1.76 ->
+    // 1.80 ms, y 2.72 -> 2.93 ms, fused z 5.40 -> 5.79 ms per step) -- the extra LSU requests cost more in these
+    // LSU-bound kernels than the shorter first-load wait gains.
+    static const int prefetch_ctas = getenv("MIFGPU_SWEEP_PREFETCH") ? atoi(getenv("MIFGPU_SWEEP_PREFETCH")) : 0;
+    fj.prefetch_ctas = prefetch_ctas;
     fj.load_map = lay.load_map; fj.store_map = lay.store_map;
     fj.div_u = lay.div_u; fj.div_v = lay.div_v; fj.div_w = lay.div_w;
     fj.one_over_dx = lay.one_over_dx; fj.one_over_dy = lay.one_over_dy; fj.one_over_dz = lay.one_over_dz;

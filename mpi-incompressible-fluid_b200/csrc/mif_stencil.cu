@@ -172,6 +172,172 @@ stage_kernel(const Geom g, const double *__restrict__ in_u, const double *__rest
 
 
 // ------------------------------------------------------------------------------------------------
+// RK stage kernel, two x-adjacent points per thread.  The pair (i, i+1), i even, is 16-byte aligned in every array
+// (rows start on 128-byte boundaries), so the 31 values per point of stage_kernel become 20 128-bit loads plus 11
+// scalar loads (the x-1 / x+2 ends of the rows) per PAIR: half the load instructions and about 70% of the L1
+// wavefronts per point of the one-point kernel, which is bound by exactly those.  Arithmetic per point is identical.
+// ------------------------------------------------------------------------------------------------
+struct StageCoef {
+  double a1, a2, a3, b;
+};
+
+template <int STAGE>
+__device__ __forceinline__ void rk_combine(double c_val, double rhs, double p_grad, double a_old, const StageCoef &k,
+                                           double &a_new, double &b_new) {
+  if (STAGE == 1) {
+    a_new = c_val + k.a1 * rhs - k.b * p_grad;  // src/Timestep.cpp:18
+    b_new = rhs;                                // src/Timestep.cpp:19
+  } else if (STAGE == 2) {
+    const double rhs_1 = a_old;
+    const double rhs_2_scaled = k.a2 * rhs;
+    a_new = c_val + k.a1 * rhs_1 + rhs_2_scaled - k.b * p_grad;  // src/Timestep.cpp:35-36
+    b_new = rhs_2_scaled;                                        // src/Timestep.cpp:37
+  } else {
+    const double rhs_2_scaled = -a_old;
+    a_new = c_val + rhs_2_scaled + k.a3 * rhs - k.b * p_grad;  // src/Timestep.cpp:51-52
+    b_new = 0.0;
+  }
+}
+
+// Loads / stores of one component's pair: 128-bit when both points are written, scalar otherwise (the other point is
+// a boundary value that must stay untouched).
+__device__ __forceinline__ double2 load_pair_if(const double *ptr, bool any) {
+  return any ? *reinterpret_cast<const double2 *>(ptr) : make_double2(0.0, 0.0);
+}
+__device__ __forceinline__ void store_pair(double *ptr, bool w0, bool w1, double v0, double v1) {
+  if (w0 && w1) *reinterpret_cast<double2 *>(ptr) = make_double2(v0, v1);
+  else if (w0) ptr[0] = v0;
+  else if (w1) ptr[1] = v1;
+}
+
+template <int STAGE>
+__global__ void __launch_bounds__(128, 4)
+stage_kernel_pair(const Geom g, const double *__restrict__ in_u, const double *__restrict__ in_v,
+                  const double *__restrict__ in_w, const double *__restrict__ p, double *__restrict__ a_u,
+                  double *__restrict__ a_v, double *__restrict__ a_w, double *__restrict__ b_u, double *__restrict__ b_v,
+                  double *__restrict__ b_w, int prefetch_planes, int nk, int chunk_blocks_y) {
+  const int y_chunk = blockIdx.z / nk;  // see stage_kernel
+  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int j = (y_chunk * chunk_blocks_y + blockIdx.y) * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z - y_chunk * nk + 1;
+  if (prefetch_planes > 0 && (threadIdx.x & 1) == 0 && k + prefetch_planes < g.PZ && i < g.PX && j < g.PY) {
+    const long long ahead = gidx(g, i, j, k + prefetch_planes);
+    prefetch_l2(in_u + ahead);
+    prefetch_l2(in_v + ahead);
+    prefetch_l2(in_w + ahead);
+    prefetch_l2(p + ahead);
+    if (STAGE >= 2) {
+      prefetch_l2(a_u + ahead);
+      prefetch_l2(a_v + ahead);
+      prefetch_l2(a_w + ahead);
+    }
+  }
+  if (i > max(g.sx[0], g.Nx) - 2) return;
+  const bool in_j_v = j <= g.sy[1] - 2, in_j_o = j <= g.Ny - 2;
+  if (!in_j_v && !in_j_o) return;
+  const bool in_k_w = k <= g.sz[2] - 2, in_k_o = k <= g.Nz - 2;
+  bool do_u[2], do_v[2], do_w[2];
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    const int ii = i + e;
+    const bool in_i_u = ii >= 1 && ii <= g.sx[0] - 2, in_i_o = ii >= 1 && ii <= g.Nx - 2;
+    do_u[e] = in_i_u && in_j_o && in_k_o;
+    do_v[e] = in_i_o && in_j_v && in_k_o;
+    do_w[e] = in_i_o && in_j_o && in_k_w;
+  }
+  if (!(do_u[0] || do_u[1] || do_v[0] || do_v[1] || do_w[0] || do_w[1])) return;
+
+  const long long c = gidx(g, i, j, k);
+  const long long sj = g.PX, sk = g.plane;
+  const bool has_left = i >= 2, has_right = i + 2 < g.PX;
+  auto pair = [](const double *ptr) { return *reinterpret_cast<const double2 *>(ptr); };
+
+  // rows of u, v, w, p (pairs) and the row ends one to the left / two to the right
+  const double2 U_c = pair(in_u + c), U_ym = pair(in_u + c - sj), U_yp = pair(in_u + c + sj);
+  const double2 U_zm = pair(in_u + c - sk), U_zp = pair(in_u + c + sk);
+  const double u_l = has_left ? in_u[c - 1] : 0.0, u_r = has_right ? in_u[c + 2] : 0.0;
+  const double u_r_ym = has_right ? in_u[c + 2 - sj] : 0.0, u_r_zm = has_right ? in_u[c + 2 - sk] : 0.0;
+  const double2 V_c = pair(in_v + c), V_ym = pair(in_v + c - sj), V_yp = pair(in_v + c + sj);
+  const double2 V_zm = pair(in_v + c - sk), V_zp = pair(in_v + c + sk), V_yp_zm = pair(in_v + c + sj - sk);
+  const double v_l = has_left ? in_v[c - 1] : 0.0, v_r = has_right ? in_v[c + 2] : 0.0;
+  const double v_l_yp = has_left ? in_v[c - 1 + sj] : 0.0;
+  const double2 W_c = pair(in_w + c), W_ym = pair(in_w + c - sj), W_yp = pair(in_w + c + sj);
+  const double2 W_zm = pair(in_w + c - sk), W_zp = pair(in_w + c + sk), W_ym_zp = pair(in_w + c - sj + sk);
+  const double w_l = has_left ? in_w[c - 1] : 0.0, w_r = has_right ? in_w[c + 2] : 0.0;
+  const double w_l_zp = has_left ? in_w[c - 1 + sk] : 0.0;
+  const double2 P_c = pair(p + c), P_ym = pair(p + c - sj), P_zm = pair(p + c - sk);
+  const double p_l = has_left ? p[c - 1] : 0.0;
+
+  const double dt = g.dt;
+  StageCoef coef;
+  if (STAGE == 1) {
+    coef.a1 = 64.0 / 120.0 * dt; coef.a2 = 0.0; coef.a3 = 0.0; coef.b = coef.a1;
+  } else if (STAGE == 2) {
+    coef.a1 = -34.0 / 120.0 * dt; coef.a2 = 50.0 / 120.0 * dt; coef.a3 = 0.0; coef.b = coef.a1 + coef.a2;
+  } else {
+    coef.a1 = 0.0; coef.a2 = -50.0 / 120.0 * dt; coef.a3 = 90.0 / 120.0 * dt; coef.b = coef.a2 + coef.a3;
+  }
+
+  const double2 A_u = (STAGE >= 2) ? load_pair_if(a_u + c, do_u[0] || do_u[1]) : make_double2(0.0, 0.0);
+  const double2 A_v = (STAGE >= 2) ? load_pair_if(a_v + c, do_v[0] || do_v[1]) : make_double2(0.0, 0.0);
+  const double2 A_w = (STAGE >= 2) ? load_pair_if(a_w + c, do_w[0] || do_w[1]) : make_double2(0.0, 0.0);
+  double na_u[2], nb_u[2], na_v[2], nb_v[2], na_w[2], nb_w[2];
+
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    // neighbourhood of point i + e (names as in stage_kernel)
+    const double u_c = e ? U_c.y : U_c.x, u_xm = e ? U_c.x : u_l, u_xp = e ? u_r : U_c.y;
+    const double u_ym = e ? U_ym.y : U_ym.x, u_yp = e ? U_yp.y : U_yp.x, u_zm = e ? U_zm.y : U_zm.x, u_zp = e ? U_zp.y : U_zp.x;
+    const double u_xp_ym = e ? u_r_ym : U_ym.y, u_xp_zm = e ? u_r_zm : U_zm.y;
+    const double v_c = e ? V_c.y : V_c.x, v_xm = e ? V_c.x : v_l, v_xp = e ? v_r : V_c.y;
+    const double v_ym = e ? V_ym.y : V_ym.x, v_yp = e ? V_yp.y : V_yp.x, v_zm = e ? V_zm.y : V_zm.x, v_zp = e ? V_zp.y : V_zp.x;
+    const double v_xm_yp = e ? V_yp.x : v_l_yp, v_yp_zm = e ? V_yp_zm.y : V_yp_zm.x;
+    const double w_c = e ? W_c.y : W_c.x, w_xm = e ? W_c.x : w_l, w_xp = e ? w_r : W_c.y;
+    const double w_ym = e ? W_ym.y : W_ym.x, w_yp = e ? W_yp.y : W_yp.x, w_zm = e ? W_zm.y : W_zm.x, w_zp = e ? W_zp.y : W_zp.x;
+    const double w_xm_zp = e ? W_zp.x : w_l_zp, w_ym_zp = e ? W_ym_zp.y : W_ym_zp.x;
+    const double p_c = e ? P_c.y : P_c.x, p_xm = e ? P_c.x : p_l, p_ym = e ? P_ym.y : P_ym.x, p_zm = e ? P_zm.y : P_zm.x;
+    {
+      // include/MomentumEquation.h:50-96
+      const double convection = -u_c * (u_xp - u_xm) * g.one_over_2_dx -
+                                (v_yp + v_c + v_xm_yp + v_xm) * (u_yp - u_ym) * g.one_over_8_dy -
+                                (w_zp + w_c + w_xm_zp + w_xm) * (u_zp - u_zm) * g.one_over_8_dz;
+      const double diffusion = (u_xp - 2 * u_c + u_xm) * g.one_over_dx2_Re + (u_yp - 2 * u_c + u_ym) * g.one_over_dy2_Re +
+                               (u_zp - 2 * u_c + u_zm) * g.one_over_dz2_Re;
+      const double p_grad = (p_c - p_xm) * g.one_over_dx;  // include/PressureGradient.h:9-12
+      rk_combine<STAGE>(u_c, convection + diffusion, p_grad, e ? A_u.y : A_u.x, coef, na_u[e], nb_u[e]);
+    }
+    {
+      // include/MomentumEquation.h:126-165
+      const double convection = -(u_xp + u_c + u_xp_ym + u_ym) * (v_xp - v_xm) * g.one_over_8_dx -
+                                v_c * (v_yp - v_ym) * g.one_over_2_dy -
+                                (w_zp + w_c + w_ym_zp + w_ym) * (v_zp - v_zm) * g.one_over_8_dz;
+      const double diffusion = (v_xp - 2 * v_c + v_xm) * g.one_over_dx2_Re + (v_yp - 2 * v_c + v_ym) * g.one_over_dy2_Re +
+                               (v_zp - 2 * v_c + v_zm) * g.one_over_dz2_Re;
+      const double p_grad = (p_c - p_ym) * g.one_over_dy;  // include/PressureGradient.h:15-18
+      rk_combine<STAGE>(v_c, convection + diffusion, p_grad, e ? A_v.y : A_v.x, coef, na_v[e], nb_v[e]);
+    }
+    {
+      // include/MomentumEquation.h:196-236
+      const double convection = -(u_xp + u_c + u_xp_zm + u_zm) * (w_xp - w_xm) * g.one_over_8_dx -
+                                (v_yp + v_c + v_yp_zm + v_zm) * (w_yp - w_ym) * g.one_over_8_dy -
+                                w_c * (w_zp - w_zm) * g.one_over_2_dz;
+      const double diffusion = (w_xp - 2 * w_c + w_xm) * g.one_over_dx2_Re + (w_yp - 2 * w_c + w_ym) * g.one_over_dy2_Re +
+                               (w_zp - 2 * w_c + w_zm) * g.one_over_dz2_Re;
+      const double p_grad = (p_c - p_zm) * g.one_over_dz;  // include/PressureGradient.h:21-24
+      rk_combine<STAGE>(w_c, convection + diffusion, p_grad, e ? A_w.y : A_w.x, coef, na_w[e], nb_w[e]);
+    }
+  }
+  store_pair(a_u + c, do_u[0], do_u[1], na_u[0], na_u[1]);
+  store_pair(a_v + c, do_v[0], do_v[1], na_v[0], na_v[1]);
+  store_pair(a_w + c, do_w[0], do_w[1], na_w[0], na_w[1]);
+  if (STAGE != 3) {
+    store_pair(b_u + c, do_u[0], do_u[1], nb_u[0], nb_u[1]);
+    store_pair(b_v + c, do_v[0], do_v[1], nb_v[0], nb_v[1]);
+    store_pair(b_w + c, do_w[0], do_w[1], nb_w[0], nb_w[1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // RK stage kernel, z-marching: a thread owns a column (i, j) and walks kz planes, keeping the z neighbours of its
 // own point (and the diagonal neighbours that are in-plane neighbours one plane earlier or later) in registers, so
 // a plane costs 20 loads per point instead of 31 -- the kernel is bound by load-issue / L1 wavefronts and latency,
@@ -761,6 +927,22 @@ void launch_stage(cudaStream_t stream, const Geom &g, int stage, CVec3 in, const
     n_chunks = (int)cdiv(blocks_y, chunk_blocks_y);
   }
   chunk_blocks_y = (int)cdiv(blocks_y, n_chunks);  // equal chunks
+  static const bool one_point = getenv("MIFGPU_STAGE_ONE_POINT") != nullptr;  // A/B switch for profiling
+  if (!one_point) {
+    const dim3 pblock(32, 4, 1);  // 64 x-points by 4 rows per CTA, as below
+    const dim3 pgrid(cdiv(ni + 1, 2 * pblock.x), chunk_blocks_y, nk * n_chunks);
+    if (stage == 1)
+      stage_kernel_pair<1><<<pgrid, pblock, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
+                                                         b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y);
+    else if (stage == 2)
+      stage_kernel_pair<2><<<pgrid, pblock, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
+                                                         b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y);
+    else
+      stage_kernel_pair<3><<<pgrid, pblock, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
+                                                         b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y);
+    ++*launches;
+    return;
+  }
   const dim3 grid(cdiv(ni, block.x), chunk_blocks_y, nk * n_chunks);
   if (stage == 1)
     stage_kernel<1><<<grid, block, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],

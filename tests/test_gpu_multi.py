@@ -18,7 +18,7 @@ def device_count():
 
 
 @pytest.mark.parametrize("case", ["full_16_2", "full_17_1", "lid1_12x10x14_2", "full_65x17x9_1", "full_6x65x9_1",
-                                  "es:9x257x257", "es:7x513x257"])
+                                  "es:9x257x257", "es:7x513x257", "es:5x1025x1025"])
 @pytest.mark.parametrize("world", [2, 4])
 def test_slab_decomposition_matches_single_rank_reference(case, world):
     if device_count() < world:
