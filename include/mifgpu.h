@@ -154,6 +154,24 @@ int mifgpu_apply_bc(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], const mif
 int mifgpu_solve_pressure(mifgpu_ctx *ctx, mifgpu_tensor *pressure, mifgpu_tensor *const velocity[3], double dt,
                           const mifgpu_bc *nhn_bc, double nhn_time);
 
+/* ---- diagnostics ------------------------------------------------------------------------------------ */
+
+/* ErrorL1Norm / ErrorL2Norm / ErrorLInfNorm of the velocity (src/Norms.cpp:11-86) and of a scalar tensor
+ * (src/Norms.cpp:88-118) against an analytic family evaluated on the device -- `exact->kind` is one of the
+ * device-evaluated kinds; its pressure is p_exact of generators/manufsol.py:58-72 for Ethier-Steinman and 0 for
+ * the two lid-driven test cases.  norms[] = {L1, L2, LInf} of THIS rank's part of the domain, exactly what the
+ * reference's functions return before accumulate_error_mpi_* (src/Norms.cpp:122-162) combines the ranks.  Only
+ * a few kB of per-CTA partial sums cross PCIe instead of four whole fields.  MIFGPU_ERR_UNSUPPORTED for
+ * MIFGPU_BC_HOST_CALLBACK (arbitrary std::functions: download the tensors, use the host layer's norms). */
+int mifgpu_velocity_error_norms(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], const mifgpu_bc *exact, double time,
+                                double norms[3]);
+int mifgpu_pressure_error_norms(mifgpu_ctx *ctx, const mifgpu_tensor *pressure, const mifgpu_bc *exact, double time,
+                                double norms[3]);
+/* mif::adjust_pressure (include/PressureEquation.h:25-26, src/PressureEquation.cpp:288-343): adds the mean of
+ * (exact - pressure) over all owner points of all ranks to every point of the tensor, ghosts included.
+ * Collective over the ranks of a distributed context. */
+int mifgpu_adjust_pressure(mifgpu_ctx *ctx, mifgpu_tensor *pressure, const mifgpu_bc *exact, double time);
+
 /* Blocks until all work queued by this context has finished (cudaStreamSynchronize). */
 int mifgpu_synchronize(mifgpu_ctx *ctx);
 

@@ -30,7 +30,8 @@ EXPORTED_SYMBOLS = [
     "mifgpu_tensor_create", "mifgpu_tensor_destroy", "mifgpu_tensor_upload", "mifgpu_tensor_download",
     "mifgpu_tensor_swap", "mifgpu_timestep", "mifgpu_apply_bc", "mifgpu_solve_pressure", "mifgpu_synchronize",
     "mifgpu_stream", "mifgpu_launch_count", "mifgpu_profile_enable", "mifgpu_profile_read", "mifgpu_comm_unique_id",
-    "mifgpu_create_distributed", "mifgpu_slab_plan",
+    "mifgpu_create_distributed", "mifgpu_slab_plan", "mifgpu_velocity_error_norms", "mifgpu_pressure_error_norms",
+    "mifgpu_adjust_pressure",
 ]
 
 
@@ -101,6 +102,9 @@ def lib() -> ctypes.CDLL:
     l.mifgpu_apply_bc.argtypes = [c_void_p, POINTER(c_void_p), POINTER(Bc), c_double]
     l.mifgpu_solve_pressure.argtypes = [c_void_p, c_void_p, POINTER(c_void_p), c_double, POINTER(Bc), c_double]
     l.mifgpu_synchronize.argtypes = [c_void_p]
+    l.mifgpu_velocity_error_norms.argtypes = [c_void_p, POINTER(c_void_p), POINTER(Bc), c_double, POINTER(c_double)]
+    l.mifgpu_pressure_error_norms.argtypes = [c_void_p, c_void_p, POINTER(Bc), c_double, POINTER(c_double)]
+    l.mifgpu_adjust_pressure.argtypes = [c_void_p, c_void_p, POINTER(Bc), c_double]
     l.mifgpu_stream.argtypes = [c_void_p]
     l.mifgpu_stream.restype = c_void_p
     l.mifgpu_launch_count.argtypes = [c_void_p]
@@ -231,6 +235,21 @@ class Context:
                        nhn_time: float = 0.0) -> None:
         bc_ptr = ctypes.byref(nhn_bc) if nhn_bc is not None else None
         _check(lib().mifgpu_solve_pressure(self.handle, pressure.handle, self._triple(vel), dt, bc_ptr, nhn_time))
+
+    def velocity_error_norms(self, vel, exact: Bc, time: float):
+        """(L1, L2, LInf) of src/Norms.cpp:49-86 for this rank, computed on the device."""
+        out = (c_double * 3)()
+        _check(lib().mifgpu_velocity_error_norms(self.handle, self._triple(vel), ctypes.byref(exact), time, out))
+        return float(out[0]), float(out[1]), float(out[2])
+
+    def pressure_error_norms(self, pressure: Tensor, exact: Bc, time: float):
+        """(L1, L2, LInf) of src/Norms.cpp:103-118 for this rank, computed on the device."""
+        out = (c_double * 3)()
+        _check(lib().mifgpu_pressure_error_norms(self.handle, pressure.handle, ctypes.byref(exact), time, out))
+        return float(out[0]), float(out[1]), float(out[2])
+
+    def adjust_pressure(self, pressure: Tensor, exact: Bc, time: float) -> None:
+        _check(lib().mifgpu_adjust_pressure(self.handle, pressure.handle, ctypes.byref(exact), time))
 
     def synchronize(self) -> None:
         _check(lib().mifgpu_synchronize(self.handle))

@@ -4,6 +4,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -827,6 +828,101 @@ int mifgpu_timestep(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], mifgpu_te
     launch_correct(s, g, vec3(velocity), pressure->data, pressure_buffer->data, dt_3, &ctx->launches);
   }
   if ((rc = exchange_z(ctx, velocity, 3))) return rc;  // src/Timestep.cpp:68-75
+  return check_launch(ctx);
+}
+
+// ---- diagnostics on the device -----------------------------------------------------------------------------------
+static int analytic_family(const mifgpu_bc *exact, double time, BcDev &dev) {
+  if (!exact) return fail(MIFGPU_ERR_INVALID, "NULL analytic family");
+  if (exact->kind != MIFGPU_BC_TEST_CASE_1 && exact->kind != MIFGPU_BC_TEST_CASE_2 && exact->kind != MIFGPU_BC_ETHIER_STEINMAN)
+    return fail(MIFGPU_ERR_UNSUPPORTED, "device-side diagnostics need an analytic family evaluated on the device (kind %d given); "
+                "download the tensors and use the host-side norms for arbitrary functions", exact->kind);
+  std::memset(&dev, 0, sizeof(dev));
+  dev.kind = exact->kind;
+  dev.time = time;
+  dev.Re = exact->Re;
+  return MIFGPU_OK;
+}
+
+// Runs one of the error kernels and adds the per-CTA partial results up in CTA order: sums[0..3].
+static int run_error_kernel(mifgpu_ctx *ctx, bool velocity, CVec3 vel, const double *p, const BcDev &dev, double sums[4]) {
+  sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
+  const int blocks = diag_blocks(ctx->g, velocity);
+  if (blocks == 0) return MIFGPU_OK;
+  double *partial = nullptr;
+  CUDA_TRY(cudaMalloc(&partial, sizeof(double) * 4 * blocks));
+  if (velocity) launch_velocity_error(ctx->stream, ctx->g, vel, dev, partial, &ctx->launches);
+  else launch_pressure_error(ctx->stream, ctx->g, p, dev, partial, &ctx->launches);
+  std::vector<double> host(4 * (size_t)blocks);
+  cudaError_t err = cudaMemcpyAsync(host.data(), partial, sizeof(double) * host.size(), cudaMemcpyDeviceToHost, ctx->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+  cudaFree(partial);
+  if (err != cudaSuccess) return fail(MIFGPU_ERR_CUDA, "error kernel failed: %s", cudaGetErrorString(err));
+  for (int b = 0; b < blocks; b++) {
+    sums[0] += host[4 * b];
+    sums[1] += host[4 * b + 1];
+    sums[2] = std::max(sums[2], host[4 * b + 2]);
+    sums[3] += host[4 * b + 3];
+  }
+  return MIFGPU_OK;
+}
+
+int mifgpu_velocity_error_norms(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], const mifgpu_bc *exact, double time,
+                                double norms[3]) {
+  if (!ctx || !norms) return fail(MIFGPU_ERR_INVALID, "NULL argument");
+  int rc = check_triple(ctx, velocity, "velocity");
+  if (rc) return rc;
+  BcDev dev;
+  if ((rc = analytic_family(exact, time, dev))) return rc;
+  CUDA_TRY(cudaSetDevice(ctx->params.device));
+  double sums[4];
+  if ((rc = run_error_kernel(ctx, true, cvec3(velocity), nullptr, dev, sums))) return rc;
+  const double cell = ctx->g.dx * ctx->g.dy * ctx->g.dz;
+  norms[0] = sums[0] * cell;             // src/Norms.cpp:49-62
+  norms[1] = std::sqrt(sums[1] * cell);  // src/Norms.cpp:64-76
+  norms[2] = sums[2];                    // src/Norms.cpp:78-86
+  return MIFGPU_OK;
+}
+
+int mifgpu_pressure_error_norms(mifgpu_ctx *ctx, const mifgpu_tensor *pressure, const mifgpu_bc *exact, double time,
+                                double norms[3]) {
+  if (!ctx || !norms) return fail(MIFGPU_ERR_INVALID, "NULL argument");
+  int rc = check_scalar(ctx, pressure, "pressure");
+  if (rc) return rc;
+  BcDev dev;
+  if ((rc = analytic_family(exact, time, dev))) return rc;
+  CUDA_TRY(cudaSetDevice(ctx->params.device));
+  double sums[4];
+  if ((rc = run_error_kernel(ctx, false, CVec3{}, pressure->data, dev, sums))) return rc;
+  const double cell = ctx->g.dx * ctx->g.dy * ctx->g.dz;
+  norms[0] = sums[0] * cell;             // src/Norms.cpp:103-107
+  norms[1] = std::sqrt(sums[1] * cell);  // src/Norms.cpp:109-113
+  norms[2] = sums[2];                    // src/Norms.cpp:115-118
+  return MIFGPU_OK;
+}
+
+int mifgpu_adjust_pressure(mifgpu_ctx *ctx, mifgpu_tensor *pressure, const mifgpu_bc *exact, double time) {
+  if (!ctx) return fail(MIFGPU_ERR_INVALID, "NULL argument");
+  int rc = check_scalar(ctx, pressure, "pressure");
+  if (rc) return rc;
+  BcDev dev;
+  if ((rc = analytic_family(exact, time, dev))) return rc;
+  CUDA_TRY(cudaSetDevice(ctx->params.device));
+  double sums[4];
+  if ((rc = run_error_kernel(ctx, false, CVec3{}, pressure->data, dev, sums))) return rc;
+  double difference = sums[3];
+  if (ctx->nranks > 1) {
+    // the rank-0 gather and broadcast of src/PressureEquation.cpp:298-333 as one all-reduce
+    double *word = nullptr;
+    CUDA_TRY(cudaMalloc(&word, sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(word, &difference, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_TRY(g_nccl.AllReduce(word, word, 1, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(&difference, word, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaFree(word);
+  }
+  difference /= (double)ctx->n_points[0] * (double)ctx->n_points[1] * (double)ctx->n_points[2];  // :316-319
+  launch_add_constant(ctx->stream, ctx->g, pressure->data, difference, &ctx->launches);
   return check_launch(ctx);
 }
 

@@ -37,6 +37,16 @@ void launch_nhn_rhs(cudaStream_t stream, const Geom &g, double *rhs, const BcDev
 void launch_correct(cudaStream_t stream, const Geom &g, Vec3 vel, double *pressure, const double *dp, double dt_s,
                     uint64_t *launches);
 
+// Diagnostics (src/Norms.cpp:11-118, src/PressureEquation.cpp:288-343) against an analytic family evaluated on the
+// device.  `partial` receives 4 doubles per CTA (diag_blocks CTAs): velocity {sum |e|, sum |e|^2, max, 0}, pressure
+// {sum |e|, sum e^2, max |e|, sum e} with e = exact - field; the host adds them up in CTA order.
+int diag_blocks(const Geom &g, bool velocity);
+void launch_velocity_error(cudaStream_t stream, const Geom &g, CVec3 vel, const BcDev &bc, double *partial,
+                           uint64_t *launches);
+void launch_pressure_error(cudaStream_t stream, const Geom &g, const double *p, const BcDev &bc, double *partial,
+                           uint64_t *launches);
+void launch_add_constant(cudaStream_t stream, const Geom &g, double *p, double difference, uint64_t *launches);
+
 // ---- mif_poisson.cu ------------------------------------------------------------------------------
 
 struct PoissonPlan;  // transform tables + eigenvalues for one context

@@ -358,7 +358,7 @@ struct FastJob {
   long long stride_y, stride_z;
 };
 
-// Optional L2 prefetch (MIFGPU_SWEEP_PREFETCH=<CTAs>, off by default) of the tile that the CTA `job.prefetch_ctas`
+// Optional L2 prefetch (build with -DMIFGPU_SWEEP_PREFETCH_CTAS=296; MIFGPU_SWEEP_PREFETCH=<CTAs> then tunes it) of the tile that the CTA `job.prefetch_ctas`
 // positions further down the launch order will load (CTAs start in linear order, so with prefetch_ctas = resident
 // CTAs per GPU that tile is needed roughly when this CTA retires).  Motivation: each warp of the sweep kernels is a
 // serial load -> transform -> store chain and only 16 warps fit an SM, so about a fifth of the issue slots are lost
@@ -366,8 +366,12 @@ struct FastJob {
 // Measured: a net loss, see launch_sweep.
 __device__ __forceinline__ void prefetch_l2_sector(const double *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
+#ifndef MIFGPU_SWEEP_PREFETCH_CTAS
+#define MIFGPU_SWEEP_PREFETCH_CTAS 0  // compile-time switch: even a disabled run-time branch costs the x sweep a spill
+#endif
 template <bool CONTIG, int LINES, int THREADS>
 __device__ __forceinline__ void prefetch_next_tile(const FastJob &job, const double *field, int npts) {
+  if (MIFGPU_SWEEP_PREFETCH_CTAS == 0) return;
   if (job.prefetch_ctas <= 0 || job.load_map.n != 0 || job.div_u != nullptr) return;
   const long long id = (long long)blockIdx.x + (long long)gridDim.x * blockIdx.y + job.prefetch_ctas;
   const int by = (int)(id / gridDim.x), bx = (int)(id - (long long)by * gridDim.x);
@@ -494,7 +498,9 @@ void launch_fast(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid
 // ------------------------------------------------------------------------------------------------
 // Warp-per-line path: DCT-I sweeps with M = 2^LOGM, 256 <= M <= 1024 (see mif_fft_warp.cuh).
 // ------------------------------------------------------------------------------------------------
-template <int LOGM, bool CONTIG>
+// FUSED_DIV (forward x sweep only): the input line is div(u, v, w) / dt formed in registers.  A separate instantiation,
+// so that the plain sweeps do not pay for its registers.
+template <int LOGM, bool CONTIG, bool FUSED_DIV = false>
 __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 : 2)) warp_dct_kernel(const FastJob job, double *__restrict__ field) {
   using namespace warpfft;
   using C = Cfg<LOGM>;
@@ -512,14 +518,15 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
   double *base = field + job.origin + (long long)first_line * job.tile_stride + (long long)blockIdx.y * job.outer_stride;
   double2 v[EPT];
 
-  prefetch_next_tile<CONTIG, kLines, C::THREADS>(job, field, NPTS);
-  load_twiddles<LOGM>(T, job.tw);
+  // x sweeps issue their global loads first and fill the twiddle tables while those are in flight (this order also
+  // keeps ptxas from spilling in the 128-register x sweep)
+  if (!CONTIG) load_twiddles<LOGM>(T, job.tw);
   if (CONTIG) {
     // x sweep: lane j loads its first-pass inputs c[j + s*TL] = (e[2q], e[2q+1]) straight from global memory;
     // slots q >= M/2 are the mirror images (x[2M-2q], x[2M-2q-1]).  No shared-memory staging, no CTA barrier.
     const double *src = base + (long long)line * job.lstride;
     const bool live = line < lines;
-    if (job.div_u == nullptr) {
+    if constexpr (!FUSED_DIV) {
 #pragma unroll
       for (int s = 0; s < EPT; s++) {
         const int q = j + s * TL;
@@ -527,32 +534,46 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
         else if (s < EPT / 2) v[s] = *reinterpret_cast<const double2 *>(src + 2 * q);
         else v[s] = make_double2(src[2 * M - 2 * q], src[2 * M - 2 * q - 1]);
       }
+    } else if constexpr (!SHUFFLE) {
+      __trap();  // the fused right-hand side exists for one warp per line only (poisson_can_fuse_divergence)
     } else {
       // Fused right-hand side: rhs(e) = ((u[e+1]-u[e])/dx + (v[e+PX]-v[e])/dy + (w[e+plane]-w[e])/dz) / dt
-      // (include/VelocityDivergence.h:9-20, src/PressureEquation.cpp:59-61), computed once per point with
-      // coalesced loads along x and packed into the line's shared-memory region.
+      // (include/VelocityDivergence.h:9-20, src/PressureEquation.cpp:59-61) computed in registers: lane j forms the
+      // pairs (rhs(2q), rhs(2q+1)), q = j + 32 s < M/2, from 128-bit loads of u, v, w (rows are 16-byte aligned), and
+      // the mirrored slots q >= M/2 of the even extension, (rhs(2M-2q), rhs(2M-2q-1)), come from the lanes that hold
+      // those values (32 - j and 31 - j) by shuffles -- the right-hand side never exists in memory.
       const long long off = src - field;
       const double *pu = job.div_u + off, *pv = job.div_v + off, *pw = job.div_w + off;
-      constexpr int NIT = (NPTS + TL - 1) / TL;
-      double vals[NIT];
+      auto ld2 = [](const double *ptr) { return *reinterpret_cast<const double2 *>(ptr); };
+      double2 d[EPT / 2];
 #pragma unroll
-      for (int it = 0; it < NIT; it++) {
-        const int e = j + it * TL;
-        if (live && e < NPTS) {
-          const double du_dx = (pu[e + 1] - pu[e]) * job.one_over_dx;
-          const double dv_dy = (pv[e + job.stride_y] - pv[e]) * job.one_over_dy;
-          const double dw_dz = (pw[e + job.stride_z] - pw[e]) * job.one_over_dz;
-          vals[it] = (du_dx + dv_dy + dw_dz) / job.dt;
+      for (int s = 0; s < EPT / 2; s++) {
+        const int e = 2 * (j + s * TL);
+        if (live) {
+          const double2 U = ld2(pu + e), V0 = ld2(pv + e), V1 = ld2(pv + e + job.stride_y);
+          const double2 W0 = ld2(pw + e), W1 = ld2(pw + e + job.stride_z);
+          const double u2 = pu[e + 2];
+          d[s].x = ((U.y - U.x) * job.one_over_dx + (V1.x - V0.x) * job.one_over_dy + (W1.x - W0.x) * job.one_over_dz) / job.dt;
+          d[s].y = ((u2 - U.y) * job.one_over_dx + (V1.y - V0.y) * job.one_over_dy + (W1.y - W0.y) * job.one_over_dz) / job.dt;
         } else {
-          vals[it] = 0.0;
+          d[s] = make_double2(0.0, 0.0);
         }
+        v[s] = d[s];
       }
+      double rhs_last = 0.0;  // rhs(M), the last point of the line (same address in all lanes: one broadcast request)
+      if (live)
+        rhs_last = ((pu[M + 1] - pu[M]) * job.one_over_dx + (pv[M + job.stride_y] - pv[M]) * job.one_over_dy +
+                    (pw[M + job.stride_z] - pw[M]) * job.one_over_dz) / job.dt;
 #pragma unroll
-      for (int it = 0; it < NIT; it++) {
-        const int e = j + it * TL;
-        if (e < NPTS) put_packed(Sd, M, e, vals[it]);
+      for (int sp = 1; sp <= EPT / 2; sp++) {
+        // slot q = j + 32 (EPT - sp):  2M - 2q = 64 sp - 2j
+        double x = __shfl_sync(0xffffffffu, d[sp - 1].x, (32 - j) & 31);
+        const double y = __shfl_sync(0xffffffffu, d[sp - 1].y, 31 - j);
+        if (j == 0) x = (sp < EPT / 2) ? d[sp < EPT / 2 ? sp : 0].x : rhs_last;
+        v[EPT - sp] = make_double2(x, y);
       }
     }
+    load_twiddles<LOGM>(T, job.tw);
     __syncthreads();  // twiddle tables are in place
   } else {
     // y / z sweep: line-fastest mapping (the 8 lines are 8 consecutive x, so every request is a set of 64-byte
@@ -580,8 +601,7 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
   double lo[PAIRS], hi[PAIRS], mid = 0.0, e_last = 0.0;
   double spec[EPT];  // shuffle path: spec[u + G t] = E_k, k = j + 32 u + NS t
   if (!CONTIG) fft_line<LOGM, false, SHUFFLE, true>(S, T, j, line, v);                     // first pass already done
-  else if (job.div_u == nullptr) fft_line<LOGM, true, SHUFFLE>(S, T, j, line, v);       // first pass from registers
-  else fft_line<LOGM, false, SHUFFLE>(S, T, j, line, v);
+  else fft_line<LOGM, true, SHUFFLE>(S, T, j, line, v);                                   // first pass from registers
   if constexpr (SHUFFLE) unpack_regs<LOGM>(v, j, job.cs, spec, e_last);
   else unpack_line<LOGM>(S, j, job.cs, lo, hi, mid);
 
@@ -1036,8 +1056,20 @@ void launch_warp(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid
     cudaFuncSetAttribute(warp_dct_kernel<LOGM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     attr_set = true;
   }
-  if (contig) warp_dct_kernel<LOGM, true><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
-  else warp_dct_kernel<LOGM, false><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
+  if (contig && job.div_u != nullptr) {
+    if constexpr (C::WPL == 1) {
+      static bool fused_attr_set = false;
+      if (!fused_attr_set) {
+        cudaFuncSetAttribute(warp_dct_kernel<LOGM, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        fused_attr_set = true;
+      }
+      warp_dct_kernel<LOGM, true, true><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
+    }
+  } else if (contig) {
+    warp_dct_kernel<LOGM, true><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
+  } else {
+    warp_dct_kernel<LOGM, false><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
+  }
 }
 
 template <typename T>
@@ -1222,7 +1254,7 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
     // Off by default: measured on B200 at 513^3 with distances 148 / 296 / 592 the sweeps got 2-7 % SLOWER (x 1.76 ->
     // 1.80 ms, y 2.72 -> 2.93 ms, fused z 5.40 -> 5.79 ms per step) -- the extra LSU requests cost more in these
     // LSU-bound kernels than the shorter first-load wait gains.
-    static const int prefetch_ctas = getenv("MIFGPU_SWEEP_PREFETCH") ? atoi(getenv("MIFGPU_SWEEP_PREFETCH")) : 0;
+    static const int prefetch_ctas = getenv("MIFGPU_SWEEP_PREFETCH") ? atoi(getenv("MIFGPU_SWEEP_PREFETCH")) : MIFGPU_SWEEP_PREFETCH_CTAS;
     fj.prefetch_ctas = prefetch_ctas;
     fj.load_map = lay.load_map; fj.store_map = lay.store_map;
     fj.div_u = lay.div_u; fj.div_v = lay.div_v; fj.div_w = lay.div_w;
@@ -1250,7 +1282,7 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
       default: {
         static const bool use_two_warp_variant = getenv("MIFGPU_FFT_NO_SPLIT") != nullptr;  // A/B switch for profiling
         if (use_cta_sync_variant) launch_fast<10>(stream, fj, lay.contig, fgrid, field);
-        else if (use_two_warp_variant || fj.div_u != nullptr) launch_warp<10>(stream, fj, lay.contig, fgrid, field);
+        else if (use_two_warp_variant) launch_warp<10>(stream, fj, lay.contig, fgrid, field);
         else {
           static const int lines_contig = getenv("MIFGPU_SPLIT_LINES_X") ? atoi(getenv("MIFGPU_SPLIT_LINES_X")) : 4;
           static const int lines_strided = getenv("MIFGPU_SPLIT_LINES_YZ") ? atoi(getenv("MIFGPU_SPLIT_LINES_YZ")) : 4;
@@ -1283,10 +1315,14 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
 }  // namespace
 
 bool poisson_can_fuse_divergence(const PoissonPlan *plan) {
-  // Measured on B200 at 513^3: the fused launch takes 1.94 ms against 0.73 ms (divergence_kernel) + 0.70 ms (plain
-  // forward x sweep), so the fusion is kept as an experiment only (MIFGPU_FUSED_DIVERGENCE=1).
-  static const bool enabled = getenv("MIFGPU_FUSED_DIVERGENCE") != nullptr && getenv("MIFGPU_FFT_CTA_SYNC") == nullptr;
-  return enabled && plan->fast_logm[0] >= 8;
+  // The forward x sweep of the one-warp-per-line kernel (513- and 257-point lines) can form its input, div(u)/dt, in
+  // registers (128-bit loads of u, v, w; mirrored half of the even extension by shuffles).  Measured on B200 at 513^3:
+  // the fused launch takes 1.42 ms against 0.74 ms (divergence_kernel) + 0.65 ms (plain forward x sweep) -- it saves
+  // 16 B/point of HBM traffic but no time, because with 16 warps per SM the sweep cannot keep enough loads in flight
+  // to stream four arrays.  Kept as an experiment only (MIFGPU_FUSED_DIVERGENCE=1).
+  static const bool enabled = getenv("MIFGPU_FUSED_DIVERGENCE") && atoi(getenv("MIFGPU_FUSED_DIVERGENCE")) != 0 &&
+                              getenv("MIFGPU_FFT_CTA_SYNC") == nullptr;
+  return enabled && (plan->fast_logm[0] == 8 || plan->fast_logm[0] == 9);
 }
 
 void launch_poisson_sweep(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *field, int d, int mode,

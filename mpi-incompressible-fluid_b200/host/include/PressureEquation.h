@@ -19,6 +19,9 @@ void solve_pressure_equation_non_homogeneous_neumann(StaggeredTensor &pressure, 
 
 // Shift the pressure by the mean difference to the exact one (src/PressureEquation.cpp:288-343).
 void adjust_pressure(StaggeredTensor &pressure, const std::function<Real(Real, Real, Real)> &exact_pressure);
+// Extension: the same with the time-dependent function passed unfrozen.  When it is p_exact (Manufactured.h) the
+// reduction and the shift run on the device (mifgpu_adjust_pressure) and the tensor is not downloaded.
+void adjust_pressure(StaggeredTensor &pressure, const std::function<Real(Real, Real, Real, Real)> &exact_pressure, Real time);
 
 }  // namespace mif
 

@@ -43,6 +43,11 @@ def lib():
         l.mo_exact_velocity.restype = c_double
         l.mo_es_pressure_gradient.argtypes = [c_int] + [c_double] * 5
         l.mo_es_pressure_gradient.restype = c_double
+        l.mo_exact_pressure.argtypes = [c_int] + [c_double] * 5
+        l.mo_exact_pressure.restype = c_double
+        l.mo_velocity_error_norms.argtypes = [c_void_p, c_int, c_double, dp, dp, dp, dp]
+        l.mo_pressure_error_norms.argtypes = [c_void_p, c_int, c_double, dp, dp]
+        l.mo_adjust_pressure.argtypes = [c_void_p, c_int, c_double, dp]
         _lib = l
     return _lib
 
@@ -90,6 +95,22 @@ class Grid:
             faces = (POINTER(c_double) * 6)(*[_ptr(f) for f in keep])
         lib().mo_solve_pressure(self._buf, _ptr(p), _ptr(u), _ptr(v), _ptr(w), dt, faces, int(direct))
         return p
+
+    def velocity_error_norms(self, kind, t, u, v, w):
+        """(L1, L2, LInf) of src/Norms.cpp:49-86."""
+        out = np.zeros(3)
+        lib().mo_velocity_error_norms(self._buf, kind, t, _ptr(u), _ptr(v), _ptr(w), _ptr(out))
+        return tuple(out)
+
+    def pressure_error_norms(self, kind, t, p):
+        """(L1, L2, LInf) of src/Norms.cpp:103-118."""
+        out = np.zeros(3)
+        lib().mo_pressure_error_norms(self._buf, kind, t, _ptr(p), _ptr(out))
+        return tuple(out)
+
+    def adjust_pressure(self, kind, t, p):
+        """src/PressureEquation.cpp:288-343, in place."""
+        lib().mo_adjust_pressure(self._buf, kind, t, _ptr(p))
 
     def timestep(self, kind, t_n, vel, buf, buf2, p, dp, nhn=False, direct=False):
         args = [_ptr(a) for a in (*vel, *buf, *buf2, p, dp)]

@@ -171,6 +171,38 @@ def test_apply_bc_device_and_host_callback_agree_with_oracle(mif, N, periodic):
     ctx.close()
 
 
+@pytest.mark.parametrize("N,periodic", [((16, 16, 16), (False, False, False)), ((70, 9, 11), (False, False, False)),
+                                        ((10, 12, 9), (False, False, True)), ((11, 9, 8), (True, False, False)),
+                                        ((130, 67, 5), (False, True, False))])
+def test_device_norms_and_adjust_pressure_match_oracle(mif, N, periodic):
+    """ErrorL1/L2/LInfNorm (src/Norms.cpp) and adjust_pressure (src/PressureEquation.cpp:288-343)
+    on the device against the oracle's serial restatement; the summation order differs, hence 1e-12 and not 0."""
+    ctx, grid = make_pair(mif, N, periodic)
+    rng = np.random.default_rng(21)
+    t = 0.37
+    h_vel = [a + 1e-3 * rng.uniform(-1, 1, a.shape) for a in grid.set_velocity(mo.BC_ETHIER_STEINMAN, t)]
+    h_p = rng.uniform(-1, 1, grid.shape(3))
+    vel, p = ctx.velocity(), ctx.tensor(mif.STAGGER_NONE)
+    for ten, h in zip(vel + [p], h_vel + [h_p]):
+        ten.upload(h)
+    exact = ctx.make_bc(mif.BC_ETHIER_STEINMAN, 1e3)
+    for got, want in zip(ctx.velocity_error_norms(vel, exact, t), grid.velocity_error_norms(mo.BC_ETHIER_STEINMAN, t, *h_vel)):
+        assert abs(got - want) <= 1e-12 * abs(want)
+    for got, want in zip(ctx.pressure_error_norms(p, exact, t), grid.pressure_error_norms(mo.BC_ETHIER_STEINMAN, t, h_p)):
+        assert abs(got - want) <= 1e-12 * abs(want)
+    ctx.adjust_pressure(p, exact, t)
+    grid.adjust_pressure(mo.BC_ETHIER_STEINMAN, t, h_p)
+    assert rel(p.download(), h_p) <= 1e-13
+    # the lid-driven families have p = 0 as their reference pressure and an exact velocity that is zero inside
+    lid = ctx.make_bc(mif.BC_TEST_CASE_1, 1e3)
+    for got, want in zip(ctx.velocity_error_norms(vel, lid, t), grid.velocity_error_norms(mo.BC_TEST_CASE_1, t, *h_vel)):
+        assert abs(got - want) <= 1e-12 * abs(want)
+    # arbitrary host functions cannot be evaluated on the device: refused, never silently computed elsewhere
+    with pytest.raises(mif.MifGpuError):
+        ctx.velocity_error_norms(vel, ctx.make_bc(mif.BC_HOST_CALLBACK, 1e3, lambda *a: None), t)
+    ctx.close()
+
+
 def test_upload_download_roundtrip_and_swap(mif):
     ctx, grid = make_pair(mif, (7, 5, 6), (False, True, False))
     rng = np.random.default_rng(0)

@@ -57,6 +57,34 @@ def test_pressure_solve_restatement_matches_reference(case):
     assert rel(p, f["p_out"]) <= 1e-11
 
 
+def test_norms_and_adjust_pressure_match_the_numbers_printed_by_the_reference():
+    """full_test 16 2: the reference prints ErrorL1/L2/LInf of the velocity and, after adjust_pressure, of the pressure
+    (test/full_test.cpp:139-170); tests/golden/norms.json holds its output for N = 16, 1 step -- the golden case
+    full_16_2 is the same set-up run for 2 steps, so the oracle's norms are pinned on the 1-step state instead."""
+    import json
+    meta, f = load_golden("full_16_2")
+    g = grid_from(meta)
+    with open(os.path.join(ROOT, "tests", "golden", "norms.json")) as fh:
+        printed = json.load(fh)["full_test 16 1 1"]
+    # one step of 1e-4 (full_test 16 1): recompute with the oracle, whose fields are pinned to 1e-11 above
+    g1 = mo.Grid(16, 16, 16, meta["x_size"], meta["y_size"], meta["z_size"], *meta["min"], meta["Re"], 1e-4, 1)
+    vel = list(g1.set_velocity(mo.BC_ETHIER_STEINMAN, 0.0))
+    buf, buf2 = [g1.zeros(c) for c in range(3)], [g1.zeros(c) for c in range(3)]
+    # pressure.set(p_exact(0), true) (test/full_test.cpp:84-85)
+    h = [1.0 / 15, 1.0 / 15, 2.0 / 15]
+    zz, yy, xx = np.meshgrid(-1.0 + h[2] * np.arange(16), h[1] * np.arange(16), h[0] * np.arange(16), indexing="ij")
+    p = np.vectorize(lambda x, y, z: mo.lib().mo_exact_pressure(mo.BC_ETHIER_STEINMAN, 0.0, x, y, z, meta["Re"]))(xx, yy, zz)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    assert rel(p, f["p_s0"]) <= 1e-14  # the reference's own initial pressure (same for every step count)
+    dp = g1.zeros(3)
+    g1.timestep(mo.BC_ETHIER_STEINMAN, 0.0, vel, buf, buf2, p, dp)
+    got = list(g1.velocity_error_norms(mo.BC_ETHIER_STEINMAN, 1e-4, *vel))
+    g1.adjust_pressure(mo.BC_ETHIER_STEINMAN, 1e-4, p)
+    got += list(g1.pressure_error_norms(mo.BC_ETHIER_STEINMAN, 1e-4, p))
+    for mine, ref in zip(got, printed[:6]):
+        assert abs(mine - ref) <= 1e-5 * abs(ref), (got, printed)  # the reference prints 6 significant digits
+
+
 def test_initial_condition_matches_reference():
     meta, f = load_golden("full_16_2")
     g = grid_from(meta)
