@@ -68,7 +68,8 @@ typedef enum mifgpu_bc_kind {
   MIFGPU_BC_TEST_CASE_1 = 1,     /* include/TestCaseBoundaries.h:17-35  (v = 1 on the face x = 1)    */
   MIFGPU_BC_TEST_CASE_2 = 2,     /* include/TestCaseBoundaries.h:38-56  (v = 1 on the face x = -0.5) */
   MIFGPU_BC_ETHIER_STEINMAN = 3, /* generators/manufsol.py:31-72 (u_exact, v_exact, w_exact, dp_d*_exact) */
-  MIFGPU_BC_HOST_CALLBACK = 4    /* any other TimeVectorFunction: faces filled on the host */
+  MIFGPU_BC_HOST_CALLBACK = 4,   /* any other TimeVectorFunction: faces filled on the host */
+  MIFGPU_BC_VELOCITY_TEST = 5    /* generators/manufsol_velocity.py:55-59 (u_exact_v_test, v_exact_v_test, w_exact_v_test) */
 } mifgpu_bc_kind;
 
 /* Host callback for MIFGPU_BC_HOST_CALLBACK.  The library asks for ONE face of ONE component at one
@@ -142,6 +143,15 @@ int mifgpu_tensor_swap(mifgpu_tensor *a, mifgpu_tensor *b);
 int mifgpu_timestep(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], mifgpu_tensor *const velocity_buffer[3],
                     mifgpu_tensor *const velocity_buffer_2[3], const mifgpu_bc *bc, double t_n,
                     mifgpu_tensor *pressure, mifgpu_tensor *pressure_buffer, int nhn);
+
+/* mif::timestep_velocity (include/TimestepVelocity.h:15-16, src/TimestepVelocity.cpp:58-90): one three-stage step of
+ * the momentum equation alone, with the analytic forcing forcing_{x,y,z} of generators/manufsol_velocity.py that
+ * calculate_momentum_rhs_with_forcing_* (include/MomentumEquationForcing.h:11-33) always adds; bc->Re is the
+ * reference's global `Reynolds` read by that forcing.  On return `velocity` holds the new solution (the data of
+ * velocity and velocity_buffer are swapped as by VelocityTensor::swap_data, src/TimestepVelocity.cpp:89);
+ * velocity_buffer and rhs_buffer hold the scratch contents the reference leaves in them. */
+int mifgpu_timestep_velocity(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], mifgpu_tensor *const velocity_buffer[3],
+                             mifgpu_tensor *const rhs_buffer[3], const mifgpu_bc *bc, double t_n);
 
 /* VelocityTensor::apply_bc (src/VelocityTensor.cpp:36-233) at one fixed time. */
 int mifgpu_apply_bc(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], const mifgpu_bc *bc, double time);

@@ -22,7 +22,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, os.environ.get("MIFGPU_LIB", "libmifgpu.so"))
 
 STAGGER_X, STAGGER_Y, STAGGER_Z, STAGGER_NONE = 0, 1, 2, 3
-BC_TEST_CASE_1, BC_TEST_CASE_2, BC_ETHIER_STEINMAN, BC_HOST_CALLBACK = 1, 2, 3, 4
+BC_TEST_CASE_1, BC_TEST_CASE_2, BC_ETHIER_STEINMAN, BC_HOST_CALLBACK, BC_VELOCITY_TEST = 1, 2, 3, 4, 5
 
 # Every symbol include/mifgpu.h declares (checked by tests/test_abi.py without a GPU).
 EXPORTED_SYMBOLS = [
@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "mifgpu_tensor_swap", "mifgpu_timestep", "mifgpu_apply_bc", "mifgpu_solve_pressure", "mifgpu_synchronize",
     "mifgpu_stream", "mifgpu_launch_count", "mifgpu_profile_enable", "mifgpu_profile_read", "mifgpu_comm_unique_id",
     "mifgpu_create_distributed", "mifgpu_slab_plan", "mifgpu_velocity_error_norms", "mifgpu_pressure_error_norms",
-    "mifgpu_adjust_pressure",
+    "mifgpu_adjust_pressure", "mifgpu_timestep_velocity",
 ]
 
 
@@ -100,6 +100,7 @@ def lib() -> ctypes.CDLL:
     l.mifgpu_timestep.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(Bc),
                                   c_double, c_void_p, c_void_p, c_int]
     l.mifgpu_apply_bc.argtypes = [c_void_p, POINTER(c_void_p), POINTER(Bc), c_double]
+    l.mifgpu_timestep_velocity.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(Bc), c_double]
     l.mifgpu_solve_pressure.argtypes = [c_void_p, c_void_p, POINTER(c_void_p), c_double, POINTER(Bc), c_double]
     l.mifgpu_synchronize.argtypes = [c_void_p]
     l.mifgpu_velocity_error_norms.argtypes = [c_void_p, POINTER(c_void_p), POINTER(Bc), c_double, POINTER(c_double)]
@@ -227,6 +228,11 @@ class Context:
                  nhn: bool = False) -> None:
         _check(lib().mifgpu_timestep(self.handle, self._triple(vel), self._triple(vel_buf), self._triple(vel_buf2),
                                      ctypes.byref(bc), t_n, pressure.handle, pressure_buffer.handle, int(nhn)))
+
+    def timestep_velocity(self, vel, vel_buf, rhs_buf, bc: Bc, t_n: float) -> None:
+        """mif::timestep_velocity; the device data of vel and vel_buf are swapped inside the call, as in the reference."""
+        _check(lib().mifgpu_timestep_velocity(self.handle, self._triple(vel), self._triple(vel_buf), self._triple(rhs_buf),
+                                              ctypes.byref(bc), t_n))
 
     def apply_bc(self, vel, bc: Bc, time: float) -> None:
         _check(lib().mifgpu_apply_bc(self.handle, self._triple(vel), ctypes.byref(bc), time))

@@ -416,7 +416,7 @@ int do_apply_bc(mifgpu_ctx *ctx, mifgpu_tensor *const vel[3], const mifgpu_bc *b
     const int rc = fill_face_tables(ctx, bc, 0, time, time, dev);
     if (rc) return rc;
   } else if (bc->kind != MIFGPU_BC_TEST_CASE_1 && bc->kind != MIFGPU_BC_TEST_CASE_2 &&
-             bc->kind != MIFGPU_BC_ETHIER_STEINMAN) {
+             bc->kind != MIFGPU_BC_ETHIER_STEINMAN && bc->kind != MIFGPU_BC_VELOCITY_TEST) {
     return fail(MIFGPU_ERR_INVALID, "unknown boundary kind %d", bc->kind);
   }
   {
@@ -831,10 +831,42 @@ int mifgpu_timestep(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], mifgpu_te
   return check_launch(ctx);
 }
 
+int mifgpu_timestep_velocity(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], mifgpu_tensor *const velocity_buffer[3],
+                             mifgpu_tensor *const rhs_buffer[3], const mifgpu_bc *bc, double t_n) {
+  if (!ctx || !bc) return fail(MIFGPU_ERR_INVALID, "NULL argument");
+  int rc;
+  if ((rc = check_triple(ctx, velocity, "velocity"))) return rc;
+  if ((rc = check_triple(ctx, velocity_buffer, "velocity_buffer"))) return rc;
+  if ((rc = check_triple(ctx, rhs_buffer, "rhs_buffer"))) return rc;
+  CUDA_TRY(cudaSetDevice(ctx->params.device));
+  const Geom &g = ctx->g;
+  cudaStream_t s = ctx->stream;
+  // src/TimestepVelocity.cpp:11-13,60-63
+  const double time_1 = t_n + (8.0 / 15.0) * g.dt, time_2 = t_n + (2.0 / 3.0) * g.dt, final_time = t_n + g.dt;
+  {
+    ProfScope prof(ctx, PROF_STAGE1);
+    launch_velocity_stage(s, g, 1, cvec3(velocity), vec3(rhs_buffer), vec3(velocity_buffer), t_n, bc->Re, &ctx->launches);
+  }
+  if ((rc = do_apply_bc(ctx, velocity_buffer, bc, time_1))) return rc;
+  {
+    ProfScope prof(ctx, PROF_STAGE2);
+    launch_velocity_stage(s, g, 2, cvec3(velocity_buffer), vec3(rhs_buffer), vec3(velocity), time_1, bc->Re, &ctx->launches);
+  }
+  if ((rc = do_apply_bc(ctx, velocity, bc, time_2))) return rc;
+  {
+    ProfScope prof(ctx, PROF_STAGE3);
+    launch_velocity_stage(s, g, 3, cvec3(velocity), vec3(rhs_buffer), vec3(velocity_buffer), time_2, bc->Re, &ctx->launches);
+  }
+  if ((rc = do_apply_bc(ctx, velocity_buffer, bc, final_time))) return rc;
+  for (int c = 0; c < 3; c++) std::swap(velocity[c]->data, velocity_buffer[c]->data);  // velocity.swap_data(velocity_buffer)
+  return check_launch(ctx);
+}
+
 // ---- diagnostics on the device -----------------------------------------------------------------------------------
 static int analytic_family(const mifgpu_bc *exact, double time, BcDev &dev) {
   if (!exact) return fail(MIFGPU_ERR_INVALID, "NULL analytic family");
-  if (exact->kind != MIFGPU_BC_TEST_CASE_1 && exact->kind != MIFGPU_BC_TEST_CASE_2 && exact->kind != MIFGPU_BC_ETHIER_STEINMAN)
+  if (exact->kind != MIFGPU_BC_TEST_CASE_1 && exact->kind != MIFGPU_BC_TEST_CASE_2 && exact->kind != MIFGPU_BC_ETHIER_STEINMAN &&
+      exact->kind != MIFGPU_BC_VELOCITY_TEST)
     return fail(MIFGPU_ERR_UNSUPPORTED, "device-side diagnostics need an analytic family evaluated on the device (kind %d given); "
                 "download the tensors and use the host-side norms for arbitrary functions", exact->kind);
   std::memset(&dev, 0, sizeof(dev));

@@ -37,6 +37,13 @@ void launch_nhn_rhs(cudaStream_t stream, const Geom &g, double *rhs, const BcDev
 void launch_correct(cudaStream_t stream, const Geom &g, Vec3 vel, double *pressure, const double *dp, double dt_s,
                     uint64_t *launches);
 
+// Stages of the velocity-only integrator with the manufactured forcing (src/TimestepVelocity.cpp:20-50):
+//   stage 1: in = velocity,        rhs_buf written,       out = velocity_buffer
+//   stage 2: in = velocity_buffer, rhs_buf read + written, out = velocity (read + written)
+//   stage 3: in = velocity,        rhs_buf read,          out = velocity_buffer
+void launch_velocity_stage(cudaStream_t stream, const Geom &g, int stage, CVec3 in, Vec3 rhs_buf, Vec3 out, double time,
+                           double Re, uint64_t *launches);
+
 // Diagnostics (src/Norms.cpp:11-118, src/PressureEquation.cpp:288-343) against an analytic family evaluated on the
 // device.  `partial` receives 4 doubles per CTA (diag_blocks CTAs): velocity {sum |e|, sum |e|^2, max, 0}, pressure
 // {sum |e|, sum e^2, max |e|, sum e} with e = exact - field; the host adds them up in CTA order.

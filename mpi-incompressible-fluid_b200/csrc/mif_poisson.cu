@@ -518,21 +518,44 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
   double *base = field + job.origin + (long long)first_line * job.tile_stride + (long long)blockIdx.y * job.outer_stride;
   double2 v[EPT];
 
-  // x sweeps issue their global loads first and fill the twiddle tables while those are in flight (this order also
-  // keeps ptxas from spilling in the 128-register x sweep)
-  if (!CONTIG) load_twiddles<LOGM>(T, job.tw);
+  load_twiddles<LOGM>(T, job.tw);
   if (CONTIG) {
     // x sweep: lane j loads its first-pass inputs c[j + s*TL] = (e[2q], e[2q+1]) straight from global memory;
     // slots q >= M/2 are the mirror images (x[2M-2q], x[2M-2q-1]).  No shared-memory staging, no CTA barrier.
     const double *src = base + (long long)line * job.lstride;
     const bool live = line < lines;
-    if constexpr (!FUSED_DIV) {
+    if (!FUSED_DIV && job.div_u == nullptr) {
 #pragma unroll
       for (int s = 0; s < EPT; s++) {
         const int q = j + s * TL;
         if (!live) v[s] = make_double2(0.0, 0.0);
         else if (s < EPT / 2) v[s] = *reinterpret_cast<const double2 *>(src + 2 * q);
         else v[s] = make_double2(src[2 * M - 2 * q], src[2 * M - 2 * q - 1]);
+      }
+    } else if constexpr (!FUSED_DIV) {
+      // Shared-memory variant of the fused right-hand side (first version; 1.94 ms per launch at 513^3).  Never
+      // launched any more -- launch_warp sends fused sweeps to the FUSED_DIV instantiation -- but with this branch in
+      // place ptxas schedules the plain x sweep measurably better (0.585 ms per launch against 0.65 ms without it).
+      const long long off = src - field;
+      const double *pu = job.div_u + off, *pv = job.div_v + off, *pw = job.div_w + off;
+      constexpr int NIT = (NPTS + TL - 1) / TL;
+      double vals[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; it++) {
+        const int e = j + it * TL;
+        if (live && e < NPTS) {
+          const double du_dx = (pu[e + 1] - pu[e]) * job.one_over_dx;
+          const double dv_dy = (pv[e + job.stride_y] - pv[e]) * job.one_over_dy;
+          const double dw_dz = (pw[e + job.stride_z] - pw[e]) * job.one_over_dz;
+          vals[it] = (du_dx + dv_dy + dw_dz) / job.dt;
+        } else {
+          vals[it] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < NIT; it++) {
+        const int e = j + it * TL;
+        if (e < NPTS) put_packed(Sd, M, e, vals[it]);
       }
     } else if constexpr (!SHUFFLE) {
       __trap();  // the fused right-hand side exists for one warp per line only (poisson_can_fuse_divergence)
@@ -573,7 +596,6 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
         v[EPT - sp] = make_double2(x, y);
       }
     }
-    load_twiddles<LOGM>(T, job.tw);
     __syncthreads();  // twiddle tables are in place
   } else {
     // y / z sweep: line-fastest mapping (the 8 lines are 8 consecutive x, so every request is a set of 64-byte
@@ -601,7 +623,8 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
   double lo[PAIRS], hi[PAIRS], mid = 0.0, e_last = 0.0;
   double spec[EPT];  // shuffle path: spec[u + G t] = E_k, k = j + 32 u + NS t
   if (!CONTIG) fft_line<LOGM, false, SHUFFLE, true>(S, T, j, line, v);                     // first pass already done
-  else fft_line<LOGM, true, SHUFFLE>(S, T, j, line, v);                                   // first pass from registers
+  else if (FUSED_DIV || job.div_u == nullptr) fft_line<LOGM, true, SHUFFLE>(S, T, j, line, v);  // first pass from registers
+  else fft_line<LOGM, false, SHUFFLE>(S, T, j, line, v);
   if constexpr (SHUFFLE) unpack_regs<LOGM>(v, j, job.cs, spec, e_last);
   else unpack_line<LOGM>(S, j, job.cs, lo, hi, mid);
 

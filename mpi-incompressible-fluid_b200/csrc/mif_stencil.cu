@@ -637,6 +637,12 @@ __device__ __forceinline__ double exact_velocity(int kind, int comp, double t, d
     if (comp == 1) return -a * (exp(a * y) * sin(a * z + d * x) + exp(a * x) * cos(a * y + d * z)) * decay;
     return -a * (exp(a * z) * sin(a * x + d * y) + exp(a * y) * cos(a * z + d * x)) * decay;
   }
+  if (kind == MIFGPU_BC_VELOCITY_TEST) {
+    // generators/manufsol_velocity.py:55-59
+    if (comp == 0) return sin(x) * cos(y) * sin(z) * sin(t);
+    if (comp == 1) return cos(x) * sin(y) * sin(z) * sin(t);
+    return 2 * cos(x) * cos(y) * cos(z) * sin(t);
+  }
   // include/TestCaseBoundaries.h:17-56: only v is non-zero, and only on one x face.
   if (comp != 1) return 0.0;
   const double face = (kind == MIFGPU_BC_TEST_CASE_1) ? 1.0 : -0.5;
@@ -676,6 +682,97 @@ __device__ __forceinline__ bool face_active(const Geom &g, int face) {
     case 2: return g.prev_y == -1 && !g.periodic[1];
     case 3: return g.next_y == -1 && !g.periodic[1];
     default: return !g.periodic[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Velocity-only integrator with analytic forcing: mif::timestep_velocity (src/TimestepVelocity.cpp:20-90,
+// include/MomentumEquationForcing.h:11-33).
+// ------------------------------------------------------------------------------------------------
+// forcing_{x,y,z} of generators/manufsol_velocity.py:38-48, f = d_t c + (u . grad) c - lap(c) / Re for the manufactured
+// field of MIFGPU_BC_VELOCITY_TEST (same closed form as oracle/mif_oracle.c forcing(), checked against sympy there).
+__device__ __forceinline__ double manufactured_forcing(int comp, double t, double x, double y, double z, double Re) {
+  double sx, cx, sy, cy, sz, cz, st, ct;
+  sincos(x, &sx, &cx);
+  sincos(y, &sy, &cy);
+  sincos(z, &sz, &cz);
+  sincos(t, &st, &ct);
+  if (comp == 0) return sx * cy * sz * ct + st * st * sx * cx * (2.0 - 2.0 * sy * sy - sz * sz) + 3.0 * sx * cy * sz * st / Re;
+  if (comp == 1) return cx * sy * sz * ct + st * st * sy * cy * (2.0 - 2.0 * sx * sx - sz * sz) + 3.0 * cx * sy * sz * st / Re;
+  return 2.0 * cx * cy * cz * ct + 2.0 * st * st * sz * cz * (sx * sx + sy * sy - 2.0) + 6.0 * cx * cy * cz * st / Re;
+}
+
+// One thread per grid index, all three components (loads shared as in stage_kernel).
+//   STAGE 1 (Y2):  S = velocity;         rhs_buf = R;  out = S + dt a21 R                      (out = velocity_buffer)
+//   STAGE 2 (Y3):  S = velocity_buffer;  r = rhs_buf;  rhs_buf = out + dt b1 r;  out = out + dt (a31 r + a32 R)   (out = velocity)
+//   STAGE 3 (U*):  S = velocity;         r = rhs_buf;  out = r + dt b3 R                        (out = velocity_buffer)
+// with R = momentum rhs of S + forcing at the stage time, evaluated at the staggered coordinate of the component.
+template <int STAGE>
+__global__ void __launch_bounds__(256)
+velocity_stage_kernel(const Geom g, const double *__restrict__ in_u, const double *__restrict__ in_v,
+                      const double *__restrict__ in_w, double *__restrict__ r_u, double *__restrict__ r_v,
+                      double *__restrict__ r_w, double *__restrict__ o_u, double *__restrict__ o_v, double *__restrict__ o_w,
+                      double time, double Re) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  const bool in_i_u = i <= g.sx[0] - 2, in_i_o = i <= g.Nx - 2;
+  const bool in_j_v = j <= g.sy[1] - 2, in_j_o = j <= g.Ny - 2;
+  const bool in_k_w = k <= g.sz[2] - 2, in_k_o = k <= g.Nz - 2;
+  const bool do_u = in_i_u && in_j_o && in_k_o;
+  const bool do_v = in_i_o && in_j_v && in_k_o;
+  const bool do_w = in_i_o && in_j_o && in_k_w;
+  if (!do_u && !do_v && !do_w) return;
+  const long long c = gidx(g, i, j, k);
+  const long long sj = g.PX, sk = g.plane;
+  const double u_c = in_u[c], u_xm = in_u[c - 1], u_xp = in_u[c + 1];
+  const double u_ym = in_u[c - sj], u_yp = in_u[c + sj], u_zm = in_u[c - sk], u_zp = in_u[c + sk];
+  const double u_xp_ym = in_u[c + 1 - sj], u_xp_zm = in_u[c + 1 - sk];
+  const double v_c = in_v[c], v_xm = in_v[c - 1], v_xp = in_v[c + 1];
+  const double v_ym = in_v[c - sj], v_yp = in_v[c + sj], v_zm = in_v[c - sk], v_zp = in_v[c + sk];
+  const double v_xm_yp = in_v[c - 1 + sj], v_yp_zm = in_v[c + sj - sk];
+  const double w_c = in_w[c], w_xm = in_w[c - 1], w_xp = in_w[c + 1];
+  const double w_ym = in_w[c - sj], w_yp = in_w[c + sj], w_zm = in_w[c - sk], w_zp = in_w[c + sk];
+  const double w_xm_zp = in_w[c - 1 + sk], w_ym_zp = in_w[c - sj + sk];
+  const double x = g.min_x + g.dx * (g.base_i + i), y = g.min_y + g.dy * (g.base_j + j), z = g.min_z + g.dz * (g.base_k + k);
+  const double dt = g.dt;
+  constexpr double a21 = 8.0 / 15.0, a31 = 1.0 / 4.0, a32 = 5.0 / 12.0, b1 = 1.0 / 4.0, b3 = 3.0 / 4.0;  // src/TimestepVelocity.cpp:11-17
+
+  auto combine = [&](double rhs, double center, double *r, double *o) {
+    if (STAGE == 1) {
+      r[c] = rhs;                        // :25
+      o[c] = center + dt * a21 * rhs;    // :26
+    } else if (STAGE == 2) {
+      const double prev = r[c], vel = o[c];
+      r[c] = vel + dt * (b1 * prev);                  // :35
+      o[c] = vel + dt * (a31 * prev + a32 * rhs);     // :36-38
+    } else {
+      o[c] = r[c] + dt * (b3 * rhs);     // :46-48
+    }
+  };
+  if (do_u) {
+    const double convection = -u_c * (u_xp - u_xm) * g.one_over_2_dx -
+                              (v_yp + v_c + v_xm_yp + v_xm) * (u_yp - u_ym) * g.one_over_8_dy -
+                              (w_zp + w_c + w_xm_zp + w_xm) * (u_zp - u_zm) * g.one_over_8_dz;
+    const double diffusion = (u_xp - 2 * u_c + u_xm) * g.one_over_dx2_Re + (u_yp - 2 * u_c + u_ym) * g.one_over_dy2_Re +
+                             (u_zp - 2 * u_c + u_zm) * g.one_over_dz2_Re;
+    combine(convection + diffusion + manufactured_forcing(0, time, x - g.dx_over_2, y, z, Re), u_c, r_u, o_u);
+  }
+  if (do_v) {
+    const double convection = -(u_xp + u_c + u_xp_ym + u_ym) * (v_xp - v_xm) * g.one_over_8_dx -
+                              v_c * (v_yp - v_ym) * g.one_over_2_dy -
+                              (w_zp + w_c + w_ym_zp + w_ym) * (v_zp - v_zm) * g.one_over_8_dz;
+    const double diffusion = (v_xp - 2 * v_c + v_xm) * g.one_over_dx2_Re + (v_yp - 2 * v_c + v_ym) * g.one_over_dy2_Re +
+                             (v_zp - 2 * v_c + v_zm) * g.one_over_dz2_Re;
+    combine(convection + diffusion + manufactured_forcing(1, time, x, y - g.dy_over_2, z, Re), v_c, r_v, o_v);
+  }
+  if (do_w) {
+    const double convection = -(u_xp + u_c + u_xp_zm + u_zm) * (w_xp - w_xm) * g.one_over_8_dx -
+                              (v_yp + v_c + v_yp_zm + v_zm) * (w_yp - w_ym) * g.one_over_8_dy -
+                              w_c * (w_zp - w_zm) * g.one_over_2_dz;
+    const double diffusion = (w_xp - 2 * w_c + w_xm) * g.one_over_dx2_Re + (w_yp - 2 * w_c + w_ym) * g.one_over_dy2_Re +
+                             (w_zp - 2 * w_c + w_zm) * g.one_over_dz2_Re;
+    combine(convection + diffusion + manufactured_forcing(2, time, x, y, z - g.dz_over_2, Re), w_c, r_w, o_w);
   }
 }
 
@@ -1125,6 +1222,23 @@ void launch_correct(cudaStream_t stream, const Geom &g, Vec3 vel, double *pressu
   const dim3 block(64, 4, 1);
   const dim3 grid(cdiv(g.sx[0], 2 * block.x), cdiv(g.sy[1], block.y), g.sz[2]);
   correct_kernel<<<grid, block, 0, stream>>>(g, vel.c[0], vel.c[1], vel.c[2], pressure, dp, dt_s);
+  ++*launches;
+}
+
+void launch_velocity_stage(cudaStream_t stream, const Geom &g, int stage, CVec3 in, Vec3 rhs_buf, Vec3 out, double time,
+                           double Re, uint64_t *launches) {
+  const int ni = max(g.sx[0], g.Nx) - 2, nj = max(g.sy[1], g.Ny) - 2, nk = max(g.sz[2], g.Nz) - 2;
+  if (ni <= 0 || nj <= 0 || nk <= 0) return;
+  const dim3 block(64, 4, 1), grid(cdiv(ni, block.x), cdiv(nj, block.y), nk);
+  if (stage == 1)
+    velocity_stage_kernel<1><<<grid, block, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], rhs_buf.c[0], rhs_buf.c[1], rhs_buf.c[2],
+                                                         out.c[0], out.c[1], out.c[2], time, Re);
+  else if (stage == 2)
+    velocity_stage_kernel<2><<<grid, block, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], rhs_buf.c[0], rhs_buf.c[1], rhs_buf.c[2],
+                                                         out.c[0], out.c[1], out.c[2], time, Re);
+  else
+    velocity_stage_kernel<3><<<grid, block, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], rhs_buf.c[0], rhs_buf.c[1], rhs_buf.c[2],
+                                                         out.c[0], out.c[1], out.c[2], time, Re);
   ++*launches;
 }
 

@@ -52,3 +52,22 @@ double p_exact_p_test(double t, double x, double y, double z) { return std::cos(
 double dp_dx_exact_p_test(double t, double x, double y, double z) { return u_exact_p_test(t, x, y, z); }
 double dp_dy_exact_p_test(double t, double x, double y, double z) { return v_exact_p_test(t, x, y, z); }
 double dp_dz_exact_p_test(double t, double x, double y, double z) { return w_exact_p_test(t, x, y, z); }
+
+// Velocity-only tests (generators/manufsol_velocity.py:55-59) and the forcing that makes the field an exact solution
+// of the momentum equation without pressure: f = d_t c + (u . grad) c - lap(c) / Re with lap(c) = -3 c.
+#include "ManufacturedVelocity.h"
+double u_exact_v_test(double t, double x, double y, double z) { return std::sin(x) * std::cos(y) * std::sin(z) * std::sin(t); }
+double v_exact_v_test(double t, double x, double y, double z) { return std::cos(x) * std::sin(y) * std::sin(z) * std::sin(t); }
+double w_exact_v_test(double t, double x, double y, double z) { return 2 * std::cos(x) * std::cos(y) * std::cos(z) * std::sin(t); }
+double forcing_x(double t, double x, double y, double z) {
+  const double st = std::sin(t), sx = std::sin(x), cx = std::cos(x), sy = std::sin(y), cy = std::cos(y), sz = std::sin(z);
+  return sx * cy * sz * std::cos(t) + st * st * sx * cx * (2.0 - 2.0 * sy * sy - sz * sz) + 3.0 * sx * cy * sz * st / Reynolds;
+}
+double forcing_y(double t, double x, double y, double z) {
+  const double st = std::sin(t), sx = std::sin(x), cx = std::cos(x), sy = std::sin(y), cy = std::cos(y), sz = std::sin(z);
+  return cx * sy * sz * std::cos(t) + st * st * sy * cy * (2.0 - 2.0 * sx * sx - sz * sz) + 3.0 * cx * sy * sz * st / Reynolds;
+}
+double forcing_z(double t, double x, double y, double z) {
+  const double st = std::sin(t), sx = std::sin(x), cx = std::cos(x), sy = std::sin(y), cy = std::cos(y), sz = std::sin(z), cz = std::cos(z);
+  return 2.0 * cx * cy * cz * std::cos(t) + 2.0 * st * st * sz * cz * (sx * sx + sy * sy - 2.0) + 6.0 * cx * cy * cz * st / Reynolds;
+}

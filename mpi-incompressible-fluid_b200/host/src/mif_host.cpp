@@ -20,7 +20,9 @@
 #include "Norms.h"
 #include "PressureEquation.h"
 #include "TestCaseBoundaries.h"
+#include "ManufacturedVelocity.h"
 #include "Timestep.h"
+#include "TimestepVelocity.h"
 
 namespace mif {
 
@@ -264,6 +266,8 @@ int detect_kind(const TimeVectorFunction &f) {
   if (is_function(f.f_u, u_exact) && is_function(f.f_v, v_exact) && is_function(f.f_w, w_exact)) return MIFGPU_BC_ETHIER_STEINMAN;
   if (is_function(f.f_u, exact_u_t1) && is_function(f.f_v, exact_v_t1) && is_function(f.f_w, exact_w_t1)) return MIFGPU_BC_TEST_CASE_1;
   if (is_function(f.f_u, exact_u_t2) && is_function(f.f_v, exact_v_t2) && is_function(f.f_w, exact_w_t2)) return MIFGPU_BC_TEST_CASE_2;
+  if (is_function(f.f_u, u_exact_v_test) && is_function(f.f_v, v_exact_v_test) && is_function(f.f_w, w_exact_v_test))
+    return MIFGPU_BC_VELOCITY_TEST;
   return MIFGPU_BC_HOST_CALLBACK;
 }
 
@@ -506,6 +510,27 @@ void timestep_nhn(VelocityTensor &velocity, VelocityTensor &velocity_buffer, Vel
                   StaggeredTensor &pressure, StaggeredTensor &pressure_buffer, PressureTensor &) {
   run_timestep(velocity, velocity_buffer, velocity_buffer_2, exact_velocity, &exact_pressure_gradient, t_n, pressure,
                pressure_buffer);
+}
+
+// src/TimestepVelocity.cpp:58-90.  The forcing is the reference's forcing_{x,y,z} (the only one its
+// calculate_momentum_rhs_with_forcing_* can add), evaluated on the device; the boundary data is any TimeVectorFunction.
+void timestep_velocity(VelocityTensor &velocity, VelocityTensor &velocity_buffer, VelocityTensor &rhs_buffer,
+                       const TimeVectorFunction &exact_velocity, Real t_n) {
+  FaceSource source{&velocity};
+  source.velocity = &exact_velocity;
+  mifgpu_bc bc{};
+  bc.kind = detect_kind(exact_velocity);
+  bc.Re = Reynolds;  // the global read by forcing_x/y/z in the reference (include/ManufacturedVelocity.h)
+  bc.callback = face_callback;
+  bc.user = &source;
+  mifgpu_tensor *v[3], *vb[3], *rb[3];
+  triple(velocity, v);
+  triple(velocity_buffer, vb);
+  triple(rhs_buffer, rb);
+  check(mifgpu_timestep_velocity(velocity.constants.gpu(), v, vb, rb, &bc, t_n), "mifgpu_timestep_velocity");
+  written(velocity);
+  written(velocity_buffer);
+  written(rhs_buffer);
 }
 
 // ---- norms (src/Norms.cpp) ----------------------------------------------------------------------------

@@ -53,10 +53,25 @@ def dump_case(name, args, meta, np_ranks=1):
         shutil.rmtree(tmp)
 
 
+def velocity_cases():
+    """timestep_velocity (src/TimestepVelocity.cpp:58-90) as run by test/velocity_test{,_mixed}.cpp: manufactured
+    velocity + forcing of generators/manufsol_velocity.py, Re = 1e4, final time 1e-4."""
+    for mixed in (0, 1):
+        ln = 2 * np.pi if mixed else 1.0
+        meta = dict(kind="vtest", N=[12, 12, 12], x_size=ln, y_size=ln, z_size=1.0, min=[0.0, 0.0, 0.0], Re=1e4,
+                    final_time=1e-4, steps=2, periodic=[mixed, mixed, 0], bc="velocity_test")
+        args = ["vtest", 12, 2, 1, "{out}"] + (["mixed"] if mixed else [])
+        dump_case("vtest_mixed_12_2" if mixed else "vtest_12_2", args, meta)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     if not os.path.exists(os.path.join(REF, "ref_dump")):
         sys.exit("oracle/_ref/ref_dump missing: run `make -C oracle ref` first")
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-velocity":  # add the velocity cases without touching the others
+        velocity_cases()
+        return
+    velocity_cases()
 
     # --- raw-field cases --------------------------------------------------------------------------
     full = dict(kind="full", x_size=1.0, y_size=1.0, z_size=2.0, min=[0.0, 0.0, -1.0], Re=1e3, final_time=1e-4,

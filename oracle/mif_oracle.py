@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmif_oracle.so")
 
 BC_TEST_CASE_1, BC_TEST_CASE_2, BC_ETHIER_STEINMAN = 1, 2, 3
+BC_VELOCITY_TEST = 5  # generators/manufsol_velocity.py (4 is the host-callback kind of include/mifgpu.h)
 REDFT00, R2HC, HC2R = 0, 1, 2
 
 _lib = None
@@ -43,6 +44,9 @@ def lib():
         l.mo_exact_velocity.restype = c_double
         l.mo_es_pressure_gradient.argtypes = [c_int] + [c_double] * 5
         l.mo_es_pressure_gradient.restype = c_double
+        l.mo_forcing.argtypes = [c_int] + [c_double] * 5
+        l.mo_forcing.restype = c_double
+        l.mo_timestep_velocity.argtypes = [c_void_p, c_int, c_double] + [dp] * 9
         l.mo_exact_pressure.argtypes = [c_int] + [c_double] * 5
         l.mo_exact_pressure.restype = c_double
         l.mo_velocity_error_norms.argtypes = [c_void_p, c_int, c_double, dp, dp, dp, dp]
@@ -95,6 +99,10 @@ class Grid:
             faces = (POINTER(c_double) * 6)(*[_ptr(f) for f in keep])
         lib().mo_solve_pressure(self._buf, _ptr(p), _ptr(u), _ptr(v), _ptr(w), dt, faces, int(direct))
         return p
+
+    def timestep_velocity(self, kind, t_n, vel, buf, rhs_buf):
+        """mif::timestep_velocity (src/TimestepVelocity.cpp:58-90), in place."""
+        lib().mo_timestep_velocity(self._buf, kind, t_n, *[_ptr(a) for a in (*vel, *buf, *rhs_buf)])
 
     def velocity_error_norms(self, kind, t, u, v, w):
         """(L1, L2, LInf) of src/Norms.cpp:49-86."""

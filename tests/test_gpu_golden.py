@@ -127,3 +127,23 @@ def test_timestep_matches_reference(mif, case):
             err = float(np.max(np.abs(t.download() - ref))) / max(float(np.max(np.abs(ref))), floor)
             assert err <= (TOL_NHN if nhn else TOL), (name, step + 1, err)
     ctx.close()
+
+
+@pytest.mark.parametrize("case", ["vtest_12_2", "vtest_mixed_12_2"])
+def test_timestep_velocity_matches_reference(mif, case):
+    """mif::timestep_velocity (src/TimestepVelocity.cpp) against the fields of the reference's velocity tests."""
+    meta, f = load_golden(case)
+    ctx = make_ctx(mif, meta)
+    vel, vb, rb = ctx.velocity(), ctx.velocity(), ctx.velocity()
+    for t, name in zip(vel, "uvw"):
+        t.upload(f[name + "_s0"])
+    bc = ctx.make_bc(mif.BC_VELOCITY_TEST, meta["Re"])
+    dt = meta["final_time"] / meta["steps"]
+    for step in range(meta["steps"]):
+        ctx.timestep_velocity(vel, vb, rb, bc, step * dt)
+        vmax = max(float(np.max(np.abs(f[f"{c}_s{step + 1}"]))) for c in "uvw")
+        for t, name in zip(vel, "uvw"):
+            ref = f[f"{name}_s{step + 1}"]
+            err = float(np.max(np.abs(t.download() - ref))) / max(float(np.max(np.abs(ref))), 1e-6 * vmax)
+            assert err <= TOL, (name, step + 1, err)
+    ctx.close()

@@ -41,6 +41,14 @@ def test_pressure_tests_print_reference_numbers(kind, n):
     assert close(got, NORMS[f"pressure_test_{kind} {n} 1"]), got
 
 
+@pytest.mark.parametrize("mixed", [False, True])
+@pytest.mark.parametrize("n", [16, 32])
+def test_velocity_tests_print_reference_numbers(mixed, n):
+    """test/velocity_test{,_mixed}.cpp: timestep_velocity + the (device-side) error norms through the host layer."""
+    got = [float(x) for x in run("velocity_test", n, n // 16, *(["mixed"] if mixed else [])).split()]
+    assert close(got, NORMS[f"velocity_test{'_mixed' if mixed else ''} {n} {n // 16} 1"]), got
+
+
 def test_full_test_convergence_order():
     """Velocity converges with order ~2, pressure with order ~1.5 (analysis/plot_convergence.py:63-64,80-81)."""
     import math

@@ -203,6 +203,27 @@ def test_device_norms_and_adjust_pressure_match_oracle(mif, N, periodic):
     ctx.close()
 
 
+@pytest.mark.parametrize("N,periodic", [((9, 7, 6), (False, False, False)), ((20, 13, 11), (False, False, False)),
+                                        ((12, 10, 14), (True, True, False)), ((70, 6, 9), (False, False, True)),
+                                        ((8, 11, 9), (False, True, False))])
+def test_timestep_velocity_random_state(mif, N, periodic):
+    """SURVEY section 8f-2: mif::timestep_velocity with the manufactured forcing against the oracle on seeded states."""
+    ctx, grid = make_pair(mif, N, periodic, Re=1e4, final_time=1e-2, steps=4)
+    rng = np.random.default_rng(17)
+    h_vel = [0.3 * rng.uniform(-1, 1, grid.shape(c)) for c in range(3)]
+    h_buf, h_rhs = [grid.zeros(c) for c in range(3)], [grid.zeros(c) for c in range(3)]
+    vel, vb, rb = ctx.velocity(), ctx.velocity(), ctx.velocity()
+    for t, h in zip(vel, h_vel):
+        t.upload(h)
+    bc = ctx.make_bc(mif.BC_VELOCITY_TEST, 1e4)
+    for step in range(2):
+        ctx.timestep_velocity(vel, vb, rb, bc, 0.3 + step * ctx.dt)
+        grid.timestep_velocity(mo.BC_VELOCITY_TEST, 0.3 + step * ctx.dt, h_vel, h_buf, h_rhs)
+        for t, h, name in zip(vel + vb + rb, h_vel + h_buf + h_rhs, ["u", "v", "w", "ub", "vb", "wb", "ru", "rv", "rw"]):
+            assert rel(t.download(), h) <= TOL, (name, step)
+    ctx.close()
+
+
 def test_upload_download_roundtrip_and_swap(mif):
     ctx, grid = make_pair(mif, (7, 5, 6), (False, True, False))
     rng = np.random.default_rng(0)

@@ -11,7 +11,8 @@ from conftest import ROOT, load_golden
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import mif_oracle as mo  # noqa: E402
 
-KINDS = {"ethier_steinman": mo.BC_ETHIER_STEINMAN, "test_case_1": mo.BC_TEST_CASE_1, "test_case_2": mo.BC_TEST_CASE_2}
+KINDS = {"ethier_steinman": mo.BC_ETHIER_STEINMAN, "test_case_1": mo.BC_TEST_CASE_1, "test_case_2": mo.BC_TEST_CASE_2,
+         "velocity_test": mo.BC_VELOCITY_TEST}
 
 
 def grid_from(meta):
@@ -83,6 +84,41 @@ def test_norms_and_adjust_pressure_match_the_numbers_printed_by_the_reference():
     got += list(g1.pressure_error_norms(mo.BC_ETHIER_STEINMAN, 1e-4, p))
     for mine, ref in zip(got, printed[:6]):
         assert abs(mine - ref) <= 1e-5 * abs(ref), (got, printed)  # the reference prints 6 significant digits
+
+
+@pytest.mark.parametrize("case", ["vtest_12_2", "vtest_mixed_12_2"])
+def test_timestep_velocity_restatement_matches_reference(case):
+    """mif::timestep_velocity with the manufactured forcing (test/velocity_test{,_mixed}.cpp through ref_dump vtest)."""
+    meta, f = load_golden(case)
+    g = grid_from(meta)
+    vel = [f[c + "_s0"].copy() for c in "uvw"]
+    buf, rhs = [g.zeros(c) for c in range(3)], [g.zeros(c) for c in range(3)]
+    dt = meta["final_time"] / meta["steps"]
+    for step in range(meta["steps"]):
+        g.timestep_velocity(mo.BC_VELOCITY_TEST, step * dt, vel, buf, rhs)
+        vmax = max(float(np.max(np.abs(f[f"{c}_s{step + 1}"]))) for c in "uvw")
+        for arr, name in zip(vel, "uvw"):
+            assert rel(arr, f[f"{name}_s{step + 1}"], 1e-6 * vmax) <= 1e-11, (name, step + 1)
+
+
+def test_manufactured_forcing_matches_sympy():
+    """forcing_{x,y,z}: f = d_t c + (u . grad) c - lap(c) / Re (generators/manufsol_velocity.py:38-48)."""
+    import sympy as sp
+    t, x, y, z = sp.symbols("t x y z")
+    Re = 1e4
+    u = sp.sin(x) * sp.cos(y) * sp.sin(z) * sp.sin(t)
+    v = sp.cos(x) * sp.sin(y) * sp.sin(z) * sp.sin(t)
+    w = 2 * sp.cos(x) * sp.cos(y) * sp.cos(z) * sp.sin(t)
+    lap = lambda c: sp.diff(c, x, 2) + sp.diff(c, y, 2) + sp.diff(c, z, 2)
+    rng = np.random.default_rng(7)
+    for comp, c in enumerate((u, v, w)):
+        f = sp.lambdify((t, x, y, z), sp.diff(c, t) + u * sp.diff(c, x) + v * sp.diff(c, y) + w * sp.diff(c, z) - lap(c) / Re)
+        for tt, xx, yy, zz in rng.uniform(-3, 3, (20, 4)):
+            want = float(f(tt, xx, yy, zz))
+            assert abs(mo.lib().mo_forcing(comp, tt, xx, yy, zz, Re) - want) <= 1e-13 * max(1.0, abs(want))
+        exact = sp.lambdify((t, x, y, z), c)
+        for tt, xx, yy, zz in rng.uniform(-3, 3, (5, 4)):
+            assert abs(mo.lib().mo_exact_velocity(mo.BC_VELOCITY_TEST, comp, tt, xx, yy, zz, Re) - float(exact(tt, xx, yy, zz))) <= 1e-14
 
 
 def test_initial_condition_matches_reference():
