@@ -326,19 +326,24 @@ __global__ void __launch_bounds__(256) sweep_kernel(const SweepJob job, double *
 // Fast path: DCT-I sweeps with N - 1 = M = 2^LOGM (64 <= M <= 1024), 8 lines per CTA, M threads.
 // ------------------------------------------------------------------------------------------------
 // Piecewise-strided addressing of a line for the multi-GPU sweeps: the points [lo[r], lo[r+1]) of every line live
-// in segment r (a block of a staging buffer, possibly in the memory of peer GPU r mapped over NVLink):
-//   address(e, outer, x) = base[r] + (e - lo[r]) * estride[r] + outer * outer_stride[r] + x.
+// in segment r (a block of a staging buffer, possibly in the memory of peer GPU r mapped over NVLink).  The buffers
+// are blocked in x by tiles of 8 doubles, with the line direction next:
+//   address(e, outer, x) = base[r] + (x >> 3) * xtile_stride[r] + outer * outer_stride[r] + (e - lo[r]) * estride[r] + (x & 7)
+// and estride = 8 wherever a sweep STORES: the 8 lines of a CTA times consecutive points of the lines are then one
+// contiguous run in the destination, so a warp-wide store is 256 contiguous bytes (4 points x 8 lines) instead of
+// four separate 64-byte pieces -- NVLink moves small writes at well under half its bandwidth.
 constexpr int kMaxRanks = 8;
 struct SegMap {
   int n = 0;  // 0: plain strided addressing
   int lo[kMaxRanks + 1];
   double *base[kMaxRanks];
-  long long estride[kMaxRanks], outer_stride[kMaxRanks];
+  long long estride[kMaxRanks], outer_stride[kMaxRanks], xtile_stride[kMaxRanks];
 };
 __device__ __forceinline__ double *seg_address(const SegMap &m, int e, int outer, int x) {
   int r = 0;
   while (r + 1 < m.n && e >= m.lo[r + 1]) r++;
-  return m.base[r] + (long long)(e - m.lo[r]) * m.estride[r] + (long long)outer * m.outer_stride[r] + x;
+  return m.base[r] + (long long)(x >> 3) * m.xtile_stride[r] + (long long)outer * m.outer_stride[r] +
+         (long long)(e - m.lo[r]) * m.estride[r] + (x & 7);
 }
 
 struct FastJob {
@@ -1253,6 +1258,7 @@ struct SweepLayout {
   int lam_y_offset;  // first global y index of outer index 0 (z sweeps on a y-distributed pencil)
   bool has_origin;   // this rank holds the (0,0,0) mode
   SegMap load_map, store_map;
+  bool peer = false;  // peer-memory sweeps: tiles of exactly 8 lines (the x tiles of the blocked buffers)
   const double *div_u = nullptr, *div_v = nullptr, *div_w = nullptr;  // fused right-hand side (forward x sweep only)
   double one_over_dx = 0, one_over_dy = 0, one_over_dz = 0, dt = 1;
   long long stride_y = 0, stride_z = 0;
@@ -1309,7 +1315,7 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
         else {
           static const int lines_contig = getenv("MIFGPU_SPLIT_LINES_X") ? atoi(getenv("MIFGPU_SPLIT_LINES_X")) : 4;
           static const int lines_strided = getenv("MIFGPU_SPLIT_LINES_YZ") ? atoi(getenv("MIFGPU_SPLIT_LINES_YZ")) : 4;
-          if ((lay.contig ? lines_contig : lines_strided) == 8) launch_split<8>(stream, fj, lay.contig, lay.outer, field);
+          if (lay.peer || (lay.contig ? lines_contig : lines_strided) == 8) launch_split<8>(stream, fj, lay.contig, lay.outer, field);
           else launch_split<4>(stream, fj, lay.contig, lay.outer, field);
         }
         break;
@@ -1376,27 +1382,34 @@ void launch_poisson_sweep(cudaStream_t stream, const Geom &g, PoissonPlan *plan,
 
 bool poisson_peer_capable(const PoissonPlan *plan) { return plan->fast_logm[1] >= 8 && plan->fast_logm[2] >= 8; }
 
-static void fill_map(SegMap &m, const PeerLayout &p, int which, int x_origin, const Geom &g) {
+// Blocked buffer layouts of the peer path (nxt = PX / 8 x tiles; all extents in doubles):
+//   zbuf[r]  z pencil of rank r:          [z (all N_z)][x tile][y in r's range][8]
+//   xfer[r]  slab staging of rank r:      blocks per source rank s (its y range), each [x tile][y in s's range][z in r's slab][8]
+static void fill_map(SegMap &m, const PeerLayout &p, int which, const Geom &g) {
   const int me = p.rank, P = p.nranks;
+  const long long nxt = g.PX / 8;
   const long long nz_me = p.zlo[me + 1] - p.zlo[me], ny_me = p.ylo[me + 1] - p.ylo[me];
   m.n = P;
   for (int r = 0; r < P; r++) {
     const long long ny_r = p.ylo[r + 1] - p.ylo[r], nz_r = p.zlo[r + 1] - p.zlo[r];
     if (which == 0) {         // forward y sweep -> z pencils: segments are y ranges, outer index is the local z plane
       m.lo[r] = p.ylo[r];
-      m.base[r] = p.zbuf[r] + (long long)p.zlo[me] * ny_r * g.PX + x_origin;
-      m.estride[r] = g.PX;
-      m.outer_stride[r] = ny_r * g.PX;
+      m.xtile_stride[r] = ny_r * 8;
+      m.estride[r] = 8;
+      m.outer_stride[r] = nxt * ny_r * 8;
+      m.base[r] = p.zbuf[r] + (long long)p.zlo[me] * m.outer_stride[r];
     } else if (which == 1) {  // fused z sweep -> slab staging of the owners: segments are z ranges, outer is local y
       m.lo[r] = p.zlo[r];
-      m.base[r] = p.xfer[r] + nz_r * g.PX * p.ylo[me] + x_origin;
-      m.estride[r] = ny_me * g.PX;
-      m.outer_stride[r] = g.PX;
+      m.xtile_stride[r] = ny_me * nz_r * 8;
+      m.outer_stride[r] = nz_r * 8;
+      m.estride[r] = 8;
+      m.base[r] = p.xfer[r] + nz_r * g.PX * p.ylo[me];
     } else {                  // inverse y sweep <- own slab staging: segments are the y ranges of the sources
       m.lo[r] = p.ylo[r];
-      m.base[r] = p.xfer[me] + nz_me * g.PX * p.ylo[r] + x_origin;
-      m.estride[r] = g.PX;
-      m.outer_stride[r] = ny_r * g.PX;
+      m.xtile_stride[r] = ny_r * nz_me * 8;
+      m.estride[r] = nz_me * 8;
+      m.outer_stride[r] = 8;
+      m.base[r] = p.xfer[me] + nz_me * g.PX * p.ylo[r];
     }
   }
   m.lo[P] = (which == 1) ? p.zlo[P] : p.ylo[P];
@@ -1412,26 +1425,29 @@ void launch_poisson_sweep_peer(cudaStream_t stream, const Geom &g, PoissonPlan *
   lay.contig = false;
   lay.n_tile_lines = nx;
   lay.lstride = 1;
-  lay.tile_stride = 1;
+  lay.peer = true;  // 8-line tiles: the x tiles of the blocked buffers
   if (which == 0 || which == 2) {
     // y sweeps on the local slab: lines along y, tile over x, outer over the local owner z planes
     lay.origin = gidx(g, g.own_lo[0], g.own_lo[1], g.own_lo[2]);
+    lay.tile_stride = 1;
     lay.estride = g.PX;
     lay.outer_stride = g.plane;
     lay.outer = nz;
-    if (which == 0) fill_map(lay.store_map, peer, 0, g.own_lo[0], g);
-    else fill_map(lay.load_map, peer, 2, g.own_lo[0], g);
+    if (which == 0) fill_map(lay.store_map, peer, 0, g);
+    else fill_map(lay.load_map, peer, 2, g);
     launch_sweep(stream, plan, field, 1, which == 0 ? 0 : 1, lay, launches);
   } else {
-    // fused z sweep on the local z pencil zbuf[z][y_local][x]
-    const int ny_local = peer.ylo[me + 1] - peer.ylo[me];
-    lay.origin = g.own_lo[0];
-    lay.estride = (long long)ny_local * g.PX;
-    lay.outer_stride = g.PX;
-    lay.outer = ny_local;
+    // fused z sweep on the local z pencil zbuf[z][x tile][y_local][8]: the tile of 8 lines starting at x = 8 t begins
+    // at t * ny_local * 8, i.e. first_line * ny_local
+    const long long ny_local = peer.ylo[me + 1] - peer.ylo[me];
+    lay.origin = 0;
+    lay.tile_stride = ny_local;
+    lay.estride = (long long)(g.PX / 8) * ny_local * 8;
+    lay.outer_stride = 8;
+    lay.outer = (int)ny_local;
     lay.lam_y_offset = peer.ylo[me];
     lay.has_origin = peer.ylo[me] == 0;
-    fill_map(lay.store_map, peer, 1, g.own_lo[0], g);
+    fill_map(lay.store_map, peer, 1, g);
     launch_sweep(stream, plan, peer.zbuf[me], 2, 2, lay, launches);
   }
 }

@@ -866,18 +866,34 @@ __global__ void __launch_bounds__(256) periodic_copy_kernel(const Geom g, double
   }
 }
 
+// Two x-adjacent points per thread, 128-bit accesses (see correct_kernel below).
 __global__ void __launch_bounds__(256)
 divergence_kernel(const Geom g, const double *__restrict__ u, const double *__restrict__ v,
                   const double *__restrict__ w, double dt, double *__restrict__ rhs) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + g.own_lo[0];
+  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int j = blockIdx.y * blockDim.y + threadIdx.y + g.own_lo[1];
   const int k = blockIdx.z + g.own_lo[2];
   if (i >= g.own_hi[0] || j >= g.own_hi[1]) return;
+  const bool do0 = i >= g.own_lo[0], do1 = i + 1 < g.own_hi[0];
   const long long c = gidx(g, i, j, k);
-  const double du_dx = (u[c + 1] - u[c]) * g.one_over_dx;
-  const double dv_dy = (v[c + g.PX] - v[c]) * g.one_over_dy;
-  const double dw_dz = (w[c + g.plane] - w[c]) * g.one_over_dz;
-  rhs[c] = (du_dx + dv_dy + dw_dz) / dt;
+  auto pair = [](const double *ptr) { return *reinterpret_cast<const double2 *>(ptr); };
+  const double2 U = pair(u + c), V0 = pair(v + c), V1 = pair(v + c + g.PX), W0 = pair(w + c), W1 = pair(w + c + g.plane);
+  double r0 = 0.0, r1 = 0.0;
+  if (do0) {
+    const double du_dx = (U.y - U.x) * g.one_over_dx;
+    const double dv_dy = (V1.x - V0.x) * g.one_over_dy;
+    const double dw_dz = (W1.x - W0.x) * g.one_over_dz;
+    r0 = (du_dx + dv_dy + dw_dz) / dt;
+  }
+  if (do1) {
+    const double du_dx = (u[c + 2] - U.y) * g.one_over_dx;
+    const double dv_dy = (V1.y - V0.y) * g.one_over_dy;
+    const double dw_dz = (W1.y - W0.y) * g.one_over_dz;
+    r1 = (du_dx + dv_dy + dw_dz) / dt;
+  }
+  if (do0 && do1) *reinterpret_cast<double2 *>(rhs + c) = make_double2(r0, r1);
+  else if (do0) rhs[c] = r0;
+  else if (do1) rhs[c + 1] = r1;
 }
 
 // Two x-adjacent points per thread with 128-bit accesses (rows start on 128-byte boundaries and PX is even, so the
@@ -1187,9 +1203,9 @@ void launch_apply_bc(cudaStream_t stream, const Geom &g, Vec3 vel, const BcDev &
 
 void launch_divergence(cudaStream_t stream, const Geom &g, CVec3 vel, double, double dt, double *rhs,
                        uint64_t *launches) {
-  const int ni = g.own_hi[0] - g.own_lo[0], nj = g.own_hi[1] - g.own_lo[1], nk = g.own_hi[2] - g.own_lo[2];
+  const int nj = g.own_hi[1] - g.own_lo[1], nk = g.own_hi[2] - g.own_lo[2];
   const dim3 block(64, 4, 1);
-  const dim3 grid(cdiv(ni, block.x), cdiv(nj, block.y), nk);
+  const dim3 grid(cdiv(g.own_hi[0], 2 * block.x), cdiv(nj, block.y), nk);  // pairs (i, i+1), i even, from i = 0
   divergence_kernel<<<grid, block, 0, stream>>>(g, vel.c[0], vel.c[1], vel.c[2], dt, rhs);
   ++*launches;
 }
