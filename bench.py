@@ -138,18 +138,26 @@ def rank_grid(cores):
 
 def run_reference_sample(points, iters, warmup, cores=None):
     """Times the unmodified reference (oracle/_ref/ref_bench) on the host cores; ranks are threads."""
-    exe = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
-    if not os.path.exists(exe):
-        return None
     ranks, py, pz = rank_grid(cores or host_core_count())
     env = dict(os.environ, MIF_SHIM_NP=str(ranks))
-    out = subprocess.run([exe, "step", str(points), str(points), str(points), str(iters), str(warmup), str(pz)],
-                         env=env, capture_output=True, text=True, timeout=1800)
-    if out.returncode != 0:
-        return None
-    res = json.loads(out.stdout.strip().splitlines()[-1])
-    res["cores"] = ranks
-    return res
+    # oracle/_ref/ref_bench is built with the reference's -march=native on the build machine; if this host's CPU
+    # lacks one of its instructions (SIGILL) the -march=x86-64-v3 build of the same sources is used instead.
+    for build, exe in (("native", os.path.join(ROOT, "oracle", "_ref", "ref_bench")),
+                       ("x86-64-v3", os.path.join(ROOT, "oracle", "_ref", "portable", "ref_bench"))):
+        if not os.path.exists(exe):
+            continue
+        try:
+            out = subprocess.run([exe, "step", str(points), str(points), str(points), str(iters), str(warmup), str(pz)],
+                                 env=env, capture_output=True, text=True, timeout=1800)
+            if out.returncode != 0:
+                continue
+            res = json.loads(out.stdout.strip().splitlines()[-1])
+        except (OSError, ValueError, IndexError, subprocess.TimeoutExpired):
+            continue
+        res["cores"] = ranks
+        res["build"] = build
+        return res
+    return None
 
 
 def reference_arm(args):
@@ -165,7 +173,8 @@ def reference_arm(args):
     value = res["cell_iters_per_s"]
     sample = (f"{points}^3 pressure points ({points - 1}^3 cells) of the same test-case-1 set-up, {args.steps} timed "
               f"steps + {args.warmup} warm-up, {res['ranks']} ranks (Py={res['Py']}, Pz={res['Pz']}) as threads of one "
-              "process; reference stencils/transposes + in-repo FFT and MPI stand-ins (no FFTW/MPI in the image)")
+              f"process, -march={res['build']}; reference stencils/transposes + in-repo FFT and MPI stand-ins (no FFTW/MPI "
+              "in the image)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / args.steps, "higher_is_better": True,
@@ -430,13 +439,17 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        res = run_reference_sample(args.ref_size, 2, 1)
+        try:
+            res = run_reference_sample(args.ref_size, 2, 1)
+        except Exception as exc:  # the optional CPU leg must never cost the GPU line
+            print(f"bench.py: cpu_baseline leg failed: {exc!r}", file=sys.stderr)
+            res = None
         if res is not None:
             cpu_baseline = {
                 "value": res["cell_iters_per_s"], "unit": UNIT, "cores": res["cores"], "kind": "reference",
                 "sample": (f"{args.ref_size}^3 points of the same set-up, 2 timed steps + 1 warm-up, {res['ranks']} ranks "
-                           f"(Py={res['Py']}, Pz={res['Pz']}) as threads; unmodified reference sources + in-repo FFT/MPI "
-                           "stand-ins (oracle/_ref)")}
+                           f"(Py={res['Py']}, Pz={res['Pz']}) as threads, -march={res['build']}; unmodified reference "
+                           "sources + in-repo FFT/MPI stand-ins (oracle/_ref)")}
 
     if rank == 0:
         line = {
@@ -447,7 +460,9 @@ def main():
                                     f"{dims[0] - 1}x{dims[1] - 1}x{dims[2] - 1} cells ({cells_1d}^3 cells per GPU)"),
                        "points": dims, "dt": dt, "Re": 1e3,
                        "parallelism": "single GPU" if world == 1 else
-                       f"z slabs Py=1 Pz={world}: NCCL plane halos + grouped send/recv all-to-all pencil transposes",
+                       (f"z slabs Py=1 Pz={world}: NCCL plane halos; Y<->Z pencil transposes " +
+                        ("fused into the y/z sweeps as NVLink peer-memory stores (no separate all-to-all)"
+                         if os.environ.get("MIFGPU_NO_PEER") is None else "as grouped NCCL send/recv all-to-all")),
                        "l2": "inputs larger than L2 (each field %.2f GB)" % (points * 8 / 1e9), "finite": finite},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "kernels": kernels, "clocks": clocks,
