@@ -15,7 +15,7 @@
  *
  * Two implementations are provided for each transform: a direct O(n^2) sum that reads exactly like the
  * definition (mo_*_direct, the oracle of the oracle), and an O(n log n) version built on one complex FFT
- * (radix-2 for powers of two, Bluestein's chirp-z otherwise) that is used by the fftw3.h shim so the
+ * (radix-4 Stockham passes for powers of two, Bluestein's chirp-z otherwise) that is used by the fftw3.h shim so the
  * compiled reference doubles as the CPU timing baseline.
  */
 #ifndef MIF_ORACLE_FFT_CPU_H
@@ -84,9 +84,9 @@ static inline void mo_hc2r_direct(int n, const double *y, double *x) {
 typedef struct mo_cfft_plan {
   int n;
   int is_pow2;
-  /* power-of-two path */
-  double *tw;   /* stage-major twiddles: for half-size h (1,2,4..n/2) entries tw[2*(h+k)], k<h */
-  int *bitrev;
+  /* power-of-two path: radix-4 Stockham autosort passes (one radix-2 pass last when log2 n is odd) */
+  double *tw;   /* per radix-4 pass of length len = n, n/4, ...: 3 * len/4 complex twiddles w^p, w^2p, w^3p (forward) */
+  double *ping; /* n complex scratch */
   /* Bluestein path */
   int m;
   struct mo_cfft_plan *sub;
@@ -98,35 +98,94 @@ typedef struct mo_cfft_plan {
 static inline mo_cfft_plan *mo_cfft_create(int n);
 static inline void mo_cfft_destroy(mo_cfft_plan *p);
 
+/* One radix-4 decimation-in-frequency Stockham pass: the sequence of length len (stride s, n = len * s) is split
+ * into four interleaved sub-sequences of length len/4 (stride 4 s).  sg = +1 forward, -1 inverse. */
+static inline void mo_stockham4_pass(int len, int s, const double *tw, double sg, const double *__restrict__ x,
+                                     double *__restrict__ y) {
+  const int n1 = len / 4;
+  if (s == 1) {
+    for (int p = 0; p < n1; p++) {
+      const double w1r = tw[6 * p], w1i = sg * tw[6 * p + 1];
+      const double w2r = tw[6 * p + 2], w2i = sg * tw[6 * p + 3];
+      const double w3r = tw[6 * p + 4], w3i = sg * tw[6 * p + 5];
+      const double ar = x[2 * p], ai = x[2 * p + 1];
+      const double br = x[2 * (p + n1)], bi = x[2 * (p + n1) + 1];
+      const double cr = x[2 * (p + 2 * n1)], ci = x[2 * (p + 2 * n1) + 1];
+      const double dr = x[2 * (p + 3 * n1)], di = x[2 * (p + 3 * n1) + 1];
+      const double apcr = ar + cr, apci = ai + ci, amcr = ar - cr, amci = ai - ci;
+      const double bpdr = br + dr, bpdi = bi + di;
+      const double jr = -sg * (bi - di), ji = sg * (br - dr); /* sg * i * (b - d) */
+      double *o = y + 8 * p;
+      o[0] = apcr + bpdr;
+      o[1] = apci + bpdi;
+      const double t1r = amcr - jr, t1i = amci - ji;
+      o[2] = t1r * w1r - t1i * w1i;
+      o[3] = t1r * w1i + t1i * w1r;
+      const double t2r = apcr - bpdr, t2i = apci - bpdi;
+      o[4] = t2r * w2r - t2i * w2i;
+      o[5] = t2r * w2i + t2i * w2r;
+      const double t3r = amcr + jr, t3i = amci + ji;
+      o[6] = t3r * w3r - t3i * w3i;
+      o[7] = t3r * w3i + t3i * w3r;
+    }
+    return;
+  }
+  for (int p = 0; p < n1; p++) {
+    const double w1r = tw[6 * p], w1i = sg * tw[6 * p + 1];
+    const double w2r = tw[6 * p + 2], w2i = sg * tw[6 * p + 3];
+    const double w3r = tw[6 * p + 4], w3i = sg * tw[6 * p + 5];
+    const double *xa = x + 2 * (size_t)s * p, *xb = xa + 2 * (size_t)s * n1, *xc = xb + 2 * (size_t)s * n1,
+                 *xd = xc + 2 * (size_t)s * n1;
+    double *y0 = y + 2 * (size_t)s * (4 * p), *y1 = y0 + 2 * (size_t)s, *y2 = y1 + 2 * (size_t)s, *y3 = y2 + 2 * (size_t)s;
+    for (int q = 0; q < s; q++) {
+      const double ar = xa[2 * q], ai = xa[2 * q + 1], br = xb[2 * q], bi = xb[2 * q + 1];
+      const double cr = xc[2 * q], ci = xc[2 * q + 1], dr = xd[2 * q], di = xd[2 * q + 1];
+      const double apcr = ar + cr, apci = ai + ci, amcr = ar - cr, amci = ai - ci;
+      const double bpdr = br + dr, bpdi = bi + di;
+      const double jr = -sg * (bi - di), ji = sg * (br - dr);
+      y0[2 * q] = apcr + bpdr;
+      y0[2 * q + 1] = apci + bpdi;
+      const double t1r = amcr - jr, t1i = amci - ji;
+      y1[2 * q] = t1r * w1r - t1i * w1i;
+      y1[2 * q + 1] = t1r * w1i + t1i * w1r;
+      const double t2r = apcr - bpdr, t2i = apci - bpdi;
+      y2[2 * q] = t2r * w2r - t2i * w2i;
+      y2[2 * q + 1] = t2r * w2i + t2i * w2r;
+      const double t3r = amcr + jr, t3i = amci + ji;
+      y3[2 * q] = t3r * w3r - t3i * w3i;
+      y3[2 * q + 1] = t3r * w3i + t3i * w3r;
+    }
+  }
+}
+
 static inline void mo_cfft_pow2_exec(const mo_cfft_plan *p, double *z, int inverse) {
   const int n = p->n;
-  for (int i = 0; i < n; i++) {
-    const int j = p->bitrev[i];
-    if (j > i) {
-      const double tr = z[2 * i], ti = z[2 * i + 1];
-      z[2 * i] = z[2 * j];
-      z[2 * i + 1] = z[2 * j + 1];
-      z[2 * j] = tr;
-      z[2 * j + 1] = ti;
-    }
+  const double sg = inverse ? -1.0 : 1.0;
+  double *x = z, *y = p->ping;
+  const double *tw = p->tw;
+  int len = n, s = 1;
+  while (len >= 4) {
+    mo_stockham4_pass(len, s, tw, sg, x, y);
+    tw += 6 * (len / 4);
+    len /= 4;
+    s *= 4;
+    double *t = x;
+    x = y;
+    y = t;
   }
-  const double s = inverse ? -1.0 : 1.0;
-  for (int h = 1; h < n; h <<= 1) {
-    const double *tw = p->tw + 2 * h;
-    for (int base = 0; base < n; base += 2 * h) {
-      double *lo = z + 2 * base;
-      double *hi = z + 2 * (base + h);
-      for (int k = 0; k < h; k++) {
-        const double wr = tw[2 * k], wi = s * tw[2 * k + 1];
-        const double xr = hi[2 * k] * wr - hi[2 * k + 1] * wi;
-        const double xi = hi[2 * k] * wi + hi[2 * k + 1] * wr;
-        hi[2 * k] = lo[2 * k] - xr;
-        hi[2 * k + 1] = lo[2 * k + 1] - xi;
-        lo[2 * k] += xr;
-        lo[2 * k + 1] += xi;
-      }
+  if (len == 2) { /* last pass: n/2 butterflies without twiddles, stride s = n/2 */
+    for (int q = 0; q < s; q++) {
+      const double ar = x[2 * q], ai = x[2 * q + 1], br = x[2 * (q + s)], bi = x[2 * (q + s) + 1];
+      y[2 * q] = ar + br;
+      y[2 * q + 1] = ai + bi;
+      y[2 * (q + s)] = ar - br;
+      y[2 * (q + s) + 1] = ai - bi;
     }
+    double *t = x;
+    x = y;
+    y = t;
   }
+  if (x != z) memcpy(z, x, sizeof(double) * 2 * (size_t)n);
 }
 
 /* Forward (inverse=0: exp(-2 pi i jk/n)) or unnormalised inverse (inverse=1) DFT, in place. */
@@ -171,21 +230,16 @@ static inline mo_cfft_plan *mo_cfft_create(int n) {
   p->is_pow2 = (n > 0) && ((n & (n - 1)) == 0);
   if (n <= 1) return p;
   if (p->is_pow2) {
-    p->tw = (double *)malloc(sizeof(double) * 2 * (size_t)n);
-    for (int h = 1; h < n; h <<= 1)
-      for (int k = 0; k < h; k++) {
-        const double a = -MO_PI * (double)k / (double)h;
-        p->tw[2 * (h + k)] = cos(a);
-        p->tw[2 * (h + k) + 1] = sin(a);
-      }
-    p->bitrev = (int *)malloc(sizeof(int) * (size_t)n);
-    int bits = 0;
-    while ((1 << bits) < n) bits++;
-    for (int i = 0; i < n; i++) {
-      int r = 0;
-      for (int b = 0; b < bits; b++)
-        if (i & (1 << b)) r |= 1 << (bits - 1 - b);
-      p->bitrev[i] = r;
+    p->tw = (double *)malloc(sizeof(double) * 2 * (size_t)n + 64);
+    p->ping = (double *)malloc(sizeof(double) * 2 * (size_t)n);
+    double *tw = p->tw;
+    for (int len = n; len >= 4; len /= 4) {
+      for (int q = 0; q < len / 4; q++)
+        for (int r = 1; r <= 3; r++) {
+          const double a = -2.0 * MO_PI * (double)(q * r) / (double)len;
+          *tw++ = cos(a);
+          *tw++ = sin(a);
+        }
     }
     return p;
   }
@@ -217,7 +271,7 @@ static inline mo_cfft_plan *mo_cfft_create(int n) {
 static inline void mo_cfft_destroy(mo_cfft_plan *p) {
   if (!p) return;
   free(p->tw);
-  free(p->bitrev);
+  free(p->ping);
   free(p->chirp);
   free(p->filt);
   free(p->work);
