@@ -130,6 +130,12 @@ void mifgpu_tensor_destroy(mifgpu_tensor *tensor);
 /* Host <-> device copies of a whole tensor in the reference layout (Tensor::raw_data(), include/Tensor.h:118). */
 int mifgpu_tensor_upload(mifgpu_tensor *tensor, const double *host);
 int mifgpu_tensor_download(const mifgpu_tensor *tensor, double *host);
+/* The index box lo[d] <= index < hi[d] of a tensor as a compact array, x fastest:
+ * host[(i - lo[0]) + (j - lo[1]) * bx + (k - lo[2]) * bx * by], bx = hi[0] - lo[0], by = hi[1] - lo[1].  This is what
+ * the output path needs instead of whole fields: writeVTK reads three planes, writeDat one line with its
+ * interpolation neighbours (src/VTKDatExport.cpp:115-312,342-583); the box is gathered on the device and crosses
+ * PCIe as one contiguous block.  MIFGPU_ERR_INVALID if the box is empty or leaves the tensor. */
+int mifgpu_tensor_download_box(const mifgpu_tensor *tensor, const int32_t lo[3], const int32_t hi[3], double *host);
 /* Tensor::swap_data (include/Tensor.h:108-110) as used by VelocityTensor::swap_data (src/VelocityTensor.cpp:13-27). */
 int mifgpu_tensor_swap(mifgpu_tensor *a, mifgpu_tensor *b);
 

@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "mifgpu_tensor_swap", "mifgpu_timestep", "mifgpu_apply_bc", "mifgpu_solve_pressure", "mifgpu_synchronize",
     "mifgpu_stream", "mifgpu_launch_count", "mifgpu_profile_enable", "mifgpu_profile_read", "mifgpu_comm_unique_id",
     "mifgpu_create_distributed", "mifgpu_slab_plan", "mifgpu_velocity_error_norms", "mifgpu_pressure_error_norms",
-    "mifgpu_adjust_pressure", "mifgpu_timestep_velocity",
+    "mifgpu_adjust_pressure", "mifgpu_timestep_velocity", "mifgpu_tensor_download_box",
 ]
 
 
@@ -97,6 +97,7 @@ def lib() -> ctypes.CDLL:
     l.mifgpu_tensor_upload.argtypes = [c_void_p, c_void_p]
     l.mifgpu_tensor_download.argtypes = [c_void_p, c_void_p]
     l.mifgpu_tensor_swap.argtypes = [c_void_p, c_void_p]
+    l.mifgpu_tensor_download_box.argtypes = [c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]
     l.mifgpu_timestep.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(Bc),
                                   c_double, c_void_p, c_void_p, c_int]
     l.mifgpu_apply_bc.argtypes = [c_void_p, POINTER(c_void_p), POINTER(Bc), c_double]
@@ -162,6 +163,13 @@ class Tensor:
         if out is None:
             out = np.empty((sz, sy, sx), dtype=np.float64)
         _check(lib().mifgpu_tensor_download(self.handle, out.ctypes.data_as(c_void_p)))
+        return out
+
+    def download_box(self, lo: Sequence[int], hi: Sequence[int]) -> np.ndarray:
+        """The index box lo <= (i, j, k) < hi as an array of shape (hi[2]-lo[2], hi[1]-lo[1], hi[0]-lo[0])."""
+        out = np.empty((hi[2] - lo[2], hi[1] - lo[1], hi[0] - lo[0]), dtype=np.float64)
+        _check(lib().mifgpu_tensor_download_box(self.handle, (c_int32 * 3)(*lo), (c_int32 * 3)(*hi),
+                                                out.ctypes.data_as(c_void_p)))
         return out
 
     def close(self) -> None:

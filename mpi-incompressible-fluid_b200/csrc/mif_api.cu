@@ -763,6 +763,41 @@ static int copy_tensor(const mifgpu_tensor *t, double *host, bool to_device) {
 int mifgpu_tensor_upload(mifgpu_tensor *t, const double *host) { return copy_tensor(t, const_cast<double *>(host), true); }
 int mifgpu_tensor_download(const mifgpu_tensor *t, double *host) { return copy_tensor(t, host, false); }
 
+// Sub-box [lo, hi) of a tensor as one compact array: a device-to-device 3-D copy gathers the box from the padded
+// tensor into the staging buffer (srcPos.x is in bytes, y / z in rows / slices), one contiguous copy crosses PCIe.
+int mifgpu_tensor_download_box(const mifgpu_tensor *t, const int32_t lo[3], const int32_t hi[3], double *host) {
+  if (!t || !lo || !hi || !host) return fail(MIFGPU_ERR_INVALID, "NULL argument");
+  mifgpu_ctx *ctx = t->ctx;
+  const Geom &g = ctx->g;
+  const int s = t->staggering;
+  const int ext[3] = {g.sx[s], g.sy[s], g.sz[s]};
+  for (int d = 0; d < 3; d++)
+    if (lo[d] < 0 || hi[d] <= lo[d] || hi[d] > ext[d])
+      return fail(MIFGPU_ERR_INVALID, "box [%d, %d) outside the tensor extent %d in direction %d", lo[d], hi[d], ext[d], d);
+  CUDA_TRY(cudaSetDevice(ctx->params.device));
+  const size_t bx = (size_t)(hi[0] - lo[0]), by = (size_t)(hi[1] - lo[1]), bz = (size_t)(hi[2] - lo[2]);
+  const size_t bytes = bx * by * bz * sizeof(double);
+  if (ctx->staging_bytes < bytes) {
+    if (ctx->staging) cudaFree(ctx->staging);
+    ctx->staging = nullptr;
+    ctx->staging_bytes = 0;
+    CUDA_TRY(cudaMalloc(&ctx->staging, bytes));
+    ctx->staging_bytes = bytes;
+  }
+  cudaMemcpy3DParms parms;
+  std::memset(&parms, 0, sizeof(parms));
+  parms.srcPtr = make_cudaPitchedPtr(t->data, (size_t)g.PX * sizeof(double), g.PX, g.PY);
+  parms.srcPos = make_cudaPos((size_t)lo[0] * sizeof(double), (size_t)lo[1], (size_t)lo[2]);
+  parms.dstPtr = make_cudaPitchedPtr(ctx->staging, bx * sizeof(double), bx, by);
+  parms.dstPos = make_cudaPos(0, 0, 0);
+  parms.extent = make_cudaExtent(bx * sizeof(double), by, bz);
+  parms.kind = cudaMemcpyDeviceToDevice;
+  CUDA_TRY(cudaMemcpy3DAsync(&parms, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(host, ctx->staging, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MIFGPU_OK;
+}
+
 int mifgpu_tensor_swap(mifgpu_tensor *a, mifgpu_tensor *b) {
   if (!a || !b || a->ctx != b->ctx || a->staggering != b->staggering) return fail(MIFGPU_ERR_INVALID, "tensors are not swappable");
   std::swap(a->data, b->data);

@@ -94,6 +94,12 @@ public:
   mifgpu_tensor *device() const;    // device tensor, up to date with the host copy
   void device_was_written() const;  // libmifgpu changed the device copy: the host copy is stale
   void sync_host() const { host_for_read(); }
+  // Output path (src/VTKDatExport.cpp reads three planes and a few lines, not whole fields): when the newest copy
+  // is on the device, fetch_box brings only the index box [lo, hi) into the host array -- the host copy as a whole
+  // stays stale -- and peek reads the host array without synchronising.  A box that leaves the tensor (the
+  // reference's own out-of-row reads next to periodic / last planes) falls back to refreshing the whole field.
+  void fetch_box(const std::array<int, 3> &lo, const std::array<int, 3> &hi) const;
+  const Real &peek(size_t i, size_t j, size_t k) const { return Tensor::operator()(i, j, k); }
 
 private:
   void host_for_read() const;

@@ -4,6 +4,7 @@
 #include "VTKDatExport.h"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -51,9 +52,27 @@ WriteRange write_range(const Constants &c) {
   return r;
 }
 
-Real u_at_point(const VelocityTensor &v, int i, int j, int k) { return (v.u(i, j, k) + v.u(i + 1, j, k)) / 2; }
-Real v_at_point(const VelocityTensor &v, int i, int j, int k) { return (v.v(i, j, k) + v.v(i, j + 1, k)) / 2; }
-Real w_at_point(const VelocityTensor &v, int i, int j, int k) { return (v.w(i, j, k) + v.w(i, j, k + 1)) / 2; }
+// The writers read through peek(): the values they need were brought to the host by prefetch() (planes / lines
+// gathered on the device) or by a whole-field refresh, never by a per-element synchronisation.
+Real u_at_point(const VelocityTensor &v, int i, int j, int k) { return (v.u.peek(i, j, k) + v.u.peek(i + 1, j, k)) / 2; }
+Real v_at_point(const VelocityTensor &v, int i, int j, int k) { return (v.v.peek(i, j, k) + v.v.peek(i, j + 1, k)) / 2; }
+Real w_at_point(const VelocityTensor &v, int i, int j, int k) { return (v.w.peek(i, j, k) + v.w.peek(i, j, k + 1)) / 2; }
+
+// Makes everything the writers read for the pressure points of the index box [lo, hi) available on the host.
+// reach_all = false: the cell-centre averages above read index + 1 along the staggering direction of the tensor
+// only; reach_all = true: the profile interpolation of writeDat reads index + 1 in every direction.
+void prefetch(const StaggeredTensor &t, std::array<int, 3> lo, std::array<int, 3> hi, bool reach_all) {
+  for (int d = 0; d < 3; d++)
+    if (reach_all || static_cast<int>(t.staggering) == d) hi[d] += 1;
+  t.fetch_box(lo, hi);
+}
+void prefetch(const VelocityTensor &velocity, const StaggeredTensor &pressure, const std::array<int, 3> &lo,
+              const std::array<int, 3> &hi, bool reach_all) {
+  prefetch(velocity.u, lo, hi, reach_all);
+  prefetch(velocity.v, lo, hi, reach_all);
+  prefetch(velocity.w, lo, hi, reach_all);
+  prefetch(pressure, lo, hi, reach_all);
+}
 
 void append_big_endian(std::string &out, const std::vector<Real> &values) {
   for (Real value : values) {
@@ -85,19 +104,21 @@ void writeVTK(const std::string &filename, const VelocityTensor &velocity, const
     su.push_back(u_at_point(velocity, i, j, k));
     sv.push_back(v_at_point(velocity, i, j, k));
     sw.push_back(w_at_point(velocity, i, j, k));
-    sp.push_back(pressure(i, j, k));
+    sp.push_back(pressure.peek(i, j, k));
   };
   // Planes in the reference's order: z = 0 (i outer, j inner), x = 0 (j outer, k inner), y = 0 (i outer, k inner).
   {
     const int k_global = locate(0.0, c.min_z_global, c.dz).index;
     if (k_global >= r.global_lo[2] && k_global < r.global_lo[2] + (r.hi[2] - r.lo[2])) {
       const int k = k_global - r.global_lo[2] + r.lo[2];
+      prefetch(velocity, pressure, {r.lo[0], r.lo[1], k}, {r.hi[0], r.hi[1], k + 1}, false);
       for (int i = r.lo[0]; i < r.hi[0]; i++)
         for (int j = r.lo[1]; j < r.hi[1]; j++) add_point(i, j, k);
     }
   }
   {
     const int i = locate(0.0, c.min_x_global, c.dx).index - r.global_lo[0] + r.lo[0];
+    prefetch(velocity, pressure, {i, r.lo[1], r.lo[2]}, {i + 1, r.hi[1], r.hi[2]}, false);
     for (int j = r.lo[1]; j < r.hi[1]; j++)
       for (int k = r.lo[2]; k < r.hi[2]; k++) add_point(i, j, k);
   }
@@ -105,6 +126,7 @@ void writeVTK(const std::string &filename, const VelocityTensor &velocity, const
     const int j_global = locate(0.0, c.min_y_global, c.dy).index;
     if (j_global >= r.global_lo[1] && j_global < r.global_lo[1] + (r.hi[1] - r.lo[1])) {
       const int j = j_global - r.global_lo[1] + r.lo[1];
+      prefetch(velocity, pressure, {r.lo[0], j, r.lo[2]}, {r.hi[0], j + 1, r.hi[2]}, false);
       for (int i = r.lo[0]; i < r.hi[0]; i++)
         for (int k = r.lo[2]; k < r.hi[2]; k++) add_point(i, j, k);
     }
@@ -139,10 +161,10 @@ void writeDat(const std::string &filename, const VelocityTensor &velocity, const
   bool aligned[3];
   for (int d = 0; d < 3; d++) aligned[d] = std::abs(at[d].weight - 1.0) < precision;
   const Real wi = at[0].weight, wj = at[1].weight, wk = at[2].weight;
-  const auto &U = velocity.u;
-  const auto &V = velocity.v;
-  const auto &W = velocity.w;
-  const auto &P = pressure;
+  auto U = [&](int i, int j, int k) { return velocity.u.peek(i, j, k); };
+  auto V = [&](int i, int j, int k) { return velocity.v.peek(i, j, k); };
+  auto W = [&](int i, int j, int k) { return velocity.w.peek(i, j, k); };
+  auto P = [&](int i, int j, int k) { return pressure.peek(i, j, k); };
 
   std::vector<Real> coordinate, su, sv, sw, sp;
   auto inside = [&](int d) { return at[d].index >= r.global_lo[d] && at[d].index < r.global_lo[d] + (r.hi[d] - r.lo[d]); };
@@ -151,6 +173,7 @@ void writeDat(const std::string &filename, const VelocityTensor &velocity, const
   // the second term of the unaligned-u branches of the y and z profiles.
   if (direction == 0 && inside(1) && inside(2)) {
     const int j = local(1), k = local(2);
+    prefetch(velocity, pressure, {r.lo[0], j, k}, {r.hi[0], j + 1, k + 1}, true);
     for (int i = r.lo[0]; i < r.hi[0]; i++) {
       coordinate.push_back(c.min_x_global + (c.base_i + i) * c.dx);
       su.push_back(wj * wk * (U(i, j, k) + U(i + 1, j, k)) / 2 + (1 - wj) * wk * (U(i, j + 1, k) + U(i + 1, j + 1, k)) / 2 +
@@ -165,6 +188,7 @@ void writeDat(const std::string &filename, const VelocityTensor &velocity, const
     }
   } else if (direction == 1 && inside(0) && inside(2)) {
     const int i = local(0), k = local(2);
+    prefetch(velocity, pressure, {i, r.lo[1], k}, {i + 1, r.hi[1], k + 1}, true);
     for (int j = r.lo[1]; j < r.hi[1]; j++) {
       coordinate.push_back(c.min_y_global + (c.base_j + j) * c.dy);
       if (aligned[0]) su.push_back(wk * (U(i, j, k) + U(i + 1, j, k)) / 2 + (1 - wk) * (U(i, j, k + 1) + U(i + 1, j, k + 1)) / 2);
@@ -179,6 +203,7 @@ void writeDat(const std::string &filename, const VelocityTensor &velocity, const
     }
   } else if (direction == 2 && inside(0) && inside(1)) {
     const int i = local(0), j = local(1);
+    prefetch(velocity, pressure, {i, j, r.lo[2]}, {i + 1, j + 1, r.hi[2]}, true);
     for (int k = r.lo[2]; k < r.hi[2]; k++) {
       coordinate.push_back(c.min_z_global + (c.base_k + k) * c.dz);
       if (aligned[0]) su.push_back(wj * (U(i, j, k) + U(i + 1, j, k)) / 2 + (1 - wj) * (U(i, j + 1, k) + U(i + 1, j + 1, k)) / 2);
@@ -209,6 +234,10 @@ void writeVTKFullMesh(const std::string &filename, const mif::VelocityTensor &ve
   const Constants &c = velocity.constants;
   if (c.Py * c.Pz != 1) throw std::invalid_argument("writeVTKFullMesh needs a single rank");
   const WriteRange r = write_range(c);
+  velocity.u.sync_host();  // every point is written: whole fields
+  velocity.v.sync_host();
+  velocity.w.sync_host();
+  pressure.sync_host();
   const int nx = r.hi[0] - r.lo[0], ny = r.hi[1] - r.lo[1], nz = r.hi[2] - r.lo[2];
   std::ofstream out(filename);
   out << "# vtk DataFile Version 3.0\npressure mesh solution\nASCII\nDATASET STRUCTURED_POINTS\n"
@@ -229,7 +258,7 @@ void writeVTKFullMesh(const std::string &filename, const mif::VelocityTensor &ve
     const Real ux = u_at_point(velocity, i, j, k), uy = v_at_point(velocity, i, j, k), uz = w_at_point(velocity, i, j, k);
     return std::sqrt(ux * ux + uy * uy + uz * uz);
   });
-  scalar("p", [&](int i, int j, int k) { return pressure(i, j, k); });
+  scalar("p", [&](int i, int j, int k) { return pressure.peek(i, j, k); });
 }
 
 }  // namespace mif

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <sstream>
@@ -138,6 +139,27 @@ void StaggeredTensor::host_for_read() const {
   if (host_valid_) return;
   check(mifgpu_tensor_download(device_, const_cast<Real *>(data_.data())), "mifgpu_tensor_download");
   host_valid_ = true;
+}
+
+void StaggeredTensor::fetch_box(const std::array<int, 3> &lo, const std::array<int, 3> &hi) const {
+  if (host_valid_) return;
+  static const bool whole_fields = std::getenv("MIF_EXPORT_WHOLE_FIELDS") != nullptr;  // A/B switch
+  const auto &s = sizes();
+  bool inside = !whole_fields;
+  for (int d = 0; d < 3; d++)
+    if (lo[d] < 0 || hi[d] <= lo[d] || hi[d] > static_cast<int>(s[d])) inside = false;
+  if (!inside) {
+    host_for_read();
+    return;
+  }
+  const size_t bx = hi[0] - lo[0], by = hi[1] - lo[1], bz = hi[2] - lo[2];
+  std::vector<Real> box(bx * by * bz);
+  const int32_t lo32[3] = {lo[0], lo[1], lo[2]}, hi32[3] = {hi[0], hi[1], hi[2]};
+  check(mifgpu_tensor_download_box(device_, lo32, hi32, box.data()), "mifgpu_tensor_download_box");
+  Real *host = const_cast<Real *>(data_.data());
+  for (size_t k = 0; k < bz; k++)
+    for (size_t j = 0; j < by; j++)
+      std::memcpy(host + offset(lo[0], lo[1] + j, lo[2] + k), box.data() + (k * by + j) * bx, bx * sizeof(Real));
 }
 
 void StaggeredTensor::swap_data(StaggeredTensor &other) {
