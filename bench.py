@@ -411,6 +411,20 @@ def main():
                        "frac": round(value / world * BYTES_PER_CELL_STEP / 1e9 / peak, 4)},
     }
 
+    # NVLink traffic of the Y<->Z pencil transposes: per all-to-all every GPU sends
+    # 8 B * points/P * (P-1)/P; slab decomposition: 2 per solve, 6 per step.  With the peer-memory path these bytes are
+    # the remote stores of the forward y sweep and of the fused z sweep, so their launch times bound the link rate.
+    nvlink = None
+    if world > 1:
+        sent = 6.0 * 8.0 * points * (world - 1) / world
+        carrier_ms = sum(kernels.get(k, 0.0) for k in ("sweep_y_fwd", "sweep_z_fused", "transpose_alltoall"))
+        nvlink = {"bytes_sent_per_gpu_per_step": sent, "peak_GBs_per_direction": 900.0,
+                  "GBs_over_carrier_kernels": round(sent / (carrier_ms * 1e-3) / 1e9, 1) if carrier_ms > 0 else None,
+                  "carrier_kernels_ms_per_step": round(carrier_ms, 4),
+                  "GBs_over_whole_step": round(sent / (elapsed_ms / steps * 1e-3) / 1e9, 1),
+                  "what": "6 pencil transposes per step, 8 B * points/P * (P-1)/P each way per transpose; carried by the "
+                          "forward y sweep and the fused z sweep (peer stores) or by the NCCL all-to-all (fallback)"}
+
     # End to end through the C ABI with HOST buffers: every step uploads u, v, w, p from pinned host memory,
     # runs mifgpu_timestep and downloads u, v, w, p (host <-> device copies inside the timed region).
     e2e = None
@@ -464,7 +478,7 @@ def main():
                         ("fused into the y/z sweeps as NVLink peer-memory stores (no separate all-to-all)"
                          if os.environ.get("MIFGPU_NO_PEER") is None else "as grouped NCCL send/recv all-to-all")),
                        "l2": "inputs larger than L2 (each field %.2f GB)" % (points * 8 / 1e9), "finite": finite},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "nvlink": nvlink, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "kernels": kernels, "clocks": clocks,
         }
         print(json.dumps(line))
