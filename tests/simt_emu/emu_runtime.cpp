@@ -1,0 +1,214 @@
+// tests/simt_emu/emu_runtime.cpp -- TEST INFRASTRUCTURE ONLY: SIMT interpreter + CUDA runtime stand-ins (see
+// include/cuda_runtime.h).  One OS thread; the CUDA threads of one block are ucontext fibers that run until they reach
+// a scheduling point (block / warp / named barrier, shuffle) or return; blocks run one after the other.
+#include <cuda_runtime.h>
+#include <ucontext.h>
+
+#include <chrono>
+#include <cstdio>
+#include <vector>
+
+uint3 threadIdx, blockIdx;
+dim3 blockDim, gridDim;
+
+namespace {
+
+enum State { RUNNABLE, WAIT_BLOCK, WAIT_WARP, WAIT_NAMED, DONE };
+constexpr size_t kStackBytes = 256 * 1024;
+constexpr int kMaxThreads = 1024;
+
+struct Fiber {
+  ucontext_t ctx;
+  State state = DONE;
+  int named_id = 0, named_count = 0;
+  char *stack = nullptr;
+};
+
+Fiber g_fibers[kMaxThreads];
+ucontext_t g_scheduler;
+int g_current = -1, g_nthreads = 0;
+const std::function<void()> *g_body = nullptr;
+std::vector<unsigned char> g_dynamic_smem;
+uint64_t g_shuffle[kMaxThreads / 32][2][32];
+int g_parity[kMaxThreads];
+uint3 g_tid[kMaxThreads];
+
+void trampoline() {
+  (*g_body)();
+  g_fibers[g_current].state = DONE;
+  swapcontext(&g_fibers[g_current].ctx, &g_scheduler);
+}
+
+void yield(State why) {
+  Fiber &f = g_fibers[g_current];
+  f.state = why;
+  swapcontext(&f.ctx, &g_scheduler);
+  threadIdx = g_tid[g_current];
+}
+
+void run_block() {
+  for (int t = 0; t < g_nthreads; t++) {
+    Fiber &f = g_fibers[t];
+    if (!f.stack) f.stack = static_cast<char *>(aligned_alloc(64, kStackBytes));
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack;
+    f.ctx.uc_stack.ss_size = kStackBytes;
+    f.ctx.uc_link = nullptr;
+    makecontext(&f.ctx, trampoline, 0);
+    f.state = RUNNABLE;
+    g_parity[t] = 0;
+  }
+  for (;;) {
+    bool ran = false;
+    for (int t = 0; t < g_nthreads; t++) {
+      if (g_fibers[t].state != RUNNABLE) continue;
+      g_current = t;
+      threadIdx = g_tid[t];
+      swapcontext(&g_scheduler, &g_fibers[t].ctx);
+      ran = true;
+    }
+    // release the barriers whose participants have all arrived (threads that returned do not take part)
+    int live = 0, at_block = 0;
+    for (int t = 0; t < g_nthreads; t++) {
+      if (g_fibers[t].state != DONE) live++;
+      if (g_fibers[t].state == WAIT_BLOCK) at_block++;
+    }
+    if (live == 0) return;
+    bool released = false;
+    if (at_block == live) {
+      for (int t = 0; t < g_nthreads; t++)
+        if (g_fibers[t].state == WAIT_BLOCK) g_fibers[t].state = RUNNABLE;
+      released = true;
+    }
+    for (int w = 0; w * 32 < g_nthreads; w++) {
+      int wl = 0, ww = 0;
+      for (int t = w * 32; t < g_nthreads && t < w * 32 + 32; t++) {
+        if (g_fibers[t].state != DONE) wl++;
+        if (g_fibers[t].state == WAIT_WARP) ww++;
+      }
+      if (wl > 0 && ww == wl) {
+        for (int t = w * 32; t < g_nthreads && t < w * 32 + 32; t++)
+          if (g_fibers[t].state == WAIT_WARP) g_fibers[t].state = RUNNABLE;
+        released = true;
+      }
+    }
+    for (int id = 0; id < 16; id++) {
+      int waiting = 0, expected = 0;
+      for (int t = 0; t < g_nthreads; t++)
+        if (g_fibers[t].state == WAIT_NAMED && g_fibers[t].named_id == id) {
+          waiting++;
+          expected = g_fibers[t].named_count;
+        }
+      if (waiting > 0 && waiting >= expected) {
+        for (int t = 0; t < g_nthreads; t++)
+          if (g_fibers[t].state == WAIT_NAMED && g_fibers[t].named_id == id) g_fibers[t].state = RUNNABLE;
+        released = true;
+      }
+    }
+    if (!ran && !released) {
+      std::fprintf(stderr, "simt_emu: deadlock in block (%u, %u, %u): %d live threads wait at barriers that cannot complete\n",
+                   blockIdx.x, blockIdx.y, blockIdx.z, live);
+      abort();
+    }
+  }
+}
+
+}  // namespace
+
+namespace emu {
+
+void launch(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::function<void()> &thread_body) {
+  const size_t n = (size_t)block.x * block.y * block.z;
+  if (n == 0 || n > kMaxThreads) {
+    std::fprintf(stderr, "simt_emu: block of %zu threads\n", n);
+    abort();
+  }
+  if ((size_t)grid.x * grid.y * grid.z == 0) return;
+  g_nthreads = (int)n;
+  g_body = &thread_body;
+  blockDim = block;
+  gridDim = grid;
+  g_dynamic_smem.assign(dynamic_smem_bytes + 64, 0);
+  int t = 0;
+  for (unsigned z = 0; z < block.z; z++)
+    for (unsigned y = 0; y < block.y; y++)
+      for (unsigned x = 0; x < block.x; x++) g_tid[t++] = uint3{x, y, z};
+  for (unsigned bz = 0; bz < grid.z; bz++)
+    for (unsigned by = 0; by < grid.y; by++)
+      for (unsigned bx = 0; bx < grid.x; bx++) {
+        blockIdx = uint3{bx, by, bz};
+        // shared memory is uninitialised on the device: poison it with NaNs so stale reads show up
+        for (size_t i = 0; i + 8 <= g_dynamic_smem.size(); i += 8) {
+          const uint64_t nan_bits = 0x7ff8dead00000000ull;
+          memcpy(&g_dynamic_smem[i], &nan_bits, 8);
+        }
+        run_block();
+      }
+  g_body = nullptr;
+}
+
+void *dynamic_smem() {
+  uintptr_t p = reinterpret_cast<uintptr_t>(g_dynamic_smem.data());
+  return reinterpret_cast<void *>((p + 63) & ~uintptr_t(63));
+}
+void block_barrier() { yield(WAIT_BLOCK); }
+void warp_barrier() { yield(WAIT_WARP); }
+void named_barrier(int id, int count) {
+  g_fibers[g_current].named_id = id;
+  g_fibers[g_current].named_count = count;
+  yield(WAIT_NAMED);
+}
+void *shuffle_slot(int lane, int parity) { return &g_shuffle[g_current / 32][parity][lane & 31]; }
+int lane_id() { return g_current & 31; }
+int &shuffle_parity() { return g_parity[g_current]; }
+
+}  // namespace emu
+
+// ---- CUDA runtime stand-ins: "device" memory is host memory --------------------------------------------------
+struct emu_stream { int unused; };
+struct emu_event { std::chrono::steady_clock::time_point when; };
+
+cudaError_t emu_malloc(void **ptr, size_t bytes) {
+  const size_t rounded = (bytes + 255) / 256 * 256;
+  *ptr = aligned_alloc(256, rounded ? rounded : 256);
+  if (!*ptr) return cudaErrorEmu;
+  // device memory is uninitialised: NaN pattern
+  const uint64_t nan_bits = 0x7ff8beef00000000ull;
+  for (size_t i = 0; i + 8 <= rounded; i += 8) memcpy(static_cast<char *>(*ptr) + i, &nan_bits, 8);
+  return cudaSuccess;
+}
+cudaError_t cudaFree(void *ptr) { free(ptr); return cudaSuccess; }
+cudaError_t cudaFreeHost(void *ptr) { free(ptr); return cudaSuccess; }
+cudaError_t cudaMemcpy(void *dst, const void *src, size_t bytes, cudaMemcpyKind) { memmove(dst, src, bytes); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t bytes, cudaMemcpyKind, cudaStream_t) { memmove(dst, src, bytes); return cudaSuccess; }
+cudaError_t cudaMemset(void *dst, int value, size_t bytes) { memset(dst, value, bytes); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *dst, int value, size_t bytes, cudaStream_t) { memset(dst, value, bytes); return cudaSuccess; }
+cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms *p, cudaStream_t) {
+  const cudaPitchedPtr &s = p->srcPtr, &d = p->dstPtr;
+  for (size_t z = 0; z < p->extent.depth; z++)
+    for (size_t y = 0; y < p->extent.height; y++) {
+      const char *src = static_cast<const char *>(s.ptr) + ((p->srcPos.z + z) * s.ysize + p->srcPos.y + y) * s.pitch + p->srcPos.x;
+      char *dst = static_cast<char *>(d.ptr) + ((p->dstPos.z + z) * d.ysize + p->dstPos.y + y) * d.pitch + p->dstPos.x;
+      memmove(dst, src, p->extent.width);
+    }
+  return cudaSuccess;
+}
+cudaError_t cudaGetDeviceCount(int *count) { *count = 1; return cudaSuccess; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+cudaError_t cudaGetLastError() { return cudaSuccess; }
+const char *cudaGetErrorString(cudaError_t err) { return err == cudaSuccess ? "no error" : "simt_emu: unsupported call"; }
+cudaError_t cudaStreamCreate(cudaStream_t *stream) { *stream = new emu_stream(); return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *stream, unsigned) { *stream = new emu_stream(); return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t stream) { delete stream; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t *event) { *event = new emu_event(); return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t event) { delete event; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t event, cudaStream_t) { event->when = std::chrono::steady_clock::now(); return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t start, cudaEvent_t stop) {
+  *ms = std::chrono::duration<float, std::milli>(stop->when - start->when).count();
+  return cudaSuccess;
+}
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorEmu; }
+cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorEmu; }
+cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorEmu; }

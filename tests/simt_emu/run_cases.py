@@ -1,0 +1,39 @@
+"""TEST INFRASTRUCTURE ONLY: runs a few bodies of the GPU parity tests with libmifgpu's kernels executed by the SIMT
+interpreter (MIFGPU_LIB must point at tests/simt_emu/build/libmifgpu_simt.so).  Called by tests/test_simt_emu.py in a
+subprocess, because the library a process binds is fixed at first use."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    assert "simt" in os.environ.get("MIFGPU_LIB", ""), "MIFGPU_LIB must point at the SIMT build"
+    import mif_b200 as mif
+    assert "simt" in mif.LIB_PATH
+    import __graft_entry__ as entry
+    import test_gpu_golden as golden
+    import test_gpu_vs_oracle as parity
+
+    F, T = False, True
+    entry.smoke()                                                     # 16^3, generic sweeps, stage / bc / correct kernels
+    solve = parity.test_pressure_solve_random_velocity
+    for N, periodic in [((513, 4, 9), (F, F, F)),                     # warp-per-line DCT-I, x sweep (M = 512)
+                        ((9, 257, 3), (F, F, F)),                     # ... strided y sweep (M = 256)
+                        ((11, 3, 513), (F, F, F)),                    # ... fused z sweep
+                        ((1025, 3, 4), (F, F, F)),                    # split kernel (two 512-point halves)
+                        ((20, 9, 513), (F, F, T)),                    # warp real-FFT path, fused z sweep
+                        ((65, 9, 65), (F, F, F)),                     # CTA-synchronous fast path
+                        ((12, 10, 14), (F, F, T))]:                   # Bluestein
+        solve(mif, N, periodic)
+        print("solve ok", N, periodic, flush=True)
+    parity.test_timestep_random_state(mif, (9, 10, 12), (T, T, T), "test_case_2")
+    parity.test_timestep_nhn_matches_oracle(mif)
+    golden.test_timestep_velocity_matches_reference(mif, "vtest_12_2")
+    print("simt cases ok")
+
+
+if __name__ == "__main__":
+    main()
