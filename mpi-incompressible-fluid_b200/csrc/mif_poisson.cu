@@ -62,31 +62,79 @@ __device__ __forceinline__ double2 cmul_conj(double2 a, double2 b) {  // a * con
   return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
 
-// Radix-2 decimation-in-frequency passes: natural order in, bit-reversed order out.
+// Radix-2 decimation-in-frequency stages, natural order in, bit-reversed order out -- executed two stages per pass
+// over shared memory (a radix-4 butterfly on w[i0 + {0, 1, 2, 3} q]): the same butterflies and table twiddles as two
+// single-stage passes, half the shared-memory round trips and barriers.  A last single stage remains when logP is odd.
 __device__ void fft_dif(double2 *W, int L, int P, int logP, const double2 *__restrict__ tw, bool conj_tw) {
-  const int halfP = P >> 1;
-  for (int s = logP - 1; s >= 0; s--) {
-    const int half = 1 << s;
-    const int tstride = halfP >> s;
-    for (int item = threadIdx.x; item < L * halfP; item += blockDim.x) {
-      const int l = item / halfP, bfly = item - l * halfP;
-      const int k = bfly & (half - 1);
-      const int i0 = ((bfly >> s) << (s + 1)) + k;
+  const int halfP = P >> 1, quarterP = P >> 2;
+  int s = logP - 1;
+  for (; s >= 1; s -= 2) {
+    const int q = 1 << (s - 1);      // stage s pairs (i, i + 2q), stage s - 1 pairs (i, i + q)
+    const int tstride = halfP >> s;  // twiddle stride of stage s; stage s - 1 uses 2 * tstride
+    for (int item = threadIdx.x; item < L * quarterP; item += blockDim.x) {
+      const int l = item / quarterP, g = item - l * quarterP;
+      const int k = g & (q - 1);
+      const int i0 = ((g >> (s - 1)) << (s + 1)) + k;
       double2 *w = W + (size_t)l * P;
-      const double2 a = w[i0], b = w[i0 + half];
-      double2 t = __ldg(&tw[k * tstride]);
+      const double2 a = w[i0], b = w[i0 + q], c = w[i0 + 2 * q], d = w[i0 + 3 * q];
+      double2 t0 = __ldg(&tw[k * tstride]), t1 = __ldg(&tw[(k + q) * tstride]), t2 = __ldg(&tw[2 * k * tstride]);
+      if (conj_tw) {
+        t0.y = -t0.y;
+        t1.y = -t1.y;
+        t2.y = -t2.y;
+      }
+      const double2 a1 = make_double2(a.x + c.x, a.y + c.y), c1 = cmul(make_double2(a.x - c.x, a.y - c.y), t0);
+      const double2 b1 = make_double2(b.x + d.x, b.y + d.y), d1 = cmul(make_double2(b.x - d.x, b.y - d.y), t1);
+      w[i0] = make_double2(a1.x + b1.x, a1.y + b1.y);
+      w[i0 + q] = cmul(make_double2(a1.x - b1.x, a1.y - b1.y), t2);
+      w[i0 + 2 * q] = make_double2(c1.x + d1.x, c1.y + d1.y);
+      w[i0 + 3 * q] = cmul(make_double2(c1.x - d1.x, c1.y - d1.y), t2);
+    }
+    __syncthreads();
+  }
+  if (s == 0) {  // half = 1, twiddle 1
+    for (int item = threadIdx.x; item < L * halfP; item += blockDim.x) {
+      const int l = item / halfP, i0 = (item - l * halfP) << 1;
+      double2 *w = W + (size_t)l * P;
+      const double2 a = w[i0], b = w[i0 + 1];
+      double2 t = __ldg(&tw[0]);
       if (conj_tw) t.y = -t.y;
       w[i0] = make_double2(a.x + b.x, a.y + b.y);
-      w[i0 + half] = cmul(make_double2(a.x - b.x, a.y - b.y), t);
+      w[i0 + 1] = cmul(make_double2(a.x - b.x, a.y - b.y), t);
     }
     __syncthreads();
   }
 }
 
-// Radix-2 decimation-in-time passes: bit-reversed order in, natural order out.
+// Radix-2 decimation-in-time stages, bit-reversed order in, natural order out, two stages per pass like fft_dif.
 __device__ void fft_dit(double2 *W, int L, int P, int logP, const double2 *__restrict__ tw, bool conj_tw) {
-  const int halfP = P >> 1;
-  for (int s = 0; s < logP; s++) {
+  const int halfP = P >> 1, quarterP = P >> 2;
+  int s = 0;
+  for (; s + 1 < logP; s += 2) {
+    const int h = 1 << s;                    // stage s pairs (i, i + h), stage s + 1 pairs (i, i + 2h)
+    const int tstride = halfP >> (s + 1);    // twiddle stride of stage s + 1; stage s uses 2 * tstride
+    for (int item = threadIdx.x; item < L * quarterP; item += blockDim.x) {
+      const int l = item / quarterP, g = item - l * quarterP;
+      const int k = g & (h - 1);
+      const int i0 = ((g >> s) << (s + 2)) + k;
+      double2 *w = W + (size_t)l * P;
+      double2 t0 = __ldg(&tw[2 * k * tstride]), t1 = __ldg(&tw[k * tstride]), t2 = __ldg(&tw[(k + h) * tstride]);
+      if (conj_tw) {
+        t0.y = -t0.y;
+        t1.y = -t1.y;
+        t2.y = -t2.y;
+      }
+      const double2 a = w[i0], b = cmul(w[i0 + h], t0), c = w[i0 + 2 * h], d = cmul(w[i0 + 3 * h], t0);
+      const double2 a1 = make_double2(a.x + b.x, a.y + b.y), b1 = make_double2(a.x - b.x, a.y - b.y);
+      const double2 c1 = cmul(make_double2(c.x + d.x, c.y + d.y), t1), d1 = cmul(make_double2(c.x - d.x, c.y - d.y), t2);
+      w[i0] = make_double2(a1.x + c1.x, a1.y + c1.y);
+      w[i0 + 2 * h] = make_double2(a1.x - c1.x, a1.y - c1.y);
+      w[i0 + h] = make_double2(b1.x + d1.x, b1.y + d1.y);
+      w[i0 + 3 * h] = make_double2(b1.x - d1.x, b1.y - d1.y);
+    }
+    __syncthreads();
+  }
+  if (s < logP) {  // last single stage, half = P / 2
     const int half = 1 << s;
     const int tstride = halfP >> s;
     for (int item = threadIdx.x; item < L * halfP; item += blockDim.x) {
