@@ -50,10 +50,13 @@ NcclApi g_nccl;
 
 bool load_nccl() {
   if (g_nccl.ok) return true;
-  void *handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
-  if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+  // MIFGPU_NCCL_LIB names the library to bind instead (a system NCCL next to a framework's bundled one; the tests'
+  // in-process stand-in on machines without GPUs).
+  const char *override_path = getenv("MIFGPU_NCCL_LIB");
+  void *handle = override_path ? dlopen(override_path, RTLD_NOW | RTLD_LOCAL) : dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!handle && !override_path) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
   if (!handle) {
-    g_last_error = std::string("cannot load libnccl.so.2: ") + dlerror();
+    g_last_error = std::string("cannot load ") + (override_path ? override_path : "libnccl.so.2") + ": " + dlerror();
     return false;
   }
   auto sym = [&](const char *name) { return dlsym(handle, name); };

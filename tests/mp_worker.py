@@ -25,7 +25,8 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
     dist.init_process_group("gloo")
-    torch.cuda.set_device(local_rank)
+    if torch.cuda.is_available():  # (the CPU run of this worker under the SIMT interpreter has no device to select)
+        torch.cuda.set_device(local_rank)
     ids = [mif.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
 

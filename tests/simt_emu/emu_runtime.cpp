@@ -2,10 +2,15 @@
 // include/cuda_runtime.h).  One OS thread; the CUDA threads of one block are ucontext fibers that run until they reach
 // a scheduling point (block / warp / named barrier, shuffle) or return; blocks run one after the other.
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <ucontext.h>
+#include <unistd.h>
 
 #include <chrono>
 #include <cstdio>
+#include <string>
 #include <vector>
 
 uint3 threadIdx, blockIdx;
@@ -168,17 +173,64 @@ int &shuffle_parity() { return g_parity[g_current]; }
 struct emu_stream { int unused; };
 struct emu_event { std::chrono::steady_clock::time_point when; };
 
+// With MIF_SIMT_IPC=1 (multi-process runs) every allocation is a shared-memory file, so that cudaIpcGetMemHandle /
+// cudaIpcOpenMemHandle can map a buffer of another rank's process: the handle carries the file name.
+namespace {
+struct Allocation { void *ptr; size_t bytes; std::string shm_name; bool mapped_peer; };
+std::vector<Allocation> g_allocations;
+bool ipc_mode() {
+  static const bool on = getenv("MIF_SIMT_IPC") != nullptr;
+  return on;
+}
+void unlink_all() {
+  for (Allocation &a : g_allocations)
+    if (!a.shm_name.empty() && !a.mapped_peer) shm_unlink(a.shm_name.c_str());
+}
+}  // namespace
+
 cudaError_t emu_malloc(void **ptr, size_t bytes) {
-  const size_t rounded = (bytes + 255) / 256 * 256;
-  *ptr = aligned_alloc(256, rounded ? rounded : 256);
-  if (!*ptr) return cudaErrorEmu;
+  const size_t rounded = bytes ? (bytes + 4095) / 4096 * 4096 : 4096;
+  std::string name;
+  if (ipc_mode()) {
+    static int counter = 0;
+    static bool registered = false;
+    if (!registered) {
+      atexit(unlink_all);
+      registered = true;
+    }
+    char buf[64];
+    std::snprintf(buf, sizeof(buf), "/mif_simt_%d_%d", (int)getpid(), counter++);
+    name = buf;
+    const int fd = shm_open(name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0 || ftruncate(fd, (off_t)rounded) != 0) return cudaErrorEmu;
+    *ptr = mmap(nullptr, rounded, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (*ptr == MAP_FAILED) return cudaErrorEmu;
+  } else {
+    *ptr = aligned_alloc(4096, rounded);
+    if (!*ptr) return cudaErrorEmu;
+  }
   // device memory is uninitialised: NaN pattern
   const uint64_t nan_bits = 0x7ff8beef00000000ull;
   for (size_t i = 0; i + 8 <= rounded; i += 8) memcpy(static_cast<char *>(*ptr) + i, &nan_bits, 8);
+  g_allocations.push_back(Allocation{*ptr, rounded, name, false});
   return cudaSuccess;
 }
-cudaError_t cudaFree(void *ptr) { free(ptr); return cudaSuccess; }
-cudaError_t cudaFreeHost(void *ptr) { free(ptr); return cudaSuccess; }
+cudaError_t cudaFree(void *ptr) {
+  if (!ptr) return cudaSuccess;
+  for (size_t i = 0; i < g_allocations.size(); i++)
+    if (g_allocations[i].ptr == ptr) {
+      if (g_allocations[i].shm_name.empty()) free(ptr);
+      else {
+        munmap(ptr, g_allocations[i].bytes);
+        shm_unlink(g_allocations[i].shm_name.c_str());
+      }
+      g_allocations.erase(g_allocations.begin() + i);
+      return cudaSuccess;
+    }
+  return cudaErrorEmu;
+}
+cudaError_t cudaFreeHost(void *ptr) { return cudaFree(ptr); }
 cudaError_t cudaMemcpy(void *dst, const void *src, size_t bytes, cudaMemcpyKind) { memmove(dst, src, bytes); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t bytes, cudaMemcpyKind, cudaStream_t) { memmove(dst, src, bytes); return cudaSuccess; }
 cudaError_t cudaMemset(void *dst, int value, size_t bytes) { memset(dst, value, bytes); return cudaSuccess; }
@@ -193,7 +245,7 @@ cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms *p, cudaStream_t) {
     }
   return cudaSuccess;
 }
-cudaError_t cudaGetDeviceCount(int *count) { *count = 1; return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int *count) { *count = 64; return cudaSuccess; }  // any ordinal a rank asks for exists
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 cudaError_t cudaGetLastError() { return cudaSuccess; }
@@ -209,6 +261,36 @@ cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t start, cudaEvent_t stop)
   *ms = std::chrono::duration<float, std::milli>(stop->when - start->when).count();
   return cudaSuccess;
 }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorEmu; }
-cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorEmu; }
-cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorEmu; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *handle, void *ptr) {
+  for (const Allocation &a : g_allocations)
+    if (a.ptr == ptr && !a.shm_name.empty()) {
+      memset(handle, 0, sizeof(*handle));
+      std::snprintf(handle->reserved, sizeof(handle->reserved), "%s", a.shm_name.c_str());
+      return cudaSuccess;
+    }
+  return cudaErrorEmu;
+}
+cudaError_t cudaIpcOpenMemHandle(void **ptr, cudaIpcMemHandle_t handle, unsigned) {
+  handle.reserved[sizeof(handle.reserved) - 1] = 0;
+  const int fd = shm_open(handle.reserved, O_RDWR, 0600);
+  if (fd < 0) return cudaErrorEmu;
+  struct stat st;
+  if (fstat(fd, &st) != 0) {
+    close(fd);
+    return cudaErrorEmu;
+  }
+  *ptr = mmap(nullptr, (size_t)st.st_size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (*ptr == MAP_FAILED) return cudaErrorEmu;
+  g_allocations.push_back(Allocation{*ptr, (size_t)st.st_size, handle.reserved, true});
+  return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void *ptr) {
+  for (size_t i = 0; i < g_allocations.size(); i++)
+    if (g_allocations[i].ptr == ptr && g_allocations[i].mapped_peer) {
+      munmap(ptr, g_allocations[i].bytes);
+      g_allocations.erase(g_allocations.begin() + i);
+      return cudaSuccess;
+    }
+  return cudaErrorEmu;
+}

@@ -1,0 +1,136 @@
+// tests/simt_emu/fake_nccl.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// The nine NCCL entry points libmifgpu binds with dlopen (csrc/mif_api.cu, load_nccl), implemented between PROCESSES
+// of one machine through mailbox files in /dev/shm, so that the multi-rank paths of the library (plane halos, the
+// grouped send/recv all-to-all, the rank barriers of the peer-memory transposes) can run under the SIMT interpreter
+// on a machine without GPUs.  Everything is synchronous: a send writes its payload to a file named after
+// (communicator, source, destination, sequence number) and renames it into place; a receive polls for the file of
+// the next sequence number of that pair.  Sends never block, so any order of calls inside a group is deadlock free.
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+extern "C" {
+
+typedef struct FakeComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+typedef int ncclDataType_t;  // ncclChar = 0, ncclInt = 2, ncclDouble = 8 (nccl.h)
+typedef int ncclRedOp_t;
+typedef void *cudaStream_t;
+
+struct FakeComm {
+  std::string tag;
+  int rank, nranks;
+  std::vector<uint64_t> sent, received;  // per peer sequence numbers
+};
+
+static size_t type_size(ncclDataType_t t) {
+  switch (t) {
+    case 0: case 1: return 1;
+    case 2: case 3: return 4;
+    case 4: case 5: case 8: return 8;
+    case 7: return 4;
+    default: return 1;
+  }
+}
+
+static std::string mailbox(const FakeComm *c, int src, int dst, uint64_t seq) {
+  char name[256];
+  std::snprintf(name, sizeof(name), "/dev/shm/mif_fake_nccl_%s_%d_%d_%llu", c->tag.c_str(), src, dst, (unsigned long long)seq);
+  return name;
+}
+
+ncclResult_t ncclGetUniqueId(ncclUniqueId *id) {
+  std::memset(id, 0, sizeof(*id));
+  std::snprintf(id->internal, sizeof(id->internal), "%d_%ld", (int)getpid(), (long)random());
+  return 0;
+}
+
+ncclResult_t ncclCommInitRank(ncclComm_t *comm, int nranks, ncclUniqueId id, int rank) {
+  FakeComm *c = new FakeComm();
+  id.internal[127] = 0;
+  c->tag = id.internal;
+  c->rank = rank;
+  c->nranks = nranks;
+  c->sent.assign(nranks, 0);
+  c->received.assign(nranks, 0);
+  *comm = c;
+  return 0;
+}
+
+ncclResult_t ncclCommDestroy(ncclComm_t comm) {
+  delete comm;
+  return 0;
+}
+
+ncclResult_t ncclGroupStart() { return 0; }
+ncclResult_t ncclGroupEnd() { return 0; }
+
+ncclResult_t ncclSend(const void *buf, size_t count, ncclDataType_t type, int peer, ncclComm_t c, cudaStream_t) {
+  const size_t bytes = count * type_size(type);
+  const std::string final_name = mailbox(c, c->rank, peer, c->sent[peer]++);
+  const std::string tmp = final_name + ".tmp";
+  FILE *f = std::fopen(tmp.c_str(), "wb");
+  if (!f) return 1;
+  const size_t written = bytes ? std::fwrite(buf, 1, bytes, f) : 0;
+  std::fclose(f);
+  if (written != bytes || std::rename(tmp.c_str(), final_name.c_str()) != 0) return 1;
+  return 0;
+}
+
+ncclResult_t ncclRecv(void *buf, size_t count, ncclDataType_t type, int peer, ncclComm_t c, cudaStream_t) {
+  const size_t bytes = count * type_size(type);
+  const std::string name = mailbox(c, peer, c->rank, c->received[peer]++);
+  for (long spins = 0;; spins++) {
+    struct stat st;
+    if (stat(name.c_str(), &st) == 0) break;
+    if (spins > 600000) {  // 10 minutes
+      std::fprintf(stderr, "fake_nccl: rank %d timed out waiting for %s\n", c->rank, name.c_str());
+      return 1;
+    }
+    usleep(1000);
+  }
+  FILE *f = std::fopen(name.c_str(), "rb");
+  if (!f) return 1;
+  const size_t got = bytes ? std::fread(buf, 1, bytes, f) : 0;
+  std::fclose(f);
+  unlink(name.c_str());
+  return got == bytes ? 0 : 1;
+}
+
+ncclResult_t ncclAllReduce(const void *send, void *recv, size_t count, ncclDataType_t type, ncclRedOp_t, ncclComm_t c,
+                           cudaStream_t s) {
+  // every rank sends its contribution to every other rank and adds them up in rank order (sum only)
+  const size_t bytes = count * type_size(type);
+  std::vector<char> mine(bytes);
+  std::memcpy(mine.data(), send, bytes);
+  for (int r = 0; r < c->nranks; r++)
+    if (r != c->rank && ncclSend(mine.data(), count, type, r, c, s)) return 1;
+  std::vector<char> acc(bytes, 0), other(bytes);
+  for (int r = 0; r < c->nranks; r++) {
+    const char *src = mine.data();
+    if (r != c->rank) {
+      if (ncclRecv(other.data(), count, type, r, c, s)) return 1;
+      src = other.data();
+    }
+    for (size_t i = 0; i < count; i++) {
+      if (type == 8) reinterpret_cast<double *>(acc.data())[i] += reinterpret_cast<const double *>(src)[i];
+      else if (type == 2) reinterpret_cast<int *>(acc.data())[i] += reinterpret_cast<const int *>(src)[i];
+      else return 1;
+    }
+  }
+  std::memcpy(recv, acc.data(), bytes);
+  return 0;
+}
+
+const char *ncclGetErrorString(ncclResult_t r) { return r == 0 ? "no error" : "fake_nccl: failure"; }
+
+}  // extern "C"
