@@ -106,7 +106,10 @@ void mifgpu_destroy(mifgpu_ctx *ctx);
  * calls mifgpu_comm_unique_id, the host program distributes the MIFGPU_UNIQUE_ID_BYTES bytes to all ranks by any
  * means (MPI_Bcast, torch.distributed, a file), and every rank calls mifgpu_create_distributed collectively.
  * Halos (src/StaggeredTensor.cpp:60-165) and pencil transposes (deps/2Decomp_C/Transpose*.cpp) then run inside the
- * library over NCCL.  This build supports slab decompositions (Py = 1, Pz = number of GPUs). */
+ * library over NCCL.  Py = 1 (z slabs, Pz = number of GPUs) is the fast configuration on one NVSwitch box: its Y<->Z
+ * transposes are fused into the sweep kernels over peer memory.  Py > 1 gives the reference's Py x Pz pencils
+ * (rank = y_rank * Pz + z_rank, src/Constants.cpp:68): two-phase halos (y sheets, then whole z planes) and the four
+ * 2Decomp transposes as grouped send/recv box exchanges; a periodic y direction cannot be distributed. */
 #define MIFGPU_UNIQUE_ID_BYTES 128
 int mifgpu_comm_unique_id(void *unique_id);
 int mifgpu_create_distributed(const mifgpu_params *params, const void *unique_id, mifgpu_ctx **ctx);

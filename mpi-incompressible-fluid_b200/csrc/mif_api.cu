@@ -126,6 +126,15 @@ struct mifgpu_ctx {
   double *zbuf_peer[8] = {};
   double *xfer_peer[8] = {};
   int *barrier_word = nullptr;
+  // Py > 1: pencil decomposition in the 2Decomp layout (deps/2Decomp_C/C2Decomp.cpp:241-423): x pencil (this rank's
+  // sub-domain) -> y pencil (x distributed over the Py ranks of the same z_rank) -> z pencil (y distributed over the
+  // Pz ranks of the same y_rank).  Block distributions as in src/Constants.cpp:78-79 (bigger blocks on the low ranks).
+  int Py = 1, Pz = 1, y_rank = 0, z_rank = 0;
+  std::vector<int> ys, xs;   // Py + 1: owner y rows of y_rank r; x columns of the y / z pencils of y_rank r
+  std::vector<int> zs, yzs;  // Pz + 1: owner z planes of z_rank r; y rows of the z pencil of z_rank r
+  double *ypen = nullptr, *zpen = nullptr;           // pencil buffers, rows of pen_pitch doubles
+  double *box_send = nullptr, *box_recv = nullptr;   // compact staging of the box exchanges
+  int pen_pitch = 0;
   double *staging = nullptr; // compact device copy of one tensor for host transfers
   size_t staging_bytes = 0;
   // host-callback boundary faces: pinned staging + device copies, [which][component][face]
@@ -410,6 +419,142 @@ int transpose_slab(mifgpu_ctx *ctx, double *field, bool forward) {
   return MIFGPU_OK;
 }
 
+// ---- Py > 1: box exchanges ---------------------------------------------------------------------------------------
+// A sub-box of a pitched 3-D array (x fastest): element (x, y, z) at base[x + pitch * (y + ysize * z)].
+struct Box {
+  double *base;
+  size_t pitch, ysize;
+  int x0, y0, z0, nx, ny, nz;
+  size_t count() const { return (size_t)nx * ny * nz; }
+};
+
+int copy_box(mifgpu_ctx *ctx, const Box &dst, const Box &src) {
+  if (src.count() == 0) return MIFGPU_OK;
+  cudaMemcpy3DParms parms;
+  std::memset(&parms, 0, sizeof(parms));
+  parms.srcPtr = make_cudaPitchedPtr(src.base, src.pitch * sizeof(double), src.pitch, src.ysize);
+  parms.srcPos = make_cudaPos((size_t)src.x0 * sizeof(double), (size_t)src.y0, (size_t)src.z0);
+  parms.dstPtr = make_cudaPitchedPtr(dst.base, dst.pitch * sizeof(double), dst.pitch, dst.ysize);
+  parms.dstPos = make_cudaPos((size_t)dst.x0 * sizeof(double), (size_t)dst.y0, (size_t)dst.z0);
+  parms.extent = make_cudaExtent((size_t)src.nx * sizeof(double), (size_t)src.ny, (size_t)src.nz);
+  parms.kind = cudaMemcpyDeviceToDevice;
+  CUDA_TRY(cudaMemcpy3DAsync(&parms, ctx->stream));
+  return MIFGPU_OK;
+}
+
+Box compact_box(double *base, const Box &like) {
+  return Box{base, (size_t)like.nx, (size_t)like.ny, 0, 0, 0, like.nx, like.ny, like.nz};
+}
+
+// Entry i: send box send[i] to rank peers[i] and receive recv[i] from it (the own rank copies directly).  Boxes are
+// gathered into / scattered from compact staging with 3-D device copies; the transfers are one NCCL group.  This is
+// the alltoallv of 2Decomp's transposes (deps/2Decomp_C/TransposeX2Y.cpp ... TransposeZ2Y.cpp) and, with one-row
+// boxes, the y halo exchange.
+int exchange_boxes(mifgpu_ctx *ctx, const std::vector<int> &peers, const std::vector<Box> &send, const std::vector<Box> &recv) {
+  const int me = ctx->params.rank;
+  std::vector<size_t> soff(peers.size()), roff(peers.size());
+  size_t stotal = 0, rtotal = 0;
+  for (size_t i = 0; i < peers.size(); i++) {
+    soff[i] = stotal;
+    roff[i] = rtotal;
+    if (peers[i] == me) continue;
+    stotal += send[i].count();
+    rtotal += recv[i].count();
+  }
+  int rc;
+  for (size_t i = 0; i < peers.size(); i++) {
+    if (peers[i] == me) {
+      if ((rc = copy_box(ctx, recv[i], send[i]))) return rc;
+    } else if ((rc = copy_box(ctx, compact_box(ctx->box_send + soff[i], send[i]), send[i]))) {
+      return rc;
+    }
+  }
+  NCCL_TRY(g_nccl.GroupStart());
+  for (size_t i = 0; i < peers.size(); i++) {
+    if (peers[i] == me) continue;
+    if (send[i].count()) NCCL_TRY(g_nccl.Send(ctx->box_send + soff[i], send[i].count(), ncclDouble, peers[i], ctx->comm, ctx->stream));
+    if (recv[i].count()) NCCL_TRY(g_nccl.Recv(ctx->box_recv + roff[i], recv[i].count(), ncclDouble, peers[i], ctx->comm, ctx->stream));
+  }
+  NCCL_TRY(g_nccl.GroupEnd());
+  for (size_t i = 0; i < peers.size(); i++) {
+    if (peers[i] == me) continue;
+    if ((rc = copy_box(ctx, recv[i], compact_box(ctx->box_recv + roff[i], recv[i])))) return rc;
+  }
+  return MIFGPU_OK;
+}
+
+// 1-cell halo exchange in y of whole x-z sheets (src/StaggeredTensor.cpp:137-165): row 1 -> prev rank's last row, row
+// sy-2 -> next rank's row 0.  Run BEFORE exchange_z, whose whole planes then carry the fresh y ghosts into the edge
+// regions (SURVEY.md section 8a "edge ghosts": the result equals the single-rank one).
+int exchange_y(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count) {
+  const Geom &g = ctx->g;
+  if (g.prev_y == -1 && g.next_y == -1) return MIFGPU_OK;
+  ProfScope prof(ctx, PROF_HALO);
+  std::vector<int> peers;
+  std::vector<Box> send, recv;
+  for (int t = 0; t < count; t++) {
+    const int s = tensors[t]->staggering;
+    const int sy = g.sy[s];
+    auto row = [&](int j) { return Box{tensors[t]->data, (size_t)g.PX, (size_t)g.PY, 0, j, 0, g.sx[s], 1, g.sz[s]}; };
+    if (g.prev_y != -1) {
+      peers.push_back(g.prev_y);
+      send.push_back(row(1));
+      recv.push_back(row(0));
+    }
+    if (g.next_y != -1) {
+      peers.push_back(g.next_y);
+      send.push_back(row(sy - 2));
+      recv.push_back(row(sy - 1));
+    }
+  }
+  return exchange_boxes(ctx, peers, send, recv);
+}
+
+// The four 2Decomp transposes of the pencil decomposition as box exchanges.  which = 0: x pencil (owner region of
+// `field`) -> y pencil; 1: y pencil -> z pencil; 2: z pencil -> y pencil; 3: y pencil -> x pencil.
+int transpose_pencil(mifgpu_ctx *ctx, double *field, int which) {
+  const Geom &g = ctx->g;
+  ProfScope prof(ctx, PROF_TRANSPOSE);
+  const int yr = ctx->y_rank, zr = ctx->z_rank, Py = ctx->Py, Pz = ctx->Pz;
+  const int nxl = ctx->xs[yr + 1] - ctx->xs[yr], nyl = ctx->ys[yr + 1] - ctx->ys[yr], nzl = ctx->zs[zr + 1] - ctx->zs[zr];
+  const int ny = ctx->ys[Py], nz = ctx->zs[Pz], nyz = ctx->yzs[zr + 1] - ctx->yzs[zr];
+  const size_t pitch = (size_t)ctx->pen_pitch;
+  std::vector<int> peers;
+  std::vector<Box> a, b;  // a: boxes of the "earlier" layout, b: boxes of the "later" layout
+  if (which == 0 || which == 3) {
+    for (int r = 0; r < Py; r++) {
+      peers.push_back(r * Pz + zr);
+      // x pencil side: the x columns of y_rank r's pencils, my y rows, my z planes
+      a.push_back(Box{field, (size_t)g.PX, (size_t)g.PY, g.own_lo[0] + ctx->xs[r], g.own_lo[1], g.own_lo[2],
+                      ctx->xs[r + 1] - ctx->xs[r], nyl, nzl});
+      // y pencil side: my x columns, the y rows of y_rank r, my z planes
+      b.push_back(Box{ctx->ypen, pitch, (size_t)ny, 0, ctx->ys[r], 0, nxl, ctx->ys[r + 1] - ctx->ys[r], nzl});
+    }
+  } else {
+    for (int r = 0; r < Pz; r++) {
+      peers.push_back(yr * Pz + r);
+      // y pencil side: my x columns, the y rows of z_rank r's z pencil, my z planes
+      a.push_back(Box{ctx->ypen, pitch, (size_t)ny, 0, ctx->yzs[r], 0, nxl, ctx->yzs[r + 1] - ctx->yzs[r], nzl});
+      // z pencil side: my x columns, my y rows, the z planes of z_rank r
+      b.push_back(Box{ctx->zpen, pitch, (size_t)nyz, 0, 0, ctx->zs[r], nxl, nyz, ctx->zs[r + 1] - ctx->zs[r]});
+    }
+  }
+  (void)nz;
+  return (which == 0 || which == 1) ? exchange_boxes(ctx, peers, a, b) : exchange_boxes(ctx, peers, b, a);
+}
+
+int exchange_z(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count);
+
+// Ghost refresh of `count` tensors in both split directions, y first (see exchange_y).
+int exchange_halos(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count) {
+  if (ctx->nranks == 1) return MIFGPU_OK;
+  if (ctx->Py > 1) {
+    const int rc = exchange_y(ctx, tensors, count);
+    if (rc) return rc;
+  }
+  return exchange_z(ctx, tensors, count);
+}
+
 // Inside mifgpu_timestep the exchange that follows apply_bc (src/VelocityTensor.cpp:225-232) only has to deliver what
 // is read before the next exchange of the same tensors (after the velocity correction, src/Timestep.cpp:68-75): the
 // divergence reads w one plane above every owner point, i.e. w's ghost plane towards the next rank.  The correction
@@ -446,8 +591,8 @@ int do_apply_bc(mifgpu_ctx *ctx, mifgpu_tensor *const vel[3], const mifgpu_bc *b
     launch_apply_bc(ctx->stream, ctx->g, vec3(vel), dev, &ctx->launches);
   }
   static const bool full_exchange = getenv("MIFGPU_FULL_BC_EXCHANGE") != nullptr;  // A/B switch
-  if (inside_timestep && !full_exchange) return exchange_w_from_next(ctx, vel[2]);
-  return exchange_z(ctx, vel, 3);  // send_mpi_data / receive_mpi_data of the three components (src/VelocityTensor.cpp:225-232)
+  if (inside_timestep && !full_exchange && ctx->Py == 1) return exchange_w_from_next(ctx, vel[2]);
+  return exchange_halos(ctx, vel, 3);  // send_mpi_data / receive_mpi_data of the three components (src/VelocityTensor.cpp:225-232)
 }
 
 // solve_pressure_equation_homogeneous_periodic / _non_homogeneous_neumann (src/PressureEquation.cpp:266-286).
@@ -455,7 +600,7 @@ int do_solve(mifgpu_ctx *ctx, mifgpu_tensor *dp, mifgpu_tensor *const vel[3], do
              double t_new, double t_prev) {
   // Without Neumann face terms the right-hand side is consumed only by the forward x sweep, which can compute it
   // on the fly; otherwise it is materialised first (src/PressureEquation.cpp:59-61).
-  const bool fuse_rhs = !nhn_bc && poisson_can_fuse_divergence(ctx->plan);
+  const bool fuse_rhs = !nhn_bc && ctx->nranks == 1 && poisson_can_fuse_divergence(ctx->plan);
   if (!fuse_rhs) {
     ProfScope prof(ctx, PROF_DIVERGENCE);
     launch_divergence(ctx->stream, ctx->g, cvec3(vel), 0.0, dt, dp->data, &ctx->launches);
@@ -477,6 +622,40 @@ int do_solve(mifgpu_ctx *ctx, mifgpu_tensor *dp, mifgpu_tensor *const vel[3], do
     ProfScope prof(ctx, category);
     launch_poisson_sweep(ctx->stream, ctx->g, ctx->plan, dp->data, dir, mode, &ctx->launches);
   };
+  if (ctx->Py > 1) {
+    // Pencil decomposition: x sweeps on the sub-domain, y sweeps on the y pencil, the fused z sweep on the z pencil,
+    // with 2Decomp's four transposes in between (src/PressureEquation.cpp:79-263).
+    const int yr = ctx->y_rank, zr = ctx->z_rank;
+    const int nxl = ctx->xs[yr + 1] - ctx->xs[yr], nzl = ctx->zs[zr + 1] - ctx->zs[zr];
+    const int nyz = ctx->yzs[zr + 1] - ctx->yzs[zr];
+    const int x0 = ctx->xs[yr], y0 = ctx->yzs[zr];
+    int rc;
+    sweep(0, 0, PROF_SWEEP_X_FWD);
+    if ((rc = transpose_pencil(ctx, dp->data, 0))) return rc;
+    {
+      ProfScope prof(ctx, PROF_SWEEP_Y_FWD);
+      launch_poisson_pencil(ctx->stream, ctx->plan, ctx->ypen, 1, 0, nxl, ctx->pen_pitch, nzl, x0, 0, false, &ctx->launches);
+    }
+    if ((rc = transpose_pencil(ctx, dp->data, 1))) return rc;
+    {
+      ProfScope prof(ctx, PROF_SWEEP_Z);
+      launch_poisson_pencil(ctx->stream, ctx->plan, ctx->zpen, 2, 2, nxl, ctx->pen_pitch, nyz, x0, y0, x0 == 0 && y0 == 0,
+                            &ctx->launches);
+    }
+    if ((rc = transpose_pencil(ctx, dp->data, 2))) return rc;
+    {
+      ProfScope prof(ctx, PROF_SWEEP_Y_INV);
+      launch_poisson_pencil(ctx->stream, ctx->plan, ctx->ypen, 1, 1, nxl, ctx->pen_pitch, nzl, x0, 0, false, &ctx->launches);
+    }
+    if ((rc = transpose_pencil(ctx, dp->data, 3))) return rc;
+    sweep(0, 1, PROF_SWEEP_X_INV);
+    {
+      ProfScope prof(ctx, PROF_PERIODIC);
+      launch_periodic(ctx->stream, ctx->g, dp->data, 3, &ctx->launches);
+    }
+    mifgpu_tensor *one_pencil[1] = {dp};
+    return exchange_halos(ctx, one_pencil, 1);
+  }
   if (ctx->nranks > 1 && ctx->peer_mode && poisson_peer_capable(ctx->plan)) {
     // Transposes fused into the sweeps: the forward y sweep stores into the z pencils of the owning GPUs, the fused
     // z sweep stores into their slab staging buffers, the inverse y sweep reads its staging buffer (NVLink peer
@@ -585,11 +764,12 @@ static int create_context(const mifgpu_params *params, const void *unique_id, mi
   int n_points[3];
   int rc = build_geometry(*params, g, n_points);
   if (rc) return rc;
-  if (params->Py != 1)
-    return fail(MIFGPU_ERR_UNSUPPORTED, "only slab decompositions (Py = 1, Pz = number of GPUs) are available in this build, got Py = %d",
-                params->Py);
+  if (params->Py > 1 && params->periodic_bc[1])
+    return fail(MIFGPU_ERR_UNSUPPORTED, "a periodic y direction cannot be distributed (Py = %d) in this build", params->Py);
   if (params->Pz > 1 && (params->Nz_global - (params->periodic_bc[2] ? 1 : 0)) / params->Pz < 2)
     return fail(MIFGPU_ERR_INVALID, "fewer than 2 owner planes per rank");
+  if (params->Py > 1 && (params->Ny_global / params->Py < 2 || (params->Nx_global - (params->periodic_bc[0] ? 1 : 0)) / params->Py < 1))
+    return fail(MIFGPU_ERR_INVALID, "fewer than 2 owner rows (or no x column of the y pencil) per rank");
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
     return fail(MIFGPU_ERR_CUDA, "no CUDA device available (libmifgpu has no CPU fallback)");
@@ -608,8 +788,49 @@ static int create_context(const mifgpu_params *params, const void *unique_id, mi
   const double h[3] = {g.dx, g.dy, g.dz};
   const int n_global[3] = {(int)params->Nx_global, (int)params->Ny_global, (int)params->Nz_global};
   ctx->plan = poisson_plan_create(g, n_points, per, h, n_global);
-  ctx->nranks = params->Pz;
-  if (ctx->nranks > 1) {
+  ctx->nranks = params->Py * params->Pz;
+  ctx->Py = params->Py;
+  ctx->Pz = params->Pz;
+  ctx->y_rank = params->rank / params->Pz;
+  ctx->z_rank = params->rank % params->Pz;
+  if (ctx->Py > 1) {
+    // Pencil decomposition: block distributions of the transform points (src/Constants.cpp:78-79), NCCL communicator
+    // over all Py * Pz ranks, pencil buffers and compact staging for the box exchanges.
+    auto blocks = [](int n, int parts) {
+      std::vector<int> first(parts + 1, 0);
+      for (int r = 0; r < parts; r++) first[r + 1] = first[r] + n / parts + (r < n % parts ? 1 : 0);
+      return first;
+    };
+    ctx->ys = blocks(n_points[1], ctx->Py);
+    ctx->xs = blocks(n_points[0], ctx->Py);
+    ctx->zs = blocks(n_points[2], ctx->Pz);
+    ctx->yzs = blocks(n_points[1], ctx->Pz);
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id, sizeof(id));
+    if (!load_nccl()) {
+      mifgpu_destroy(ctx);
+      return MIFGPU_ERR_COMM;
+    }
+    ncclResult_t nerr = g_nccl.CommInitRank(&ctx->comm, ctx->nranks, id, params->rank);
+    if (nerr != ncclSuccess) {
+      mifgpu_destroy(ctx);
+      return fail(MIFGPU_ERR_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(nerr));
+    }
+    const int yr = ctx->y_rank, zr = ctx->z_rank;
+    const size_t nxl = ctx->xs[yr + 1] - ctx->xs[yr], nzl = ctx->zs[zr + 1] - ctx->zs[zr], nyz = ctx->yzs[zr + 1] - ctx->yzs[zr];
+    ctx->pen_pitch = (int)((nxl + 7) / 8 * 8);
+    const size_t ypen = (size_t)ctx->pen_pitch * n_points[1] * nzl, zpen = (size_t)ctx->pen_pitch * nyz * n_points[2];
+    // staging: the largest of one sub-domain (owner block or three halo sheets) and one pencil
+    const size_t sub = (size_t)g.PX * g.PY * g.PZ;
+    const size_t stage = std::max(std::max(ypen, zpen), sub);
+    if (cudaMalloc(&ctx->ypen, ypen * sizeof(double)) != cudaSuccess || cudaMalloc(&ctx->zpen, zpen * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&ctx->box_send, stage * sizeof(double)) != cudaSuccess || cudaMalloc(&ctx->box_recv, stage * sizeof(double)) != cudaSuccess) {
+      mifgpu_destroy(ctx);
+      return fail(MIFGPU_ERR_CUDA, "allocating the pencil buffers failed");
+    }
+    cudaMemset(ctx->ypen, 0, ypen * sizeof(double));
+    cudaMemset(ctx->zpen, 0, zpen * sizeof(double));
+  } else if (ctx->nranks > 1) {
     // MIF block distribution: the first (n mod P) ranks own one more point (src/Constants.cpp:78-79,
     // deps/2Decomp_C/C2Decomp.cpp:273-324).
     const int P = ctx->nranks;
@@ -673,6 +894,10 @@ void mifgpu_destroy(mifgpu_ctx *ctx) {
   poisson_plan_destroy(ctx->plan);
   if (ctx->xfer) cudaFree(ctx->xfer);
   if (ctx->zbuf) cudaFree(ctx->zbuf);
+  if (ctx->ypen) cudaFree(ctx->ypen);
+  if (ctx->zpen) cudaFree(ctx->zpen);
+  if (ctx->box_send) cudaFree(ctx->box_send);
+  if (ctx->box_recv) cudaFree(ctx->box_recv);
   for (int r = 0; r < 8; r++) {
     if (r == ctx->params.rank) continue;
     if (ctx->zbuf_peer[r]) cudaIpcCloseMemHandle(ctx->zbuf_peer[r]);
@@ -860,7 +1085,7 @@ int mifgpu_timestep(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], mifgpu_te
     ProfScope prof(ctx, PROF_CORRECT);
     launch_correct(s, g, vec3(velocity_buffer), pressure->data, pressure_buffer->data, dt_1, &ctx->launches);
   }
-  if ((rc = exchange_z(ctx, velocity_buffer, 3))) return rc;  // src/Timestep.cpp:68-75
+  if ((rc = exchange_halos(ctx, velocity_buffer, 3))) return rc;  // src/Timestep.cpp:68-75
 
   // Stage 2 (src/Timestep.cpp:119-129).
   {
@@ -873,7 +1098,7 @@ int mifgpu_timestep(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], mifgpu_te
     ProfScope prof(ctx, PROF_CORRECT);
     launch_correct(s, g, vec3(velocity_buffer_2), pressure->data, pressure_buffer->data, dt_2, &ctx->launches);
   }
-  if ((rc = exchange_z(ctx, velocity_buffer_2, 3))) return rc;  // src/Timestep.cpp:68-75
+  if ((rc = exchange_halos(ctx, velocity_buffer_2, 3))) return rc;  // src/Timestep.cpp:68-75
 
   // Stage 3 (src/Timestep.cpp:131-141).
   {
@@ -886,7 +1111,7 @@ int mifgpu_timestep(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], mifgpu_te
     ProfScope prof(ctx, PROF_CORRECT);
     launch_correct(s, g, vec3(velocity), pressure->data, pressure_buffer->data, dt_3, &ctx->launches);
   }
-  if ((rc = exchange_z(ctx, velocity, 3))) return rc;  // src/Timestep.cpp:68-75
+  if ((rc = exchange_halos(ctx, velocity, 3))) return rc;  // src/Timestep.cpp:68-75
   return check_launch(ctx);
 }
 

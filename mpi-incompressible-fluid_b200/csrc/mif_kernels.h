@@ -73,6 +73,13 @@ bool poisson_can_fuse_divergence(const PoissonPlan *plan);
 void launch_poisson_zpencil(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *zbuf, int ny_local,
                             int y_offset, bool has_origin, uint64_t *launches);
 
+// One sweep on a pencil buffer of the Py x Pz decomposition (rows of `pitch` doubles, nx_local of them used):
+// dir = 1: y pencil buf[z_local][y (all)][x_local], n_outer = local z planes; dir = 2: z pencil
+// buf[z (all)][y_local][x_local], n_outer = local y rows.  x_offset / y_offset: global transform indices of the
+// first local x column / y row (eigenvalues, origin mode).
+void launch_poisson_pencil(cudaStream_t stream, PoissonPlan *plan, double *buf, int dir, int mode, int nx_local, int pitch,
+                           int n_outer, int x_offset, int y_offset, bool has_origin, uint64_t *launches);
+
 // Peer-memory variant of the slab <-> pencil exchange: zbuf[r] / xfer[r] are the pencil and slab staging buffers of
 // every rank, mapped into this process (CUDA IPC).  which = 0: forward y sweep whose results are stored straight into
 // the z pencils of the owning GPUs; 1: fused z sweep on the local pencil, results stored into the slab staging of

@@ -1304,6 +1304,7 @@ struct SweepLayout {
   int n_tile_lines, outer;
   bool contig;       // estride == 1 (x sweeps)
   int lam_y_offset;  // first global y index of outer index 0 (z sweeps on a y-distributed pencil)
+  int lam_x_offset = 0;  // first global x index of tile line 0 (pencils whose x range is distributed, Py > 1)
   bool has_origin;   // this rank holds the (0,0,0) mode
   SegMap load_map, store_map;
   bool peer = false;  // peer-memory sweeps: tiles of exactly 8 lines (the x tiles of the blocked buffers)
@@ -1325,7 +1326,7 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
     fj.tile_stride = lay.tile_stride; fj.outer_stride = lay.outer_stride;
     fj.n_tile_lines = lay.n_tile_lines; fj.mode = mode;
     fj.tw = plan->dir[d].tw_full; fj.cs = plan->dir[d].unpack;
-    fj.lam_x = plan->dir[0].lambda; fj.lam_y = plan->dir[1].lambda + lay.lam_y_offset; fj.lam_z = plan->dir[2].lambda;
+    fj.lam_x = plan->dir[0].lambda + lay.lam_x_offset; fj.lam_y = plan->dir[1].lambda + lay.lam_y_offset; fj.lam_z = plan->dir[2].lambda;
     fj.inv_norm = plan->dir[d].inv_norm;
     fj.has_origin = lay.has_origin;
     // Off by default: measured on B200 at 513^3 with distances 148 / 296 / 592 the sweeps got 2-7 % SLOWER (x 1.76 ->
@@ -1378,7 +1379,7 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
   job.L = plan->L[d];
   job.r_pitch = plan->dir[d].n | 1;
   job.mode = mode;
-  job.lam_a = plan->dir[0].lambda;
+  job.lam_a = plan->dir[0].lambda + lay.lam_x_offset;
   job.lam_b = plan->dir[1].lambda + lay.lam_y_offset;
   job.has_origin = lay.has_origin;
   job.n_tile_lines = lay.n_tile_lines;
@@ -1515,6 +1516,32 @@ void launch_poisson_zpencil(cudaStream_t stream, const Geom &g, PoissonPlan *pla
   lay.lam_y_offset = y_offset;
   lay.has_origin = has_origin;
   launch_sweep(stream, plan, zbuf, 2, 2, lay, launches);
+}
+
+// One sweep on a pencil buffer of the Py x Pz decomposition (rows of `pitch` doubles, nx_local of them used):
+//   dir = 1: y pencil buf[z_local][y (all points)][x_local], n_outer = local z planes: lines along y;
+//   dir = 2: z pencil buf[z (all points)][y_local][x_local], n_outer = local y rows: lines along z (mode 2: fused).
+// x_offset / y_offset: global transform indices of local x = 0 and (dir = 2) local y = 0, for the eigenvalues.
+void launch_poisson_pencil(cudaStream_t stream, PoissonPlan *plan, double *buf, int dir, int mode, int nx_local, int pitch,
+                           int n_outer, int x_offset, int y_offset, bool has_origin, uint64_t *launches) {
+  SweepLayout lay;
+  lay.origin = 0;
+  lay.n_tile_lines = nx_local;
+  lay.lstride = 1;
+  lay.tile_stride = 1;
+  lay.contig = false;
+  lay.outer = n_outer;
+  if (dir == 1) {
+    lay.estride = pitch;
+    lay.outer_stride = (long long)plan->dir[1].n * pitch;
+  } else {
+    lay.estride = (long long)n_outer * pitch;
+    lay.outer_stride = pitch;
+  }
+  lay.lam_x_offset = x_offset;
+  lay.lam_y_offset = y_offset;
+  lay.has_origin = has_origin;
+  launch_sweep(stream, plan, buf, dir, mode, lay, launches);
 }
 
 }  // namespace mifgpu

@@ -53,18 +53,28 @@ def main():
     N = meta["N"]
     periodic = [bool(p) for p in meta["periodic"]]
     assert not periodic[2], "slab tests use the decomposition-independent (non-periodic z) goldens"
+    # MIF_PY > 1 selects a Py x Pz pencil decomposition (rank = y_rank * Pz + z_rank, src/Constants.cpp:68) instead of
+    # z slabs.
+    Py = int(os.environ.get("MIF_PY", "1"))
+    assert world % Py == 0
+    Pz = world // Py
+    y_rank, z_rank = rank // Pz, rank % Pz
     ctx = mif.Context(N[0], N[1], N[2], meta["x_size"], meta["y_size"], meta["z_size"], *meta["min"], meta["Re"],
-                      meta["final_time"], meta["steps"], Py=1, Pz=world, rank=rank, periodic=periodic,
+                      meta["final_time"], meta["steps"], Py=Py, Pz=Pz, rank=rank, periodic=periodic,
                       device=local_rank, comm_id=ids[0])
-    # z range of this rank's local arrays inside the global (single-rank) arrays: owner planes plus one ghost
-    # plane towards each neighbour (src/Constants.cpp:78-94); staggered w has one more plane on the last rank.
-    first = mif.slab_plan(N[2], world)
-    klo = first[rank] - (1 if rank > 0 else 0)
-    khi = first[rank + 1] + (1 if rank < world - 1 else 0)
+    # y / z range of this rank's local arrays inside the global (single-rank) arrays: owner points plus one ghost
+    # towards each neighbour (src/Constants.cpp:78-94); the staggered component has one more on the last rank.
+    first = mif.slab_plan(N[2], Pz)
+    klo = first[z_rank] - (1 if z_rank > 0 else 0)
+    khi = first[z_rank + 1] + (1 if z_rank < Pz - 1 else 0)
+    first_y = mif.slab_plan(N[1], Py)
+    jlo = first_y[y_rank] - (1 if y_rank > 0 else 0)
+    jhi = first_y[y_rank + 1] + (1 if y_rank < Py - 1 else 0)
 
     def cut(name, arr):
-        extra = 1 if (name == "w" and rank == world - 1) else 0
-        return local_slab(arr, klo, khi + extra)
+        extra_k = 1 if (name == "w" and z_rank == Pz - 1) else 0
+        extra_j = 1 if (name == "v" and y_rank == Py - 1) else 0
+        return np.ascontiguousarray(arr[klo:khi + extra_k, jlo:jhi + extra_j])
 
     vel, vb, vb2 = ctx.velocity(), ctx.velocity(), ctx.velocity()
     p, dp = ctx.tensor(mif.STAGGER_NONE), ctx.tensor(mif.STAGGER_NONE)
@@ -90,7 +100,7 @@ def main():
     dist.all_gather_object(errs, worst)
     ctx.close()
     if rank == 0:
-        print(json.dumps({"case": case, "world": world, "max_rel_err": max(errs)}))
+        print(json.dumps({"case": case, "world": world, "Py": Py, "Pz": Pz, "max_rel_err": max(errs)}))
     dist.destroy_process_group()
     return 0 if max(errs) <= 1e-11 else 1
 

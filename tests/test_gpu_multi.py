@@ -43,3 +43,19 @@ def test_peer_memory_and_nccl_transposes_agree(no_peer):
            "--master-port", "29533", os.path.join(ROOT, "tests", "mp_worker.py"), "es:9x257x257"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+@pytest.mark.parametrize("case", ["full_16_2", "full_17_1", "lid1_12x10x14_2", "full_65x17x9_1", "es:9x257x257"])
+@pytest.mark.parametrize("world,py", [(2, 2), (4, 2), (4, 4), (8, 2), (8, 4)])
+def test_pencil_decomposition_matches_single_rank_reference(case, world, py):
+    """Py x Pz pencils (the reference's decomposition, src/Constants.cpp:68-101): two-phase halos and the four
+    2Decomp transposes as box exchanges; every rank's block reproduces the single-rank goldens."""
+    if device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29560 + world + py), os.path.join(ROOT, "tests", "mp_worker.py"), case]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MIF_PY=str(py)))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    res = json.loads(line)
+    assert res["Py"] == py and res["max_rel_err"] <= 1e-11

@@ -25,7 +25,8 @@ def simt_env():
                 MIFGPU_NCCL_LIB=os.path.join(EMU, "build", "libmif_fake_nccl.so"), MIF_SIMT_IPC="1")
 
 
-def run_worker(env, case, world, port):
+def run_worker(env, case, world, port, py=1):
+    env = dict(env, MIF_PY=str(py))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "mp_worker.py"), case]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
@@ -44,3 +45,10 @@ def test_two_rank_slabs_with_peer_memory_transposes(simt_env):
     # 257-point y and z lines: the sweeps store straight into the other rank's (blocked) pencil / staging buffers
     res = run_worker(simt_env, "es:3x257x257", 2, 29712)
     assert res["world"] == 2 and res["max_rel_err"] <= 1e-11
+
+
+def test_four_rank_pencils(simt_env):
+    # Py x Pz = 2 x 2 on 17^3 points (uneven blocks 9 + 8): y sheets then z planes as halos, the four 2Decomp transposes
+    # as box exchanges, x / y / z sweeps on the sub-domain, the y pencil and the z pencil
+    res = run_worker(simt_env, "full_17_1", 4, 29714, py=2)
+    assert res["world"] == 4 and res["Py"] == 2 and res["Pz"] == 2 and res["max_rel_err"] <= 1e-11
