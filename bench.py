@@ -270,11 +270,15 @@ def main():
     ap.add_argument("--workload", default="timestep", choices=["timestep", "poisson"],
                     help="timestep: the north-star metric (default); poisson: BASELINE.json configs[1], the pressure "
                          "solve alone on a pressure_test_mixed-type grid (x, y Neumann / DCT-I, z periodic / real FFT)")
+    ap.add_argument("--py", type=int, default=1,
+                    help="Py of a Py x Pz pencil decomposition (Pz = GPUs / Py); default 1 = z slabs, the fast configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
+    if args.py < 1 or int(os.environ.get("WORLD_SIZE", "1")) % args.py != 0:
+        raise SystemExit("--py must divide the number of GPUs")
     if args.workload == "poisson":
         return poisson_workload(args)
 
@@ -318,7 +322,8 @@ def main():
         comm_id = bytes(ident.cpu().numpy().tobytes())
     # src/main.cpp:121-131, test case 1.
     ctx = mif.Context(dims[0], dims[1], dims[2], 1.0 * mult[0], 1.0 * mult[1], 2.0 * mult[2], 0.0, 0.0, -1.0 * mult[2], 1e3,
-                      dt * total_steps, total_steps, Py=1, Pz=world, rank=rank, device=local_rank, comm_id=comm_id)
+                      dt * total_steps, total_steps, Py=args.py, Pz=world // args.py, rank=rank, device=local_rank,
+                      comm_id=comm_id)
     vel, vb, vb2 = ctx.velocity(), ctx.velocity(), ctx.velocity()
     p, dp = ctx.tensor(mif.STAGGER_NONE), ctx.tensor(mif.STAGGER_NONE)
     bc = ctx.make_bc(mif.BC_TEST_CASE_1, 1e3)
@@ -474,6 +479,8 @@ def main():
                                     f"{dims[0] - 1}x{dims[1] - 1}x{dims[2] - 1} cells ({cells_1d}^3 cells per GPU)"),
                        "points": dims, "dt": dt, "Re": 1e3,
                        "parallelism": "single GPU" if world == 1 else
+                       f"pencils Py={args.py} Pz={world // args.py}: NCCL halos (y sheets, z planes), 2Decomp transposes as "
+                       "grouped send/recv box exchanges" if args.py > 1 else
                        (f"z slabs Py=1 Pz={world}: NCCL plane halos; Y<->Z pencil transposes " +
                         ("fused into the y/z sweeps as NVLink peer-memory stores (no separate all-to-all)"
                          if os.environ.get("MIFGPU_NO_PEER") is None else "as grouped NCCL send/recv all-to-all")),
