@@ -191,6 +191,18 @@ int mifgpu_pressure_error_norms(mifgpu_ctx *ctx, const mifgpu_tensor *pressure, 
  * Collective over the ranks of a distributed context. */
 int mifgpu_adjust_pressure(mifgpu_ctx *ctx, mifgpu_tensor *pressure, const mifgpu_bc *exact, double time);
 
+/* ---- host-side collectives --------------------------------------------------------------------------- */
+
+/* What the reference's host code does with MPI around the path, for the ranks of a distributed context (single-rank
+ * contexts: identity / copy).  mifgpu_allreduce: values[] <- sum (op = 0) or max (op = 1) over all ranks, in place, on
+ * every rank.  mifgpu_gather: MPI_Gather of the counts + MPI_Gatherv of the data to rank 0 -- recv (rank 0 only; may
+ * be NULL elsewhere) receives the ranks' arrays one after the other in rank order and counts[r] (every rank, nranks
+ * entries) the number of values of rank r.  Used by accumulate_error_mpi_* (src/Norms.cpp:120-162) and by the
+ * writers' MPI-IO offsets / gathers (src/VTKDatExport.cpp:54-69,219-311,519-554) in the host layer. */
+int mifgpu_allreduce(mifgpu_ctx *ctx, double *values, int32_t count, int32_t op);
+int mifgpu_gather(mifgpu_ctx *ctx, const double *send, uint64_t count, double *recv, uint64_t *counts);
+int mifgpu_rank_count(const mifgpu_ctx *ctx);
+
 /* Blocks until all work queued by this context has finished (cudaStreamSynchronize). */
 int mifgpu_synchronize(mifgpu_ctx *ctx);
 

@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = [
     "mifgpu_stream", "mifgpu_launch_count", "mifgpu_profile_enable", "mifgpu_profile_read", "mifgpu_comm_unique_id",
     "mifgpu_create_distributed", "mifgpu_slab_plan", "mifgpu_velocity_error_norms", "mifgpu_pressure_error_norms",
     "mifgpu_adjust_pressure", "mifgpu_timestep_velocity", "mifgpu_tensor_download_box",
+    "mifgpu_allreduce", "mifgpu_gather", "mifgpu_rank_count",
 ]
 
 
@@ -107,6 +108,9 @@ def lib() -> ctypes.CDLL:
     l.mifgpu_velocity_error_norms.argtypes = [c_void_p, POINTER(c_void_p), POINTER(Bc), c_double, POINTER(c_double)]
     l.mifgpu_pressure_error_norms.argtypes = [c_void_p, c_void_p, POINTER(Bc), c_double, POINTER(c_double)]
     l.mifgpu_adjust_pressure.argtypes = [c_void_p, c_void_p, POINTER(Bc), c_double]
+    l.mifgpu_allreduce.argtypes = [c_void_p, POINTER(c_double), c_int32, c_int32]
+    l.mifgpu_gather.argtypes = [c_void_p, POINTER(c_double), c_uint64, POINTER(c_double), POINTER(c_uint64)]
+    l.mifgpu_rank_count.argtypes = [c_void_p]
     l.mifgpu_stream.argtypes = [c_void_p]
     l.mifgpu_stream.restype = c_void_p
     l.mifgpu_launch_count.argtypes = [c_void_p]

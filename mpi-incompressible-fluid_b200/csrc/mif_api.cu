@@ -1242,6 +1242,72 @@ int mifgpu_adjust_pressure(mifgpu_ctx *ctx, mifgpu_tensor *pressure, const mifgp
   return check_launch(ctx);
 }
 
+int mifgpu_rank_count(const mifgpu_ctx *ctx) { return ctx ? ctx->nranks : 0; }
+
+int mifgpu_allreduce(mifgpu_ctx *ctx, double *values, int32_t count, int32_t op) {
+  if (!ctx || !values || count < 0 || (op != 0 && op != 1)) return fail(MIFGPU_ERR_INVALID, "bad argument");
+  if (ctx->nranks == 1 || count == 0) return MIFGPU_OK;
+  CUDA_TRY(cudaSetDevice(ctx->params.device));
+  double *dev = nullptr;
+  CUDA_TRY(cudaMalloc(&dev, sizeof(double) * count));
+  CUDA_TRY(cudaMemcpyAsync(dev, values, sizeof(double) * count, cudaMemcpyHostToDevice, ctx->stream));
+  const ncclResult_t nerr = g_nccl.AllReduce(dev, dev, (size_t)count, ncclDouble, op == 0 ? ncclSum : ncclMax, ctx->comm, ctx->stream);
+  cudaError_t err = cudaMemcpyAsync(values, dev, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dev);
+  if (nerr != ncclSuccess) return fail(MIFGPU_ERR_COMM, "ncclAllReduce failed: %s", g_nccl.GetErrorString(nerr));
+  if (err != cudaSuccess) return fail(MIFGPU_ERR_CUDA, "all-reduce copy failed: %s", cudaGetErrorString(err));
+  return MIFGPU_OK;
+}
+
+int mifgpu_gather(mifgpu_ctx *ctx, const double *send, uint64_t count, double *recv, uint64_t *counts) {
+  if (!ctx || !counts || (count > 0 && !send)) return fail(MIFGPU_ERR_INVALID, "bad argument");
+  const int P = ctx->nranks, me = ctx->params.rank;
+  std::vector<double> sizes(P, 0.0);
+  sizes[me] = (double)count;
+  int rc = mifgpu_allreduce(ctx, sizes.data(), P, 0);
+  if (rc) return rc;
+  uint64_t total = 0;
+  for (int r = 0; r < P; r++) {
+    counts[r] = (uint64_t)sizes[r];
+    total += counts[r];
+  }
+  if (me == 0 && total > 0 && !recv) return fail(MIFGPU_ERR_INVALID, "rank 0 needs a receive buffer");
+  if (P == 1) {
+    if (count) std::memcpy(recv, send, sizeof(double) * count);
+    return MIFGPU_OK;
+  }
+  CUDA_TRY(cudaSetDevice(ctx->params.device));
+  const uint64_t dev_count = (me == 0) ? total : count;
+  if (dev_count == 0) return MIFGPU_OK;
+  double *dev = nullptr;
+  CUDA_TRY(cudaMalloc(&dev, sizeof(double) * dev_count));
+  cudaError_t err = cudaSuccess;
+  ncclResult_t nerr = ncclSuccess;
+  if (count) err = cudaMemcpyAsync(dev, send, sizeof(double) * count, cudaMemcpyHostToDevice, ctx->stream);  // rank 0: its own part comes first
+  if (err == cudaSuccess) {
+    nerr = g_nccl.GroupStart();
+    if (me == 0) {
+      uint64_t offset = counts[0];
+      for (int r = 1; r < P && nerr == ncclSuccess; r++) {
+        if (counts[r]) nerr = g_nccl.Recv(dev + offset, counts[r], ncclDouble, r, ctx->comm, ctx->stream);
+        offset += counts[r];
+      }
+    } else if (count && nerr == ncclSuccess) {
+      nerr = g_nccl.Send(dev, count, ncclDouble, 0, ctx->comm, ctx->stream);
+    }
+    const ncclResult_t end = g_nccl.GroupEnd();
+    if (nerr == ncclSuccess) nerr = end;
+  }
+  if (err == cudaSuccess && nerr == ncclSuccess && me == 0)
+    err = cudaMemcpyAsync(recv, dev, sizeof(double) * total, cudaMemcpyDeviceToHost, ctx->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dev);
+  if (nerr != ncclSuccess) return fail(MIFGPU_ERR_COMM, "gather failed: %s", g_nccl.GetErrorString(nerr));
+  if (err != cudaSuccess) return fail(MIFGPU_ERR_CUDA, "gather copy failed: %s", cudaGetErrorString(err));
+  return MIFGPU_OK;
+}
+
 int mifgpu_slab_plan(uint64_t n_points, int32_t parts, int32_t *first) {
   if (!first || parts < 1) return fail(MIFGPU_ERR_INVALID, "bad argument");
   first[0] = 0;

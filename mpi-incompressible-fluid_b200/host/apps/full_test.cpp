@@ -1,11 +1,12 @@
 // full_test -- the reference's velocity + pressure convergence test (test/full_test.cpp) on the GPU path:
 // Ethier-Steinman solution on [0,1]x[0,1]x[-1,1], all walls, Re = 1e3, T = 1e-4.
-//   usage: full_test N steps [nhn]
-// Prints the same nine numbers: velocity L1 L2 Linf, pressure L1 L2 Linf, pressure-gradient L1 L2 Linf.
+//   usage: full_test N steps [Pz] [nhn]        (several ranks: scripts/mifrun -n P full_test N steps Pz, Py = P / Pz)
+// Prints the same nine numbers: velocity L1 L2 Linf, pressure L1 L2 Linf, pressure-gradient L1 L2 Linf (rank 0).
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
 
+#include "Launch.h"
 #include "Manufactured.h"
 #include "Norms.h"
 #include "PressureEquation.h"
@@ -21,9 +22,17 @@ int main(int argc, char *argv[]) {
   }
   const size_t N = std::atol(argv[1]);
   const unsigned int steps = std::atoi(argv[2]);
-  const bool nhn = argc > 3 && std::strcmp(argv[3], "nhn") == 0;
+  const bool nhn = std::strcmp(argv[argc - 1], "nhn") == 0;
+  // test/full_test.cpp:24-28,55-59: rank and size from the launcher, Pz from the command line, Py = size / Pz
+  const int rank = launch_rank(), size = launch_size();
+  const int Pz = (argc > 3 && std::strcmp(argv[3], "nhn") != 0) ? std::atoi(argv[3]) : 1;
+  const int Py = Pz > 0 ? size / Pz : 0;
+  if (Pz < 1 || Py < 1 || Py * Pz != size) {
+    if (rank == 0) std::cerr << "full_test: Pz must divide the number of processes" << std::endl;
+    return 1;
+  }
   constexpr Real Re = 1e3, final_time = 1e-4;
-  const Constants constants(N, N, N, 1.0, 1.0, 2.0, 0.0, 0.0, -1.0, Re, final_time, steps, 1, 1, 0, {false, false, false});
+  const Constants constants(N, N, N, 1.0, 1.0, 2.0, 0.0, 0.0, -1.0, Re, final_time, steps, Py, Pz, rank, {false, false, false});
   PressureSolverStructures structures(constants);
   Reynolds = Re;
 
@@ -57,11 +66,20 @@ int main(int argc, char *argv[]) {
 
   adjust_pressure(pressure, [](Real x, Real y, Real z) { return p_exact(1e-4, x, y, z); });
 
-  std::cout << ErrorL1Norm(velocity, exact_velocity, final_time) << " " << ErrorL2Norm(velocity, exact_velocity, final_time) << " "
-            << ErrorLInfNorm(velocity, exact_velocity, final_time) << " " << ErrorL1Norm(pressure, p_exact, final_time) << " "
-            << ErrorL2Norm(pressure, p_exact, final_time) << " " << ErrorLInfNorm(pressure, p_exact, final_time) << " "
-            << ErrorL1Norm(pressure_gradient, exact_pressure_gradient, final_time) << " "
-            << ErrorL2Norm(pressure_gradient, exact_pressure_gradient, final_time) << " "
-            << ErrorLInfNorm(pressure_gradient, exact_pressure_gradient, final_time) << std::endl;
+  // test/full_test.cpp:150-176: local norms, folded on rank 0
+  const Real errors[9] = {
+      accumulate_error_mpi_l1(ErrorL1Norm(velocity, exact_velocity, final_time), constants),
+      accumulate_error_mpi_l2(ErrorL2Norm(velocity, exact_velocity, final_time), constants),
+      accumulate_error_mpi_linf(ErrorLInfNorm(velocity, exact_velocity, final_time), constants),
+      accumulate_error_mpi_l1(ErrorL1Norm(pressure, p_exact, final_time), constants),
+      accumulate_error_mpi_l2(ErrorL2Norm(pressure, p_exact, final_time), constants),
+      accumulate_error_mpi_linf(ErrorLInfNorm(pressure, p_exact, final_time), constants),
+      accumulate_error_mpi_l1(ErrorL1Norm(pressure_gradient, exact_pressure_gradient, final_time), constants),
+      accumulate_error_mpi_l2(ErrorL2Norm(pressure_gradient, exact_pressure_gradient, final_time), constants),
+      accumulate_error_mpi_linf(ErrorLInfNorm(pressure_gradient, exact_pressure_gradient, final_time), constants)};
+  if (rank == 0) {
+    for (int e = 0; e < 9; e++) std::cout << errors[e] << (e < 8 ? " " : "");
+    std::cout << std::endl;
+  }
   return 0;
 }

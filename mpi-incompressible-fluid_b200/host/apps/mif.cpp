@@ -1,11 +1,12 @@
 // mif -- the reference's driver (src/main.cpp) on the GPU path: `mif <input file>` with the reference's input format
 // (Nt, dt, Nx, Ny, Nz, Py, Pz, test_case_2), Re = 1e3, test case 1 on [0,1]x[0,1]x[-1,1] (all walls) or test case 2 on
 // [-0.5,0.5]^3 (z periodic); writes solution.vtk and profile1.dat, profile2.dat (and profile3.dat for case 2).
-// One process drives one GPU, so Py = Pz = 1 is required here (multi-GPU runs go through mifgpu_create_distributed).
+// One process drives one GPU; `scripts/mifrun -n P mif input.txt` starts Py * Pz = P of them (the reference's mpirun).
 #include <cstdio>
 #include <iostream>
 
 #include "InputParser.h"
+#include "Launch.h"
 #include "PressureEquation.h"
 #include "TestCaseBoundaries.h"
 #include "Timestep.h"
@@ -19,6 +20,7 @@ int main(int argc, char *argv[]) {
     std::cerr << "Usage: ./mif [input parameter file]" << std::endl;
     return 1;
   }
+  const int rank = launch_rank();  // MPI_Comm_rank (src/main.cpp:52-56): one process per GPU, started by scripts/mifrun
   size_t Nx_global = 0, Ny_global = 0, Nz_global = 0;
   Real dt = 0;
   unsigned int num_time_steps = 0;
@@ -30,8 +32,9 @@ int main(int argc, char *argv[]) {
       std::cerr << "The number of processors in each direction must be at least 1." << std::endl;
       return 0;
     }
-    if (Pz * Py != 1) {
-      std::cerr << "The number of precessors in the input file do not match with the ones provided to mpirun." << std::endl;
+    if (Pz * Py != launch_size()) {
+      if (rank == 0)
+        std::cerr << "The number of precessors in the input file do not match with the ones provided to mpirun." << std::endl;
       return 0;
     }
   } catch (const std::exception &ex) {
@@ -42,7 +45,7 @@ int main(int argc, char *argv[]) {
   constexpr Real Re = 1e3;
   const Constants constants(Nx_global, Ny_global, Nz_global, 1.0, 1.0, test_case_2 ? 1.0 : 2.0, test_case_2 ? -0.5 : 0.0,
                             test_case_2 ? -0.5 : 0.0, test_case_2 ? -0.5 : -1.0, Re, dt * num_time_steps, num_time_steps, Py, Pz,
-                            0, {false, false, test_case_2});
+                            rank, {false, false, test_case_2});
   PressureSolverStructures structures(constants);
   Reynolds = Re;
 
@@ -59,7 +62,8 @@ int main(int argc, char *argv[]) {
     timestep(velocity, velocity_buffer, velocity_buffer_2, exact_velocity, time_step * constants.dt, pressure, pressure_buffer,
              pressure_solver_buffer);
 
-  for (const char *old : {"profile1.dat", "profile2.dat", "profile3.dat", "solution.vtk"}) std::remove(old);
+  if (rank == 0)
+    for (const char *old : {"profile1.dat", "profile2.dat", "profile3.dat", "solution.vtk"}) std::remove(old);
   writeVTK("solution.vtk", velocity, pressure);
   if (!test_case_2) {
     writeDat("profile1.dat", velocity, pressure, 1, 0.5, 0.5, 0);

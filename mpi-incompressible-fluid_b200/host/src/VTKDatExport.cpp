@@ -3,6 +3,8 @@
 // reduce to sequential writes; the byte layout of the files is the reference's.
 #include "VTKDatExport.h"
 
+#include "../../../include/mifgpu.h"
+
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -33,14 +35,15 @@ PlaneIndex locate(Real pos, Real min_pos_global, Real delta) {
 }
 
 // Which local indices are written: all owned pressure points; in a periodic direction the range starts on the
-// ghost plane and covers N_global points (the reference's COMPUTE_INDEXING, src/VTKDatExport.cpp:89-113, for one rank).
+// ghost plane and the last rank covers one more point (the reference's COMPUTE_INDEXING, src/VTKDatExport.cpp:89-113).
 struct WriteRange {
   int lo[3], hi[3], global_lo[3];
 };
 WriteRange write_range(const Constants &c) {
   WriteRange r;
-  const int count[3] = {static_cast<int>(c.Nx_global), static_cast<int>(c.Ny_owner + (c.periodic_bc[1] ? 1 : 0)),
-                        static_cast<int>(c.Nz_owner + (c.periodic_bc[2] ? 1 : 0))};
+  const int count[3] = {static_cast<int>(c.Nx_global),
+                        static_cast<int>(c.Ny_owner + ((c.y_rank == c.Py - 1 && c.periodic_bc[1]) ? 1 : 0)),
+                        static_cast<int>(c.Nz_owner + ((c.z_rank == c.Pz - 1 && c.periodic_bc[2]) ? 1 : 0))};
   r.lo[0] = c.periodic_bc[0] ? 1 : 0;
   r.lo[1] = c.prev_proc_y == -1 ? 0 : 1;
   r.lo[2] = c.prev_proc_z == -1 ? 0 : 1;
@@ -91,6 +94,27 @@ void write_file(const std::string &filename, const std::string &content) {
   std::fclose(file);
 }
 
+// MPI_Allgather of the counts + the MPI-IO offsets / MPI_Gatherv of the reference's writers (src/VTKDatExport.cpp:
+// 54-69,219-311,519-554): on several ranks every local array travels to rank 0, which receives the ranks' parts one
+// after the other in rank order -- the order the reference's file offsets produce.  Returns false on the ranks that do
+// not write.
+bool gather_to_root(const Constants &c, std::vector<Real> &values) {
+  if (c.P == 1) return true;
+  std::vector<uint64_t> counts(c.P, 0);
+  // first call: sizes only, so that rank 0 can allocate
+  std::vector<double> sizes(c.P, 0.0);
+  sizes[c.rank] = static_cast<double>(values.size());
+  if (mifgpu_allreduce(c.gpu(), sizes.data(), c.P, 0) != MIFGPU_OK) throw std::runtime_error(std::string("mifgpu_allreduce: ") + mifgpu_last_error());
+  size_t total = 0;
+  for (double n : sizes) total += static_cast<size_t>(n);
+  std::vector<Real> all(c.rank == 0 ? total : 0);
+  if (mifgpu_gather(c.gpu(), values.data(), values.size(), all.data(), counts.data()) != MIFGPU_OK)
+    throw std::runtime_error(std::string("mifgpu_gather: ") + mifgpu_last_error());
+  if (c.rank != 0) return false;
+  values.swap(all);
+  return true;
+}
+
 }  // namespace
 
 void writeVTK(const std::string &filename, const VelocityTensor &velocity, const StaggeredTensor &pressure) {
@@ -131,6 +155,9 @@ void writeVTK(const std::string &filename, const VelocityTensor &velocity, const
         for (int k = r.lo[2]; k < r.hi[2]; k++) add_point(i, j, k);
     }
   }
+  bool writer = true;
+  for (std::vector<Real> *part : {&xyz, &su, &sv, &sw, &sp}) writer = gather_to_root(c, *part);
+  if (!writer) return;
   const int points = static_cast<int>(su.size());
   char text[256];
   std::string out;
@@ -217,6 +244,9 @@ void writeDat(const std::string &filename, const VelocityTensor &velocity, const
                    (1 - wi) * (1 - wj) * P(i + 1, j + 1, k));
     }
   }
+  bool writer = true;
+  for (std::vector<Real> *part : {&coordinate, &su, &sv, &sw, &sp}) writer = gather_to_root(c, *part);
+  if (!writer) return;
   // rows ordered by coordinate (stable, like the reference's insertion sort)
   std::vector<size_t> order(coordinate.size());
   std::iota(order.begin(), order.end(), size_t{0});

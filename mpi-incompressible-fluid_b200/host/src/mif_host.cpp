@@ -12,11 +12,19 @@
 #include <iostream>
 #include <sstream>
 #include <stdexcept>
+#include <cctype>
+#include <initializer_list>
 #include <string>
+#include <vector>
+#include <thread>
+#include <chrono>
+#include <cstdio>
+#include <unistd.h>
 
 #include "../../../include/mifgpu.h"
 #include "Constants.h"
 #include "InputParser.h"
+#include "Launch.h"
 #include "Manufactured.h"
 #include "Norms.h"
 #include "PressureEquation.h"
@@ -34,6 +42,24 @@ namespace {
 }
 void check(int rc, const char *what) {
   if (rc != MIFGPU_OK) throw_gpu_error(what);
+}
+
+// Rendezvous file of the n-th context of this job: $MIF_RENDEZVOUS_DIR (default /tmp) / mif_comm_<job>_<n>, where
+// <job> is MIF_JOB_ID (scripts/mifrun), else what the launcher at hand provides, else the parent process id (the
+// ranks of one mpirun / shell loop share their parent).
+std::string rendezvous_file(int n) {
+  const char *dir = std::getenv("MIF_RENDEZVOUS_DIR");
+  std::string job;
+  for (const char *name : {"MIF_JOB_ID", "PMIX_NAMESPACE", "OMPI_MCA_ess_base_jobid", "SLURM_STEP_ID", "TORCHELASTIC_RUN_ID"})
+    if (const char *value = std::getenv(name)) {
+      job = value;
+      if (std::string(name) == "SLURM_STEP_ID" && std::getenv("SLURM_JOB_ID")) job = std::string(std::getenv("SLURM_JOB_ID")) + "." + job;
+      break;
+    }
+  if (job.empty()) job = "ppid" + std::to_string(static_cast<long>(getppid()));
+  for (char &c : job)
+    if (!(std::isalnum(static_cast<unsigned char>(c)) || c == '.' || c == '-' || c == '_')) c = '_';
+  return std::string(dir ? dir : "/tmp") + "/mif_comm_" + job + "_" + std::to_string(n);
 }
 
 size_t owners(size_t points, int parts, int index) {
@@ -101,9 +127,51 @@ mifgpu_ctx *Constants::gpu() const {
   p.Py = Py; p.Pz = Pz; p.rank = rank;
   for (int d = 0; d < 3; d++) p.periodic_bc[d] = periodic_bc[d];
   const char *device = std::getenv("MIFGPU_DEVICE");
-  p.device = device ? std::atoi(device) : 0;
-  check(mifgpu_create(&p, &gpu_ctx_), "mifgpu_create");
+  p.device = device ? std::atoi(device) : (P > 1 ? launch_local_rank() : 0);
+  if (P == 1) {
+    check(mifgpu_create(&p, &gpu_ctx_), "mifgpu_create");
+    return gpu_ctx_;
+  }
+  // Several ranks (one process per GPU): rank 0 publishes a fresh communicator id in a rendezvous file, the others wait
+  // for it; creating the context is collective, so once it returns on rank 0 every rank has read the file.
+  static int contexts_created = 0;  // all ranks create their contexts in the same order
+  const std::string path = rendezvous_file(contexts_created++);
+  char id[MIFGPU_UNIQUE_ID_BYTES];
+  if (rank == 0) {
+    check(mifgpu_comm_unique_id(id), "mifgpu_comm_unique_id");
+    const std::string tmp = path + ".tmp";
+    FILE *f = std::fopen(tmp.c_str(), "wb");
+    if (!f || std::fwrite(id, 1, sizeof(id), f) != sizeof(id)) throw std::runtime_error("cannot write " + tmp);
+    std::fclose(f);
+    if (std::rename(tmp.c_str(), path.c_str()) != 0) throw std::runtime_error("cannot publish " + path);
+  } else {
+    FILE *f = nullptr;
+    for (int waited_ms = 0; !(f = std::fopen(path.c_str(), "rb")); waited_ms += 5) {
+      if (waited_ms > 120000) throw std::runtime_error("no communicator id from rank 0 after 120 s (" + path + ")");
+      std::this_thread::sleep_for(std::chrono::milliseconds(5));
+    }
+    const size_t got = std::fread(id, 1, sizeof(id), f);
+    std::fclose(f);
+    if (got != sizeof(id)) throw std::runtime_error("short communicator id in " + path);
+  }
+  const int rc = mifgpu_create_distributed(&p, id, &gpu_ctx_);
+  if (rank == 0) std::remove(path.c_str());
+  check(rc, "mifgpu_create_distributed");
   return gpu_ctx_;
+}
+
+// ---- Launch (replaces MPI_Init / MPI_Comm_rank / MPI_Comm_size) ----------------------------------------
+namespace {
+int env_int(std::initializer_list<const char *> names, int fallback) {
+  for (const char *name : names)
+    if (const char *value = std::getenv(name)) return std::atoi(value);
+  return fallback;
+}
+}  // namespace
+int launch_rank() { return env_int({"MIF_RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", "SLURM_PROCID", "RANK"}, 0); }
+int launch_size() { return env_int({"MIF_WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "SLURM_NTASKS", "WORLD_SIZE"}, 1); }
+int launch_local_rank() {
+  return env_int({"MIF_LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID", "SLURM_LOCALID", "LOCAL_RANK"}, launch_rank());
 }
 
 // ---- StaggeredTensor --------------------------------------------------------------------------------
@@ -512,6 +580,18 @@ void adjust_pressure(StaggeredTensor &pressure, const std::function<Real(Real, R
   for_each_owner_point(pressure, [&](size_t i, size_t j, size_t k) {
     difference += pressure.evaluate_function_at_index(i, j, k, exact_pressure) - pressure(i, j, k);
   });
+  if (c.P > 1) {
+    // rank 0 adds the ranks' sums in rank order and sends the result back (src/PressureEquation.cpp:298-333)
+    std::vector<double> all(c.P, 0.0);
+    std::vector<uint64_t> counts(c.P, 0);
+    const double mine = difference;
+    check(mifgpu_gather(c.gpu(), &mine, 1, all.data(), counts.data()), "mifgpu_gather");
+    double total = 0.0;
+    if (c.rank == 0)
+      for (int r = 0; r < c.P; r++) total += all[r];
+    check(mifgpu_allreduce(c.gpu(), &total, 1, 0), "mifgpu_allreduce");  // only rank 0 contributes: a broadcast
+    difference = total;
+  }
   const size_t nx = c.Nx_global - (c.periodic_bc[0] ? 1 : 0), ny = c.Ny_global - (c.periodic_bc[1] ? 1 : 0),
                nz = c.Nz_global - (c.periodic_bc[2] ? 1 : 0);
   difference /= static_cast<Real>(nx * ny * nz);
@@ -667,9 +747,31 @@ Real ErrorLInfNorm(const StaggeredTensor &pressure, const std::function<Real(Rea
   return pressure_error(pressure, exact_pressure, time, [](Real s, Real e) { return std::max(s, std::abs(e)); });
 }
 // One process drives the whole domain, so the rank-0 gather of the reference degenerates to the identity.
-Real accumulate_error_mpi_l1(Real local_error, const Constants &) { return local_error; }
-Real accumulate_error_mpi_l2(Real local_error, const Constants &) { return local_error; }
-Real accumulate_error_mpi_linf(Real local_error, const Constants &) { return local_error; }
+// src/Norms.cpp:120-162: the local errors travel to rank 0, which folds them in rank order with the reference's
+// reduction (so the result has the reference's rounding); every other rank gets -1.
+namespace {
+template <typename Reduction>
+Real accumulate_error(Real local_error, const Constants &constants, Reduction reduction) {
+  if (constants.P == 1) return local_error;
+  std::vector<double> all(constants.P, 0.0);
+  std::vector<uint64_t> counts(constants.P, 0);
+  const double mine = local_error;
+  check(mifgpu_gather(constants.gpu(), &mine, 1, all.data(), counts.data()), "mifgpu_gather");
+  if (constants.rank != 0) return -1;
+  Real global_error = local_error;
+  for (int r = 1; r < constants.P; r++) global_error = reduction(global_error, static_cast<Real>(all[r]));
+  return global_error;
+}
+}  // namespace
+Real accumulate_error_mpi_l1(Real local_error, const Constants &constants) {
+  return accumulate_error(local_error, constants, [](Real global, Real other) { return global + other; });
+}
+Real accumulate_error_mpi_l2(Real local_error, const Constants &constants) {
+  return accumulate_error(local_error, constants, [](Real global, Real other) { return std::sqrt(global * global + other * other); });
+}
+Real accumulate_error_mpi_linf(Real local_error, const Constants &constants) {
+  return accumulate_error(local_error, constants, [](Real global, Real other) { return std::max(global, other); });
+}
 
 // ---- input file (src/InputParser.cpp) -----------------------------------------------------------------
 void parse_input_file(const std::string &filename, size_t &Nx_global, size_t &Ny_global, size_t &Nz_global, Real &dt,

@@ -48,6 +48,9 @@ static std::string mailbox(const FakeComm *c, int src, int dst, uint64_t seq) {
   return name;
 }
 
+ncclResult_t ncclAllReduce(const void *send, void *recv, size_t count, ncclDataType_t type, ncclRedOp_t op, ncclComm_t c,
+                           cudaStream_t s);
+
 ncclResult_t ncclGetUniqueId(ncclUniqueId *id) {
   std::memset(id, 0, sizeof(*id));
   std::snprintf(id->internal, sizeof(id->internal), "%d_%ld", (int)getpid(), (long)random());
@@ -63,7 +66,9 @@ ncclResult_t ncclCommInitRank(ncclComm_t *comm, int nranks, ncclUniqueId id, int
   c->sent.assign(nranks, 0);
   c->received.assign(nranks, 0);
   *comm = c;
-  return 0;
+  // like the real call, return only after every rank has joined
+  int one = 1, sum = 0;
+  return ncclAllReduce(&one, &sum, 1, 2 /* ncclInt */, 0 /* ncclSum */, c, nullptr);
 }
 
 ncclResult_t ncclCommDestroy(ncclComm_t comm) {
@@ -106,9 +111,10 @@ ncclResult_t ncclRecv(void *buf, size_t count, ncclDataType_t type, int peer, nc
   return got == bytes ? 0 : 1;
 }
 
-ncclResult_t ncclAllReduce(const void *send, void *recv, size_t count, ncclDataType_t type, ncclRedOp_t, ncclComm_t c,
+ncclResult_t ncclAllReduce(const void *send, void *recv, size_t count, ncclDataType_t type, ncclRedOp_t op, ncclComm_t c,
                            cudaStream_t s) {
-  // every rank sends its contribution to every other rank and adds them up in rank order (sum only)
+  // every rank sends its contribution to every other rank and combines them in rank order (ncclSum = 0, ncclMax = 2)
+  if (op != 0 && op != 2) return 1;
   const size_t bytes = count * type_size(type);
   std::vector<char> mine(bytes);
   std::memcpy(mine.data(), send, bytes);
@@ -122,9 +128,17 @@ ncclResult_t ncclAllReduce(const void *send, void *recv, size_t count, ncclDataT
       src = other.data();
     }
     for (size_t i = 0; i < count; i++) {
-      if (type == 8) reinterpret_cast<double *>(acc.data())[i] += reinterpret_cast<const double *>(src)[i];
-      else if (type == 2) reinterpret_cast<int *>(acc.data())[i] += reinterpret_cast<const int *>(src)[i];
-      else return 1;
+      if (type == 8) {
+        double &a = reinterpret_cast<double *>(acc.data())[i];
+        const double v = reinterpret_cast<const double *>(src)[i];
+        a = (r == 0) ? v : (op == 0 ? a + v : (v > a ? v : a));
+      } else if (type == 2) {
+        int &a = reinterpret_cast<int *>(acc.data())[i];
+        const int v = reinterpret_cast<const int *>(src)[i];
+        a = (r == 0) ? v : (op == 0 ? a + v : (v > a ? v : a));
+      } else {
+        return 1;
+      }
     }
   }
   std::memcpy(recv, acc.data(), bytes);

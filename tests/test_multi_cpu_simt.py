@@ -52,3 +52,45 @@ def test_four_rank_pencils(simt_env):
     # as box exchanges, x / y / z sweeps on the sub-domain, the y pencil and the z pencil
     res = run_worker(simt_env, "full_17_1", 4, 29714, py=2)
     assert res["world"] == 4 and res["Py"] == 2 and res["Pz"] == 2 and res["max_rel_err"] <= 1e-11
+
+
+def test_ported_driver_on_four_ranks_writes_the_reference_files(simt_env, tmp_path):
+    """`scripts/mifrun -n 4 mif input.txt` with Py = Pz = 2 (the reference's `mpirun -n 4 ./mif`): rank and size from the
+    launcher's environment, communicator id through the rendezvous file, norms / writers through mifgpu_gather.  The
+    files hold the single-rank golden's points rank by rank; the profiles (sorted on rank 0) are the golden's."""
+    import shutil
+
+    import numpy as np
+
+    from conftest import GOLDEN_DIR
+    from vtk_util import check_multi_rank_solution
+    golden = os.path.join(GOLDEN_DIR, "mif_case1")
+    text = open(os.path.join(golden, "input.txt")).read().replace("Py : 1", "Py : 2").replace("Pz : 1", "Pz : 2")
+    (tmp_path / "input.txt").write_text(text)
+    env = dict(simt_env, LD_LIBRARY_PATH=os.path.join(EMU, "build", "as_libmifgpu"))
+    exe = os.path.join(ROOT, "mpi-incompressible-fluid_b200", "host", "bin", "mif")
+    out = subprocess.run([os.path.join(ROOT, "scripts", "mifrun"), "-n", "4", exe, "input.txt"], cwd=tmp_path, env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    check_multi_rank_solution(tmp_path / "solution.vtk", os.path.join(golden, "solution.vtk"), (17, 13, 15), (0.0, 0.0, -1.0),
+                              (1.0 / 16, 1.0 / 12, 2.0 / 14), 2, 2)
+    for name in ("profile1.dat", "profile2.dat"):
+        a, b = np.loadtxt(os.path.join(golden, name)), np.loadtxt(tmp_path / name)
+        assert a.shape == b.shape and np.max(np.abs(a - b)) <= 1e-12, name
+
+
+def test_ported_full_test_on_four_ranks_prints_the_reference_numbers(simt_env):
+    """`mifrun -n 4 full_test 16 1 2` (Py = Pz = 2): per-rank norms folded on rank 0 as in src/Norms.cpp:120-162, the
+    pressure gauge fixed across ranks (src/PressureEquation.cpp:288-343); the nine numbers are the ones the reference
+    prints for `mpirun -n 4 full_test 16 1 2` (tests/golden/norms.json)."""
+    from conftest import GOLDEN_DIR
+    want = json.load(open(os.path.join(GOLDEN_DIR, "norms.json")))["full_test 16 1 2 (4 ranks)"]
+    env = dict(simt_env, LD_LIBRARY_PATH=os.path.join(EMU, "build", "as_libmifgpu"))
+    exe = os.path.join(ROOT, "mpi-incompressible-fluid_b200", "host", "bin", "full_test")
+    out = subprocess.run([os.path.join(ROOT, "scripts", "mifrun"), "-n", "4", exe, "16", "1", "2"], env=env, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    got = [float(x) for x in out.stdout.split()]
+    assert len(got) == 9
+    for a, b in zip(got, want):
+        assert abs(a - b) <= 2e-5 * abs(b), (got, want)
