@@ -94,3 +94,19 @@ def test_ported_full_test_on_four_ranks_prints_the_reference_numbers(simt_env):
     assert len(got) == 9
     for a, b in zip(got, want):
         assert abs(a - b) <= 2e-5 * abs(b), (got, want)
+
+
+def test_ported_pressure_tests_on_several_ranks_print_the_reference_numbers(simt_env):
+    """pressure_test_hn / _nhn (the latter with host-callback Neumann faces per rank) on 2 x 2 and 3 x 1 ranks."""
+    from conftest import GOLDEN_DIR
+    norms = json.load(open(os.path.join(GOLDEN_DIR, "norms.json")))
+    env = dict(simt_env, LD_LIBRARY_PATH=os.path.join(EMU, "build", "as_libmifgpu"))
+    exe = os.path.join(ROOT, "mpi-incompressible-fluid_b200", "host", "bin", "pressure_test")
+    for kind, ranks, pz in (("hn", 4, 2), ("nhn", 3, 1)):
+        out = subprocess.run([os.path.join(ROOT, "scripts", "mifrun"), "-n", str(ranks), exe, kind, "8", str(pz)], env=env,
+                             capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+        line = [l for l in out.stdout.splitlines() if l.startswith("Errors:")][-1]
+        got, want = [float(x) for x in line.split()[1:]], norms[f"pressure_test_{kind} 8 1"]
+        for a, b in zip(got, want):
+            assert abs(a - b) <= 2e-5 * abs(b), (kind, got, want)
