@@ -2,7 +2,7 @@
 //
 // Same mathematics as mif_fft_fast.cuh (even extension packed two reals per complex, one complex FFT of
 // length M = 2^LOGM, real-FFT unpack), different mapping: every line of a tile of 8 lines belongs to ONE warp
-// (two warps for M = 1024), which keeps M/32 complex values per lane in registers and exchanges them through
+// (two warps for M = 1024, four for M = 2048), which keeps 16 complex values per lane in registers and exchanges them through
 // its own shared-memory region between the radix-8 Stockham passes.  Because no other warp touches that
 // region, the passes need only __syncwarp(): the 16 resident warps of an SM run their lines completely
 // asynchronously, which is what hides the shared-memory and global latencies (the CTA-synchronous variant
@@ -31,16 +31,17 @@ constexpr int kLines = 8;
 template <int LOGM>
 struct Cfg {
   static constexpr int M = 1 << LOGM;
-  static constexpr int WPL = (LOGM >= 10) ? 2 : 1;         // warps per line
+  static constexpr int WPL = (LOGM >= 11) ? 4 : ((LOGM >= 10) ? 2 : 1);  // warps per line
   static constexpr int TL = 32 * WPL;                       // threads per line
   static constexpr int EPT = M / TL;                        // complex values per thread
-  static constexpr int THREADS = kLines * TL;
+  static constexpr int LINES = (LOGM >= 11) ? 4 : kLines;   // lines per CTA (M = 2048: 4 lines x 128 threads)
+  static constexpr int THREADS = LINES * TL;
   static constexpr int LINE_PITCH = M + M / 8 + 1;          // complex elements between lines
   static constexpr int TW_PASS2 = 3 * 8;                    // twiddles t = 1, 2, 4 of the NS = 8 pass
   static constexpr int TW_PASS3 = 3 * 64;                   // ... of the NS = 64 pass
-  static constexpr int TW_PASS4 = (LOGM == 10) ? 512 : 0;   // radix-2 pass of M = 1024
+  static constexpr int TW_PASS4 = (LOGM == 10) ? 512 : ((LOGM == 11) ? 2 * 512 : 0);  // NS = 512 pass: radix 2 (M = 1024), radix 4 (M = 2048)
   static constexpr int TW_TOTAL = TW_PASS2 + TW_PASS3 + TW_PASS4;
-  static constexpr size_t SMEM = (size_t)(kLines * LINE_PITCH + TW_TOTAL) * sizeof(double2);
+  static constexpr size_t SMEM = (size_t)(LINES * LINE_PITCH + TW_TOTAL) * sizeof(double2);
 };
 
 __device__ __forceinline__ int pad(int q) { return q + (q >> 3); }
@@ -67,6 +68,9 @@ __device__ __forceinline__ void load_twiddles(double2 *T, const double2 *__restr
     } else if (idx < C::TW_PASS2 + C::TW_PASS3) {
       const int r = idx - C::TW_PASS2, ti = r / 64, k = r - ti * 64;
       q = (k << ti) * (M / (64 * R3));
+    } else if (LOGM == 11) {
+      const int r = idx - C::TW_PASS2 - C::TW_PASS3, ti = r / 512, k = r - ti * 512;  // NS = 512, R = 4: W_2048^(k t), t = 1, 2
+      q = k << ti;
     } else {
       q = idx - C::TW_PASS2 - C::TW_PASS3;  // NS = 512, R = 2: W_1024^k
     }
@@ -140,7 +144,7 @@ __device__ __forceinline__ void pass(double2 *S, const double2 *T, int j, int li
 // Radix of the last pass and the number of butterflies per lane in it.
 template <int LOGM>
 struct LastPass {
-  static constexpr int R = (LOGM == 7 || LOGM == 10) ? 2 : (LOGM == 8 ? 4 : 8);
+  static constexpr int R = (LOGM == 7 || LOGM == 10) ? 2 : ((LOGM == 8 || LOGM == 11) ? 4 : 8);
   static constexpr int NS = (1 << LOGM) / R;
   static constexpr int G = Cfg<LOGM>::EPT / R;
 };
@@ -161,6 +165,10 @@ __device__ __forceinline__ void fft_line(double2 *S, const double2 *T, int j, in
   if (LOGM == 10) {
     pass<LOGM, 8, 64>(S, T3, j, line, v);
     pass<LOGM, 2, 512, true, !KEEP>(S, T4, j, line, v);
+  }
+  if (LOGM == 11) {
+    pass<LOGM, 8, 64>(S, T3, j, line, v);
+    pass<LOGM, 4, 512, true, !KEEP>(S, T4, j, line, v);
   }
 }
 

@@ -561,13 +561,13 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
   constexpr int M = C::M, TL = C::TL, NPTS = M + 1, EPT = C::EPT, PAIRS = EPT / 2;
   constexpr bool SHUFFLE = (C::WPL == 1);  // whole line in one warp: unpack with shuffles, spectrum stays in registers
   extern __shared__ double2 smem2[];
-  double2 *T = smem2 + kLines * C::LINE_PITCH;  // twiddle tables behind the line regions
+  double2 *T = smem2 + C::LINES * C::LINE_PITCH;  // twiddle tables behind the line regions
   const int tid = threadIdx.x;
   const int line = tid / TL, j = tid - line * TL;  // FFT mapping: a line is one warp (two for M = 1024)
   double2 *S = smem2 + line * C::LINE_PITCH;
   double *Sd = reinterpret_cast<double *>(S);
-  const int first_line = blockIdx.x * kLines;
-  const int lines = min(kLines, job.n_tile_lines - first_line);
+  const int first_line = blockIdx.x * C::LINES;
+  const int lines = min(C::LINES, job.n_tile_lines - first_line);
   double *base = field + job.origin + (long long)first_line * job.tile_stride + (long long)blockIdx.y * job.outer_stride;
   double2 v[EPT];
 
@@ -656,7 +656,7 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
     // global memory -- slots jj + (M/8) t, i.e. elements (2q, 2q+1) or their mirror images (2M-2q, 2M-2q-1) -- runs
     // that pass in registers and stores its output into line l's region: the packed even extension never exists
     // in shared memory.
-    const int l = tid & 7, b = tid >> 3;
+    const int l = tid % C::LINES, b = tid / C::LINES;
     const bool live = l < lines;
     const double *src = base + (long long)l * job.lstride;
     auto element = [&](int e) -> double {
@@ -764,8 +764,8 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
     }
   } else {
     __syncthreads();
-    const int l = tid & 7, q0 = tid >> 3;
-    constexpr int QSTEP = C::THREADS / 8;
+    const int l = tid % C::LINES, q0 = tid / C::LINES;
+    constexpr int QSTEP = C::THREADS / C::LINES;
     if (l < lines) {
       const double *srcl = reinterpret_cast<const double *>(smem2 + l * C::LINE_PITCH);
       double *out = base + (long long)l * job.lstride;
@@ -1126,6 +1126,7 @@ void launch_split(cudaStream_t stream, const FastJob &job, bool contig, int oute
 template <int LOGM>
 void launch_warp(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid, double *field) {
   using C = warpfft::Cfg<LOGM>;
+  grid.x = (job.n_tile_lines + C::LINES - 1) / C::LINES;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(warp_dct_kernel<LOGM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -1276,7 +1277,7 @@ PoissonPlan *poisson_plan_create(const Geom &g, const int n_points[3], const int
     // src/PressureEquation.cpp:167,200,234: N_domains_global * (periodic ? 1 : 2)
     pl.inv_norm = 1.0 / ((double)(n_global[d] - 1) * (periodic[d] ? 1.0 : 2.0));
 
-    plan->fast_logm[d] = (!periodic[d] && pow2 && pl.logP >= 6 && pl.logP <= 10) ? pl.logP : 0;
+    plan->fast_logm[d] = (!periodic[d] && pow2 && pl.logP >= 6 && pl.logP <= 11) ? pl.logP : 0;
     static const bool no_rfft = getenv("MIFGPU_NO_WARP_RFFT") != nullptr;  // A/B switch for profiling
     plan->rfft_logm[d] = (periodic[d] && n % 2 == 0 && pow2 && (pl.logP == 8 || pl.logP == 9) && !no_rfft) ? pl.logP : 0;
     // lines per CTA: the largest power of two <= 8 that fits a ~100 KB shared-memory budget (two CTAs per SM)
@@ -1357,6 +1358,9 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
         if (use_cta_sync_variant) launch_fast<9>(stream, fj, lay.contig, fgrid, field);
         else launch_warp<9>(stream, fj, lay.contig, fgrid, field);
         break;
+      case 11:  // 2049-point lines (BASELINE configs[4]): four warps per line, 4-line CTAs
+        launch_warp<11>(stream, fj, lay.contig, fgrid, field);
+        break;
       default: {
         static const bool use_two_warp_variant = getenv("MIFGPU_FFT_NO_SPLIT") != nullptr;  // A/B switch for profiling
         if (use_cta_sync_variant) launch_fast<10>(stream, fj, lay.contig, fgrid, field);
@@ -1429,7 +1433,9 @@ void launch_poisson_sweep(cudaStream_t stream, const Geom &g, PoissonPlan *plan,
   launch_sweep(stream, plan, field, d, mode, lay, launches);
 }
 
-bool poisson_peer_capable(const PoissonPlan *plan) { return plan->fast_logm[1] >= 8 && plan->fast_logm[2] >= 8; }
+bool poisson_peer_capable(const PoissonPlan *plan) {
+  return plan->fast_logm[1] >= 8 && plan->fast_logm[1] <= 10 && plan->fast_logm[2] >= 8 && plan->fast_logm[2] <= 10;
+}
 
 // Blocked buffer layouts of the peer path (nxt = PX / 8 x tiles; all extents in doubles):
 //   zbuf[r]  z pencil of rank r:          [z (all N_z)][x tile][y in r's range][8]
