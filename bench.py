@@ -267,9 +267,11 @@ def main():
     ap.add_argument("--dims", type=int, nargs=3, default=None, metavar=("NX", "NY", "NZ"),
                     help="explicit pressure points per direction (kernel studies on non-cubic grids; single GPU only)")
     ap.add_argument("--ref-size", type=int, default=257, help="points per direction of the CPU reference sample")
-    ap.add_argument("--workload", default="timestep", choices=["timestep", "poisson"],
+    ap.add_argument("--workload", default="timestep", choices=["timestep", "poisson", "aniso"],
                     help="timestep: the north-star metric (default); poisson: BASELINE.json configs[1], the pressure "
-                         "solve alone on a pressure_test_mixed-type grid (x, y Neumann / DCT-I, z periodic / real FFT)")
+                         "solve alone on a pressure_test_mixed-type grid (x, y Neumann / DCT-I, z periodic / real FFT); "
+                         "aniso: BASELINE.json configs[4], the full time step on the anisotropic grid weak-scaled in x, "
+                         "256 x 512 x 512 cells per GPU (8 GPUs: 2048 x 512 x 512 cells, 2049-point x lines)")
     ap.add_argument("--py", type=int, default=1,
                     help="Py of a Py x Pz pencil decomposition (Pz = GPUs / Py); default 1 = z slabs, the fast configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -308,6 +310,10 @@ def main():
     for level in range(max(world.bit_length() - 1, 0)):
         mult[2 - level % 3] *= 2
     dims = [cells_1d * m + 1 for m in mult]
+    if args.workload == "aniso":
+        # SURVEY.md section 8d "config 5": constant 256 x 512 x 512 cells per GPU, x is never split, the GPUs split z
+        dims = [256 * world + 1, 513, 513]
+        mult = [256 * world / cells_1d, 512 / cells_1d, 512 / cells_1d]
     if args.dims is not None:
         if world != 1:
             raise SystemExit("--dims is a single-GPU option")
@@ -476,7 +482,8 @@ def main():
             "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": ("full projection timestep, input.txt boundary-layer set-up (test case 1) at "
-                                    f"{dims[0] - 1}x{dims[1] - 1}x{dims[2] - 1} cells ({cells_1d}^3 cells per GPU)"),
+                                    f"{dims[0] - 1}x{dims[1] - 1}x{dims[2] - 1} cells (" +
+                                    (f"{cells_1d}^3" if args.workload != "aniso" else "256x512x512") + " cells per GPU)"),
                        "points": dims, "dt": dt, "Re": 1e3,
                        "parallelism": "single GPU" if world == 1 else
                        f"pencils Py={args.py} Pz={world // args.py}: NCCL halos (y sheets, z planes), 2Decomp transposes as "
