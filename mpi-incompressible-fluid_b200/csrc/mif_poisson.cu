@@ -553,7 +553,10 @@ void launch_fast(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid
 // ------------------------------------------------------------------------------------------------
 // FUSED_DIV (forward x sweep only): the input line is div(u, v, w) / dt formed in registers.  A separate instantiation,
 // so that the plain sweeps do not pay for its registers.
-template <int LOGM, bool CONTIG, bool FUSED_DIV = false>
+// PLAIN (strided sweeps only, experiment MIFGPU_PLAIN_STRIDED=1): an instantiation without the piecewise-strided
+// segment maps of the multi-GPU sweeps -- no per-element map test, no indexed constant loads of the map arrays -- for
+// launches that use neither map.  The default instantiation is unchanged.
+template <int LOGM, bool CONTIG, bool FUSED_DIV = false, bool PLAIN = false>
 __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 : 2)) warp_dct_kernel(const FastJob job, double *__restrict__ field) {
   using namespace warpfft;
   using C = Cfg<LOGM>;
@@ -661,7 +664,8 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
     const double *src = base + (long long)l * job.lstride;
     auto element = [&](int e) -> double {
       if (!live) return 0.0;
-      return job.load_map.n ? *seg_address(job.load_map, e, blockIdx.y, first_line + l) : src[(long long)e * job.estride];
+      if constexpr (PLAIN) return src[(long long)e * job.estride];
+      else return job.load_map.n ? *seg_address(job.load_map, e, blockIdx.y, first_line + l) : src[(long long)e * job.estride];
     };
 #pragma unroll
     for (int s = 0; s < EPT; s++) {
@@ -769,7 +773,9 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
     if (l < lines) {
       const double *srcl = reinterpret_cast<const double *>(smem2 + l * C::LINE_PITCH);
       double *out = base + (long long)l * job.lstride;
-      if (job.store_map.n) {
+      if constexpr (PLAIN) {
+        for (int e = q0; e < NPTS; e += QSTEP) out[(long long)e * job.estride] = srcl[e];
+      } else if (job.store_map.n) {
         // Fused transpose: the results go straight into the pencil / slab buffers of the owning GPUs (peer stores
         // over NVLink for r != this rank), so no pack kernel and no separate all-to-all copy exist.
         for (int e = q0; e < NPTS; e += QSTEP) *seg_address(job.store_map, e, blockIdx.y, first_line + l) = srcl[e];
@@ -1145,7 +1151,18 @@ void launch_warp(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid
   } else if (contig) {
     warp_dct_kernel<LOGM, true><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
   } else {
-    warp_dct_kernel<LOGM, false><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
+    // A/B switch (default off, not measured yet): strided sweeps without the segment-map code when no map is in use
+    static const bool plain_strided = getenv("MIFGPU_PLAIN_STRIDED") != nullptr;
+    if (plain_strided && job.load_map.n == 0 && job.store_map.n == 0) {
+      static bool plain_attr_set = false;
+      if (!plain_attr_set) {
+        cudaFuncSetAttribute(warp_dct_kernel<LOGM, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        plain_attr_set = true;
+      }
+      warp_dct_kernel<LOGM, false, false, true><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
+    } else {
+      warp_dct_kernel<LOGM, false><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
+    }
   }
 }
 
