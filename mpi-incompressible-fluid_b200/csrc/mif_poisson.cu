@@ -394,6 +394,20 @@ __device__ __forceinline__ double *seg_address(const SegMap &m, int e, int outer
          (long long)(e - m.lo[r]) * m.estride[r] + (x & 7);
 }
 
+// The same address with a segment cursor: `r` remembers the segment of the previous lookup, so a thread whose
+// elements ascend (UP) or descend (!UP) pays at most n - 1 search steps in total instead of up to n - 1 per element
+// (experiment MIFGPU_SEG_CARRY=1; the search reads the map arrays with indexed constant loads).
+template <bool UP>
+__device__ __forceinline__ double *seg_address_from(const SegMap &m, int &r, int e, int outer, int x) {
+  if (UP) {
+    while (r + 1 < m.n && e >= m.lo[r + 1]) r++;
+  } else {
+    while (r > 0 && e < m.lo[r]) r--;
+  }
+  return m.base[r] + (long long)(x >> 3) * m.xtile_stride[r] + (long long)outer * m.outer_stride[r] +
+         (long long)(e - m.lo[r]) * m.estride[r] + (x & 7);
+}
+
 struct FastJob {
   SegMap load_map, store_map;  // strided (y / z) sweeps of the warp-per-line kernel only
   long long origin, lstride, estride, tile_stride, outer_stride;
@@ -553,10 +567,11 @@ void launch_fast(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid
 // ------------------------------------------------------------------------------------------------
 // FUSED_DIV (forward x sweep only): the input line is div(u, v, w) / dt formed in registers.  A separate instantiation,
 // so that the plain sweeps do not pay for its registers.
-// PLAIN (strided sweeps only, experiment MIFGPU_PLAIN_STRIDED=1): an instantiation without the piecewise-strided
-// segment maps of the multi-GPU sweeps -- no per-element map test, no indexed constant loads of the map arrays -- for
-// launches that use neither map.  The default instantiation is unchanged.
-template <int LOGM, bool CONTIG, bool FUSED_DIV = false, bool PLAIN = false>
+// SEG (strided sweeps only): 0 = default; 1 = experiment MIFGPU_PLAIN_STRIDED=1, an instantiation without the
+// piecewise-strided segment maps of the multi-GPU sweeps -- no per-element map test, no indexed constant loads of the
+// map arrays -- for launches that use neither map; 2 = experiment MIFGPU_SEG_CARRY=1, maps searched with cursors
+// (seg_address_from).  The default instantiation is unchanged.
+template <int LOGM, bool CONTIG, bool FUSED_DIV = false, int SEG = 0>
 __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 : 2)) warp_dct_kernel(const FastJob job, double *__restrict__ field) {
   using namespace warpfft;
   using C = Cfg<LOGM>;
@@ -664,14 +679,42 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
     const double *src = base + (long long)l * job.lstride;
     auto element = [&](int e) -> double {
       if (!live) return 0.0;
-      if constexpr (PLAIN) return src[(long long)e * job.estride];
+      if constexpr (SEG == 1) return src[(long long)e * job.estride];
       else return job.load_map.n ? *seg_address(job.load_map, e, blockIdx.y, first_line + l) : src[(long long)e * job.estride];
     };
+    if (SEG == 2 && job.load_map.n > 0) {
+      // elements 2q, 2q+1 ascend with s, their mirror images 2M-2q, 2M-2q-1 descend: one cursor each
+      int r_up = 0, r_dn = job.load_map.n - 1;
 #pragma unroll
-    for (int s = 0; s < EPT; s++) {
-      const int q = b + s * TL;
-      if (s < EPT / 2) v[s] = make_double2(element(2 * q), element(2 * q + 1));
-      else v[s] = make_double2(element(2 * M - 2 * q), element(2 * M - 2 * q - 1));
+      for (int s = 0; s < EPT; s++) {
+        const int q = b + s * TL;
+        if (!live) {
+          v[s] = make_double2(0.0, 0.0);
+        } else if (s < EPT / 2) {
+          const double x0 = *seg_address_from<true>(job.load_map, r_up, 2 * q, blockIdx.y, first_line + l);
+          const double x1 = *seg_address_from<true>(job.load_map, r_up, 2 * q + 1, blockIdx.y, first_line + l);
+          v[s] = make_double2(x0, x1);
+        } else {
+          const double x0 = *seg_address_from<false>(job.load_map, r_dn, 2 * M - 2 * q, blockIdx.y, first_line + l);
+          const double x1 = *seg_address_from<false>(job.load_map, r_dn, 2 * M - 2 * q - 1, blockIdx.y, first_line + l);
+          v[s] = make_double2(x0, x1);
+        }
+      }
+    } else if (SEG == 2) {
+#pragma unroll
+      for (int s = 0; s < EPT; s++) {
+        const int q = b + s * TL;
+        auto plain = [&](int e) { return live ? src[(long long)e * job.estride] : 0.0; };
+        if (s < EPT / 2) v[s] = make_double2(plain(2 * q), plain(2 * q + 1));
+        else v[s] = make_double2(plain(2 * M - 2 * q), plain(2 * M - 2 * q - 1));
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < EPT; s++) {
+        const int q = b + s * TL;
+        if (s < EPT / 2) v[s] = make_double2(element(2 * q), element(2 * q + 1));
+        else v[s] = make_double2(element(2 * M - 2 * q), element(2 * M - 2 * q - 1));
+      }
     }
     first_pass_in_place<LOGM>(smem2 + l * C::LINE_PITCH, b, v);
     __syncthreads();  // all lines and the twiddle tables are in place
@@ -773,7 +816,12 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
     if (l < lines) {
       const double *srcl = reinterpret_cast<const double *>(smem2 + l * C::LINE_PITCH);
       double *out = base + (long long)l * job.lstride;
-      if constexpr (PLAIN) {
+      if constexpr (SEG == 1) {
+        for (int e = q0; e < NPTS; e += QSTEP) out[(long long)e * job.estride] = srcl[e];
+      } else if (SEG == 2 && job.store_map.n > 0) {
+        int r = 0;
+        for (int e = q0; e < NPTS; e += QSTEP) *seg_address_from<true>(job.store_map, r, e, blockIdx.y, first_line + l) = srcl[e];
+      } else if (SEG == 2) {
         for (int e = q0; e < NPTS; e += QSTEP) out[(long long)e * job.estride] = srcl[e];
       } else if (job.store_map.n) {
         // Fused transpose: the results go straight into the pencil / slab buffers of the owning GPUs (peer stores
@@ -996,7 +1044,7 @@ __device__ __forceinline__ void first_pass_both(double2 *even_region, double2 *o
 
 // LINES lines per CTA (64 threads each): 8 lines fill the register file with ONE CTA per SM, whose 16 warps then load,
 // transform and store in lockstep; 4 lines give two independent CTAs per SM that overlap each other's phases.
-template <bool CONTIG, int LINES>
+template <bool CONTIG, int LINES, bool CARRY = false>
 __global__ void __launch_bounds__(64 * LINES, 8 / LINES) warp_dct_split_kernel(const FastJob job, double *__restrict__ field) {
   using namespace warpfft;
   using namespace split;
@@ -1027,15 +1075,33 @@ __global__ void __launch_bounds__(64 * LINES, 8 / LINES) warp_dct_split_kernel(c
       return job.load_map.n ? *seg_address(job.load_map, e, blockIdx.y, first_line + ll) : src[(long long)e * job.estride];
     };
     double2 *a = v, *b = v + 8;
+    if (CARRY && !CONTIG && job.load_map.n > 0) {
+      // segment cursors (MIFGPU_SEG_CARRY=1): 2q, 2q+1 ascend with t, the mirror images descend
+      int r_up = 0, r_dn = job.load_map.n - 1;
 #pragma unroll
-    for (int t = 0; t < 8; t++) {
-      const int q = jj + 64 * t;
-      double2 lo;
-      if (CONTIG) lo = live ? *reinterpret_cast<const double2 *>(src + 2 * q) : make_double2(0.0, 0.0);
-      else lo = make_double2(element(2 * q), element(2 * q + 1));
-      const double2 hi = make_double2(element(kFull - 2 * q), element(kFull - 1 - 2 * q));
-      a[t] = cadd(lo, hi);
-      b[t] = csub(lo, hi);
+      for (int t = 0; t < 8; t++) {
+        const int q = jj + 64 * t;
+        double2 lo = make_double2(0.0, 0.0), hi = make_double2(0.0, 0.0);
+        if (live) {
+          lo.x = *seg_address_from<true>(job.load_map, r_up, 2 * q, blockIdx.y, first_line + ll);
+          lo.y = *seg_address_from<true>(job.load_map, r_up, 2 * q + 1, blockIdx.y, first_line + ll);
+          hi.x = *seg_address_from<false>(job.load_map, r_dn, kFull - 2 * q, blockIdx.y, first_line + ll);
+          hi.y = *seg_address_from<false>(job.load_map, r_dn, kFull - 1 - 2 * q, blockIdx.y, first_line + ll);
+        }
+        a[t] = cadd(lo, hi);
+        b[t] = csub(lo, hi);
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        const int q = jj + 64 * t;
+        double2 lo;
+        if (CONTIG) lo = live ? *reinterpret_cast<const double2 *>(src + 2 * q) : make_double2(0.0, 0.0);
+        else lo = make_double2(element(2 * q), element(2 * q + 1));
+        const double2 hi = make_double2(element(kFull - 2 * q), element(kFull - 1 - 2 * q));
+        a[t] = cadd(lo, hi);
+        b[t] = csub(lo, hi);
+      }
     }
     first_pass_both(smem2 + (2 * ll) * C9::LINE_PITCH, smem2 + (2 * ll + 1) * C9::LINE_PITCH, jj, __ldg(&job.tw[jj]), a, b);
   }
@@ -1106,7 +1172,10 @@ __global__ void __launch_bounds__(64 * LINES, 8 / LINES) warp_dct_split_kernel(c
     if (l < lines) {
       const double *srcl = reinterpret_cast<const double *>(smem2 + (2 * l) * C9::LINE_PITCH);
       double *out = base + (long long)l * job.lstride;
-      if (job.store_map.n) {
+      if (CARRY && job.store_map.n > 0) {
+        int r = 0;
+        for (int e = q0; e < NPTS; e += 64) *seg_address_from<true>(job.store_map, r, e, blockIdx.y, first_line + l) = srcl[e];
+      } else if (job.store_map.n) {
         for (int e = q0; e < NPTS; e += 64) *seg_address(job.store_map, e, blockIdx.y, first_line + l) = srcl[e];
       } else {
         for (int e = q0; e < NPTS; e += 64) out[(long long)e * job.estride] = srcl[e];
@@ -1125,8 +1194,19 @@ void launch_split(cudaStream_t stream, const FastJob &job, bool contig, int oute
     attr_set = true;
   }
   const dim3 grid((job.n_tile_lines + LINES - 1) / LINES, outer, 1);
-  if (contig) warp_dct_split_kernel<true, LINES><<<grid, 64 * LINES, smem, stream>>>(job, field);
-  else warp_dct_split_kernel<false, LINES><<<grid, 64 * LINES, smem, stream>>>(job, field);
+  static const bool seg_carry = getenv("MIFGPU_SEG_CARRY") != nullptr;  // A/B switch, default off (not measured yet)
+  if (contig) {
+    warp_dct_split_kernel<true, LINES><<<grid, 64 * LINES, smem, stream>>>(job, field);
+  } else if (seg_carry && (job.load_map.n > 0 || job.store_map.n > 0)) {
+    static bool carry_attr_set = false;
+    if (!carry_attr_set) {
+      cudaFuncSetAttribute(warp_dct_split_kernel<false, LINES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      carry_attr_set = true;
+    }
+    warp_dct_split_kernel<false, LINES, true><<<grid, 64 * LINES, smem, stream>>>(job, field);
+  } else {
+    warp_dct_split_kernel<false, LINES><<<grid, 64 * LINES, smem, stream>>>(job, field);
+  }
 }
 
 template <int LOGM>
@@ -1153,13 +1233,21 @@ void launch_warp(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid
   } else {
     // A/B switch (default off, not measured yet): strided sweeps without the segment-map code when no map is in use
     static const bool plain_strided = getenv("MIFGPU_PLAIN_STRIDED") != nullptr;
+    static const bool seg_carry = getenv("MIFGPU_SEG_CARRY") != nullptr;
     if (plain_strided && job.load_map.n == 0 && job.store_map.n == 0) {
       static bool plain_attr_set = false;
       if (!plain_attr_set) {
-        cudaFuncSetAttribute(warp_dct_kernel<LOGM, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaFuncSetAttribute(warp_dct_kernel<LOGM, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         plain_attr_set = true;
       }
-      warp_dct_kernel<LOGM, false, false, true><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
+      warp_dct_kernel<LOGM, false, false, 1><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
+    } else if (seg_carry && (job.load_map.n > 0 || job.store_map.n > 0)) {
+      static bool carry_attr_set = false;
+      if (!carry_attr_set) {
+        cudaFuncSetAttribute(warp_dct_kernel<LOGM, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        carry_attr_set = true;
+      }
+      warp_dct_kernel<LOGM, false, false, 2><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
     } else {
       warp_dct_kernel<LOGM, false><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
     }
