@@ -45,8 +45,8 @@ def test_peer_memory_and_nccl_transposes_agree(no_peer):
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
 
 
-@pytest.mark.parametrize("case", ["full_16_2", "full_17_1", "lid1_12x10x14_2", "full_65x17x9_1", "es:9x257x257"])
-@pytest.mark.parametrize("world,py", [(2, 2), (4, 2), (4, 4), (8, 2), (8, 4)])
+@pytest.mark.parametrize("case", ["full_17_1", "lid1_12x10x14_2", "es:9x257x257"])
+@pytest.mark.parametrize("world,py", [(2, 2), (4, 2), (8, 2), (8, 4)])
 def test_pencil_decomposition_matches_single_rank_reference(case, world, py):
     """Py x Pz pencils (the reference's decomposition, src/Constants.cpp:68-101): two-phase halos and the four
     2Decomp transposes as box exchanges; every rank's block reproduces the single-rank goldens."""
