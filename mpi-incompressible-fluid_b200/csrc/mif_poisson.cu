@@ -1635,6 +1635,7 @@ void launch_poisson_zpencil(cudaStream_t stream, const Geom &g, PoissonPlan *pla
 // x_offset / y_offset: global transform indices of local x = 0 and (dir = 2) local y = 0, for the eigenvalues.
 void launch_poisson_pencil(cudaStream_t stream, PoissonPlan *plan, double *buf, int dir, int mode, int nx_local, int pitch,
                            int n_outer, int x_offset, int y_offset, bool has_origin, uint64_t *launches) {
+  if (nx_local <= 0 || n_outer <= 0) return;  // this rank holds no line of the pencil (fewer rows than ranks)
   SweepLayout lay;
   lay.origin = 0;
   lay.n_tile_lines = nx_local;
