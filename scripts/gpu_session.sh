@@ -23,7 +23,7 @@ echo "== ncu --set full (one step)" && timeout 900 ncu --set full --clock-contro
 # the SIMT interpreter cannot see races: racecheck the kernels that were written without a GPU (M = 2048 warp kernel,
 # two-stage generic passes, the A/B variants) on thin grids
 echo "== compute-sanitizer racecheck" && timeout 900 compute-sanitizer --tool racecheck --racecheck-report analysis \
-  python -m pytest tests/test_gpu_vs_oracle.py -m gpu -q -x -k "test_pressure_solve_random_velocity and (N0 or N5 or N14 or N17 or N27 or N28 or N29 or N30)" \
+  python -m pytest tests/test_gpu_zz_new_sizes.py -m gpu -q -x -k "test_pressure_solve_random_velocity_new_sizes" \
   > $out/${tag}_racecheck.log 2>&1; tail -5 $out/${tag}_racecheck.log
 echo "== racecheck (MIFGPU_PLAIN_STRIDED=1)" && MIFGPU_PLAIN_STRIDED=1 timeout 600 compute-sanitizer --tool racecheck --racecheck-report analysis \
   python -m pytest tests/test_gpu_vs_oracle.py -m gpu -q -x -k "test_pressure_solve_random_velocity and (N15 or N16)" \

@@ -56,11 +56,6 @@ GRIDS = [
     ((1025, 4, 5), (True, False, False)),
     ((4, 1025, 5), (False, True, False)),
     ((513, 513, 5), (True, True, False)),      # two periodic directions, full tiles
-    ((2049, 3, 4), (False, False, False)),     # 2049-point x lines of BASELINE configs[4] (2048 x 512 x 512 cells): M = 2048, four warps per line
-    ((5, 3, 2049), (False, False, False)),     # ... as a fused z sweep
-    ((3, 2049, 4), (False, False, False)),     # ... as y sweeps
-    ((4100, 3, 2), (False, False, False)),     # beyond the warp kernels: generic kernel (Bluestein, P = 8192)
-    ((33, 6, 481), (False, False, True)),      # the reference's default 480-point period (input/input.txt): Bluestein
 ]
 
 
