@@ -1044,7 +1044,8 @@ __device__ __forceinline__ void first_pass_both(double2 *even_region, double2 *o
 
 // LINES lines per CTA (64 threads each): 8 lines fill the register file with ONE CTA per SM, whose 16 warps then load,
 // transform and store in lockstep; 4 lines give two independent CTAs per SM that overlap each other's phases.
-template <bool CONTIG, int LINES, bool CARRY = false>
+// SEG as in warp_dct_kernel: 0 default, 1 no segment-map code (MIFGPU_PLAIN_STRIDED), 2 segment cursors (MIFGPU_SEG_CARRY)
+template <bool CONTIG, int LINES, int SEG = 0>
 __global__ void __launch_bounds__(64 * LINES, 8 / LINES) warp_dct_split_kernel(const FastJob job, double *__restrict__ field) {
   using namespace warpfft;
   using namespace split;
@@ -1072,10 +1073,11 @@ __global__ void __launch_bounds__(64 * LINES, 8 / LINES) warp_dct_split_kernel(c
     auto element = [&](int e) -> double {
       if (!live) return 0.0;
       if (CONTIG) return src[e];
-      return job.load_map.n ? *seg_address(job.load_map, e, blockIdx.y, first_line + ll) : src[(long long)e * job.estride];
+      if constexpr (SEG == 1) return src[(long long)e * job.estride];
+      else return job.load_map.n ? *seg_address(job.load_map, e, blockIdx.y, first_line + ll) : src[(long long)e * job.estride];
     };
     double2 *a = v, *b = v + 8;
-    if (CARRY && !CONTIG && job.load_map.n > 0) {
+    if (SEG == 2 && !CONTIG && job.load_map.n > 0) {
       // segment cursors (MIFGPU_SEG_CARRY=1): 2q, 2q+1 ascend with t, the mirror images descend
       int r_up = 0, r_dn = job.load_map.n - 1;
 #pragma unroll
@@ -1172,7 +1174,9 @@ __global__ void __launch_bounds__(64 * LINES, 8 / LINES) warp_dct_split_kernel(c
     if (l < lines) {
       const double *srcl = reinterpret_cast<const double *>(smem2 + (2 * l) * C9::LINE_PITCH);
       double *out = base + (long long)l * job.lstride;
-      if (CARRY && job.store_map.n > 0) {
+      if constexpr (SEG == 1) {
+        for (int e = q0; e < NPTS; e += 64) out[(long long)e * job.estride] = srcl[e];
+      } else if (SEG == 2 && job.store_map.n > 0) {
         int r = 0;
         for (int e = q0; e < NPTS; e += 64) *seg_address_from<true>(job.store_map, r, e, blockIdx.y, first_line + l) = srcl[e];
       } else if (job.store_map.n) {
@@ -1194,16 +1198,24 @@ void launch_split(cudaStream_t stream, const FastJob &job, bool contig, int oute
     attr_set = true;
   }
   const dim3 grid((job.n_tile_lines + LINES - 1) / LINES, outer, 1);
-  static const bool seg_carry = getenv("MIFGPU_SEG_CARRY") != nullptr;  // A/B switch, default off (not measured yet)
+  static const bool seg_carry = getenv("MIFGPU_SEG_CARRY") != nullptr;  // A/B switches, default off (not measured yet)
+  static const bool plain_strided = getenv("MIFGPU_PLAIN_STRIDED") != nullptr;
   if (contig) {
     warp_dct_split_kernel<true, LINES><<<grid, 64 * LINES, smem, stream>>>(job, field);
   } else if (seg_carry && (job.load_map.n > 0 || job.store_map.n > 0)) {
     static bool carry_attr_set = false;
     if (!carry_attr_set) {
-      cudaFuncSetAttribute(warp_dct_split_kernel<false, LINES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(warp_dct_split_kernel<false, LINES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       carry_attr_set = true;
     }
-    warp_dct_split_kernel<false, LINES, true><<<grid, 64 * LINES, smem, stream>>>(job, field);
+    warp_dct_split_kernel<false, LINES, 2><<<grid, 64 * LINES, smem, stream>>>(job, field);
+  } else if (plain_strided && job.load_map.n == 0 && job.store_map.n == 0) {
+    static bool plain_attr_set = false;
+    if (!plain_attr_set) {
+      cudaFuncSetAttribute(warp_dct_split_kernel<false, LINES, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      plain_attr_set = true;
+    }
+    warp_dct_split_kernel<false, LINES, 1><<<grid, 64 * LINES, smem, stream>>>(job, field);
   } else {
     warp_dct_split_kernel<false, LINES><<<grid, 64 * LINES, smem, stream>>>(job, field);
   }
