@@ -788,6 +788,11 @@ static int create_context(const mifgpu_params *params, const void *unique_id, mi
   const double h[3] = {g.dx, g.dy, g.dz};
   const int n_global[3] = {(int)params->Nx_global, (int)params->Ny_global, (int)params->Nz_global};
   ctx->plan = poisson_plan_create(g, n_points, per, h, n_global);
+  if (const int bad = poisson_plan_unsupported_direction(ctx->plan); bad >= 0) {
+    mifgpu_destroy(ctx);
+    return fail(MIFGPU_ERR_UNSUPPORTED, "%d transform points in direction %d: lines of more than 4097 points that are not 2^k + 1 "
+                "do not fit the shared-memory transform of this build", n_points[bad], bad);
+  }
   ctx->nranks = params->Py * params->Pz;
   ctx->Py = params->Py;
   ctx->Pz = params->Pz;

@@ -60,6 +60,9 @@ struct PoissonPlan;  // transform tables + eigenvalues for one context
 PoissonPlan *poisson_plan_create(const Geom &g, const int n_points[3], const int periodic[3], const double h[3],
                                  const int n_global[3]);
 void poisson_plan_destroy(PoissonPlan *plan);
+// -1, or the direction whose line length the generic kernel cannot hold in shared memory (Bluestein transform lengths
+// above 4096, i.e. more than 4097 points that are not 2^k + 1).
+int poisson_plan_unsupported_direction(const PoissonPlan *plan);
 // One sweep of the in-place spectral solve on the owner region of `field` (src/PressureEquation.cpp:65-264):
 // dir = 0/1/2 (x/y/z); mode = 0 forward, 1 inverse + normalisation, 2 forward, eigenvalue division, inverse.
 // The solve is the sequence (0,0) (1,0) (2,2) (1,1) (0,1).

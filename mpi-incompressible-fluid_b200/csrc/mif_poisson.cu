@@ -1407,6 +1407,13 @@ PoissonPlan *poisson_plan_create(const Geom &g, const int n_points[3], const int
   return plan;
 }
 
+// Directions whose lines go through the generic kernel need one line (FFT work array + real line) in shared memory.
+int poisson_plan_unsupported_direction(const PoissonPlan *plan) {
+  for (int d = 0; d < 3; d++)
+    if (plan->fast_logm[d] == 0 && plan->rfft_logm[d] == 0 && plan->smem[d] > 200 * 1024) return d;
+  return -1;
+}
+
 void poisson_plan_destroy(PoissonPlan *plan) {
   if (!plan) return;
   for (void *p : plan->allocations) cudaFree(p);
