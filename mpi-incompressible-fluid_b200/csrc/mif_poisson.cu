@@ -567,10 +567,10 @@ void launch_fast(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid
 // ------------------------------------------------------------------------------------------------
 // FUSED_DIV (forward x sweep only): the input line is div(u, v, w) / dt formed in registers.  A separate instantiation,
 // so that the plain sweeps do not pay for its registers.
-// SEG (strided sweeps only): 0 = default; 1 = experiment MIFGPU_PLAIN_STRIDED=1, an instantiation without the
-// piecewise-strided segment maps of the multi-GPU sweeps -- no per-element map test, no indexed constant loads of the
-// map arrays -- for launches that use neither map; 2 = experiment MIFGPU_SEG_CARRY=1, maps searched with cursors
-// (seg_address_from).  The default instantiation is unchanged.
+// SEG (strided sweeps only): 0 = launches that use a segment map (multi-GPU fused transposes); 1 = launches that use
+// neither map (every single-GPU sweep): an instantiation without the map code -- no per-element map test, no indexed
+// constant loads of the map arrays, a third fewer instructions; 2 = experiment MIFGPU_SEG_CARRY=1, maps searched with
+// cursors (seg_address_from).
 template <int LOGM, bool CONTIG, bool FUSED_DIV = false, int SEG = 0>
 __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 : 2)) warp_dct_kernel(const FastJob job, double *__restrict__ field) {
   using namespace warpfft;
@@ -1198,8 +1198,8 @@ void launch_split(cudaStream_t stream, const FastJob &job, bool contig, int oute
     attr_set = true;
   }
   const dim3 grid((job.n_tile_lines + LINES - 1) / LINES, outer, 1);
-  static const bool seg_carry = getenv("MIFGPU_SEG_CARRY") != nullptr;  // A/B switches, default off (not measured yet)
-  static const bool plain_strided = getenv("MIFGPU_PLAIN_STRIDED") != nullptr;
+  static const bool seg_carry = getenv("MIFGPU_SEG_CARRY") != nullptr;  // A/B switch, default off (not measured yet)
+  static const bool plain_strided = getenv("MIFGPU_NO_PLAIN_STRIDED") == nullptr;
   if (contig) {
     warp_dct_split_kernel<true, LINES><<<grid, 64 * LINES, smem, stream>>>(job, field);
   } else if (seg_carry && (job.load_map.n > 0 || job.store_map.n > 0)) {
@@ -1243,8 +1243,10 @@ void launch_warp(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid
   } else if (contig) {
     warp_dct_kernel<LOGM, true><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
   } else {
-    // A/B switch (default off, not measured yet): strided sweeps without the segment-map code when no map is in use
-    static const bool plain_strided = getenv("MIFGPU_PLAIN_STRIDED") != nullptr;
+    // Strided sweeps without the segment-map code when no map is in use.  Measured on B200 at 513^3: y sweeps 2.84 ->
+    // 2.62 ms, fused z sweep 5.56 -> 5.23 ms per step (profiles/r01_ab_plain_strided.json); MIFGPU_NO_PLAIN_STRIDED=1
+    // restores the common instantiation for A/B runs.
+    static const bool plain_strided = getenv("MIFGPU_NO_PLAIN_STRIDED") == nullptr;
     static const bool seg_carry = getenv("MIFGPU_SEG_CARRY") != nullptr;
     if (plain_strided && job.load_map.n == 0 && job.store_map.n == 0) {
       static bool plain_attr_set = false;

@@ -26,7 +26,8 @@ import test_gpu_vs_oracle as parity  # noqa: E402
 
 F, T = False, True
 for N, periodic in [((20, 13, 11), (F, F, F)), ((2049, 3, 4), (F, F, F)), ((5, 3, 2049), (F, F, F)), ((3, 2049, 4), (F, F, F)),
-                    ((33, 6, 481), (F, F, T)), ((513, 4, 9), (F, F, F)), ((9, 513, 3), (F, F, F)), ((3000, 3, 2), (F, F, F)), ((4097, 3, 2), (F, F, F))]:
+                    ((33, 6, 481), (F, F, T)), ((513, 4, 9), (F, F, F)), ((9, 513, 3), (F, F, F)), ((11, 3, 513), (F, F, F)), ((5, 257, 6), (F, F, F)),
+                    ((6, 5, 257), (F, F, F)), ((9, 1025, 3), (F, F, F)), ((10, 4, 1025), (F, F, F)), ((3000, 3, 2), (F, F, F))]:
     parity.test_pressure_solve_random_velocity(mif, N, periodic)
     say(f"solve parity ok {N} {periodic}")
 say("done")
