@@ -128,7 +128,18 @@ void launch(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::functio
     std::fprintf(stderr, "simt_emu: block of %zu threads\n", n);
     abort();
   }
-  if ((size_t)grid.x * grid.y * grid.z == 0) return;
+  if (dynamic_smem_bytes > 227 * 1024) {  // the opt-in maximum of an sm_100 CTA: a real launch fails with "invalid argument"
+    std::fprintf(stderr, "simt_emu: launch with %zu bytes of dynamic shared memory (limit 232448)\n", dynamic_smem_bytes);
+    abort();
+  }
+  if ((size_t)grid.x * grid.y * grid.z == 0) {
+    std::fprintf(stderr, "simt_emu: launch with an empty grid (a real launch fails with \"invalid configuration\")\n");
+    abort();
+  }
+  if (grid.y > 65535 || grid.z > 65535) {
+    std::fprintf(stderr, "simt_emu: grid (%u, %u, %u) exceeds the y / z limit of 65535\n", grid.x, grid.y, grid.z);
+    abort();
+  }
   g_nthreads = (int)n;
   g_body = &thread_body;
   blockDim = block;
