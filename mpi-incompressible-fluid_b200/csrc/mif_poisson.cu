@@ -595,7 +595,27 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
     // slots q >= M/2 are the mirror images (x[2M-2q], x[2M-2q-1]).  No shared-memory staging, no CTA barrier.
     const double *src = base + (long long)line * job.lstride;
     const bool live = line < lines;
-    if (!FUSED_DIV && job.div_u == nullptr) {
+    if constexpr (!FUSED_DIV && SEG == 1 && SHUFFLE) {
+      // Experiment MIFGPU_X_MIRROR_SHFL=1 (x sweeps, one warp per line): the mirrored slots q >= M/2 of the even
+      // extension, (x[2M-2q], x[2M-2q-1]), are not loaded a second time but fetched from the lanes that already hold
+      // those values (32 - j and 31 - j) -- 16 double shuffles instead of 16 strided 8-byte loads per lane (the x
+      // sweep is bound by the LSU data pipe, and a stride-2 warp load costs four wavefronts for two of payload).
+      double2 d[EPT / 2];
+#pragma unroll
+      for (int s = 0; s < EPT / 2; s++) {
+        d[s] = live ? *reinterpret_cast<const double2 *>(src + 2 * (j + s * TL)) : make_double2(0.0, 0.0);
+        v[s] = d[s];
+      }
+      const double x_last = live ? src[M] : 0.0;  // same address in all lanes: one broadcast request
+#pragma unroll
+      for (int sp = 1; sp <= EPT / 2; sp++) {
+        // slot q = j + 32 (EPT - sp):  2M - 2q = 64 sp - 2j
+        double x = __shfl_sync(0xffffffffu, d[sp - 1].x, (32 - j) & 31);
+        const double y = __shfl_sync(0xffffffffu, d[sp - 1].y, 31 - j);
+        if (j == 0) x = (sp < EPT / 2) ? d[sp < EPT / 2 ? sp : 0].x : x_last;
+        v[EPT - sp] = make_double2(x, y);
+      }
+    } else if (!FUSED_DIV && job.div_u == nullptr) {
 #pragma unroll
       for (int s = 0; s < EPT; s++) {
         const int q = j + s * TL;
@@ -723,7 +743,7 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
   double lo[PAIRS], hi[PAIRS], mid = 0.0, e_last = 0.0;
   double spec[EPT];  // shuffle path: spec[u + G t] = E_k, k = j + 32 u + NS t
   if (!CONTIG) fft_line<LOGM, false, SHUFFLE, true>(S, T, j, line, v);                     // first pass already done
-  else if (FUSED_DIV || job.div_u == nullptr) fft_line<LOGM, true, SHUFFLE>(S, T, j, line, v);  // first pass from registers
+  else if (FUSED_DIV || SEG == 1 || job.div_u == nullptr) fft_line<LOGM, true, SHUFFLE>(S, T, j, line, v);  // first pass from registers
   else fft_line<LOGM, false, SHUFFLE>(S, T, j, line, v);
   if constexpr (SHUFFLE) unpack_regs<LOGM>(v, j, job.cs, spec, e_last);
   else unpack_line<LOGM>(S, j, job.cs, lo, hi, mid);
@@ -1241,6 +1261,18 @@ void launch_warp(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid
       warp_dct_kernel<LOGM, true, true><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
     }
   } else if (contig) {
+    static const bool mirror_shfl = getenv("MIFGPU_X_MIRROR_SHFL") != nullptr;  // A/B switch, default off (not measured yet)
+    if constexpr (C::WPL == 1) {
+      if (mirror_shfl) {
+        static bool mirror_attr_set = false;
+        if (!mirror_attr_set) {
+          cudaFuncSetAttribute(warp_dct_kernel<LOGM, true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+          mirror_attr_set = true;
+        }
+        warp_dct_kernel<LOGM, true, false, 1><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
+        return;
+      }
+    }
     warp_dct_kernel<LOGM, true><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
   } else {
     // Strided sweeps without the segment-map code when no map is in use.  Measured on B200 at 513^3: y sweeps 2.84 ->

@@ -12,7 +12,7 @@ mkdir -p $out
 echo "== pytest -m gpu" && timeout 1200 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; tail -3 $out/${tag}_pytest.log
 echo "== bench (full step)" && timeout 600 python bench.py --steps 10 --warmup 3 > $out/${tag}_bench_1gpu.json 2> $out/${tag}_bench_1gpu.err; tail -c 1500 $out/${tag}_bench_1gpu.json
 echo "== bench (Poisson only)" && timeout 300 python bench.py --workload poisson --steps 10 --warmup 3 > $out/${tag}_bench_poisson.json 2>> $out/${tag}_bench_1gpu.err
-for ab in ${MIF_AB:-MIFGPU_NO_PLAIN_STRIDED=1}; do
+for ab in ${MIF_AB:-MIFGPU_NO_PLAIN_STRIDED=1 MIFGPU_X_MIRROR_SHFL=1}; do
   echo "== A/B $ab" && env "$ab" timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > "$out/${tag}_bench_${ab//[^A-Za-z0-9_=]/_}.json" 2>> $out/${tag}_bench_1gpu.err
 done
 # 27 kernels per step, 3 warm-up steps: skip 81 launches, list two steps
