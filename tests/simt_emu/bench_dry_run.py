@@ -32,6 +32,15 @@ torch.cuda.set_device = lambda *a, **k: None
 torch.cuda.synchronize = lambda *a, **k: None
 torch.Tensor.pin_memory = lambda self, *a, **k: self
 
+# several ranks (torchrun): gloo instead of NCCL for torch.distributed, host tensors instead of device tensors
+import torch.distributed as dist  # noqa: E402
+
+_init = dist.init_process_group
+dist.init_process_group = lambda backend=None, **kwargs: _init("gloo")
+_zeros, _tensor = torch.zeros, torch.tensor
+torch.zeros = lambda *a, **k: _zeros(*a, **{key: v for key, v in k.items() if key != "device"})
+torch.tensor = lambda *a, **k: _tensor(*a, **{key: v for key, v in k.items() if key != "device"})
+
 import bench  # noqa: E402
 
 sys.argv = ["bench.py"] + sys.argv[1:]

@@ -110,3 +110,18 @@ def test_ported_pressure_tests_on_several_ranks_print_the_reference_numbers(simt
         got, want = [float(x) for x in line.split()[1:]], norms[f"pressure_test_{kind} 8 1"]
         for a, b in zip(got, want):
             assert abs(a - b) <= 2e-5 * abs(b), (kind, got, want)
+
+
+def test_bench_line_on_two_ranks_in_a_dry_run(simt_env):
+    """bench.py's own arm under torchrun on two emulated ranks (tests/simt_emu/bench_dry_run.py: gloo for torch.distributed,
+    inert stand-ins for torch.cuda): rank 0 prints one JSON line with the multi-GPU keys.  Values are meaningless."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29716", os.path.join(EMU, "bench_dry_run.py"), "--gpus", "2", "--size", "9", "--steps", "2", "--warmup", "3"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=simt_env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    line = json.loads(lines[0])
+    assert line["n_gpus"] == 2 and line["scaling"] == "weak" and line["config"]["points"] == [9, 9, 17]
+    assert line["nvlink"]["bytes_sent_per_gpu_per_step"] == 6 * 8 * (9 * 9 * 17 / 2) * 0.5
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["gpu_launches"] > 0 and "halo_exchange" in line["kernels"]
