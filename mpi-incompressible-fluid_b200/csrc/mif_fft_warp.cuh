@@ -192,6 +192,30 @@ __device__ __forceinline__ void first_pass_in_place(double2 *S_line, int b, doub
   }
 }
 
+// The same in two steps, for kernels that want the butterflies done before the line regions may be written
+// (mif_poisson_tma.cuh: the regions alias an output stage that the copy engine may still be reading).
+template <int LOGM>
+__device__ __forceinline__ void first_pass_compute(double2 *v) {
+  constexpr int G = Cfg<LOGM>::EPT / 8;
+#pragma unroll
+  for (int u = 0; u < G; u++) {
+    double2 a[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) a[t] = v[u + G * t];
+    fast::dft8(a);
+#pragma unroll
+    for (int t = 0; t < 8; t++) v[u + G * t] = a[t];
+  }
+}
+template <int LOGM>
+__device__ __forceinline__ void first_pass_store(double2 *S_line, int b, const double2 *v) {
+  constexpr int TL = Cfg<LOGM>::TL, G = Cfg<LOGM>::EPT / 8;
+#pragma unroll
+  for (int u = 0; u < G; u++)
+#pragma unroll
+    for (int t = 0; t < 8; t++) S_line[pad((b + u * TL) * 8 + t)] = v[u + G * t];
+}
+
 // DCT-I unpack in registers (one warp per line): after the last pass lane j holds C_k for k = j + 32 u + NS t.
 // Its partners C_{M-k} all live in lane 32 - j (butterfly G-1-u, output R-1-t), so one round of shuffles
 // replaces the shared-memory round trip; lane 0 is its own partner with a slightly different index map.

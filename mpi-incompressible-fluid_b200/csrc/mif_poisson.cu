@@ -17,9 +17,12 @@
 #include <cstdlib>
 #include <vector>
 
+#include <algorithm>
+
 #include "mif_fft_fast.cuh"
 #include "mif_fft_warp.cuh"
 #include "mif_kernels.h"
+#include "mif_poisson_tma.cuh"
 
 namespace mifgpu {
 
@@ -1344,6 +1347,7 @@ struct PoissonPlan {
   int L[3];
   size_t smem[3];
   std::vector<void *> allocations;
+  tmasweep::Cache tma;  // tensor maps of the TMA-staged strided sweeps, per field / direction
 };
 
 PoissonPlan *poisson_plan_create(const Geom &g, const int n_points[3], const int periodic[3], const double h[3],
@@ -1472,6 +1476,59 @@ struct SweepLayout {
   long long stride_y = 0, stride_z = 0;
 };
 
+// TMA-staged strided sweep (mif_poisson_tma.cuh) when the geometry allows it: 257- or 513-point DCT-I lines along y or
+// z, tiles of 8 consecutive x, plain strided addressing with 16-byte aligned rows.  Returns false when the launch has
+// to take the LSU path (MIFGPU_NO_TMA=1 forces that for A/B runs; MIFGPU_REQUIRE_TMA=1 turns a refusal into an abort
+// so that tests cannot pass on the fallback by accident).
+bool launch_tma_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, int mode, const SweepLayout &lay) {
+  static const bool disabled = getenv("MIFGPU_NO_TMA") != nullptr;
+  static const bool required = getenv("MIFGPU_REQUIRE_TMA") != nullptr;
+  const int logm = plan->fast_logm[d];
+  if (disabled || lay.contig || (logm != 8 && logm != 9) || lay.load_map.n || lay.store_map.n || lay.peer) return false;
+  auto refuse = [&](const char *why) {
+    if (required) {
+      fprintf(stderr, "libmifgpu: MIFGPU_REQUIRE_TMA=1 but the sweep along %d cannot use TMA: %s\n", d, why);
+      abort();
+    }
+    return false;
+  };
+  if (lay.lstride != 1 || lay.tile_stride != 1 || (lay.estride & 1) || (lay.outer_stride & 1)) return refuse("strides");
+  tmasweep::Cache &cache = plan->tma;
+  if (cache.device < 0) {
+    cudaGetDevice(&cache.device);
+    cudaDeviceGetAttribute(&cache.sms, cudaDevAttrMultiProcessorCount, cache.device);
+  }
+  static const bool swizzle = getenv("MIFGPU_TMA_NO_SWIZZLE") == nullptr;
+  static const int promo = getenv("MIFGPU_TMA_L2PROMO") ? atoi(getenv("MIFGPU_TMA_L2PROMO")) : 2;
+  const int x_off = (int)(lay.origin & 1);
+  const tmasweep::MapSet *maps = tmasweep::maps_for(cache, field + lay.origin - x_off, x_off, lay.n_tile_lines, plan->dir[d].n,
+                                                    lay.outer, lay.estride, lay.outer_stride, swizzle, promo);
+  if (!maps) return refuse("tensor map");
+  tmasweep::Job job;
+  job.n_xtiles = (lay.n_tile_lines + warpfft::kLines - 1) / warpfft::kLines;
+  job.n_outer = lay.outer;
+  job.n_lines = lay.n_tile_lines;
+  job.x_off = x_off;
+  job.tw = plan->dir[d].tw_full;
+  job.cs = plan->dir[d].unpack;
+  job.lam_x = plan->dir[0].lambda + lay.lam_x_offset;
+  job.lam_y = plan->dir[1].lambda + lay.lam_y_offset;
+  job.lam_z = plan->dir[2].lambda;
+  job.inv_norm = plan->dir[d].inv_norm;
+  job.has_origin = lay.has_origin ? 1 : 0;
+  job.swz = swizzle ? 7u : 0u;
+  if (logm == 8) {
+    if (mode == 0) tmasweep::launch_one<8, 0>(stream, cache, *maps, job);
+    else if (mode == 1) tmasweep::launch_one<8, 1>(stream, cache, *maps, job);
+    else tmasweep::launch_one<8, 2>(stream, cache, *maps, job);
+  } else {
+    if (mode == 0) tmasweep::launch_one<9, 0>(stream, cache, *maps, job);
+    else if (mode == 1) tmasweep::launch_one<9, 1>(stream, cache, *maps, job);
+    else tmasweep::launch_one<9, 2>(stream, cache, *maps, job);
+  }
+  return true;
+}
+
 void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, int mode, const SweepLayout &lay,
                   uint64_t *launches) {
   static bool attr_set = false;
@@ -1502,6 +1559,10 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
     if (plan->rfft_logm[d] > 0) {
       if (plan->rfft_logm[d] == 8) launch_rfft<8>(stream, fj, lay.contig, fgrid, field);
       else launch_rfft<9>(stream, fj, lay.contig, fgrid, field);
+      ++*launches;
+      return;
+    }
+    if (launch_tma_sweep(stream, plan, field, d, mode, lay)) {
       ++*launches;
       return;
     }

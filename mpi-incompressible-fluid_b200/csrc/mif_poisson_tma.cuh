@@ -1,0 +1,303 @@
+// mif_poisson_tma.cuh -- strided (y / z) DCT-I sweeps of the Poisson solve staged by TMA (sm_100a, FP64).
+// Included by mif_poisson.cu.
+//
+// Replaces, for lines of 2^k + 1 points (k = 8, 9) along y or z, the reference's 1-D REDFT00 sweeps and the 2Decomp
+// pack / transpose / unpack passes around them (src/PressureEquation.cpp:106-229,
+// deps/2Decomp_C/MemSplitMerge.cpp:59-86,116-143): the lines stay where they are in the x-fastest array and a tile of
+// 8 lines (8 consecutive x, i.e. 64-byte rows) is moved by the copy engine instead of by the warps.
+//
+//   * persistent CTAs (2 per SM, 8 warps, one warp per line), tiles handed out round-robin, x tile fastest;
+//   * load: cp.async.bulk.tensor boxes of 8 x 130 doubles into a shared stage, completion on an mbarrier.  The stage
+//     is free again as soon as every thread has taken its first-pass inputs into registers, so the boxes of the NEXT
+//     tile are in flight while the current one is transformed -- no warp ever waits for HBM in steady state;
+//   * forward sweeps read the even extension e(2q), e(2q+1) and its mirror image: two tensor maps over the even and
+//     the odd rows land them in two separate areas, which makes the line-fastest first-pass reads (8 lines x 4
+//     consecutive rows per warp = 256 contiguous bytes) bank-conflict free;
+//   * inverse sweeps do not transform the even extension again.  DCT-I of a real sequence E is the unnormalised
+//     half-complex -> real transform of the real spectrum E, and that is ONE length-M complex FFT of
+//     conj Z_k = (E_k + E_{M-k}) - i exp(i pi k / M) (E_k - E_{M-k}),  x_{2q} = Re z_q, x_{2q+1} = -Im z_q:
+//     513 points are read once (natural rows), no unpack pass follows, and the mirror half of the output is never
+//     formed.  In the fused z sweep the scaled spectrum is repacked in registers (partners by shuffles) and is the
+//     first-pass input of the second FFT without touching shared memory;
+//   * store: every warp writes its line's column into a 128-byte-swizzled output stage (aliasing the FFT work area)
+//     and one thread issues cp.async.bulk.tensor stores; they drain while the next tile's inputs are read.
+#pragma once
+
+#include <map>
+#include <tuple>
+
+#include "mif_fft_warp.cuh"
+#include "mif_tma.cuh"
+
+namespace mifgpu {
+namespace tmasweep {
+
+using namespace warpfft;
+
+constexpr int kBoxRows = 130;       // rows of one load box (x 8 doubles = 8320 bytes: box bases stay 128-byte aligned)
+constexpr int kStoreRows = 128;     // rows of one store box (8192 bytes, one swizzle period = 8 rows)
+constexpr int kThreads = 256;
+
+template <int LOGM>
+struct Layout {
+  using C = Cfg<LOGM>;
+  static constexpr int M = C::M;
+  static constexpr int kLoadBoxes = 2 * ((M / 2 + 1 + kBoxRows - 1) / kBoxRows);  // even rows + odd rows; also covers M + 1 natural rows
+  static constexpr int kOddRow0 = (kLoadBoxes / 2) * kBoxRows;                    // first row of the odd area
+  static constexpr int kStoreBoxes = (M + 1 + kStoreRows - 1) / kStoreRows;
+  static constexpr size_t kWorkBytes = (size_t)kLines * C::LINE_PITCH * sizeof(double2);
+  static constexpr size_t kOutBytes = (size_t)kStoreBoxes * kStoreRows * 64;
+  static constexpr size_t kTwBytes = (size_t)C::TW_TOTAL * sizeof(double2);
+  static constexpr size_t kStageBytes = (size_t)kLoadBoxes * kBoxRows * 64;
+  static constexpr size_t kWorkArea = ((kWorkBytes > kOutBytes ? kWorkBytes : kOutBytes) + 127) / 128 * 128;
+  // [work / output stage][twiddles][input stage][mbarrier], after aligning the dynamic window to 1024 bytes
+  static constexpr size_t kSmem = 1024 + kWorkArea + (kTwBytes + 127) / 128 * 128 + kStageBytes + 64;
+  static_assert(kLoadBoxes * kBoxRows >= M + 1, "natural rows fit the stage");
+};
+
+struct Job {
+  int n_xtiles, n_outer, n_lines, x_off;
+  const double2 *tw, *cs;
+  const double *lam_x, *lam_y, *lam_z;
+  double inv_norm;
+  int has_origin;
+  unsigned swz;  // 7: the output map is 128-byte swizzled, 0: plain
+};
+
+__device__ __forceinline__ double2 dct_pack_input(double xr, double yr, double c, double sn) {
+  // conj Z_k for a real spectrum: X_k = xr, X_{M-k} = yr, (c, sn) = (cos, sin)(pi k / M); see hc2r_input
+  const double pr = xr + yr, dr = xr - yr;
+  return make_double2(pr - sn * dr, -(c * dr));
+}
+
+// conj Z_k from the registers left by unpack_regs (spec[u + G t] = E_k, k = j + 32 u + NS t, e_last = E_M in lane 0):
+// the partners E_{M-k} come from lane 32 - j, and slot u + G t is exactly first-pass slot s of the next transform.
+template <int LOGM>
+__device__ __forceinline__ void pack_dct_regs(const double *spec, double e_last, int j, const double2 *__restrict__ cs,
+                                              double2 *v) {
+  using L = LastPass<LOGM>;
+  constexpr int R = L::R, G = L::G;
+  const int src = (32 - j) & 31;
+  double2 base_w[G];
+#pragma unroll
+  for (int u = 0; u < G; u++) base_w[u] = __ldg(&cs[j + 32 * u]);
+#pragma unroll
+  for (int u = 0; u < G; u++)
+#pragma unroll
+    for (int t = 0; t < R; t++) {
+      const int partner = (G - 1 - u) + G * (R - 1 - t);
+      double yr = __shfl_sync(0xffffffffu, spec[partner], src);
+      if (j == 0) {
+        if (u == 0 && t == 0) yr = e_last;  // E_M
+        else yr = spec[(u == 0) ? G * (R - t) : (G - u) + G * (R - 1 - t)];
+      }
+      const double2 w0 = base_w[u], r = rot8((8 / R) * t);
+      const double c = w0.x * r.x - w0.y * r.y, sn = w0.x * r.y + w0.y * r.x;
+      v[u + G * t] = dct_pack_input(spec[u + G * t], yr, c, sn);
+    }
+}
+
+// MODE 0: forward; 1: inverse + normalisation; 2: forward, eigenvalue division, inverse + normalisation.
+template <int LOGM, int MODE>
+__global__ void __launch_bounds__(kThreads, 2)
+    tma_dct_kernel(const __grid_constant__ CUtensorMap map_in_a, const __grid_constant__ CUtensorMap map_in_b,
+                   const __grid_constant__ CUtensorMap map_out, const Job job) {
+  using C = Cfg<LOGM>;
+  using L = LastPass<LOGM>;
+  using Y = Layout<LOGM>;
+  constexpr int M = C::M, EPT = C::EPT, HALF = M / 2;
+  static_assert(C::WPL == 1 && C::LINES == kLines && C::THREADS == kThreads, "one warp per line, 8 lines");
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *smem = smem_raw + ((1024 - (tma::swizzle_address(smem_raw) & 1023)) & 1023);
+  double2 *W = reinterpret_cast<double2 *>(smem);                                   // FFT work area, one region per line
+  unsigned char *O = smem;                                                          // output stage (aliases W)
+  double2 *T = reinterpret_cast<double2 *>(smem + Y::kWorkArea);                    // twiddle tables
+  double *S = reinterpret_cast<double *>(smem + Y::kWorkArea + (Y::kTwBytes + 127) / 128 * 128);  // input stage
+  uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(S) + Y::kStageBytes);
+
+  const int tid = threadIdx.x;
+  const int line = tid >> 5, j = tid & 31;  // FFT mapping: warp = line
+  const int l = tid & 7, b = tid >> 3;      // stage mapping: line fastest
+  double2 *Sline = W + line * C::LINE_PITCH;
+  const int n_tiles = job.n_xtiles * job.n_outer;
+
+  auto issue_load = [&](int tile) {
+    const int xt = tile % job.n_xtiles, outer = tile / job.n_xtiles;
+    const int x0 = job.x_off + xt * kLines;
+    tma::mbar_arrive_expect_tx(full, (unsigned)Y::kStageBytes);
+    if (MODE == 1) {
+#pragma unroll
+      for (int i = 0; i < Y::kLoadBoxes; i++) tma::load_3d(S + i * kBoxRows * 8, &map_in_a, full, x0, i * kBoxRows, outer);
+    } else {
+#pragma unroll
+      for (int i = 0; i < Y::kLoadBoxes / 2; i++) {
+        tma::load_3d(S + i * kBoxRows * 8, &map_in_a, full, x0, i * kBoxRows, outer);
+        tma::load_3d(S + (Y::kOddRow0 + i * kBoxRows) * 8, &map_in_b, full, x0, i * kBoxRows, outer);
+      }
+    }
+  };
+
+  if (tid == 0) {
+    tma::prefetch_map(&map_in_a);
+    tma::prefetch_map(&map_in_b);
+    tma::prefetch_map(&map_out);
+    tma::mbar_init(full, 1);
+    tma::fence_barrier_init();
+    tma::fence_proxy_async();
+  }
+  load_twiddles<LOGM>(T, job.tw);
+  __syncthreads();
+  int tile = blockIdx.x;
+  if (tid == 0 && tile < n_tiles) issue_load(tile);
+  unsigned parity = 0;
+
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const int xt = tile % job.n_xtiles, outer = tile / job.n_xtiles;
+    double2 v[EPT];
+
+    // ---- first-pass inputs from the stage ---------------------------------------------------------------------
+    tma::mbar_wait(full, parity);
+    parity ^= 1;
+    if (MODE == 1) {
+      const double *N = S + l;  // natural rows: element e of line l at N[8 e]
+#pragma unroll
+      for (int s = 0; s < EPT; s++) {
+        const int k = b + 32 * s;
+        const double2 w = __ldg(&job.cs[k]);
+        v[s] = dct_pack_input(N[8 * k], N[8 * (M - k)], w.x, w.y);
+      }
+    } else {
+      const double *Ev = S + l, *Od = S + Y::kOddRow0 * 8 + l;  // e(2q) at Ev[8 q], e(2q+1) at Od[8 q]
+#pragma unroll
+      for (int s = 0; s < EPT; s++) {
+        const int q = b + 32 * s;
+        if (s < EPT / 2) v[s] = make_double2(Ev[8 * q], Od[8 * q]);
+        else v[s] = make_double2(Ev[8 * (M - q)], Od[8 * (M - q - 1)]);  // mirror image: e(2M-2q), e(2M-2q-1)
+      }
+    }
+    // The first radix-8 butterflies run in registers BEFORE the barrier: the bulk stores of the previous tile (which read
+    // the output stage inside W) get that time to drain, and the stage is released to the next tile's boxes right after.
+    first_pass_compute<LOGM>(v);
+    if (tid == 0) tma::wait_stores_read();  // the previous tile's output stage (in W) has been read out
+    __syncthreads();                        // the stage has been consumed, W is free
+    if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue_load(tile + gridDim.x);
+
+    // ---- transform --------------------------------------------------------------------------------------------
+    first_pass_store<LOGM>(W + l * C::LINE_PITCH, b, v);
+    __syncthreads();
+    fft_line<LOGM, false, true, true>(Sline, T, j, line, v);
+
+    double spec[EPT], e_last = 0.0;
+    if (MODE != 1) unpack_regs<LOGM>(v, j, job.cs, spec, e_last);
+    if (MODE == 2) {
+      // pressure_hat *= 1 / (lambda_x + lambda_y + lambda_z); mode (0,0,0) := 0 (src/PressureEquation.cpp:158-163)
+      const int ix = min(xt * kLines + line, job.n_lines - 1);
+      const double lam_xy = job.lam_x[ix] + job.lam_y[outer];
+      const bool origin_line = job.has_origin && (xt * kLines + line == 0) && (outer == 0);
+#pragma unroll
+      for (int u = 0; u < L::G; u++)
+#pragma unroll
+        for (int t = 0; t < L::R; t++) {
+          const int k = j + 32 * u + L::NS * t;
+          spec[u + L::G * t] *= (origin_line && k == 0) ? 0.0 : 1.0 / (lam_xy + job.lam_z[k]);
+        }
+      e_last *= 1.0 / (lam_xy + job.lam_z[M]);
+      pack_dct_regs<LOGM>(spec, e_last, j, job.cs, v);
+      __syncwarp();  // every lane has finished reading the line region (last pass of the forward transform)
+      fft_line<LOGM, true, true>(Sline, T, j, line, v);
+    }
+    __syncthreads();  // all warps are done with the work area: it becomes the output stage
+
+    // ---- results into the swizzled output stage: row e of the tile at 64 e, column `line` -------------------------
+    if (MODE == 0) {
+      // lane j holds E_k, k = j + 32 u + NS t; bits 7-9 of the offset (row >> 1) do not depend on (u, t)
+      const unsigned off = tma::swizzle_offset((unsigned)(j * 64 + line * 8), job.swz);
+#pragma unroll
+      for (int u = 0; u < L::G; u++)
+#pragma unroll
+        for (int t = 0; t < L::R; t++)
+          *reinterpret_cast<double *>(O + off + (32 * u + L::NS * t) * 64) = spec[u + L::G * t];
+      if (j == 0) *reinterpret_cast<double *>(O + tma::swizzle_offset((unsigned)(M * 64 + line * 8), job.swz)) = e_last;
+    } else {
+      // lane j holds z_q = conj(v), q = j + 32 u + NS t: x(2q) = Re z_q, x(2q+1) = Im z_q; only q <= M/2 is stored
+      const unsigned off = tma::swizzle_offset((unsigned)(j * 128 + line * 8), job.swz);
+      const double scale = job.inv_norm;
+#pragma unroll
+      for (int u = 0; u < L::G; u++)
+#pragma unroll
+        for (int t = 0; t < L::R / 2; t++) {
+          const unsigned at = off + (32 * u + L::NS * t) * 128;
+          *reinterpret_cast<double *>(O + at) = v[u + L::G * t].x * scale;
+          *reinterpret_cast<double *>(O + (at ^ 64u)) = -v[u + L::G * t].y * scale;
+        }
+      if (j == 0)  // q = M/2 = NS * R/2: slot u = 0, t = R/2 of lane 0
+        *reinterpret_cast<double *>(O + tma::swizzle_offset((unsigned)(M * 64 + line * 8), job.swz)) = v[L::G * (L::R / 2)].x * scale;
+    }
+    tma::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      const int x0 = job.x_off + xt * kLines;
+#pragma unroll
+      for (int c = 0; c < Y::kStoreBoxes; c++) tma::store_3d(&map_out, O + c * kStoreRows * 64, x0, c * kStoreRows, outer);
+      tma::commit_group();
+    }
+  }
+  if (tid == 0) tma::wait_stores_done();
+}
+
+// ---- host -----------------------------------------------------------------------------------------------------
+struct MapKey {
+  const void *base;
+  long long estride, outer_stride;
+  int nx, n, outer, x_off, kind, promo;
+  bool operator<(const MapKey &o) const {
+    return std::tie(base, estride, outer_stride, nx, n, outer, x_off, kind, promo) <
+           std::tie(o.base, o.estride, o.outer_stride, o.nx, o.n, o.outer, o.x_off, o.kind, o.promo);
+  }
+};
+struct MapSet {
+  CUtensorMap even, odd, natural, out;
+  bool ok;
+};
+
+struct Cache {
+  std::map<MapKey, MapSet> sets;
+  int device = -1, sms = 0;
+  bool attr[2][3] = {};
+};
+
+// kind: 0 plain output map, 1 swizzled output map
+inline const MapSet *maps_for(Cache &cache, double *base, int x_off, int nx, int n, int outer, long long estride,
+                              long long outer_stride, bool swizzle, int promo) {
+  const MapKey key{base, estride, outer_stride, nx, n, outer, x_off, swizzle ? 1 : 0, promo};
+  auto it = cache.sets.find(key);
+  if (it != cache.sets.end()) return it->second.ok ? &it->second : nullptr;
+  MapSet set;
+  const uint64_t dim0 = (uint64_t)(x_off + nx), row = (uint64_t)estride * 8, outer_b = (uint64_t)outer_stride * 8;
+  const int half = (n - 1) / 2;
+  const char *why = nullptr;
+  set.ok = tma::encode_map(&set.even, base, dim0, (uint64_t)half + 1, (uint64_t)outer, 2 * row, outer_b, kLines, kBoxRows, false, promo, &why) &&
+           tma::encode_map(&set.odd, base + estride, dim0, (uint64_t)half, (uint64_t)outer, 2 * row, outer_b, kLines, kBoxRows, false, promo, &why) &&
+           tma::encode_map(&set.natural, base, dim0, (uint64_t)n, (uint64_t)outer, row, outer_b, kLines, kBoxRows, false, promo, &why) &&
+           tma::encode_map(&set.out, base, dim0, (uint64_t)n, (uint64_t)outer, row, outer_b, kLines, kStoreRows, swizzle, 0, &why);
+  if (!set.ok && getenv("MIFGPU_TMA_VERBOSE")) fprintf(stderr, "libmifgpu: no tensor map for this sweep: %s\n", why ? why : "?");
+  auto ins = cache.sets.emplace(key, set);
+  return set.ok ? &ins.first->second : nullptr;
+}
+
+template <int LOGM, int MODE>
+void launch_one(cudaStream_t stream, Cache &cache, const MapSet &maps, const Job &job) {
+  using Y = Layout<LOGM>;
+  bool &attr = cache.attr[LOGM - 8][MODE];
+  if (!attr) {
+    cudaFuncSetAttribute(tma_dct_kernel<LOGM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Y::kSmem);
+    attr = true;
+  }
+  static const int per_sm = getenv("MIFGPU_TMA_CTAS_PER_SM") ? atoi(getenv("MIFGPU_TMA_CTAS_PER_SM")) : 2;
+  const int n_tiles = job.n_xtiles * job.n_outer;
+  const int grid = std::min(n_tiles, std::max(1, cache.sms * per_sm));
+  tma_dct_kernel<LOGM, MODE><<<grid, kThreads, Y::kSmem, stream>>>(MODE == 1 ? maps.natural : maps.even, maps.odd, maps.out, job);
+}
+
+}  // namespace tmasweep
+}  // namespace mifgpu

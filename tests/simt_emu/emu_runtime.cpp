@@ -2,6 +2,7 @@
 // include/cuda_runtime.h).  One OS thread; the CUDA threads of one block are ucontext fibers that run until they reach
 // a scheduling point (block / warp / named barrier, shuffle) or return; blocks run one after the other.
 #include <cuda_runtime.h>
+#include <mif_tma.cuh>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -78,7 +79,10 @@ void run_block() {
       if (g_fibers[t].state != DONE) live++;
       if (g_fibers[t].state == WAIT_BLOCK) at_block++;
     }
-    if (live == 0) return;
+    if (live == 0) {
+      emu::tma_block_end();
+      return;
+    }
     bool released = false;
     if (at_block == live) {
       for (int t = 0; t < g_nthreads; t++)
@@ -144,7 +148,7 @@ void launch(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::functio
   g_body = &thread_body;
   blockDim = block;
   gridDim = grid;
-  g_dynamic_smem.assign(dynamic_smem_bytes + 64, 0);
+  g_dynamic_smem.assign(dynamic_smem_bytes + 1024, 0);
   int t = 0;
   for (unsigned z = 0; z < block.z; z++)
     for (unsigned y = 0; y < block.y; y++)
@@ -165,7 +169,123 @@ void launch(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::functio
 
 void *dynamic_smem() {
   uintptr_t p = reinterpret_cast<uintptr_t>(g_dynamic_smem.data());
-  return reinterpret_cast<void *>((p + 63) & ~uintptr_t(63));
+  return reinterpret_cast<void *>((p + 1023) & ~uintptr_t(1023));  // like the shared window of a CTA without static shared memory
+}
+
+// ---- TMA / mbarrier stand-ins (csrc/mif_tma.cuh) -----------------------------------------------------------------
+// Copies are performed as LATE as the programming model allows, so that a kernel that skips a wait or reuses a buffer
+// too early computes with NaNs or stale data instead of passing by luck: a load poisons its destination when it is
+// issued and is carried out when a thread first tests its barrier; a store is carried out when its issuing thread
+// waits for the group (or flagged as an error when the block ends with stores still pending).
+namespace {
+struct PendingLoad { void *dst; CUtensorMap map; int c[3]; uint64_t *bar; };
+struct PendingStore { CUtensorMap map; const void *src; int c[3]; int thread; };
+struct BarState { uint64_t *bar; int count, pending, phase; long tx; };
+std::vector<PendingLoad> g_loads;
+std::vector<PendingStore> g_stores;
+std::vector<BarState> g_bars;
+long g_spins = 0;
+BarState &bar_state(uint64_t *bar) {
+  for (BarState &b : g_bars)
+    if (b.bar == bar) return b;
+  std::fprintf(stderr, "simt_emu: mbarrier %p used before mbarrier.init\n", (void *)bar);
+  abort();
+}
+size_t box_bytes(const CUtensorMap &m) { return (size_t)m.box[0] * m.box[1] * m.box[2] * 8; }
+// smem <-> global box copy, dimension 0 fastest in shared memory; 128-byte swizzle on the shared ADDRESS bits
+void copy_box(const CUtensorMap &m, char *smem, const int c[3], bool to_smem) {
+  for (uint32_t r = 0; r < m.box[1]; r++)
+    for (uint32_t x = 0; x < m.box[0]; x++) {
+      uintptr_t s = reinterpret_cast<uintptr_t>(smem) + ((size_t)r * m.box[0] + x) * 8;
+      if (m.swizzle128) s ^= ((s >> 7) & 7) << 4;
+      double *sp = reinterpret_cast<double *>(s);
+      const uint64_t g0 = (uint64_t)(c[0] + (long)x), g1 = (uint64_t)(c[1] + (long)r), g2 = (uint64_t)c[2];
+      const bool inside = c[0] + (long)x >= 0 && c[1] + (long)r >= 0 && c[2] >= 0 && g0 < m.dim[0] && g1 < m.dim[1] && g2 < m.dim[2];
+      double *gp = reinterpret_cast<double *>(static_cast<char *>(m.base) + g0 * m.stride_bytes[0] + g1 * m.stride_bytes[1] + g2 * m.stride_bytes[2]);
+      if (to_smem) *sp = inside ? *gp : 0.0;
+      else if (inside) *gp = *sp;
+    }
+}
+void check_smem_range(const void *p, size_t bytes, const char *what) {
+  const unsigned char *lo = g_dynamic_smem.data(), *hi = lo + g_dynamic_smem.size();
+  const unsigned char *q = static_cast<const unsigned char *>(p);
+  if (q < lo || q + bytes > hi || (reinterpret_cast<uintptr_t>(p) & 127)) {
+    std::fprintf(stderr, "simt_emu: %s: shared-memory box outside the dynamic window or not 128-byte aligned\n", what);
+    abort();
+  }
+}
+}  // namespace
+
+void mbar_init(uint64_t *bar, int count) {
+  for (size_t i = 0; i < g_bars.size(); i++)
+    if (g_bars[i].bar == bar) g_bars.erase(g_bars.begin() + i--);
+  g_bars.push_back(BarState{bar, count, count, 0, 0});
+}
+void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+  BarState &b = bar_state(bar);
+  b.tx += bytes;
+  b.pending -= 1;
+  if (b.pending < 0) {
+    std::fprintf(stderr, "simt_emu: more arrivals than the mbarrier's count\n");
+    abort();
+  }
+}
+bool mbar_test(uint64_t *bar, unsigned parity) {
+  BarState &b = bar_state(bar);
+  for (size_t i = 0; i < g_loads.size(); i++)
+    if (g_loads[i].bar == bar) {
+      copy_box(g_loads[i].map, static_cast<char *>(g_loads[i].dst), g_loads[i].c, true);
+      b.tx -= (long)box_bytes(g_loads[i].map);
+      g_loads.erase(g_loads.begin() + i--);
+    }
+  if (b.pending == 0 && b.tx == 0) {
+    b.phase ^= 1;
+    b.pending = b.count;
+  }
+  return (unsigned)b.phase != (parity & 1u);
+}
+void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+  check_smem_range(smem_dst, box_bytes(*map), "tma load");
+  if (map->swizzle128 && (reinterpret_cast<uintptr_t>(smem_dst) & 1023)) {
+    std::fprintf(stderr, "simt_emu: swizzled box not 1024-byte aligned\n");
+    abort();
+  }
+  bar_state(bar);
+  const uint64_t nan_bits = 0x7ff8abcd00000000ull;  // in flight: contents undefined
+  for (size_t i = 0; i < box_bytes(*map); i += 8) memcpy(static_cast<char *>(smem_dst) + i, &nan_bits, 8);
+  g_loads.push_back(PendingLoad{smem_dst, *map, {c0, c1, c2}, bar});
+}
+void tma_store_3d(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2) {
+  check_smem_range(smem_src, box_bytes(*map), "tma store");
+  if (map->swizzle128 && (reinterpret_cast<uintptr_t>(smem_src) & 1023)) {
+    std::fprintf(stderr, "simt_emu: swizzled box not 1024-byte aligned\n");
+    abort();
+  }
+  g_stores.push_back(PendingStore{*map, smem_src, {c0, c1, c2}, g_current});
+}
+void tma_commit_group() {}
+void tma_wait_group(int, bool) {
+  for (size_t i = 0; i < g_stores.size(); i++)
+    if (g_stores[i].thread == g_current) {
+      copy_box(g_stores[i].map, const_cast<char *>(static_cast<const char *>(g_stores[i].src)), g_stores[i].c, false);
+      g_stores.erase(g_stores.begin() + i--);
+    }
+}
+void spin_yield() {
+  if (++g_spins > 100000000L) {
+    std::fprintf(stderr, "simt_emu: an mbarrier wait never completes\n");
+    abort();
+  }
+  yield(RUNNABLE);
+}
+void tma_block_end() {
+  if (!g_stores.empty() || !g_loads.empty()) {
+    std::fprintf(stderr, "simt_emu: block (%u, %u, %u) ended with %zu bulk stores and %zu bulk loads still in flight\n", blockIdx.x,
+                 blockIdx.y, blockIdx.z, g_stores.size(), g_loads.size());
+    abort();
+  }
+  g_bars.clear();
+  g_spins = 0;
 }
 void block_barrier() { yield(WAIT_BLOCK); }
 void warp_barrier() { yield(WAIT_WARP); }
@@ -258,6 +378,11 @@ cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms *p, cudaStream_t) {
 }
 cudaError_t cudaGetDeviceCount(int *count) { *count = 64; return cudaSuccess; }  // any ordinal a rank asks for exists
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetDevice(int *device) { *device = 0; return cudaSuccess; }
+cudaError_t cudaDeviceGetAttribute(int *value, int attr, int) {
+  *value = (attr == cudaDevAttrMultiProcessorCount) ? 3 : 0;  // few "SMs": persistent kernels loop over several tiles per CTA
+  return cudaSuccess;
+}
 cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 cudaError_t cudaGetLastError() { return cudaSuccess; }
 const char *cudaGetErrorString(cudaError_t err) { return err == cudaSuccess ? "no error" : "simt_emu: unsupported call"; }

@@ -76,6 +76,9 @@ cudaError_t cudaMemsetAsync(void *dst, int value, size_t bytes, cudaStream_t str
 cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms *p, cudaStream_t stream = nullptr);
 cudaError_t cudaGetDeviceCount(int *count);
 cudaError_t cudaSetDevice(int device);
+cudaError_t cudaGetDevice(int *device);
+enum { cudaDevAttrMultiProcessorCount = 16 };
+cudaError_t cudaDeviceGetAttribute(int *value, int attr, int device);
 cudaError_t cudaDeviceSynchronize();
 cudaError_t cudaGetLastError();
 const char *cudaGetErrorString(cudaError_t err);
@@ -96,6 +99,7 @@ template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) {
 namespace emu {
 void launch(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::function<void()> &thread_body);
 void *dynamic_smem();
+void tma_block_end();
 void block_barrier();
 void warp_barrier();
 void named_barrier(int id, int count);

@@ -92,7 +92,35 @@ def rewrite_launches(text):
         pos = semi + 1
 
 
+def drop_device_only_blocks(text):
+    """Remove the `#ifndef MIF_SIMT_EMU` branches (inline PTX the interpreter replaces by emu:: calls); the `#else`
+    branch, if any, stays."""
+    out, keep, depth_stack = [], True, []
+    for line in text.split("\n"):
+        stripped = line.strip()
+        if stripped.startswith("#ifndef MIF_SIMT_EMU"):
+            depth_stack.append("emu")
+            keep = False
+            out.append("#if 1  // MIF_SIMT_EMU branch kept by rewrite.py")
+            continue
+        if stripped.startswith("#if") and depth_stack:
+            depth_stack.append("other")
+        elif stripped.startswith("#else") and depth_stack and depth_stack[-1] == "emu":
+            keep = True
+            continue
+        elif stripped.startswith("#endif") and depth_stack:
+            kind = depth_stack.pop()
+            if kind == "emu":
+                keep = True
+                out.append("#endif")
+                continue
+        if keep:
+            out.append(line)
+    return "\n".join(out)
+
+
 def rewrite(text):
+    text = drop_device_only_blocks(text)
     text = rewrite_launches(text)
     text = re.sub(r"extern\s+__shared__\s+([\w:]+(?:\s+[\w:]+)*?)\s+(\w+)\s*\[\s*\]\s*;",
                   r"\1 *\2 = reinterpret_cast<\1 *>(emu::dynamic_smem());", text)
