@@ -304,6 +304,16 @@ int exchange_z(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count) {
   for (int t = 0; t < count; t++) {
     double *data = tensors[t]->data;
     const int sz = g.sz[tensors[t]->staggering];
+    if (g.prev_z != -1 && g.prev_z == g.next_z) {
+      // Periodic z on two ranks: both neighbours are the same peer.  NCCL pairs the operations between two ranks in
+      // issue order (the reference tells them apart by tag, src/StaggeredTensor.cpp:60-135): the peer's first send is
+      // its plane 1, which is this rank's TOP ghost, its second send (plane sz-2) the bottom ghost.
+      NCCL_TRY(g_nccl.Send(data + plane, plane, ncclDouble, g.prev_z, ctx->comm, ctx->stream));
+      NCCL_TRY(g_nccl.Send(data + plane * (sz - 2), plane, ncclDouble, g.next_z, ctx->comm, ctx->stream));
+      NCCL_TRY(g_nccl.Recv(data + plane * (sz - 1), plane, ncclDouble, g.next_z, ctx->comm, ctx->stream));
+      NCCL_TRY(g_nccl.Recv(data, plane, ncclDouble, g.prev_z, ctx->comm, ctx->stream));
+      continue;
+    }
     if (g.prev_z != -1) {
       NCCL_TRY(g_nccl.Send(data + plane, plane, ncclDouble, g.prev_z, ctx->comm, ctx->stream));
       NCCL_TRY(g_nccl.Recv(data, plane, ncclDouble, g.prev_z, ctx->comm, ctx->stream));
@@ -897,22 +907,23 @@ void mifgpu_destroy(mifgpu_ctx *ctx) {
         if (ctx->face_dev[w][c][f]) cudaFree(ctx->face_dev[w][c][f]);
       }
   poisson_plan_destroy(ctx->plan);
-  if (ctx->xfer) cudaFree(ctx->xfer);
-  if (ctx->zbuf) cudaFree(ctx->zbuf);
   if (ctx->ypen) cudaFree(ctx->ypen);
   if (ctx->zpen) cudaFree(ctx->zpen);
   if (ctx->box_send) cudaFree(ctx->box_send);
   if (ctx->box_recv) cudaFree(ctx->box_recv);
+  // Peer-mapped buffers: close this rank's mappings of the others, wait until every rank has done so, and only then
+  // free the exported buffers (freeing memory a peer still has open through cudaIpcOpenMemHandle is undefined).
   for (int r = 0; r < 8; r++) {
     if (r == ctx->params.rank) continue;
     if (ctx->zbuf_peer[r]) cudaIpcCloseMemHandle(ctx->zbuf_peer[r]);
     if (ctx->xfer_peer[r]) cudaIpcCloseMemHandle(ctx->xfer_peer[r]);
   }
   if (ctx->peer_mode && ctx->comm && ctx->barrier_word) {
-    // nobody frees a buffer that another rank may still have mapped: destruction is collective
     g_nccl.AllReduce(ctx->barrier_word, ctx->barrier_word + 1, 1, ncclInt, ncclSum, ctx->comm, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
   }
+  if (ctx->xfer) cudaFree(ctx->xfer);
+  if (ctx->zbuf) cudaFree(ctx->zbuf);
   if (ctx->barrier_word) cudaFree(ctx->barrier_word);
   if (ctx->ylo_dev) cudaFree(ctx->ylo_dev);
   if (ctx->staging) cudaFree(ctx->staging);

@@ -1516,7 +1516,7 @@ bool launch_tma_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int
   job.lam_z = plan->dir[2].lambda;
   job.inv_norm = plan->dir[d].inv_norm;
   job.has_origin = lay.has_origin ? 1 : 0;
-  job.swz = swizzle ? 7u : 0u;
+  job.swz = swizzle ? 3u : 0u;
   if (logm == 8) {
     if (mode == 0) tmasweep::launch_one<8, 0>(stream, cache, *maps, job);
     else if (mode == 1) tmasweep::launch_one<8, 1>(stream, cache, *maps, job);

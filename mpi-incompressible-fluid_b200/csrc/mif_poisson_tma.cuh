@@ -19,7 +19,7 @@
 //     513 points are read once (natural rows), no unpack pass follows, and the mirror half of the output is never
 //     formed.  In the fused z sweep the scaled spectrum is repacked in registers (partners by shuffles) and is the
 //     first-pass input of the second FFT without touching shared memory;
-//   * store: every warp writes its line's column into a 128-byte-swizzled output stage (aliasing the FFT work area)
+//   * store: every warp writes its line's column into a swizzled output stage (aliasing the FFT work area)
 //     and one thread issues cp.async.bulk.tensor stores; they drain while the next tile's inputs are read.
 #pragma once
 
@@ -61,7 +61,7 @@ struct Job {
   const double *lam_x, *lam_y, *lam_z;
   double inv_norm;
   int has_origin;
-  unsigned swz;  // 7: the output map is 128-byte swizzled, 0: plain
+  unsigned swz;  // 3: the output map is swizzled (CU_TENSOR_MAP_SWIZZLE_64B), 0: plain
 };
 
 __device__ __forceinline__ double2 dct_pack_input(double xr, double yr, double c, double sn) {
@@ -209,8 +209,11 @@ __global__ void __launch_bounds__(kThreads, 2)
     __syncthreads();  // all warps are done with the work area: it becomes the output stage
 
     // ---- results into the swizzled output stage: row e of the tile at 64 e, column `line` -------------------------
+    // A column access of one warp (32 rows, one 8-byte column) can spread over at most 8 bank positions: the row parity
+    // picks the 64-byte half of a 128-byte line and the swizzle one of 4 chunks in it -- a 4-way conflict, half the
+    // rate of a conflict-free access and still cheaper than a transposition through the line regions.
     if (MODE == 0) {
-      // lane j holds E_k, k = j + 32 u + NS t; bits 7-9 of the offset (row >> 1) do not depend on (u, t)
+      // lane j holds E_k, k = j + 32 u + NS t; address bits 7-8 (row >> 1) do not depend on (u, t)
       const unsigned off = tma::swizzle_offset((unsigned)(j * 64 + line * 8), job.swz);
 #pragma unroll
       for (int u = 0; u < L::G; u++)
@@ -219,16 +222,21 @@ __global__ void __launch_bounds__(kThreads, 2)
           *reinterpret_cast<double *>(O + off + (32 * u + L::NS * t) * 64) = spec[u + L::G * t];
       if (j == 0) *reinterpret_cast<double *>(O + tma::swizzle_offset((unsigned)(M * 64 + line * 8), job.swz)) = e_last;
     } else {
-      // lane j holds z_q = conj(v), q = j + 32 u + NS t: x(2q) = Re z_q, x(2q+1) = Im z_q; only q <= M/2 is stored
+      // lane j holds z_q = conj(v), q = j + 32 u + NS t: x(2q) = Re z_q, x(2q+1) = Im z_q; only q <= M/2 is stored.
+      // Rows 2q of all lanes would sit in the same half of their 128-byte lines (4 bank positions): lanes with bit 2 of
+      // j set store the odd row first, so that every instruction covers both halves (8 positions).
       const unsigned off = tma::swizzle_offset((unsigned)(j * 128 + line * 8), job.swz);
+      const bool odd_first = (j >> 2) & 1;
+      const unsigned first = off + (odd_first ? 64u : 0u), second = first ^ 64u;
       const double scale = job.inv_norm;
 #pragma unroll
       for (int u = 0; u < L::G; u++)
 #pragma unroll
         for (int t = 0; t < L::R / 2; t++) {
-          const unsigned at = off + (32 * u + L::NS * t) * 128;
-          *reinterpret_cast<double *>(O + at) = v[u + L::G * t].x * scale;
-          *reinterpret_cast<double *>(O + (at ^ 64u)) = -v[u + L::G * t].y * scale;
+          const unsigned at = (32 * u + L::NS * t) * 128;
+          const double even = v[u + L::G * t].x * scale, odd = -v[u + L::G * t].y * scale;
+          *reinterpret_cast<double *>(O + first + at) = odd_first ? odd : even;
+          *reinterpret_cast<double *>(O + second + at) = odd_first ? even : odd;
         }
       if (j == 0)  // q = M/2 = NS * R/2: slot u = 0, t = R/2 of lane 0
         *reinterpret_cast<double *>(O + tma::swizzle_offset((unsigned)(M * 64 + line * 8), job.swz)) = v[L::G * (L::R / 2)].x * scale;

@@ -22,7 +22,7 @@ struct alignas(64) CUtensorMap {  // emulated descriptor: rank 3, FP64
   uint64_t dim[3];
   uint64_t stride_bytes[3];  // stride_bytes[0] = 8
   uint32_t box[3];
-  uint32_t swizzle128;
+  uint32_t swizzle_mask;  // 0: none, 3: CU_TENSOR_MAP_SWIZZLE_64B
   uint64_t pad_[5];
 };
 #define __grid_constant__
@@ -116,22 +116,24 @@ __device__ __forceinline__ void prefetch_map(const CUtensorMap *) {}
 __device__ __forceinline__ uintptr_t swizzle_address(const void *p) { return reinterpret_cast<uintptr_t>(p); }
 #endif
 
-// Byte offset of (row, column byte) inside a buffer of 64-byte rows under CU_TENSOR_MAP_SWIZZLE_128B: the 16-byte
-// chunk index (address bits 4-6) is XORed with address bits 7-9.  `mask` = 7 (swizzled map) or 0 (plain map); the
-// buffer must start on a 1024-byte boundary.
+// Byte offset inside a buffer of dense 64-byte rows (8 doubles) under CU_TENSOR_MAP_SWIZZLE_64B: the 16-byte chunk
+// index inside each 64-byte row (address bits 4-5) is XORed with address bits 7-8, i.e. with the index of the
+// 128-byte line modulo 4; `mask` = 3 (swizzled map) or 0 (plain map); the buffer starts on a 1024-byte boundary.
+// Measured on a B200 with scripts/probes/tma_probe.cu.  (CU_TENSOR_MAP_SWIZZLE_128B is not usable for 64-byte rows:
+// the copy engine then pads every row to a 128-byte line in shared memory.)
 __device__ __forceinline__ unsigned swizzle_offset(unsigned off, unsigned mask) { return off ^ (((off >> 7) & mask) << 4); }
 
 // ---- host -------------------------------------------------------------------------------------------------------
 // Rank-3 FP64 tensor map: element (c0, c1, c2) lives at base + c0 * 8 + c1 * stride1_bytes + c2 * stride2_bytes;
 // boxes of box0 x box1 x 1 elements.  Returns false (with a message in `why`) when the driver refuses the geometry.
 inline bool encode_map(CUtensorMap *map, const void *base, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1_bytes,
-                       uint64_t stride2_bytes, uint32_t box0, uint32_t box1, bool swizzle128, int l2_promotion,
+                       uint64_t stride2_bytes, uint32_t box0, uint32_t box1, bool swizzle64, int l2_promotion,
                        const char **why) {
   static const char *dummy;
   if (!why) why = &dummy;
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (stride1_bytes & 15) || (stride2_bytes & 15) || stride1_bytes >= (1ull << 40) ||
       stride2_bytes >= (1ull << 40) || box0 == 0 || box1 == 0 || box0 > 256 || box1 > 256 || ((box0 * 8) & 15) || dim0 == 0 ||
-      dim1 == 0 || dim2 == 0 || (swizzle128 && box0 * 8 > 128)) {
+      dim1 == 0 || dim2 == 0 || (swizzle64 && box0 * 8 > 64)) {
     *why = "geometry outside the tensor-map limits";
     return false;
   }
@@ -164,7 +166,7 @@ inline bool encode_map(CUtensorMap *map, const void *base, uint64_t dim0, uint64
                                        : l2_promotion == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
                                                            : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(base), dims, strides, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                              promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
     *why = "cuTensorMapEncodeTiled rejected the geometry";
@@ -177,7 +179,7 @@ inline bool encode_map(CUtensorMap *map, const void *base, uint64_t dim0, uint64
   map->dim[0] = dim0; map->dim[1] = dim1; map->dim[2] = dim2;
   map->stride_bytes[0] = 8; map->stride_bytes[1] = stride1_bytes; map->stride_bytes[2] = stride2_bytes;
   map->box[0] = box0; map->box[1] = box1; map->box[2] = 1;
-  map->swizzle128 = swizzle128 ? 1 : 0;
+  map->swizzle_mask = swizzle64 ? 3 : 0;
   return true;
 #endif
 }

@@ -192,12 +192,13 @@ BarState &bar_state(uint64_t *bar) {
   abort();
 }
 size_t box_bytes(const CUtensorMap &m) { return (size_t)m.box[0] * m.box[1] * m.box[2] * 8; }
-// smem <-> global box copy, dimension 0 fastest in shared memory; 128-byte swizzle on the shared ADDRESS bits
+// smem <-> global box copy, dimension 0 fastest in shared memory, rows dense; the swizzle XORs the shared ADDRESS bits
+// 4-5 with bits 7-8 (CU_TENSOR_MAP_SWIZZLE_64B as measured on a B200, scripts/probes/tma_probe.cu)
 void copy_box(const CUtensorMap &m, char *smem, const int c[3], bool to_smem) {
   for (uint32_t r = 0; r < m.box[1]; r++)
     for (uint32_t x = 0; x < m.box[0]; x++) {
       uintptr_t s = reinterpret_cast<uintptr_t>(smem) + ((size_t)r * m.box[0] + x) * 8;
-      if (m.swizzle128) s ^= ((s >> 7) & 7) << 4;
+      s ^= ((s >> 7) & m.swizzle_mask) << 4;
       double *sp = reinterpret_cast<double *>(s);
       const uint64_t g0 = (uint64_t)(c[0] + (long)x), g1 = (uint64_t)(c[1] + (long)r), g2 = (uint64_t)c[2];
       const bool inside = c[0] + (long)x >= 0 && c[1] + (long)r >= 0 && c[2] >= 0 && g0 < m.dim[0] && g1 < m.dim[1] && g2 < m.dim[2];
@@ -246,7 +247,7 @@ bool mbar_test(uint64_t *bar, unsigned parity) {
 }
 void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
   check_smem_range(smem_dst, box_bytes(*map), "tma load");
-  if (map->swizzle128 && (reinterpret_cast<uintptr_t>(smem_dst) & 1023)) {
+  if (map->swizzle_mask && (reinterpret_cast<uintptr_t>(smem_dst) & 1023)) {
     std::fprintf(stderr, "simt_emu: swizzled box not 1024-byte aligned\n");
     abort();
   }
@@ -257,7 +258,7 @@ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, 
 }
 void tma_store_3d(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2) {
   check_smem_range(smem_src, box_bytes(*map), "tma store");
-  if (map->swizzle128 && (reinterpret_cast<uintptr_t>(smem_src) & 1023)) {
+  if (map->swizzle_mask && (reinterpret_cast<uintptr_t>(smem_src) & 1023)) {
     std::fprintf(stderr, "simt_emu: swizzled box not 1024-byte aligned\n");
     abort();
   }

@@ -5,7 +5,9 @@
 // grouped send/recv all-to-all, the rank barriers of the peer-memory transposes) can run under the SIMT interpreter
 // on a machine without GPUs.  Everything is synchronous: a send writes its payload to a file named after
 // (communicator, source, destination, sequence number) and renames it into place; a receive polls for the file of
-// the next sequence number of that pair.  Sends never block, so any order of calls inside a group is deadlock free.
+// the next sequence number of that pair.  Sends never block; receives issued between ncclGroupStart and ncclGroupEnd are
+// queued and carried out at ncclGroupEnd, after all sends of the group -- like NCCL, where nothing of a group runs before
+// it is closed -- so rings of three or more ranks (periodic z) cannot deadlock on a receive that precedes a send.
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -76,8 +78,24 @@ ncclResult_t ncclCommDestroy(ncclComm_t comm) {
   return 0;
 }
 
-ncclResult_t ncclGroupStart() { return 0; }
-ncclResult_t ncclGroupEnd() { return 0; }
+struct QueuedRecv { void *buf; size_t count; ncclDataType_t type; int peer; ncclComm_t comm; };
+static int g_group_depth = 0;
+static std::vector<QueuedRecv> g_queued;
+static ncclResult_t recv_now(void *buf, size_t count, ncclDataType_t type, int peer, ncclComm_t c);
+
+ncclResult_t ncclGroupStart() {
+  g_group_depth++;
+  return 0;
+}
+ncclResult_t ncclGroupEnd() {
+  if (g_group_depth > 0) g_group_depth--;
+  if (g_group_depth > 0) return 0;
+  ncclResult_t rc = 0;
+  for (const QueuedRecv &q : g_queued)
+    if (recv_now(q.buf, q.count, q.type, q.peer, q.comm)) rc = 1;
+  g_queued.clear();
+  return rc;
+}
 
 ncclResult_t ncclSend(const void *buf, size_t count, ncclDataType_t type, int peer, ncclComm_t c, cudaStream_t) {
   const size_t bytes = count * type_size(type);
@@ -92,6 +110,14 @@ ncclResult_t ncclSend(const void *buf, size_t count, ncclDataType_t type, int pe
 }
 
 ncclResult_t ncclRecv(void *buf, size_t count, ncclDataType_t type, int peer, ncclComm_t c, cudaStream_t) {
+  if (g_group_depth > 0) {
+    g_queued.push_back(QueuedRecv{buf, count, type, peer, c});
+    return 0;
+  }
+  return recv_now(buf, count, type, peer, c);
+}
+
+static ncclResult_t recv_now(void *buf, size_t count, ncclDataType_t type, int peer, ncclComm_t c) {
   const size_t bytes = count * type_size(type);
   const std::string name = mailbox(c, peer, c->rank, c->received[peer]++);
   for (long spins = 0;; spins++) {
