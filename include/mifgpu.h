@@ -142,6 +142,15 @@ int mifgpu_tensor_download_box(const mifgpu_tensor *tensor, const int32_t lo[3],
 /* Tensor::swap_data (include/Tensor.h:108-110) as used by VelocityTensor::swap_data (src/VelocityTensor.cpp:13-27). */
 int mifgpu_tensor_swap(mifgpu_tensor *a, mifgpu_tensor *b);
 
+/* The same transfers without blocking the host, for callers that stream independent jobs through the device (the
+ * reference has no counterpart: its tensors live in host memory).  Each direction has its own copy stream and staging
+ * buffer; ordering is by events only: a transfer starts after the last compute call that used the tensor and after
+ * the tensor's previous transfers, and compute calls that use the tensor afterwards wait for it on the device.  So
+ * upload(A) | timestep(B) | download(C) of three different tensor sets overlap, and PCIe runs in both directions at
+ * once.  `host` should be page-locked; it must not be touched until mifgpu_synchronize has returned. */
+int mifgpu_tensor_upload_async(mifgpu_tensor *tensor, const double *host);
+int mifgpu_tensor_download_async(mifgpu_tensor *tensor, double *host);
+
 /* ---- the hot path ------------------------------------------------------------------------------- */
 
 /* mif::timestep / mif::timestep_nhn (include/Timestep.h:16-27, src/Timestep.cpp:97-156): one
@@ -203,7 +212,18 @@ int mifgpu_allreduce(mifgpu_ctx *ctx, double *values, int32_t count, int32_t op)
 int mifgpu_gather(mifgpu_ctx *ctx, const double *send, uint64_t count, double *recv, uint64_t *counts);
 int mifgpu_rank_count(const mifgpu_ctx *ctx);
 
-/* Blocks until all work queued by this context has finished (cudaStreamSynchronize). */
+/* How this context moves data between the y and the z sweeps of the Poisson solve (the 2Decomp transposes,
+ * deps/2Decomp_C/Transpose*.cpp), as decided at creation -- e.g. whether the CUDA IPC mapping of the peers' buffers
+ * succeeded.  -1 for a NULL context. */
+enum {
+  MIFGPU_TRANSPOSE_NONE = 0,           /* one rank: strided sweeps in place */
+  MIFGPU_TRANSPOSE_PEER_FUSED = 1,     /* z slabs: the sweeps store into the peers' buffers over NVLink */
+  MIFGPU_TRANSPOSE_NCCL_ALLTOALL = 2,  /* z slabs: pack, grouped ncclSend/ncclRecv, unpack */
+  MIFGPU_TRANSPOSE_PENCIL_BOXES = 3    /* Py x Pz pencils: four box exchanges per solve */
+};
+int mifgpu_transpose_path(const mifgpu_ctx *ctx);
+
+/* Blocks until all work queued by this context has finished (its compute stream and both copy streams). */
 int mifgpu_synchronize(mifgpu_ctx *ctx);
 
 /* The CUDA stream (cudaStream_t) the context launches on, for callers that time with CUDA events. */

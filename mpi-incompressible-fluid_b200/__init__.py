@@ -32,7 +32,8 @@ EXPORTED_SYMBOLS = [
     "mifgpu_stream", "mifgpu_launch_count", "mifgpu_profile_enable", "mifgpu_profile_read", "mifgpu_comm_unique_id",
     "mifgpu_create_distributed", "mifgpu_slab_plan", "mifgpu_velocity_error_norms", "mifgpu_pressure_error_norms",
     "mifgpu_adjust_pressure", "mifgpu_timestep_velocity", "mifgpu_tensor_download_box",
-    "mifgpu_allreduce", "mifgpu_gather", "mifgpu_rank_count",
+    "mifgpu_allreduce", "mifgpu_gather", "mifgpu_rank_count", "mifgpu_tensor_upload_async", "mifgpu_tensor_download_async",
+    "mifgpu_transpose_path",
 ]
 
 
@@ -98,6 +99,9 @@ def lib() -> ctypes.CDLL:
     l.mifgpu_tensor_upload.argtypes = [c_void_p, c_void_p]
     l.mifgpu_tensor_download.argtypes = [c_void_p, c_void_p]
     l.mifgpu_tensor_swap.argtypes = [c_void_p, c_void_p]
+    l.mifgpu_tensor_upload_async.argtypes = [c_void_p, c_void_p]
+    l.mifgpu_tensor_download_async.argtypes = [c_void_p, c_void_p]
+    l.mifgpu_transpose_path.argtypes = [c_void_p]
     l.mifgpu_tensor_download_box.argtypes = [c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]
     l.mifgpu_timestep.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(Bc),
                                   c_double, c_void_p, c_void_p, c_int]
@@ -162,12 +166,29 @@ class Tensor:
             raise ValueError(f"expected {sx * sy * sz} values, got {arr.size}")
         _check(lib().mifgpu_tensor_upload(self.handle, arr.ctypes.data_as(c_void_p)))
 
+    def _check_host(self, arr: np.ndarray, what: str) -> None:
+        sx, sy, sz = self.shape
+        if not isinstance(arr, np.ndarray) or arr.dtype != np.float64 or arr.size != sx * sy * sz or not arr.flags.c_contiguous:
+            raise ValueError(f"{what} must be a C-contiguous float64 array of {sx * sy * sz} values (shape ({sz}, {sy}, {sx}))")
+
     def download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         sx, sy, sz = self.shape
         if out is None:
             out = np.empty((sz, sy, sx), dtype=np.float64)
+        self._check_host(out, "out")
         _check(lib().mifgpu_tensor_download(self.handle, out.ctypes.data_as(c_void_p)))
         return out
+
+    def upload_async(self, host: np.ndarray) -> None:
+        """Enqueue the copy on the context's upload stream; `host` (page-locked) must stay alive and untouched until
+        Context.synchronize()."""
+        self._check_host(host, "host")
+        _check(lib().mifgpu_tensor_upload_async(self.handle, host.ctypes.data_as(c_void_p)))
+
+    def download_async(self, out: np.ndarray) -> None:
+        """Enqueue the copy on the context's download stream; `out` holds the values after Context.synchronize()."""
+        self._check_host(out, "out")
+        _check(lib().mifgpu_tensor_download_async(self.handle, out.ctypes.data_as(c_void_p)))
 
     def download_box(self, lo: Sequence[int], hi: Sequence[int]) -> np.ndarray:
         """The index box lo <= (i, j, k) < hi as an array of shape (hi[2]-lo[2], hi[1]-lo[1], hi[0]-lo[0])."""
@@ -289,6 +310,11 @@ class Context:
     @property
     def stream(self) -> int:
         return int(lib().mifgpu_stream(self.handle) or 0)
+
+    @property
+    def transpose_path(self) -> int:
+        """0 none (one rank), 1 peer-memory fused, 2 NCCL all-to-all, 3 pencil box exchanges (include/mifgpu.h)."""
+        return int(lib().mifgpu_transpose_path(self.handle))
 
     @property
     def launch_count(self) -> int:

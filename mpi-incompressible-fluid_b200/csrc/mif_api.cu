@@ -137,6 +137,11 @@ struct mifgpu_ctx {
   int pen_pitch = 0;
   double *staging = nullptr; // compact device copy of one tensor for host transfers
   size_t staging_bytes = 0;
+  // asynchronous host transfers (mifgpu_tensor_upload_async / _download_async): one stream and one compact staging
+  // buffer per direction, so that H2D, D2H and the kernels of independent tensors overlap
+  cudaStream_t copy_stream[2] = {nullptr, nullptr};  // [0] host -> device, [1] device -> host
+  double *copy_staging[2] = {nullptr, nullptr};
+  size_t copy_staging_bytes[2] = {0, 0};
   // host-callback boundary faces: pinned staging + device copies, [which][component][face]
   double *face_host[2][3][6] = {};
   double *face_dev[2][3][6] = {};
@@ -146,6 +151,9 @@ struct mifgpu_tensor {
   mifgpu_ctx *ctx;
   int staggering;
   double *data;
+  // ordering between the three streams: last asynchronous upload into / download out of this tensor, last compute
+  // call that used it (waiting on an event that was never recorded is a no-op)
+  cudaEvent_t ev_uploaded = nullptr, ev_downloaded = nullptr, ev_computed = nullptr;
 };
 
 namespace {
@@ -253,6 +261,27 @@ int check_scalar(const mifgpu_ctx *ctx, const mifgpu_tensor *t, const char *name
   if (t->staggering != MIFGPU_STAGGER_NONE) return fail(MIFGPU_ERR_INVALID, "%s must be unstaggered", name);
   return MIFGPU_OK;
 }
+
+// Compute entry points bracket their work with this: the context's stream first waits for asynchronous host transfers
+// of the tensors it is about to use, and on the way out every tensor remembers the point of the stream after which
+// it may be overwritten (upload) or read (download) by the copy streams.
+struct UseScope {
+  mifgpu_ctx *ctx;
+  std::vector<mifgpu_tensor *> tensors;
+  explicit UseScope(mifgpu_ctx *c) : ctx(c) {}
+  void add(mifgpu_tensor *t) {
+    if (!t || !t->ev_uploaded) return;
+    cudaStreamWaitEvent(ctx->stream, t->ev_uploaded, 0);
+    cudaStreamWaitEvent(ctx->stream, t->ev_downloaded, 0);
+    tensors.push_back(t);
+  }
+  void add(mifgpu_tensor *const t[3]) {
+    for (int c = 0; c < 3; c++) add(t[c]);
+  }
+  ~UseScope() {
+    for (mifgpu_tensor *t : tensors) cudaEventRecord(t->ev_computed, ctx->stream);
+  }
+};
 
 bool face_is_active(const Geom &g, int face) {
   switch (face) {
@@ -927,6 +956,13 @@ void mifgpu_destroy(mifgpu_ctx *ctx) {
   if (ctx->barrier_word) cudaFree(ctx->barrier_word);
   if (ctx->ylo_dev) cudaFree(ctx->ylo_dev);
   if (ctx->staging) cudaFree(ctx->staging);
+  for (int d = 0; d < 2; d++) {
+    if (ctx->copy_stream[d]) {
+      cudaStreamSynchronize(ctx->copy_stream[d]);
+      cudaStreamDestroy(ctx->copy_stream[d]);
+    }
+    if (ctx->copy_staging[d]) cudaFree(ctx->copy_staging[d]);
+  }
   if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -956,6 +992,12 @@ int mifgpu_tensor_create(mifgpu_ctx *ctx, int staggering, mifgpu_tensor **out) {
   t->ctx = ctx;
   t->staggering = staggering;
   t->data = data;
+  if (cudaEventCreateWithFlags(&t->ev_uploaded, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&t->ev_downloaded, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&t->ev_computed, cudaEventDisableTiming) != cudaSuccess) {
+    mifgpu_tensor_destroy(t);
+    return fail(MIFGPU_ERR_CUDA, "creating the tensor's events failed");
+  }
   *out = t;
   return MIFGPU_OK;
 }
@@ -964,6 +1006,11 @@ void mifgpu_tensor_destroy(mifgpu_tensor *t) {
   if (!t) return;
   cudaSetDevice(t->ctx->params.device);
   cudaStreamSynchronize(t->ctx->stream);
+  for (cudaStream_t s : t->ctx->copy_stream)
+    if (s) cudaStreamSynchronize(s);
+  if (t->ev_uploaded) cudaEventDestroy(t->ev_uploaded);
+  if (t->ev_downloaded) cudaEventDestroy(t->ev_downloaded);
+  if (t->ev_computed) cudaEventDestroy(t->ev_computed);
   cudaFree(t->data);
   delete t;
 }
@@ -993,6 +1040,9 @@ static int copy_tensor(const mifgpu_tensor *t, double *host, bool to_device) {
   parms.dstPtr = to_device ? padded : compact;
   parms.extent = make_cudaExtent((size_t)g.sx[s] * sizeof(double), g.sy[s], g.sz[s]);
   parms.kind = cudaMemcpyDeviceToDevice;
+  // asynchronous transfers of this tensor that are still in flight come first
+  CUDA_TRY(cudaStreamWaitEvent(ctx->stream, t->ev_uploaded, 0));
+  CUDA_TRY(cudaStreamWaitEvent(ctx->stream, t->ev_downloaded, 0));
   if (to_device) {
     CUDA_TRY(cudaMemcpyAsync(ctx->staging, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpy3DAsync(&parms, ctx->stream));
@@ -1000,9 +1050,58 @@ static int copy_tensor(const mifgpu_tensor *t, double *host, bool to_device) {
     CUDA_TRY(cudaMemcpy3DAsync(&parms, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(host, ctx->staging, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   }
+  CUDA_TRY(cudaEventRecord(t->ev_computed, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return MIFGPU_OK;
 }
+
+// The same transfer on the copy stream of its direction, ordered by events only: after the last compute call that
+// used the tensor and after its previous transfers; compute calls that use the tensor later wait for it (UseScope).
+// Nothing blocks the host; `host` (pinned memory, or the copy degrades to a synchronous one) must stay untouched
+// until mifgpu_synchronize.
+static int copy_tensor_async(mifgpu_tensor *t, double *host, bool to_device) {
+  if (!t || !host) return fail(MIFGPU_ERR_INVALID, "NULL argument");
+  mifgpu_ctx *ctx = t->ctx;
+  const Geom &g = ctx->g;
+  CUDA_TRY(cudaSetDevice(ctx->params.device));
+  const int dir = to_device ? 0 : 1, s = t->staggering;
+  if (!ctx->copy_stream[dir]) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream[dir], cudaStreamNonBlocking));
+  cudaStream_t cs = ctx->copy_stream[dir];
+  const size_t bytes = (size_t)g.sx[s] * g.sy[s] * g.sz[s] * sizeof(double);
+  if (ctx->copy_staging_bytes[dir] < bytes) {
+    CUDA_TRY(cudaStreamSynchronize(cs));
+    if (ctx->copy_staging[dir]) cudaFree(ctx->copy_staging[dir]);
+    ctx->copy_staging[dir] = nullptr;
+    ctx->copy_staging_bytes[dir] = 0;
+    // one size for all staggerings, so that the buffer is allocated once
+    const size_t most = (size_t)(g.sx[0]) * (size_t)(g.sy[1]) * (size_t)(g.sz[2]) * sizeof(double);
+    CUDA_TRY(cudaMalloc(&ctx->copy_staging[dir], std::max(bytes, most)));
+    ctx->copy_staging_bytes[dir] = std::max(bytes, most);
+  }
+  cudaMemcpy3DParms parms;
+  std::memset(&parms, 0, sizeof(parms));
+  const cudaPitchedPtr compact = make_cudaPitchedPtr(ctx->copy_staging[dir], (size_t)g.sx[s] * sizeof(double), g.sx[s], g.sy[s]);
+  const cudaPitchedPtr padded = make_cudaPitchedPtr(t->data, (size_t)g.PX * sizeof(double), g.PX, g.PY);
+  parms.srcPtr = to_device ? compact : padded;
+  parms.dstPtr = to_device ? padded : compact;
+  parms.extent = make_cudaExtent((size_t)g.sx[s] * sizeof(double), g.sy[s], g.sz[s]);
+  parms.kind = cudaMemcpyDeviceToDevice;
+  CUDA_TRY(cudaStreamWaitEvent(cs, t->ev_computed, 0));
+  CUDA_TRY(cudaStreamWaitEvent(cs, to_device ? t->ev_downloaded : t->ev_uploaded, 0));
+  if (to_device) {
+    CUDA_TRY(cudaMemcpyAsync(ctx->copy_staging[dir], host, bytes, cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(cudaMemcpy3DAsync(&parms, cs));
+    CUDA_TRY(cudaEventRecord(t->ev_uploaded, cs));
+  } else {
+    CUDA_TRY(cudaMemcpy3DAsync(&parms, cs));
+    CUDA_TRY(cudaMemcpyAsync(host, ctx->copy_staging[dir], bytes, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaEventRecord(t->ev_downloaded, cs));
+  }
+  return MIFGPU_OK;
+}
+
+int mifgpu_tensor_upload_async(mifgpu_tensor *t, const double *host) { return copy_tensor_async(t, const_cast<double *>(host), true); }
+int mifgpu_tensor_download_async(mifgpu_tensor *t, double *host) { return copy_tensor_async(t, host, false); }
 
 int mifgpu_tensor_upload(mifgpu_tensor *t, const double *host) { return copy_tensor(t, const_cast<double *>(host), true); }
 int mifgpu_tensor_download(const mifgpu_tensor *t, double *host) { return copy_tensor(t, host, false); }
@@ -1036,8 +1135,10 @@ int mifgpu_tensor_download_box(const mifgpu_tensor *t, const int32_t lo[3], cons
   parms.dstPos = make_cudaPos(0, 0, 0);
   parms.extent = make_cudaExtent(bx * sizeof(double), by, bz);
   parms.kind = cudaMemcpyDeviceToDevice;
+  CUDA_TRY(cudaStreamWaitEvent(ctx->stream, t->ev_uploaded, 0));
   CUDA_TRY(cudaMemcpy3DAsync(&parms, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(host, ctx->staging, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaEventRecord(t->ev_computed, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return MIFGPU_OK;
 }
@@ -1045,6 +1146,9 @@ int mifgpu_tensor_download_box(const mifgpu_tensor *t, const int32_t lo[3], cons
 int mifgpu_tensor_swap(mifgpu_tensor *a, mifgpu_tensor *b) {
   if (!a || !b || a->ctx != b->ctx || a->staggering != b->staggering) return fail(MIFGPU_ERR_INVALID, "tensors are not swappable");
   std::swap(a->data, b->data);
+  std::swap(a->ev_uploaded, b->ev_uploaded);  // the events describe the device arrays, which just changed owners
+  std::swap(a->ev_downloaded, b->ev_downloaded);
+  std::swap(a->ev_computed, b->ev_computed);
   return MIFGPU_OK;
 }
 
@@ -1053,6 +1157,8 @@ int mifgpu_apply_bc(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], const mif
   int rc = check_triple(ctx, velocity, "velocity");
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(ctx->params.device));
+  UseScope use(ctx);
+  use.add(velocity);
   rc = do_apply_bc(ctx, velocity, bc, time);
   if (rc) return rc;
   return check_launch(ctx);
@@ -1066,6 +1172,9 @@ int mifgpu_solve_pressure(mifgpu_ctx *ctx, mifgpu_tensor *pressure, mifgpu_tenso
   rc = check_scalar(ctx, pressure, "pressure");
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(ctx->params.device));
+  UseScope use(ctx);
+  use.add(velocity);
+  use.add(pressure);
   rc = do_solve(ctx, pressure, velocity, dt, nhn_bc, nhn_time, nhn_time);
   if (rc) return rc;
   return check_launch(ctx);
@@ -1082,6 +1191,12 @@ int mifgpu_timestep(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], mifgpu_te
   if ((rc = check_scalar(ctx, pressure, "pressure"))) return rc;
   if ((rc = check_scalar(ctx, pressure_buffer, "pressure_buffer"))) return rc;
   CUDA_TRY(cudaSetDevice(ctx->params.device));
+  UseScope use(ctx);
+  use.add(velocity);
+  use.add(velocity_buffer);
+  use.add(velocity_buffer_2);
+  use.add(pressure);
+  use.add(pressure_buffer);
   const Geom &g = ctx->g;
   cudaStream_t s = ctx->stream;
   // Stage times, src/Timestep.cpp:98-105.
@@ -1139,6 +1254,10 @@ int mifgpu_timestep_velocity(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], 
   if ((rc = check_triple(ctx, velocity_buffer, "velocity_buffer"))) return rc;
   if ((rc = check_triple(ctx, rhs_buffer, "rhs_buffer"))) return rc;
   CUDA_TRY(cudaSetDevice(ctx->params.device));
+  UseScope use(ctx);
+  use.add(velocity);
+  use.add(velocity_buffer);
+  use.add(rhs_buffer);
   const Geom &g = ctx->g;
   cudaStream_t s = ctx->stream;
   // src/TimestepVelocity.cpp:11-13,60-63
@@ -1207,6 +1326,8 @@ int mifgpu_velocity_error_norms(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3
   BcDev dev;
   if ((rc = analytic_family(exact, time, dev))) return rc;
   CUDA_TRY(cudaSetDevice(ctx->params.device));
+  UseScope use(ctx);
+  use.add(velocity);
   double sums[4];
   if ((rc = run_error_kernel(ctx, true, cvec3(velocity), nullptr, dev, sums))) return rc;
   const double cell = ctx->g.dx * ctx->g.dy * ctx->g.dz;
@@ -1224,6 +1345,8 @@ int mifgpu_pressure_error_norms(mifgpu_ctx *ctx, const mifgpu_tensor *pressure, 
   BcDev dev;
   if ((rc = analytic_family(exact, time, dev))) return rc;
   CUDA_TRY(cudaSetDevice(ctx->params.device));
+  UseScope use(ctx);
+  use.add(const_cast<mifgpu_tensor *>(pressure));
   double sums[4];
   if ((rc = run_error_kernel(ctx, false, CVec3{}, pressure->data, dev, sums))) return rc;
   const double cell = ctx->g.dx * ctx->g.dy * ctx->g.dz;
@@ -1240,6 +1363,8 @@ int mifgpu_adjust_pressure(mifgpu_ctx *ctx, mifgpu_tensor *pressure, const mifgp
   BcDev dev;
   if ((rc = analytic_family(exact, time, dev))) return rc;
   CUDA_TRY(cudaSetDevice(ctx->params.device));
+  UseScope use(ctx);
+  use.add(pressure);
   double sums[4];
   if ((rc = run_error_kernel(ctx, false, CVec3{}, pressure->data, dev, sums))) return rc;
   double difference = sums[3];
@@ -1335,7 +1460,16 @@ int mifgpu_synchronize(mifgpu_ctx *ctx) {
   if (!ctx) return fail(MIFGPU_ERR_INVALID, "NULL context");
   CUDA_TRY(cudaSetDevice(ctx->params.device));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  for (cudaStream_t s : ctx->copy_stream)
+    if (s) CUDA_TRY(cudaStreamSynchronize(s));
   return MIFGPU_OK;
+}
+
+int mifgpu_transpose_path(const mifgpu_ctx *ctx) {
+  if (!ctx) return -1;
+  if (ctx->nranks == 1) return MIFGPU_TRANSPOSE_NONE;
+  if (ctx->Py > 1) return MIFGPU_TRANSPOSE_PENCIL_BOXES;
+  return (ctx->peer_mode && poisson_peer_capable(ctx->plan)) ? MIFGPU_TRANSPOSE_PEER_FUSED : MIFGPU_TRANSPOSE_NCCL_ALLTOALL;
 }
 
 int mifgpu_profile_enable(mifgpu_ctx *ctx, int enable) {

@@ -392,6 +392,8 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t *stream, unsigned) { *stream 
 cudaError_t cudaStreamDestroy(cudaStream_t stream) { delete stream; return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t *event) { *event = new emu_event(); return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *event, unsigned) { *event = new emu_event(); return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }  // everything is synchronous here
 cudaError_t cudaEventDestroy(cudaEvent_t event) { delete event; return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t event, cudaStream_t) { event->when = std::chrono::steady_clock::now(); return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t start, cudaEvent_t stop) {

@@ -87,6 +87,9 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t *stream, unsigned flags);
 cudaError_t cudaStreamDestroy(cudaStream_t stream);
 cudaError_t cudaStreamSynchronize(cudaStream_t stream);
 cudaError_t cudaEventCreate(cudaEvent_t *event);
+enum { cudaEventDisableTiming = 2 };
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *event, unsigned flags);
+cudaError_t cudaStreamWaitEvent(cudaStream_t stream, cudaEvent_t event, unsigned flags = 0);
 cudaError_t cudaEventDestroy(cudaEvent_t event);
 cudaError_t cudaEventRecord(cudaEvent_t event, cudaStream_t stream = nullptr);
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t start, cudaEvent_t stop);

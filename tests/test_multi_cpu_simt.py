@@ -117,11 +117,16 @@ def test_bench_line_on_two_ranks_in_a_dry_run(simt_env):
     inert stand-ins for torch.cuda): rank 0 prints one JSON line with the multi-GPU keys.  Values are meaningless."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29716", os.path.join(EMU, "bench_dry_run.py"), "--gpus", "2", "--size", "9", "--steps", "2", "--warmup", "3"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=simt_env)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(simt_env, MIF_BENCH_PARITY_CASE="5x17x17"))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1, out.stdout
     line = json.loads(lines[0])
     assert line["n_gpus"] == 2 and line["scaling"] == "weak" and line["config"]["points"] == [9, 9, 17]
+    # the multi-rank result is checked against a single-rank context before the timed region, and the lid is where
+    # the boundary data puts it
+    assert line["parity_vs_single_rank"]["ok"] and line["parity_vs_single_rank"]["max_rel_linf"] <= 1e-11
+    assert line["config"]["lid_on_last_x_face"] is True and line["config"]["transpose_path"] == "NCCL all-to-all"
+    assert line["e2e"]["result_finite"] is True
     assert line["nvlink"]["bytes_sent_per_gpu_per_step"] == 6 * 8 * (9 * 9 * 17 / 2) * 0.5
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["gpu_launches"] > 0 and "halo_exchange" in line["kernels"]
