@@ -23,7 +23,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line (NCCL prints its version banner otherwise)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only (NCCL logs to stdout otherwise)
 sys.path.insert(0, ROOT)
 
 METRIC = "FP64 cell-steps/s, full RK timestep incl. Poisson solve"

@@ -156,12 +156,6 @@ __device__ __forceinline__ void phase_b(const double2 *region, int L, double2 *v
 // Index of the spectrum element in register r of lane L.
 __device__ __forceinline__ int k_of(int L, int r) { return (L & 15) + 16 * (r & 7) + 128 * (L >> 4) + 256 * (r >> 3); }
 
-// Partner C_{M-k} (or, for a real spectrum, E_{M-k}) of every register by shuffles.  `own` = this lane's 16 values.
-// Lanes 0 and 16 (k2 = 0) pair with each other at register 16 - r; their registers 0 and 8 pair inside the lane.
-template <class T>
-__device__ __forceinline__ T partner_of(const T *own, int L, int r);
-
-__device__ __forceinline__ double shuffle_from(double value, int src) { return __shfl_sync(0xffffffffu, value, src); }
 __device__ __forceinline__ double2 shuffle_from(double2 value, int src) {
   return make_double2(__shfl_sync(0xffffffffu, value.x, src), __shfl_sync(0xffffffffu, value.y, src));
 }
@@ -198,6 +192,22 @@ __device__ __forceinline__ double2 pack_input(double xr, double yr, double c, do
   return make_double2(pr - sn * dr, -(c * dr));
 }
 
+// First-pass inputs of the inverse transform from a real spectrum in the natural layout: nat[s] = E_k, k = L + 32 s,
+// e_last = E_M (needed in lane 0); v[s] = conj Z_k.  The partners E_{M-k} come from lane 32 - L, register 15 - s
+// (lane 0: its own register 16 - s, and E_M for s = 0).
+__device__ __forceinline__ void pack_natural(const double *nat, double e_last, int L, const double2 *__restrict__ cs, double2 *v) {
+  const int src = (32 - L) & 31;
+  const double2 base = __ldg(&cs[L]);
+#pragma unroll
+  for (int s = 0; s < 16; s++) {
+    double yr = __shfl_sync(0xffffffffu, nat[15 - s], src);
+    if (L == 0) yr = (s == 0) ? e_last : nat[(16 - s) & 15];  // k = 32 s: M - k = 32 (16 - s)
+    const double2 rt = rot16(s);
+    const double c = base.x * rt.x - base.y * rt.y, sn = base.x * rt.y + base.y * rt.x;
+    v[s] = pack_input(nat[s], yr, c, sn);
+  }
+}
+
 // From the spectrum layout of phase B (spec[r] = E_k, k = k_of(L, r); e_last = E_M in lane 0) to the first-pass inputs
 // of the inverse transform in the natural layout, v[s] = conj Z_k for k = L + 32 s: the registers whose k is not
 // congruent to L modulo 32 change places with lane L ^ 16, then the partners E_{M-k} come from lane 32 - L.
@@ -214,16 +224,7 @@ __device__ __forceinline__ void repack_for_inverse(const double *spec, double e_
       nat[a + 8 * c] = p ? got : keep;      // s = a + 8 c: from the lane with p = 0
       nat[a + 4 + 8 * c] = p ? keep : got;  // s = a + 4 + 8 c: from the lane with p = 1
     }
-  const int src = (32 - L) & 31;
-  const double2 base = __ldg(&cs[L]);
-#pragma unroll
-  for (int s = 0; s < 16; s++) {
-    double yr = __shfl_sync(0xffffffffu, nat[15 - s], src);
-    if (L == 0) yr = (s == 0) ? e_last : nat[16 - s];  // k = 32 s: M - k = 32 (16 - s)
-    const double2 rt = rot16(s);
-    const double c = base.x * rt.x - base.y * rt.y, sn = base.x * rt.y + base.y * rt.x;
-    v[s] = pack_input(nat[s], yr, c, sn);
-  }
+  pack_natural(nat, e_last, L, cs, v);
 }
 
 }  // namespace fft512

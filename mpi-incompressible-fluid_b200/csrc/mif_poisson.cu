@@ -19,6 +19,7 @@
 
 #include <algorithm>
 
+#include "mif_fft512.cuh"
 #include "mif_fft_fast.cuh"
 #include "mif_fft_warp.cuh"
 #include "mif_kernels.h"
@@ -858,6 +859,76 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
 }
 
 // ------------------------------------------------------------------------------------------------
+// x sweeps of 513-point DCT-I lines on the 16 x 32 transform (mif_fft512.cuh): one warp per line, inputs straight
+// from global memory (coalesced along the line), ONE pass through the warp's shared-memory region, results stored
+// from registers.  MODE 0: forward.  MODE 1: inverse + normalisation as the half-complex -> real transform of the
+// real spectrum (see mif_poisson_tma.cuh): 513 values are read once, no unpack pass, the mirror half of the output
+// is never formed.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) x_dct512_kernel(const FastJob job, double *__restrict__ field) {
+  constexpr int M = 512;
+  extern __shared__ double2 smem2[];
+  double2 *T = smem2 + warpfft::kLines * fft512::kLinePitch;
+  const int tid = threadIdx.x, line = tid >> 5, L = tid & 31;
+  double2 *Sline = smem2 + line * fft512::kLinePitch;
+  const int first_line = blockIdx.x * warpfft::kLines;
+  const int lines = min(warpfft::kLines, job.n_tile_lines - first_line);
+  fft512::load_twiddles<256>(T, job.tw);
+  __syncthreads();
+  if (line >= lines) return;  // whole warps: nothing below synchronises across warps
+  double *row = field + job.origin + (long long)first_line * job.tile_stride + (long long)blockIdx.y * job.outer_stride +
+                (long long)line * job.lstride;
+  double2 v[16];
+  if (MODE == 0) {
+    // packed even extension c_q = (e(2q), e(2q+1)), q = L + 32 s; slots q >= M/2 are the mirror images
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+      const int q = L + 32 * s;
+      if (s < 8) v[s] = *reinterpret_cast<const double2 *>(row + 2 * q);
+      else v[s] = make_double2(row[2 * M - 2 * q], row[2 * M - 2 * q - 1]);
+    }
+  } else {
+    double nat[16];
+#pragma unroll
+    for (int s = 0; s < 16; s++) nat[s] = row[L + 32 * s];
+    const double e_last = row[M];  // same address in all lanes: one broadcast request
+    fft512::pack_natural(nat, e_last, L, job.cs, v);
+  }
+  fft512::phase_a(v, L, T);
+  fft512::store_a(Sline, L, v);
+  __syncwarp();
+  fft512::phase_b(Sline, L, v);
+  if (MODE == 0) {
+    double spec[16], e_last;
+    fft512::unpack_dct(v, L, job.cs, spec, e_last);
+#pragma unroll
+    for (int r = 0; r < 16; r++) row[fft512::k_of(L, r)] = spec[r];  // 16 consecutive lanes = 128 contiguous bytes
+    if (L == 0) row[M] = e_last;
+  } else {
+    // register r < 8 holds z_q = conj(v[r]), q = k2 + 128 p + 16 r: x(2q) = Re z_q, x(2q+1) = Im z_q
+    const double scale = job.inv_norm;
+    const int q0 = (L & 15) + 128 * (L >> 4);
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+      *reinterpret_cast<double2 *>(row + 2 * (q0 + 16 * r)) = make_double2(v[r].x * scale, -v[r].y * scale);
+    if (L == 0) row[M] = v[8].x * scale;  // q = M/2
+  }
+}
+
+void launch_x512(cudaStream_t stream, const FastJob &job, int mode, int outer, double *field, bool *attr_set) {
+  const size_t smem = (size_t)(warpfft::kLines * fft512::kLinePitch + fft512::kTwiddles) * sizeof(double2);
+  if (!*attr_set) {
+    cudaFuncSetAttribute(x_dct512_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(x_dct512_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    *attr_set = true;
+  }
+  const dim3 grid((job.n_tile_lines + warpfft::kLines - 1) / warpfft::kLines, outer, 1);
+  if (mode == 0) x_dct512_kernel<0><<<grid, 256, smem, stream>>>(job, field);
+  else x_dct512_kernel<1><<<grid, 256, smem, stream>>>(job, field);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Periodic directions: FFTW_R2HC / FFTW_HC2R on n = 2M real points (M = 256 or 512) with the same warp-per-line
 // machinery -- the line is packed two reals per complex, transformed by ONE length-M complex FFT and unpacked to
 // FFTW's halfcomplex order r_0 .. r_{n/2}, i_{n/2-1} .. i_1 with shuffles.  The fused z sweep never leaves the
@@ -1348,6 +1419,7 @@ struct PoissonPlan {
   size_t smem[3];
   std::vector<void *> allocations;
   tmasweep::Cache tma;  // tensor maps of the TMA-staged strided sweeps, per field / direction
+  bool x512_attr = false;
 };
 
 PoissonPlan *poisson_plan_create(const Geom &g, const int n_points[3], const int periodic[3], const double h[3],
@@ -1499,6 +1571,7 @@ bool launch_tma_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int
     cudaDeviceGetAttribute(&cache.sms, cudaDevAttrMultiProcessorCount, cache.device);
   }
   static const bool swizzle = getenv("MIFGPU_TMA_NO_SWIZZLE") == nullptr;
+  static const bool radix8_fft = getenv("MIFGPU_FFT_RADIX8") != nullptr;  // A/B: 513-point lines on the radix-8 Stockham passes
   static const int promo = getenv("MIFGPU_TMA_L2PROMO") ? atoi(getenv("MIFGPU_TMA_L2PROMO")) : 2;
   const int x_off = (int)(lay.origin & 1);
   const tmasweep::MapSet *maps = tmasweep::maps_for(cache, field + lay.origin - x_off, x_off, lay.n_tile_lines, plan->dir[d].n,
@@ -1521,10 +1594,14 @@ bool launch_tma_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int
     if (mode == 0) tmasweep::launch_one<8, 0>(stream, cache, *maps, job);
     else if (mode == 1) tmasweep::launch_one<8, 1>(stream, cache, *maps, job);
     else tmasweep::launch_one<8, 2>(stream, cache, *maps, job);
-  } else {
+  } else if (radix8_fft) {
     if (mode == 0) tmasweep::launch_one<9, 0>(stream, cache, *maps, job);
     else if (mode == 1) tmasweep::launch_one<9, 1>(stream, cache, *maps, job);
     else tmasweep::launch_one<9, 2>(stream, cache, *maps, job);
+  } else {
+    if (mode == 0) tmasweep::launch_512<0>(stream, cache, *maps, job);
+    else if (mode == 1) tmasweep::launch_512<1>(stream, cache, *maps, job);
+    else tmasweep::launch_512<2>(stream, cache, *maps, job);
   }
   return true;
 }
@@ -1573,10 +1650,15 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
         if (use_cta_sync_variant) launch_fast<8>(stream, fj, lay.contig, fgrid, field);
         else launch_warp<8>(stream, fj, lay.contig, fgrid, field);
         break;
-      case 9:
+      case 9: {
+        static const bool radix8_fft = getenv("MIFGPU_FFT_RADIX8") != nullptr;  // A/B: the radix-8 Stockham passes
+        const bool aligned = ((lay.origin | lay.lstride | lay.tile_stride | lay.outer_stride) & 1) == 0;
         if (use_cta_sync_variant) launch_fast<9>(stream, fj, lay.contig, fgrid, field);
+        else if (lay.contig && !radix8_fft && aligned && lay.div_u == nullptr && mode != 2)
+          launch_x512(stream, fj, mode, lay.outer, field, &plan->x512_attr);
         else launch_warp<9>(stream, fj, lay.contig, fgrid, field);
         break;
+      }
       case 11:  // 2049-point lines (BASELINE configs[4]): four warps per line, 4-line CTAs
         launch_warp<11>(stream, fj, lay.contig, fgrid, field);
         break;

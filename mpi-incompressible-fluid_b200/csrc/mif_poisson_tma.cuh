@@ -26,6 +26,7 @@
 #include <map>
 #include <tuple>
 
+#include "mif_fft512.cuh"
 #include "mif_fft_warp.cuh"
 #include "mif_tma.cuh"
 
@@ -253,6 +254,166 @@ __global__ void __launch_bounds__(kThreads, 2)
   if (tid == 0) tma::wait_stores_done();
 }
 
+
+// ---- 513-point lines on the 16 x 32 transform of mif_fft512.cuh ------------------------------------------------------------
+// Same staging, tile loop and barriers as tma_dct_kernel; the transform crosses shared memory once instead of twice:
+// the stage threads (line fastest) run phase A -- a 16-point DFT and the W_512 twiddles in registers -- while the bulk
+// stores of the previous tile drain, the line's warp runs phase B, and in the fused z sweep the scaled spectrum goes back
+// to first-pass order by one exchange between lane pairs before the second transform.
+struct Layout512 {
+  static constexpr int M = 512;
+  static constexpr int kLoadBoxes = Layout<9>::kLoadBoxes, kOddRow0 = Layout<9>::kOddRow0, kStoreBoxes = Layout<9>::kStoreBoxes;
+  static constexpr size_t kWorkBytes = (size_t)kLines * fft512::kLinePitch * sizeof(double2);
+  static constexpr size_t kOutBytes = Layout<9>::kOutBytes;
+  static constexpr size_t kTwBytes = (size_t)fft512::kTwiddles * sizeof(double2);
+  static constexpr size_t kStageBytes = Layout<9>::kStageBytes;
+  static constexpr size_t kWorkArea = ((kWorkBytes > kOutBytes ? kWorkBytes : kOutBytes) + 127) / 128 * 128;
+  static constexpr size_t kSmem = 1024 + kWorkArea + (kTwBytes + 127) / 128 * 128 + kStageBytes + 64;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 2)
+    tma_dct512_kernel(const __grid_constant__ CUtensorMap map_in_a, const __grid_constant__ CUtensorMap map_in_b,
+                      const __grid_constant__ CUtensorMap map_out, const Job job) {
+  using Y = Layout512;
+  constexpr int M = 512;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *smem = smem_raw + ((1024 - (tma::swizzle_address(smem_raw) & 1023)) & 1023);
+  double2 *W = reinterpret_cast<double2 *>(smem);                                   // phase A -> phase B exchange, one region per line
+  unsigned char *O = smem;                                                          // output stage (aliases W)
+  double2 *T = reinterpret_cast<double2 *>(smem + Y::kWorkArea);                    // W_512^(n1 2^e)
+  double *S = reinterpret_cast<double *>(smem + Y::kWorkArea + (Y::kTwBytes + 127) / 128 * 128);  // input stage
+  uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(S) + Y::kStageBytes);
+
+  const int tid = threadIdx.x;
+  const int line = tid >> 5, j = tid & 31;  // transform mapping: warp = line, lane j = k2 + 16 p
+  const int l = tid & 7, b = tid >> 3;      // stage mapping: line fastest, b = n1
+  double2 *Sline = W + line * fft512::kLinePitch;
+  const int n_tiles = job.n_xtiles * job.n_outer;
+
+  auto issue_load = [&](int tile) {
+    const int xt = tile % job.n_xtiles, outer = tile / job.n_xtiles;
+    const int x0 = job.x_off + xt * kLines;
+    tma::mbar_arrive_expect_tx(full, (unsigned)Y::kStageBytes);
+    if (MODE == 1) {
+#pragma unroll
+      for (int i = 0; i < Y::kLoadBoxes; i++) tma::load_3d(S + i * kBoxRows * 8, &map_in_a, full, x0, i * kBoxRows, outer);
+    } else {
+#pragma unroll
+      for (int i = 0; i < Y::kLoadBoxes / 2; i++) {
+        tma::load_3d(S + i * kBoxRows * 8, &map_in_a, full, x0, i * kBoxRows, outer);
+        tma::load_3d(S + (Y::kOddRow0 + i * kBoxRows) * 8, &map_in_b, full, x0, i * kBoxRows, outer);
+      }
+    }
+  };
+
+  if (tid == 0) {
+    tma::prefetch_map(&map_in_a);
+    tma::prefetch_map(&map_in_b);
+    tma::prefetch_map(&map_out);
+    tma::mbar_init(full, 1);
+    tma::fence_barrier_init();
+    tma::fence_proxy_async();
+  }
+  fft512::load_twiddles<kThreads>(T, job.tw);
+  __syncthreads();
+  int tile = blockIdx.x;
+  if (tid == 0 && tile < n_tiles) issue_load(tile);
+  unsigned parity = 0;
+
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const int xt = tile % job.n_xtiles, outer = tile / job.n_xtiles;
+    double2 v[16];
+
+    // ---- phase A by the stage threads: inputs c[b + 32 s] of line l -------------------------------------------------
+    tma::mbar_wait(full, parity);
+    parity ^= 1;
+    if (MODE == 1) {
+      const double *N = S + l;  // natural rows: element e of line l at N[8 e]
+      const double2 base = __ldg(&job.cs[b]);
+#pragma unroll
+      for (int s = 0; s < 16; s++) {
+        const int k = b + 32 * s;
+        const double2 rt = fft512::rot16(s);  // (cos, sin)(pi k / M) = cs[b] rotated by pi s / 16
+        const double c = base.x * rt.x - base.y * rt.y, sn = base.x * rt.y + base.y * rt.x;
+        v[s] = fft512::pack_input(N[8 * k], N[8 * (M - k)], c, sn);
+      }
+    } else {
+      const double *Ev = S + l, *Od = S + Y::kOddRow0 * 8 + l;  // e(2q) at Ev[8 q], e(2q+1) at Od[8 q]
+#pragma unroll
+      for (int s = 0; s < 16; s++) {
+        const int q = b + 32 * s;
+        if (s < 8) v[s] = make_double2(Ev[8 * q], Od[8 * q]);
+        else v[s] = make_double2(Ev[8 * (M - q)], Od[8 * (M - q - 1)]);  // mirror image: e(2M-2q), e(2M-2q-1)
+      }
+    }
+    fft512::phase_a(v, b, T);
+    if (tid == 0) tma::wait_stores_read();  // the previous tile's output stage (in W) has been read out
+    __syncthreads();                        // the stage has been consumed, W is free
+    if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue_load(tile + gridDim.x);
+    fft512::store_a(W + l * fft512::kLinePitch, b, v);
+    __syncthreads();
+
+    // ---- phase B by the line's warp ------------------------------------------------------------------------------------
+    fft512::phase_b(Sline, j, v);
+    double spec[16], e_last = 0.0;
+    if (MODE != 1) fft512::unpack_dct(v, j, job.cs, spec, e_last);
+    if (MODE == 2) {
+      // pressure_hat *= 1 / (lambda_x + lambda_y + lambda_z); mode (0,0,0) := 0 (src/PressureEquation.cpp:158-163)
+      const int ix = min(xt * kLines + line, job.n_lines - 1);
+      const double lam_xy = job.lam_x[ix] + job.lam_y[outer];
+      const bool origin_line = job.has_origin && (xt * kLines + line == 0) && (outer == 0);
+#pragma unroll
+      for (int r = 0; r < 16; r++) {
+        const int k = fft512::k_of(j, r);
+        spec[r] *= (origin_line && k == 0) ? 0.0 : 1.0 / (lam_xy + job.lam_z[k]);
+      }
+      e_last *= 1.0 / (lam_xy + job.lam_z[M]);
+      fft512::repack_for_inverse(spec, e_last, j, job.cs, v);
+      fft512::phase_a(v, j, T);
+      __syncwarp();  // every lane has finished reading the line region (phase B of the forward transform)
+      fft512::store_a(Sline, j, v);
+      __syncwarp();
+      fft512::phase_b(Sline, j, v);
+    }
+    __syncthreads();  // all warps are done with the work area: it becomes the output stage
+
+    // ---- results into the swizzled output stage (see tma_dct_kernel): row e of the tile at 64 e, column `line` ----------
+    const int k2 = j & 15, p = j >> 4;
+    if (MODE == 0) {
+      // register r holds E_k, k = k2 + 128 p + 16 (r & 7) + 256 (r >> 3): the register part is a multiple of 1024 bytes
+      const unsigned off = tma::swizzle_offset((unsigned)((k2 + 128 * p) * 64 + line * 8), job.swz);
+#pragma unroll
+      for (int r = 0; r < 16; r++)
+        *reinterpret_cast<double *>(O + off + (16 * (r & 7) + 256 * (r >> 3)) * 64) = spec[r];
+      if (j == 0) *reinterpret_cast<double *>(O + tma::swizzle_offset((unsigned)(M * 64 + line * 8), job.swz)) = e_last;
+    } else {
+      // register r < 8 holds z_q = conj(v[r]), q = k2 + 128 p + 16 r: x(2q) = Re z_q, x(2q+1) = Im z_q; q = 256 is register 8
+      // of lane 0.  Lanes with bit 2 of k2 set store the odd row first (both halves of the 128-byte lines per instruction).
+      const unsigned off = tma::swizzle_offset((unsigned)((k2 + 128 * p) * 128 + line * 8), job.swz);
+      const bool odd_first = (k2 >> 2) & 1;
+      const unsigned first = off + (odd_first ? 64u : 0u), second = first ^ 64u;
+      const double scale = job.inv_norm;
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        const double even = v[r].x * scale, odd = -v[r].y * scale;
+        *reinterpret_cast<double *>(O + first + r * 16 * 128) = odd_first ? odd : even;
+        *reinterpret_cast<double *>(O + second + r * 16 * 128) = odd_first ? even : odd;
+      }
+      if (j == 0) *reinterpret_cast<double *>(O + tma::swizzle_offset((unsigned)(M * 64 + line * 8), job.swz)) = v[8].x * scale;
+    }
+    tma::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      const int x0 = job.x_off + xt * kLines;
+#pragma unroll
+      for (int c = 0; c < Y::kStoreBoxes; c++) tma::store_3d(&map_out, O + c * kStoreRows * 64, x0, c * kStoreRows, outer);
+      tma::commit_group();
+    }
+  }
+  if (tid == 0) tma::wait_stores_done();
+}
+
 // ---- host -----------------------------------------------------------------------------------------------------
 struct MapKey {
   const void *base;
@@ -272,6 +433,7 @@ struct Cache {
   std::map<MapKey, MapSet> sets;
   int device = -1, sms = 0;
   bool attr[2][3] = {};
+  bool attr512[3] = {};
 };
 
 // kind: 0 plain output map, 1 swizzled output map
@@ -305,6 +467,19 @@ void launch_one(cudaStream_t stream, Cache &cache, const MapSet &maps, const Job
   const int n_tiles = job.n_xtiles * job.n_outer;
   const int grid = std::min(n_tiles, std::max(1, cache.sms * per_sm));
   tma_dct_kernel<LOGM, MODE><<<grid, kThreads, Y::kSmem, stream>>>(MODE == 1 ? maps.natural : maps.even, maps.odd, maps.out, job);
+}
+
+template <int MODE>
+void launch_512(cudaStream_t stream, Cache &cache, const MapSet &maps, const Job &job) {
+  using Y = Layout512;
+  if (!cache.attr512[MODE]) {
+    cudaFuncSetAttribute(tma_dct512_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Y::kSmem);
+    cache.attr512[MODE] = true;
+  }
+  static const int per_sm = getenv("MIFGPU_TMA_CTAS_PER_SM") ? atoi(getenv("MIFGPU_TMA_CTAS_PER_SM")) : 2;
+  const int n_tiles = job.n_xtiles * job.n_outer;
+  const int grid = std::min(n_tiles, std::max(1, cache.sms * per_sm));
+  tma_dct512_kernel<MODE><<<grid, kThreads, Y::kSmem, stream>>>(MODE == 1 ? maps.natural : maps.even, maps.odd, maps.out, job);
 }
 
 }  // namespace tmasweep
