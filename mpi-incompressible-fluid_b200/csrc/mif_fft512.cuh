@@ -65,6 +65,13 @@ __device__ __forceinline__ double2 rot32(int t) {
                             0.63439328416364549822};
   return make_double2(co[t], si[t]);
 }
+// (cos, sin)(pi s / 32), s = 0..15
+__device__ __forceinline__ double2 rot32x(int s) {
+  if (s < 8) return rot32(s);
+  if (s == 8) return make_double2(0.70710678118654752440, 0.70710678118654752440);
+  const double2 r = rot32(16 - s);  // cos(pi s / 32) = sin(pi (16 - s) / 32)
+  return make_double2(r.y, r.x);
+}
 // (cos, sin)(pi s / 16), s = 0..15
 __device__ __forceinline__ double2 rot16(int s) {
   const double2 w = w32(s);
@@ -96,12 +103,13 @@ __device__ __forceinline__ void dft16(double2 *a) {
     }
 }
 
-// Twiddle table of the kernel's shared memory from the plan's full table tw[q] = exp(-2 pi i q / 512).
-template <int THREADS>
+// Twiddle table of the kernel's shared memory from the plan's full table tw[q * STRIDE] = exp(-2 pi i q / 512)
+// (STRIDE = 2: the table of a 1024-point transform, mif_poisson_tma.cuh tma_dct1024_kernel).
+template <int THREADS, int STRIDE = 1>
 __device__ __forceinline__ void load_twiddles(double2 *T, const double2 *__restrict__ tw) {
   for (int idx = threadIdx.x; idx < kTwiddles; idx += THREADS) {
     const int e = idx >> 5, n1 = idx & 31;
-    T[idx] = __ldg(&tw[(n1 << e) & (kM - 1)]);
+    T[idx] = __ldg(&tw[((n1 << e) & (kM - 1)) * STRIDE]);
   }
 }
 
@@ -162,11 +170,15 @@ __device__ __forceinline__ double2 shuffle_from(double2 value, int src) {
 
 // DCT-I unpack in registers: out[r] = E_k for k = k_of(L, r); E_M is returned in e_last (valid in lane 0).
 // cs[k] = (cos, sin)(pi k / 512).
+// HALF = 1 / 2: the warp holds the even (C_{2k}) / odd (C_{2k+1}) half of a radix-2 split 1024-point transform and
+// produces E_{2k} / E_{2k+1} of a 1025-point line; cs is then the table of the long transform, (cos, sin)(pi q / 1024).
+// Odd half: the partner of C_{2k+1} is C_{2(511-k)+1}, register 15 - r of lane 31 - L, with no special lanes.
+template <int HALF = 0>
 __device__ __forceinline__ void unpack_dct(const double2 *v, int L, const double2 *__restrict__ cs, double *out, double &e_last) {
   const int k2 = L & 15, p = L >> 4;
-  const bool special = (k2 == 0);
-  const int src = special ? (L ^ 16) : 32 - L;
-  const double2 base = __ldg(&cs[k2 + 128 * p]);
+  const bool special = (HALF != 2) && (k2 == 0);
+  const int src = (HALF == 2) ? 31 - L : (special ? (L ^ 16) : 32 - L);
+  const double2 base = __ldg(&cs[HALF == 0 ? k2 + 128 * p : 2 * (k2 + 128 * p) + (HALF == 2 ? 1 : 0)]);
 #pragma unroll
   for (int r = 0; r < 16; r++) {
     const double2 send = special ? v[(16 - r) & 15] : v[15 - r];

@@ -1548,6 +1548,9 @@ struct SweepLayout {
   long long stride_y = 0, stride_z = 0;
 };
 
+void launch_tma_modes(cudaStream_t stream, tmasweep::Cache &cache, const tmasweep::MapSet &maps, const tmasweep::Job &job, int logm,
+                      int mode);
+
 // TMA-staged strided sweep (mif_poisson_tma.cuh) when the geometry allows it: 257- or 513-point DCT-I lines along y or
 // z, tiles of 8 consecutive x, plain strided addressing with 16-byte aligned rows.  Returns false when the launch has
 // to take the LSU path (MIFGPU_NO_TMA=1 forces that for A/B runs; MIFGPU_REQUIRE_TMA=1 turns a refusal into an abort
@@ -1556,7 +1559,7 @@ bool launch_tma_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int
   static const bool disabled = getenv("MIFGPU_NO_TMA") != nullptr;
   static const bool required = getenv("MIFGPU_REQUIRE_TMA") != nullptr;
   const int logm = plan->fast_logm[d];
-  if (disabled || lay.contig || (logm != 8 && logm != 9) || lay.load_map.n || lay.store_map.n || lay.peer) return false;
+  if (disabled || lay.contig || (logm != 8 && logm != 9 && logm != 10) || lay.load_map.n || lay.store_map.n || lay.peer) return false;
   auto refuse = [&](const char *why) {
     if (required) {
       fprintf(stderr, "libmifgpu: MIFGPU_REQUIRE_TMA=1 but the sweep along %d cannot use TMA: %s\n", d, why);
@@ -1590,7 +1593,24 @@ bool launch_tma_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int
   job.inv_norm = plan->dir[d].inv_norm;
   job.has_origin = lay.has_origin ? 1 : 0;
   job.swz = swizzle ? 3u : 0u;
-  if (logm == 8) {
+  job.outer_fastest = 0;
+  job.in_x_tiled = 1;
+  job.in_c2_mult = 0;
+  job.in_perm_base = -1;
+  job.out.n = 0;
+  launch_tma_modes(stream, cache, *maps, job, logm, mode);
+  return true;
+}
+
+void launch_tma_modes(cudaStream_t stream, tmasweep::Cache &cache, const tmasweep::MapSet &maps_ref, const tmasweep::Job &job, int logm,
+                      int mode) {
+  static const bool radix8_fft = getenv("MIFGPU_FFT_RADIX8") != nullptr;  // A/B: 513-point lines on the radix-8 Stockham passes
+  const tmasweep::MapSet *maps = &maps_ref;
+  if (logm == 10) {
+    if (mode == 0) tmasweep::launch_1024<0>(stream, cache, *maps, job);
+    else if (mode == 1) tmasweep::launch_1024<1>(stream, cache, *maps, job);
+    else tmasweep::launch_1024<2>(stream, cache, *maps, job);
+  } else if (logm == 8) {
     if (mode == 0) tmasweep::launch_one<8, 0>(stream, cache, *maps, job);
     else if (mode == 1) tmasweep::launch_one<8, 1>(stream, cache, *maps, job);
     else tmasweep::launch_one<8, 2>(stream, cache, *maps, job);
@@ -1603,7 +1623,6 @@ bool launch_tma_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int
     else if (mode == 1) tmasweep::launch_512<1>(stream, cache, *maps, job);
     else tmasweep::launch_512<2>(stream, cache, *maps, job);
   }
-  return true;
 }
 
 void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, int mode, const SweepLayout &lay,

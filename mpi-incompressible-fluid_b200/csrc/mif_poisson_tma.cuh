@@ -56,14 +56,67 @@ struct Layout {
   static_assert(kLoadBoxes * kBoxRows >= M + 1, "natural rows fit the stage");
 };
 
+// Multi-GPU sweeps whose results go to the pencil / slab buffers of the owning ranks (fused 2Decomp transposes): rows
+// [lo[r], lo[r+1]) of every tile are one contiguous run in rank r's buffer (blocked layouts of mif_poisson.cu), so they
+// leave the output stage as one bulk copy per rank -- over NVLink for r != this rank.
+struct PeerOut {
+  int n;  // 0: one tensor store through map_out
+  int lo[9];
+  double *base[8];
+  long long xtile_stride[8], outer_stride[8];
+};
+
 struct Job {
   int n_xtiles, n_outer, n_lines, x_off;
   const double2 *tw, *cs;
   const double *lam_x, *lam_y, *lam_z;
   double inv_norm;
   int has_origin;
-  unsigned swz;  // 3: the output map is swizzled (CU_TENSOR_MAP_SWIZZLE_64B), 0: plain
+  unsigned swz;  // 3: the output stage is swizzled (CU_TENSOR_MAP_SWIZZLE_64B), 0: plain
+  // input side
+  int outer_fastest;     // tile order: 0 = x tile fastest (plain arrays), 1 = outer index fastest (blocked buffers)
+  int in_x_tiled;        // load coordinate 0 = x_off + 8 xt (plain arrays) or 0 (blocked buffers: x tile folded into coordinate 2)
+  long long in_c2_mult;  // load coordinate 2 = xt * in_c2_mult + outer
+  int in_perm_base;      // >= 0: the input rows left a swizzled output stage in which this tile's lines were row in_perm_base +
+                         // outer, so the 16-byte pairs of its 8 columns arrive XOR-permuted by ((row >> 1) & 3); -1: in order
+  PeerOut out;
 };
+
+struct Tile {
+  int xt, outer, x_in, c2, perm;
+};
+__device__ __forceinline__ Tile decode_tile(const Job &job, int tile) {
+  Tile t;
+  if (job.outer_fastest) {
+    t.xt = tile / job.n_outer;
+    t.outer = tile - t.xt * job.n_outer;
+  } else {
+    t.outer = tile / job.n_xtiles;
+    t.xt = tile - t.outer * job.n_xtiles;
+  }
+  t.x_in = job.in_x_tiled ? job.x_off + t.xt * kLines : 0;
+  t.c2 = (int)(t.xt * job.in_c2_mult) + t.outer;
+  t.perm = (job.in_perm_base >= 0 && job.swz) ? (((job.in_perm_base + t.outer) >> 1) & 3) << 1 : 0;
+  return t;
+}
+
+// The finished output stage O (rows of 64 bytes) leaves the CTA: one thread, one bulk group.
+template <int STORE_BOXES>
+__device__ __forceinline__ void store_tile(const Job &job, const CUtensorMap *map_out, const unsigned char *O, const Tile &t) {
+  if (job.out.n == 0) {
+    const int x0 = job.x_off + t.xt * kLines;
+#pragma unroll
+    for (int c = 0; c < STORE_BOXES; c++) tma::store_3d(map_out, O + c * kStoreRows * 64, x0, c * kStoreRows, t.outer);
+  } else {
+    for (int r = 0; r < job.out.n; r++) {
+      const int rows = job.out.lo[r + 1] - job.out.lo[r];
+      if (rows <= 0) continue;
+      double *dst = job.out.base[r] + (long long)t.xt * job.out.xtile_stride[r] + (long long)t.outer * job.out.outer_stride[r];
+      tma::store_bulk(dst, O + (size_t)job.out.lo[r] * 64, (unsigned)rows * 64u);
+    }
+  }
+  tma::commit_group();
+}
 
 __device__ __forceinline__ double2 dct_pack_input(double xr, double yr, double c, double sn) {
   // conj Z_k for a real spectrum: X_k = xr, X_{M-k} = yr, (c, sn) = (cos, sin)(pi k / M); see hc2r_input
@@ -123,17 +176,16 @@ __global__ void __launch_bounds__(kThreads, 2)
   const int n_tiles = job.n_xtiles * job.n_outer;
 
   auto issue_load = [&](int tile) {
-    const int xt = tile % job.n_xtiles, outer = tile / job.n_xtiles;
-    const int x0 = job.x_off + xt * kLines;
+    const Tile nt = decode_tile(job, tile);
     tma::mbar_arrive_expect_tx(full, (unsigned)Y::kStageBytes);
     if (MODE == 1) {
 #pragma unroll
-      for (int i = 0; i < Y::kLoadBoxes; i++) tma::load_3d(S + i * kBoxRows * 8, &map_in_a, full, x0, i * kBoxRows, outer);
+      for (int i = 0; i < Y::kLoadBoxes; i++) tma::load_3d(S + i * kBoxRows * 8, &map_in_a, full, nt.x_in, i * kBoxRows, nt.c2);
     } else {
 #pragma unroll
       for (int i = 0; i < Y::kLoadBoxes / 2; i++) {
-        tma::load_3d(S + i * kBoxRows * 8, &map_in_a, full, x0, i * kBoxRows, outer);
-        tma::load_3d(S + (Y::kOddRow0 + i * kBoxRows) * 8, &map_in_b, full, x0, i * kBoxRows, outer);
+        tma::load_3d(S + i * kBoxRows * 8, &map_in_a, full, nt.x_in, i * kBoxRows, nt.c2);
+        tma::load_3d(S + (Y::kOddRow0 + i * kBoxRows) * 8, &map_in_b, full, nt.x_in, i * kBoxRows, nt.c2);
       }
     }
   };
@@ -153,7 +205,8 @@ __global__ void __launch_bounds__(kThreads, 2)
   unsigned parity = 0;
 
   for (; tile < n_tiles; tile += gridDim.x) {
-    const int xt = tile % job.n_xtiles, outer = tile / job.n_xtiles;
+    const Tile t = decode_tile(job, tile);
+    const int xt = t.xt, outer = t.outer, col = line ^ t.perm;  // col: this line's x offset inside the tile
     double2 v[EPT];
 
     // ---- first-pass inputs from the stage ---------------------------------------------------------------------
@@ -192,9 +245,9 @@ __global__ void __launch_bounds__(kThreads, 2)
     if (MODE != 1) unpack_regs<LOGM>(v, j, job.cs, spec, e_last);
     if (MODE == 2) {
       // pressure_hat *= 1 / (lambda_x + lambda_y + lambda_z); mode (0,0,0) := 0 (src/PressureEquation.cpp:158-163)
-      const int ix = min(xt * kLines + line, job.n_lines - 1);
+      const int ix = min(xt * kLines + col, job.n_lines - 1);
       const double lam_xy = job.lam_x[ix] + job.lam_y[outer];
-      const bool origin_line = job.has_origin && (xt * kLines + line == 0) && (outer == 0);
+      const bool origin_line = job.has_origin && (xt * kLines + col == 0) && (outer == 0);
 #pragma unroll
       for (int u = 0; u < L::G; u++)
 #pragma unroll
@@ -215,18 +268,18 @@ __global__ void __launch_bounds__(kThreads, 2)
     // rate of a conflict-free access and still cheaper than a transposition through the line regions.
     if (MODE == 0) {
       // lane j holds E_k, k = j + 32 u + NS t; address bits 7-8 (row >> 1) do not depend on (u, t)
-      const unsigned off = tma::swizzle_offset((unsigned)(j * 64 + line * 8), job.swz);
+      const unsigned off = tma::swizzle_offset((unsigned)(j * 64 + col * 8), job.swz);
 #pragma unroll
       for (int u = 0; u < L::G; u++)
 #pragma unroll
         for (int t = 0; t < L::R; t++)
           *reinterpret_cast<double *>(O + off + (32 * u + L::NS * t) * 64) = spec[u + L::G * t];
-      if (j == 0) *reinterpret_cast<double *>(O + tma::swizzle_offset((unsigned)(M * 64 + line * 8), job.swz)) = e_last;
+      if (j == 0) *reinterpret_cast<double *>(O + tma::swizzle_offset((unsigned)(M * 64 + col * 8), job.swz)) = e_last;
     } else {
       // lane j holds z_q = conj(v), q = j + 32 u + NS t: x(2q) = Re z_q, x(2q+1) = Im z_q; only q <= M/2 is stored.
       // Rows 2q of all lanes would sit in the same half of their 128-byte lines (4 bank positions): lanes with bit 2 of
       // j set store the odd row first, so that every instruction covers both halves (8 positions).
-      const unsigned off = tma::swizzle_offset((unsigned)(j * 128 + line * 8), job.swz);
+      const unsigned off = tma::swizzle_offset((unsigned)(j * 128 + col * 8), job.swz);
       const bool odd_first = (j >> 2) & 1;
       const unsigned first = off + (odd_first ? 64u : 0u), second = first ^ 64u;
       const double scale = job.inv_norm;
@@ -240,16 +293,11 @@ __global__ void __launch_bounds__(kThreads, 2)
           *reinterpret_cast<double *>(O + second + at) = odd_first ? even : odd;
         }
       if (j == 0)  // q = M/2 = NS * R/2: slot u = 0, t = R/2 of lane 0
-        *reinterpret_cast<double *>(O + tma::swizzle_offset((unsigned)(M * 64 + line * 8), job.swz)) = v[L::G * (L::R / 2)].x * scale;
+        *reinterpret_cast<double *>(O + tma::swizzle_offset((unsigned)(M * 64 + col * 8), job.swz)) = v[L::G * (L::R / 2)].x * scale;
     }
     tma::fence_proxy_async();
     __syncthreads();
-    if (tid == 0) {
-      const int x0 = job.x_off + xt * kLines;
-#pragma unroll
-      for (int c = 0; c < Y::kStoreBoxes; c++) tma::store_3d(&map_out, O + c * kStoreRows * 64, x0, c * kStoreRows, outer);
-      tma::commit_group();
-    }
+    if (tid == 0) store_tile<Y::kStoreBoxes>(job, &map_out, O, t);
   }
   if (tid == 0) tma::wait_stores_done();
 }
@@ -292,17 +340,16 @@ __global__ void __launch_bounds__(kThreads, 2)
   const int n_tiles = job.n_xtiles * job.n_outer;
 
   auto issue_load = [&](int tile) {
-    const int xt = tile % job.n_xtiles, outer = tile / job.n_xtiles;
-    const int x0 = job.x_off + xt * kLines;
+    const Tile nt = decode_tile(job, tile);
     tma::mbar_arrive_expect_tx(full, (unsigned)Y::kStageBytes);
     if (MODE == 1) {
 #pragma unroll
-      for (int i = 0; i < Y::kLoadBoxes; i++) tma::load_3d(S + i * kBoxRows * 8, &map_in_a, full, x0, i * kBoxRows, outer);
+      for (int i = 0; i < Y::kLoadBoxes; i++) tma::load_3d(S + i * kBoxRows * 8, &map_in_a, full, nt.x_in, i * kBoxRows, nt.c2);
     } else {
 #pragma unroll
       for (int i = 0; i < Y::kLoadBoxes / 2; i++) {
-        tma::load_3d(S + i * kBoxRows * 8, &map_in_a, full, x0, i * kBoxRows, outer);
-        tma::load_3d(S + (Y::kOddRow0 + i * kBoxRows) * 8, &map_in_b, full, x0, i * kBoxRows, outer);
+        tma::load_3d(S + i * kBoxRows * 8, &map_in_a, full, nt.x_in, i * kBoxRows, nt.c2);
+        tma::load_3d(S + (Y::kOddRow0 + i * kBoxRows) * 8, &map_in_b, full, nt.x_in, i * kBoxRows, nt.c2);
       }
     }
   };
@@ -322,7 +369,8 @@ __global__ void __launch_bounds__(kThreads, 2)
   unsigned parity = 0;
 
   for (; tile < n_tiles; tile += gridDim.x) {
-    const int xt = tile % job.n_xtiles, outer = tile / job.n_xtiles;
+    const Tile t = decode_tile(job, tile);
+    const int xt = t.xt, outer = t.outer, col = line ^ t.perm;  // col: this line's x offset inside the tile
     double2 v[16];
 
     // ---- phase A by the stage threads: inputs c[b + 32 s] of line l -------------------------------------------------
@@ -360,9 +408,9 @@ __global__ void __launch_bounds__(kThreads, 2)
     if (MODE != 1) fft512::unpack_dct(v, j, job.cs, spec, e_last);
     if (MODE == 2) {
       // pressure_hat *= 1 / (lambda_x + lambda_y + lambda_z); mode (0,0,0) := 0 (src/PressureEquation.cpp:158-163)
-      const int ix = min(xt * kLines + line, job.n_lines - 1);
+      const int ix = min(xt * kLines + col, job.n_lines - 1);
       const double lam_xy = job.lam_x[ix] + job.lam_y[outer];
-      const bool origin_line = job.has_origin && (xt * kLines + line == 0) && (outer == 0);
+      const bool origin_line = job.has_origin && (xt * kLines + col == 0) && (outer == 0);
 #pragma unroll
       for (int r = 0; r < 16; r++) {
         const int k = fft512::k_of(j, r);
@@ -382,15 +430,15 @@ __global__ void __launch_bounds__(kThreads, 2)
     const int k2 = j & 15, p = j >> 4;
     if (MODE == 0) {
       // register r holds E_k, k = k2 + 128 p + 16 (r & 7) + 256 (r >> 3): the register part is a multiple of 1024 bytes
-      const unsigned off = tma::swizzle_offset((unsigned)((k2 + 128 * p) * 64 + line * 8), job.swz);
+      const unsigned off = tma::swizzle_offset((unsigned)((k2 + 128 * p) * 64 + col * 8), job.swz);
 #pragma unroll
       for (int r = 0; r < 16; r++)
         *reinterpret_cast<double *>(O + off + (16 * (r & 7) + 256 * (r >> 3)) * 64) = spec[r];
-      if (j == 0) *reinterpret_cast<double *>(O + tma::swizzle_offset((unsigned)(M * 64 + line * 8), job.swz)) = e_last;
+      if (j == 0) *reinterpret_cast<double *>(O + tma::swizzle_offset((unsigned)(M * 64 + col * 8), job.swz)) = e_last;
     } else {
       // register r < 8 holds z_q = conj(v[r]), q = k2 + 128 p + 16 r: x(2q) = Re z_q, x(2q+1) = Im z_q; q = 256 is register 8
       // of lane 0.  Lanes with bit 2 of k2 set store the odd row first (both halves of the 128-byte lines per instruction).
-      const unsigned off = tma::swizzle_offset((unsigned)((k2 + 128 * p) * 128 + line * 8), job.swz);
+      const unsigned off = tma::swizzle_offset((unsigned)((k2 + 128 * p) * 128 + col * 8), job.swz);
       const bool odd_first = (k2 >> 2) & 1;
       const unsigned first = off + (odd_first ? 64u : 0u), second = first ^ 64u;
       const double scale = job.inv_norm;
@@ -400,16 +448,218 @@ __global__ void __launch_bounds__(kThreads, 2)
         *reinterpret_cast<double *>(O + first + r * 16 * 128) = odd_first ? odd : even;
         *reinterpret_cast<double *>(O + second + r * 16 * 128) = odd_first ? even : odd;
       }
-      if (j == 0) *reinterpret_cast<double *>(O + tma::swizzle_offset((unsigned)(M * 64 + line * 8), job.swz)) = v[8].x * scale;
+      if (j == 0) *reinterpret_cast<double *>(O + tma::swizzle_offset((unsigned)(M * 64 + col * 8), job.swz)) = v[8].x * scale;
     }
     tma::fence_proxy_async();
     __syncthreads();
-    if (tid == 0) {
-      const int x0 = job.x_off + xt * kLines;
+    if (tid == 0) store_tile<Y::kStoreBoxes>(job, &map_out, O, t);
+  }
+  if (tid == 0) tma::wait_stores_done();
+}
+
+// ---- 1025-point lines: radix-2 split into two 16 x 32 transforms -----------------------------------------------------------
+// The 1024-point FFT of the packed even extension splits by one decimation-in-frequency step,
+//     a_q = c_q + c_{q+512}  ->  C_{2k},        b_q = (c_q - c_{q+512}) W_1024^q  ->  C_{2k+1},      q, k < 512,
+// into two independent 512-point transforms (mif_fft512.cuh), one warp each: 16 warps per tile of 8 lines, one CTA per
+// SM.  Stage thread (l, b, h) forms the phase-A inputs of half h of line l (the pairs (c_q, c_{q+512}), q = b + 32 s, are
+// read by both halves); warp (h, line) runs phase B and the unpack of its half: E_{2k} / E_{2k+1} with partners inside
+// the warp (even half as for 513-point lines, odd half: C_{2k+1} pairs with C_{2(511-k)+1} in lane 31 - j).  In the
+// fused z sweep the two warps of a line gather the scaled spectrum as plain reals in the line's first region (64-thread
+// named barrier) and form the inputs of the second transform from there.
+struct Layout1024 {
+  static constexpr int M = 1024;
+  static constexpr int kThreads = 512;
+  static constexpr int kLoadBoxes = 2 * ((M / 2 + 1 + kBoxRows - 1) / kBoxRows);  // 8 boxes: 4 of even rows + 4 of odd rows, or 8 of natural rows
+  static constexpr int kOddRow0 = (kLoadBoxes / 2) * kBoxRows;
+  static constexpr int kStoreBoxes = (M + 1 + kStoreRows - 1) / kStoreRows;
+  static constexpr size_t kWorkBytes = (size_t)2 * kLines * fft512::kLinePitch * sizeof(double2);
+  static constexpr size_t kOutBytes = (size_t)kStoreBoxes * kStoreRows * 64;
+  static constexpr size_t kTwBytes = (size_t)fft512::kTwiddles * sizeof(double2);
+  static constexpr size_t kStageBytes = (size_t)kLoadBoxes * kBoxRows * 64;
+  static constexpr size_t kWorkArea = ((kWorkBytes > kOutBytes ? kWorkBytes : kOutBytes) + 127) / 128 * 128;
+  static constexpr size_t kSmem = 1024 + kWorkArea + (kTwBytes + 127) / 128 * 128 + kStageBytes + 64;
+  static_assert(kLoadBoxes * kBoxRows >= M + 1, "natural rows fit the stage");
+  static_assert(kSmem <= 227 * 1024, "one CTA per SM");
+};
+
+// 64-thread named barrier of the two warps of a line (immediate barrier numbers, see pair_sync in mif_poisson.cu).
+__device__ __forceinline__ void line_pair_sync(int line) {
+  switch (line) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    case 3: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    case 4: asm volatile("bar.sync 5, 64;" ::: "memory"); break;
+    case 5: asm volatile("bar.sync 6, 64;" ::: "memory"); break;
+    case 6: asm volatile("bar.sync 7, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 8, 64;" ::: "memory"); break;
+  }
+}
+
+// Phase-A input of half h from the pair (lo, hi) = (c_q, c_{q+512}); wq = W_1024^q.
+__device__ __forceinline__ double2 split_input(double2 lo, double2 hi, int h, double2 wq) {
+  return h ? fft512::cmul(fft512::csub(lo, hi), wq) : fft512::cadd(lo, hi);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(Layout1024::kThreads, 1)
+    tma_dct1024_kernel(const __grid_constant__ CUtensorMap map_in_a, const __grid_constant__ CUtensorMap map_in_b,
+                       const __grid_constant__ CUtensorMap map_out, const Job job) {
+  using Y = Layout1024;
+  constexpr int M = 1024, H = 512;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *smem = smem_raw + ((1024 - (tma::swizzle_address(smem_raw) & 1023)) & 1023);
+  double2 *W = reinterpret_cast<double2 *>(smem);                                   // region (h, line) at (8 h + line) * kLinePitch
+  unsigned char *O = smem;                                                          // output stage (aliases W)
+  double2 *T = reinterpret_cast<double2 *>(smem + Y::kWorkArea);                    // W_512^(n1 2^e)
+  double *S = reinterpret_cast<double *>(smem + Y::kWorkArea + (Y::kTwBytes + 127) / 128 * 128);  // input stage
+  uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(S) + Y::kStageBytes);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, j = tid & 31;
+  const int line = warp & 7, half = warp >> 3;             // transform mapping: warp = (half, line), lane j = k2 + 16 p
+  const int l = tid & 7, b = (tid >> 3) & 31, h = tid >> 8;  // stage mapping: line fastest, b = n1, h = half (warp uniform)
+  double2 *Sline = W + (8 * half + line) * fft512::kLinePitch;
+  double *Rl = reinterpret_cast<double *>(W + line * fft512::kLinePitch);  // the line's 1025 reals (first region of the pair)
+  const int n_tiles = job.n_xtiles * job.n_outer;
+
+  auto issue_load = [&](int tile) {
+    const Tile nt = decode_tile(job, tile);
+    tma::mbar_arrive_expect_tx(full, (unsigned)Y::kStageBytes);
+    if (MODE == 1) {
 #pragma unroll
-      for (int c = 0; c < Y::kStoreBoxes; c++) tma::store_3d(&map_out, O + c * kStoreRows * 64, x0, c * kStoreRows, outer);
-      tma::commit_group();
+      for (int i = 0; i < Y::kLoadBoxes; i++) tma::load_3d(S + i * kBoxRows * 8, &map_in_a, full, nt.x_in, i * kBoxRows, nt.c2);
+    } else {
+#pragma unroll
+      for (int i = 0; i < Y::kLoadBoxes / 2; i++) {
+        tma::load_3d(S + i * kBoxRows * 8, &map_in_a, full, nt.x_in, i * kBoxRows, nt.c2);
+        tma::load_3d(S + (Y::kOddRow0 + i * kBoxRows) * 8, &map_in_b, full, nt.x_in, i * kBoxRows, nt.c2);
+      }
     }
+  };
+  // conj Z_k and conj Z_{k+512} of a real spectrum E given as a function, combined to the input of half hh; cs[k] =
+  // (cos, sin)(pi k / 1024) comes as cs[n1] rotated by pi s / 32, and cs[k + 512] is cs[k] rotated by pi / 2
+  auto inverse_input = [&](auto E, int n1, int s, int hh, double2 cs_n1, double2 w_n1) {
+    const int k = n1 + 32 * s;
+    const double2 rt = fft512::rot32x(s);
+    const double c = cs_n1.x * rt.x - cs_n1.y * rt.y, sn = cs_n1.x * rt.y + cs_n1.y * rt.x;
+    const double2 lo = fft512::pack_input(E(k), E(M - k), c, sn);
+    const double2 hi = fft512::pack_input(E(k + H), E(H - k), -sn, c);
+    return split_input(lo, hi, hh, fft512::cmul(w_n1, fft512::w32(s)));
+  };
+
+  if (tid == 0) {
+    tma::prefetch_map(&map_in_a);
+    tma::prefetch_map(&map_in_b);
+    tma::prefetch_map(&map_out);
+    tma::mbar_init(full, 1);
+    tma::fence_barrier_init();
+    tma::fence_proxy_async();
+  }
+  fft512::load_twiddles<Y::kThreads, 2>(T, job.tw);
+  __syncthreads();
+  int tile = blockIdx.x;
+  if (tid == 0 && tile < n_tiles) issue_load(tile);
+  unsigned parity = 0;
+
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const Tile t = decode_tile(job, tile);
+    const int xt = t.xt, outer = t.outer, col = line ^ t.perm;  // col: this line's x offset inside the tile
+    double2 v[16];
+
+    // ---- phase A by the stage threads: inputs of half h of line l -------------------------------------------------------
+    tma::mbar_wait(full, parity);
+    parity ^= 1;
+    {
+      const double2 wb = __ldg(&job.tw[b]);  // W_1024^b;  W_1024^(b + 32 s) = W_1024^b W_32^s
+      if (MODE == 1) {
+        const double *N = S + l;  // natural rows: element e of line l at N[8 e]
+        const double2 cs_b = __ldg(&job.cs[b]);
+#pragma unroll
+        for (int s = 0; s < 16; s++) v[s] = inverse_input([&](int e) { return N[8 * e]; }, b, s, h, cs_b, wb);
+      } else {
+        const double *Ev = S + l, *Od = S + Y::kOddRow0 * 8 + l;  // e(2q) at Ev[8 q], e(2q+1) at Od[8 q]
+#pragma unroll
+        for (int s = 0; s < 16; s++) {
+          const int q = b + 32 * s;
+          const double2 lo = make_double2(Ev[8 * q], Od[8 * q]);                    // c_q
+          const double2 hi = make_double2(Ev[8 * (H - q)], Od[8 * (H - q - 1)]);    // c_{q+512} = (e(2M-2q-1024), e(2M-2q-1025))
+          v[s] = split_input(lo, hi, h, fft512::cmul(wb, fft512::w32(s)));
+        }
+      }
+    }
+    fft512::phase_a(v, b, T);
+    if (tid == 0) tma::wait_stores_read();  // the previous tile's output stage (in W) has been read out
+    __syncthreads();                        // the stage has been consumed, W is free
+    if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue_load(tile + gridDim.x);
+    fft512::store_a(W + (8 * h + l) * fft512::kLinePitch, b, v);
+    __syncthreads();
+
+    // ---- phase B by warp (half, line) ----------------------------------------------------------------------------------
+    fft512::phase_b(Sline, j, v);
+    double spec[16], e_last = 0.0;  // spec[r] = E_(2 k + half), k = k_of(j, r)
+    if (MODE != 1) {
+      if (half) fft512::unpack_dct<2>(v, j, job.cs, spec, e_last);
+      else fft512::unpack_dct<1>(v, j, job.cs, spec, e_last);
+    }
+    if (MODE == 2) {
+      // pressure_hat *= 1 / (lambda_x + lambda_y + lambda_z); mode (0,0,0) := 0 (src/PressureEquation.cpp:158-163)
+      const int ix = min(xt * kLines + col, job.n_lines - 1);
+      const double lam_xy = job.lam_x[ix] + job.lam_y[outer];
+      const bool origin_line = job.has_origin && (xt * kLines + col == 0) && (outer == 0);
+#pragma unroll
+      for (int r = 0; r < 16; r++) {
+        const int k = 2 * fft512::k_of(j, r) + half;
+        spec[r] *= (origin_line && k == 0) ? 0.0 : 1.0 / (lam_xy + job.lam_z[k]);
+      }
+      e_last *= 1.0 / (lam_xy + job.lam_z[M]);
+      line_pair_sync(line);  // both warps of the line are done with their regions
+#pragma unroll
+      for (int r = 0; r < 16; r++) Rl[2 * fft512::k_of(j, r) + half] = spec[r];
+      if (half == 0 && j == 0) Rl[M] = e_last;
+      line_pair_sync(line);
+      {
+        const double2 wj = __ldg(&job.tw[j]), cs_j = __ldg(&job.cs[j]);
+#pragma unroll
+        for (int s = 0; s < 16; s++) v[s] = inverse_input([&](int e) { return Rl[e]; }, j, s, half, cs_j, wj);
+      }
+      fft512::phase_a(v, j, T);
+      line_pair_sync(line);  // the whole line has been read before the regions (which alias it) are overwritten
+      fft512::store_a(Sline, j, v);
+      __syncwarp();
+      fft512::phase_b(Sline, j, v);
+    }
+    __syncthreads();  // all warps are done with the work area: it becomes the output stage
+
+    // ---- results into the swizzled output stage: row e of the tile at 64 e, column col ----------------------------------
+    // (all rows of one warp have the parity of its half, i.e. sit in the same half of their 128-byte lines: 4 bank
+    // positions per store instruction instead of the 8 of the 513-point kernels)
+    const int k2 = j & 15, p = j >> 4;
+    if (MODE == 0) {
+      // register r holds E_e, e = 2 (k2 + 128 p + 16 (r & 7) + 256 (r >> 3)) + half
+      const unsigned off = tma::swizzle_offset((unsigned)((2 * (k2 + 128 * p) + half) * 64 + col * 8), job.swz);
+#pragma unroll
+      for (int r = 0; r < 16; r++)
+        *reinterpret_cast<double *>(O + off + (32 * (r & 7) + 512 * (r >> 3)) * 64) = spec[r];
+      if (half == 0 && j == 0) *reinterpret_cast<double *>(O + tma::swizzle_offset((unsigned)(M * 64 + col * 8), job.swz)) = e_last;
+    } else {
+      // register r < 8 holds z_q = conj(v[r]), q = 2 (k2 + 128 p + 16 r) + half: x(2q) = Re z_q, x(2q+1) = Im z_q; q = 512
+      // is register 8 of lane 0 of the even half
+      const unsigned off = tma::swizzle_offset((unsigned)((2 * (k2 + 128 * p) + half) * 128 + col * 8), job.swz);
+      const bool odd_first = (k2 >> 1) & 1;
+      const unsigned first = off + (odd_first ? 64u : 0u), second = first ^ 64u;
+      const double scale = job.inv_norm;
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        const double even = v[r].x * scale, odd = -v[r].y * scale;
+        *reinterpret_cast<double *>(O + first + r * 32 * 128) = odd_first ? odd : even;
+        *reinterpret_cast<double *>(O + second + r * 32 * 128) = odd_first ? even : odd;
+      }
+      if (half == 0 && j == 0) *reinterpret_cast<double *>(O + tma::swizzle_offset((unsigned)(M * 64 + col * 8), job.swz)) = v[8].x * scale;
+    }
+    tma::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) store_tile<Y::kStoreBoxes>(job, &map_out, O, t);
   }
   if (tid == 0) tma::wait_stores_done();
 }
@@ -434,6 +684,7 @@ struct Cache {
   int device = -1, sms = 0;
   bool attr[2][3] = {};
   bool attr512[3] = {};
+  bool attr1024[3] = {};
 };
 
 // kind: 0 plain output map, 1 swizzled output map
@@ -480,6 +731,18 @@ void launch_512(cudaStream_t stream, Cache &cache, const MapSet &maps, const Job
   const int n_tiles = job.n_xtiles * job.n_outer;
   const int grid = std::min(n_tiles, std::max(1, cache.sms * per_sm));
   tma_dct512_kernel<MODE><<<grid, kThreads, Y::kSmem, stream>>>(MODE == 1 ? maps.natural : maps.even, maps.odd, maps.out, job);
+}
+
+template <int MODE>
+void launch_1024(cudaStream_t stream, Cache &cache, const MapSet &maps, const Job &job) {
+  using Y = Layout1024;
+  if (!cache.attr1024[MODE]) {
+    cudaFuncSetAttribute(tma_dct1024_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Y::kSmem);
+    cache.attr1024[MODE] = true;
+  }
+  const int n_tiles = job.n_xtiles * job.n_outer;
+  const int grid = std::min(n_tiles, std::max(1, cache.sms));
+  tma_dct1024_kernel<MODE><<<grid, Y::kThreads, Y::kSmem, stream>>>(MODE == 1 ? maps.natural : maps.even, maps.odd, maps.out, job);
 }
 
 }  // namespace tmasweep

@@ -29,6 +29,7 @@ struct alignas(64) CUtensorMap {  // emulated descriptor: rank 3, FP64
 namespace emu {
 void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2);
 void tma_store_3d(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2);
+void tma_store_bulk(void *global_dst, const void *smem_src, unsigned bytes);
 void tma_commit_group();
 void tma_wait_group(int pending_allowed, bool read_only);
 void mbar_init(uint64_t *bar, int count);
@@ -83,6 +84,13 @@ __device__ __forceinline__ void store_3d(const CUtensorMap *map, const void *sme
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// shared -> global copy of a contiguous run of bytes (multiple of 16, both ends 16-byte aligned); the destination may be
+// memory of a peer GPU mapped into this process (NVLink).  Joins the current bulk group.
+__device__ __forceinline__ void store_bulk(void *global_dst, const void *smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(global_dst)),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ void commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // Wait until the bulk stores of this thread have finished READING shared memory (the source may be overwritten).
 __device__ __forceinline__ void wait_stores_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -107,6 +115,9 @@ __device__ __forceinline__ void load_3d(void *smem_dst, const CUtensorMap *map, 
 }
 __device__ __forceinline__ void store_3d(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2) {
   emu::tma_store_3d(map, smem_src, c0, c1, c2);
+}
+__device__ __forceinline__ void store_bulk(void *global_dst, const void *smem_src, unsigned bytes) {
+  emu::tma_store_bulk(global_dst, smem_src, bytes);
 }
 __device__ __forceinline__ void commit_group() { emu::tma_commit_group(); }
 __device__ __forceinline__ void wait_stores_read() { emu::tma_wait_group(0, true); }

@@ -179,7 +179,7 @@ void *dynamic_smem() {
 // waits for the group (or flagged as an error when the block ends with stores still pending).
 namespace {
 struct PendingLoad { void *dst; CUtensorMap map; int c[3]; uint64_t *bar; };
-struct PendingStore { CUtensorMap map; const void *src; int c[3]; int thread; };
+struct PendingStore { CUtensorMap map; const void *src; int c[3]; int thread; void *bulk_dst; unsigned bulk_bytes; };
 struct BarState { uint64_t *bar; int count, pending, phase; long tx; };
 std::vector<PendingLoad> g_loads;
 std::vector<PendingStore> g_stores;
@@ -262,13 +262,23 @@ void tma_store_3d(const CUtensorMap *map, const void *smem_src, int c0, int c1, 
     std::fprintf(stderr, "simt_emu: swizzled box not 1024-byte aligned\n");
     abort();
   }
-  g_stores.push_back(PendingStore{*map, smem_src, {c0, c1, c2}, g_current});
+  g_stores.push_back(PendingStore{*map, smem_src, {c0, c1, c2}, g_current, nullptr, 0});
+}
+void tma_store_bulk(void *global_dst, const void *smem_src, unsigned bytes) {
+  const unsigned char *lo = g_dynamic_smem.data(), *hi = lo + g_dynamic_smem.size();
+  const unsigned char *q = static_cast<const unsigned char *>(smem_src);
+  if (q < lo || q + bytes > hi || (reinterpret_cast<uintptr_t>(smem_src) & 15) || (reinterpret_cast<uintptr_t>(global_dst) & 15) || (bytes & 15)) {
+    std::fprintf(stderr, "simt_emu: bulk store: misaligned or outside the dynamic shared-memory window\n");
+    abort();
+  }
+  g_stores.push_back(PendingStore{CUtensorMap{}, smem_src, {0, 0, 0}, g_current, global_dst, bytes});
 }
 void tma_commit_group() {}
 void tma_wait_group(int, bool) {
   for (size_t i = 0; i < g_stores.size(); i++)
     if (g_stores[i].thread == g_current) {
-      copy_box(g_stores[i].map, const_cast<char *>(static_cast<const char *>(g_stores[i].src)), g_stores[i].c, false);
+      if (g_stores[i].bulk_dst) memcpy(g_stores[i].bulk_dst, g_stores[i].src, g_stores[i].bulk_bytes);
+      else copy_box(g_stores[i].map, const_cast<char *>(static_cast<const char *>(g_stores[i].src)), g_stores[i].c, false);
       g_stores.erase(g_stores.begin() + i--);
     }
 }
