@@ -1282,6 +1282,82 @@ __global__ void __launch_bounds__(64 * LINES, 8 / LINES) warp_dct_split_kernel(c
   }
 }
 
+// x sweeps of 1025-point lines: the radix-2 split of mif_poisson_tma.cuh (tma_dct1024_kernel) with the inputs straight
+// from global memory -- two warps per line (even / odd half of the 1024-point transform), 4 lines per CTA.  Both warps read
+// the whole line and each writes its half of the results, so a 64-thread barrier separates a line's loads from its stores.
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) x_dct1024_kernel(const FastJob job, double *__restrict__ field) {
+  constexpr int M = 1024, H = 512, kLinesX = 4;
+  extern __shared__ double2 smem2[];
+  double2 *T = smem2 + 2 * kLinesX * fft512::kLinePitch;
+  const int tid = threadIdx.x, warp = tid >> 5, L = tid & 31;
+  const int line = warp >> 1, half = warp & 1;
+  double2 *Sline = smem2 + warp * fft512::kLinePitch;
+  const int first_line = blockIdx.x * kLinesX;
+  const int lines = min(kLinesX, job.n_tile_lines - first_line);
+  fft512::load_twiddles<256, 2>(T, job.tw);
+  __syncthreads();
+  if (line >= lines) return;  // both warps of a line leave together; nothing below synchronises across lines
+  double *row = field + job.origin + (long long)first_line * job.tile_stride + (long long)blockIdx.y * job.outer_stride +
+                (long long)line * job.lstride;
+  const double2 wL = __ldg(&job.tw[L]);  // W_1024^L;  W_1024^(L + 32 s) = W_1024^L W_32^s
+  double2 v[16];
+  if (MODE == 0) {
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+      const int q = L + 32 * s;
+      const double2 lo = *reinterpret_cast<const double2 *>(row + 2 * q);          // c_q = (e(2q), e(2q+1))
+      const double2 hi = make_double2(row[M - 2 * q], row[M - 2 * q - 1]);         // c_{q+512}: mirror image
+      v[s] = tmasweep::split_input(lo, hi, half, fft512::cmul(wL, fft512::w32(s)));
+    }
+  } else {
+    const double2 cs_L = __ldg(&job.cs[L]);
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+      const int k = L + 32 * s;
+      const double2 rt = fft512::rot32x(s);  // cs[k] = cs[L] rotated by pi s / 32, cs[k + 512] = cs[k] rotated by pi / 2
+      const double c = cs_L.x * rt.x - cs_L.y * rt.y, sn = cs_L.x * rt.y + cs_L.y * rt.x;
+      const double2 lo = fft512::pack_input(row[k], row[M - k], c, sn);
+      const double2 hi = fft512::pack_input(row[k + H], row[H - k], -sn, c);
+      v[s] = tmasweep::split_input(lo, hi, half, fft512::cmul(wL, fft512::w32(s)));
+    }
+  }
+  fft512::phase_a(v, L, T);
+  fft512::store_a(Sline, L, v);
+  __syncwarp();
+  fft512::phase_b(Sline, L, v);
+  if (MODE == 0) {
+    double spec[16], e_last;
+    if (half) fft512::unpack_dct<2>(v, L, job.cs, spec, e_last);
+    else fft512::unpack_dct<1>(v, L, job.cs, spec, e_last);
+    split::pair_sync(line);  // both warps have read the line
+#pragma unroll
+    for (int r = 0; r < 16; r++) row[2 * fft512::k_of(L, r) + half] = spec[r];
+    if (half == 0 && L == 0) row[M] = e_last;
+  } else {
+    // register r < 8 holds z_q = conj(v[r]), q = 2 (k2 + 128 p + 16 r) + half: x(2q) = Re z_q, x(2q+1) = Im z_q
+    const double scale = job.inv_norm;
+    const int q0 = 2 * ((L & 15) + 128 * (L >> 4)) + half;
+    split::pair_sync(line);
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+      *reinterpret_cast<double2 *>(row + 2 * (q0 + 32 * r)) = make_double2(v[r].x * scale, -v[r].y * scale);
+    if (half == 0 && L == 0) row[M] = v[8].x * scale;  // q = M/2
+  }
+}
+
+void launch_x1024(cudaStream_t stream, const FastJob &job, int mode, int outer, double *field, bool *attr_set) {
+  const size_t smem = (size_t)(8 * fft512::kLinePitch + fft512::kTwiddles) * sizeof(double2);
+  if (!*attr_set) {
+    cudaFuncSetAttribute(x_dct1024_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(x_dct1024_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    *attr_set = true;
+  }
+  const dim3 grid((job.n_tile_lines + 3) / 4, outer, 1);
+  if (mode == 0) x_dct1024_kernel<0><<<grid, 256, smem, stream>>>(job, field);
+  else x_dct1024_kernel<1><<<grid, 256, smem, stream>>>(job, field);
+}
+
 template <int LINES>
 void launch_split(cudaStream_t stream, const FastJob &job, bool contig, int outer, double *field) {
   static bool attr_set = false;
@@ -1419,7 +1495,7 @@ struct PoissonPlan {
   size_t smem[3];
   std::vector<void *> allocations;
   tmasweep::Cache tma;  // tensor maps of the TMA-staged strided sweeps, per field / direction
-  bool x512_attr = false;
+  bool x512_attr = false, x1024_attr = false;
 };
 
 PoissonPlan *poisson_plan_create(const Geom &g, const int n_points[3], const int periodic[3], const double h[3],
@@ -1577,8 +1653,8 @@ bool launch_tma_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int
   static const bool radix8_fft = getenv("MIFGPU_FFT_RADIX8") != nullptr;  // A/B: 513-point lines on the radix-8 Stockham passes
   static const int promo = getenv("MIFGPU_TMA_L2PROMO") ? atoi(getenv("MIFGPU_TMA_L2PROMO")) : 2;
   const int x_off = (int)(lay.origin & 1);
-  const tmasweep::MapSet *maps = tmasweep::maps_for(cache, field + lay.origin - x_off, x_off, lay.n_tile_lines, plan->dir[d].n,
-                                                    lay.outer, lay.estride, lay.outer_stride, swizzle, promo);
+  const tmasweep::TensorDesc where{field + lay.origin - x_off, x_off + lay.n_tile_lines, lay.estride, lay.outer_stride, lay.outer};
+  const tmasweep::MapSet *maps = tmasweep::maps_for(cache, where, where, plan->dir[d].n, swizzle, promo);
   if (!maps) return refuse("tensor map");
   tmasweep::Job job;
   job.n_xtiles = (lay.n_tile_lines + warpfft::kLines - 1) / warpfft::kLines;
@@ -1683,7 +1759,10 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
         break;
       default: {
         static const bool use_two_warp_variant = getenv("MIFGPU_FFT_NO_SPLIT") != nullptr;  // A/B switch for profiling
+        static const bool radix8_fft = getenv("MIFGPU_FFT_RADIX8") != nullptr;  // A/B: the radix-8 Stockham passes
+        const bool aligned = ((lay.origin | lay.lstride | lay.tile_stride | lay.outer_stride) & 1) == 0;
         if (use_cta_sync_variant) launch_fast<10>(stream, fj, lay.contig, fgrid, field);
+        else if (lay.contig && !radix8_fft && aligned && mode != 2) launch_x1024(stream, fj, mode, lay.outer, field, &plan->x1024_attr);
         else if (use_two_warp_variant) launch_warp<10>(stream, fj, lay.contig, fgrid, field);
         else {
           static const int lines_contig = getenv("MIFGPU_SPLIT_LINES_X") ? atoi(getenv("MIFGPU_SPLIT_LINES_X")) : 4;
@@ -1759,11 +1838,24 @@ bool poisson_peer_capable(const PoissonPlan *plan) {
 
 // Blocked buffer layouts of the peer path (nxt = PX / 8 x tiles; all extents in doubles):
 //   zbuf[r]  z pencil of rank r:          [z (all N_z)][x tile][y in r's range][8]
-//   xfer[r]  slab staging of rank r:      blocks per source rank s (its y range), each [x tile][y in s's range][z in r's slab][8]
+//   xfer[r]  slab staging of rank r:      [x tile][y (all N_y)][z in r's slab][8]
+// A tile of the forward y sweep (8 x, all y, one z) is then one contiguous run per owning rank in zbuf[r], a tile of the
+// fused z sweep (8 x, one y, all z) one contiguous run per owning rank in xfer[r], and the inverse y sweep reads its own
+// xfer with one row stride for all y.
 static void fill_map(SegMap &m, const PeerLayout &p, int which, const Geom &g) {
   const int me = p.rank, P = p.nranks;
   const long long nxt = g.PX / 8;
-  const long long nz_me = p.zlo[me + 1] - p.zlo[me], ny_me = p.ylo[me + 1] - p.ylo[me];
+  const long long nz_me = p.zlo[me + 1] - p.zlo[me], ny_all = p.ylo[P];
+  if (which == 2) {  // inverse y sweep <- own slab staging: one segment
+    m.n = 1;
+    m.lo[0] = 0;
+    m.lo[1] = p.ylo[P];
+    m.base[0] = p.xfer[me];
+    m.xtile_stride[0] = ny_all * nz_me * 8;
+    m.estride[0] = nz_me * 8;
+    m.outer_stride[0] = 8;
+    return;
+  }
   m.n = P;
   for (int r = 0; r < P; r++) {
     const long long ny_r = p.ylo[r + 1] - p.ylo[r], nz_r = p.zlo[r + 1] - p.zlo[r];
@@ -1773,25 +1865,115 @@ static void fill_map(SegMap &m, const PeerLayout &p, int which, const Geom &g) {
       m.estride[r] = 8;
       m.outer_stride[r] = nxt * ny_r * 8;
       m.base[r] = p.zbuf[r] + (long long)p.zlo[me] * m.outer_stride[r];
-    } else if (which == 1) {  // fused z sweep -> slab staging of the owners: segments are z ranges, outer is local y
+    } else {                  // fused z sweep -> slab staging of the owners: segments are z ranges, outer is local y
       m.lo[r] = p.zlo[r];
-      m.xtile_stride[r] = ny_me * nz_r * 8;
+      m.xtile_stride[r] = ny_all * nz_r * 8;
       m.outer_stride[r] = nz_r * 8;
       m.estride[r] = 8;
-      m.base[r] = p.xfer[r] + nz_r * g.PX * p.ylo[me];
-    } else {                  // inverse y sweep <- own slab staging: segments are the y ranges of the sources
-      m.lo[r] = p.ylo[r];
-      m.xtile_stride[r] = ny_r * nz_me * 8;
-      m.estride[r] = nz_me * 8;
-      m.outer_stride[r] = 8;
-      m.base[r] = p.xfer[me] + nz_me * g.PX * p.ylo[r];
+      m.base[r] = p.xfer[r] + (long long)p.ylo[me] * nz_r * 8;
     }
   }
   m.lo[P] = (which == 1) ? p.zlo[P] : p.ylo[P];
 }
 
+// The three sweeps of the peer path on the TMA kernels (257-, 513- or 1025-point lines along y and z): the forward y sweep
+// reads the slab and leaves its tiles as bulk copies in the z pencils of the owners, the fused z sweep reads its pencil
+// (tiles = (x tile, local y), rows along z) and leaves its tiles in the slab staging of the owners, the inverse y sweep
+// reads its staging buffer (tiles = (x tile, local z), rows along y) and stores into the field.  The output stage is
+// copied as it is, i.e. swizzled: the consumer un-permutes the column pairs (Job::in_perm_base).
+static bool launch_tma_peer(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *field, const PeerLayout &peer, int which) {
+  static const bool disabled = getenv("MIFGPU_NO_TMA") != nullptr || getenv("MIFGPU_NO_TMA_PEER") != nullptr;
+  const int logm_y = plan->fast_logm[1], logm_z = plan->fast_logm[2];
+  if (disabled || logm_y < 8 || logm_y > 10 || logm_z < 8 || logm_z > 10) return false;
+  tmasweep::Cache &cache = plan->tma;
+  if (cache.device < 0) {
+    cudaGetDevice(&cache.device);
+    cudaDeviceGetAttribute(&cache.sms, cudaDevAttrMultiProcessorCount, cache.device);
+  }
+  static const bool swizzle = getenv("MIFGPU_TMA_NO_SWIZZLE") == nullptr;
+  static const int promo = getenv("MIFGPU_TMA_L2PROMO") ? atoi(getenv("MIFGPU_TMA_L2PROMO")) : 2;
+  const int me = peer.rank, P = peer.nranks;
+  const int nx = g.own_hi[0] - g.own_lo[0], nz_me = g.own_hi[2] - g.own_lo[2];
+  const long long nxt = g.PX / 8, ny_all = peer.ylo[P], nz_all = peer.zlo[P], ny_me = peer.ylo[me + 1] - peer.ylo[me];
+  const long long origin = gidx(g, g.own_lo[0], g.own_lo[1], g.own_lo[2]);
+  const int x_off = (int)(origin & 1);
+  if (ny_me <= 0 || nz_me <= 0) return false;
+  const tmasweep::TensorDesc slab{field + origin - x_off, x_off + nx, g.PX, g.plane, nz_me};
+  tmasweep::Job job;
+  job.n_xtiles = (nx + warpfft::kLines - 1) / warpfft::kLines;
+  job.n_lines = nx;
+  job.x_off = x_off;
+  job.lam_x = plan->dir[0].lambda;
+  job.lam_y = plan->dir[1].lambda;
+  job.lam_z = plan->dir[2].lambda;
+  job.has_origin = 0;
+  job.swz = swizzle ? 3u : 0u;
+  job.out.n = 0;
+  const int d = (which == 1) ? 2 : 1;
+  job.tw = plan->dir[d].tw_full;
+  job.cs = plan->dir[d].unpack;
+  job.inv_norm = plan->dir[d].inv_norm;
+  const tmasweep::MapSet *maps = nullptr;
+  int mode;
+  if (which == 0) {
+    maps = tmasweep::maps_for(cache, slab, slab, plan->dir[1].n, swizzle, promo);
+    job.n_outer = nz_me;
+    job.outer_fastest = 0; job.in_x_tiled = 1; job.in_c2_mult = 0; job.in_perm_base = -1;
+    job.out.n = P;
+    for (int r = 0; r < P; r++) {
+      const long long ny_r = peer.ylo[r + 1] - peer.ylo[r];
+      job.out.lo[r] = peer.ylo[r];
+      job.out.xtile_stride[r] = ny_r * 8;
+      job.out.outer_stride[r] = nxt * ny_r * 8;
+      job.out.base[r] = peer.zbuf[r] + (long long)peer.zlo[me] * job.out.outer_stride[r];
+    }
+    job.out.lo[P] = peer.ylo[P];
+    mode = 0;
+  } else if (which == 1) {
+    // zbuf[me][z][x tile][y local][8]: coordinate 2 = x tile * ny_me + local y
+    const tmasweep::TensorDesc pencil{peer.zbuf[me], 8, nxt * ny_me * 8, 8, nxt * ny_me};
+    maps = tmasweep::maps_for(cache, pencil, slab, plan->dir[2].n, swizzle, promo);
+    job.n_outer = (int)ny_me;
+    job.outer_fastest = 1; job.in_x_tiled = 0; job.in_c2_mult = ny_me; job.in_perm_base = peer.ylo[me];
+    job.lam_y = plan->dir[1].lambda + peer.ylo[me];
+    job.has_origin = peer.ylo[me] == 0;
+    job.out.n = P;
+    for (int r = 0; r < P; r++) {
+      const long long nz_r = peer.zlo[r + 1] - peer.zlo[r];
+      job.out.lo[r] = peer.zlo[r];
+      job.out.xtile_stride[r] = ny_all * nz_r * 8;
+      job.out.outer_stride[r] = nz_r * 8;
+      job.out.base[r] = peer.xfer[r] + (long long)peer.ylo[me] * nz_r * 8;
+    }
+    job.out.lo[P] = peer.zlo[P];
+    mode = 2;
+  } else {
+    // xfer[me][x tile][y][z local][8]: coordinate 2 = x tile * (N_y * nz_me) + local z
+    const tmasweep::TensorDesc staging{peer.xfer[me], 8, (long long)nz_me * 8, 8, (long long)(job.n_xtiles - 1) * ny_all * nz_me + nz_me};
+    maps = tmasweep::maps_for(cache, staging, slab, plan->dir[1].n, swizzle, promo);
+    job.n_outer = nz_me;
+    job.outer_fastest = 1; job.in_x_tiled = 0; job.in_c2_mult = ny_all * nz_me; job.in_perm_base = peer.zlo[me];
+    mode = 1;
+  }
+  (void)nz_all;
+  if (!maps) {
+    if (getenv("MIFGPU_REQUIRE_TMA")) {
+      fprintf(stderr, "libmifgpu: MIFGPU_REQUIRE_TMA=1 but peer sweep %d cannot use TMA\n", which);
+      abort();
+    }
+    return false;
+  }
+  if (getenv("MIFGPU_TMA_VERBOSE")) fprintf(stderr, "libmifgpu: rank %d peer sweep %d on the TMA path (%d-point lines)\n", me, which, plan->dir[d].n);
+  launch_tma_modes(stream, cache, *maps, job, which == 1 ? logm_z : logm_y, mode);
+  return true;
+}
+
 void launch_poisson_sweep_peer(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *field, const PeerLayout &peer,
                                int which, uint64_t *launches) {
+  if (launch_tma_peer(stream, g, plan, field, peer, which)) {
+    ++*launches;
+    return;
+  }
   const int me = peer.rank;
   const int nx = g.own_hi[0] - g.own_lo[0], nz = g.own_hi[2] - g.own_lo[2];
   SweepLayout lay;

@@ -665,14 +665,20 @@ __global__ void __launch_bounds__(Layout1024::kThreads, 1)
 }
 
 // ---- host -----------------------------------------------------------------------------------------------------
-struct MapKey {
-  const void *base;
+// Where the tiles of a sweep live: element (x, row, c2) at base + x + row * estride + c2 * outer_stride (doubles).
+struct TensorDesc {
+  const double *base;
+  int dim0;                    // valid x columns (coordinate 0 beyond it: zero fill on load, clipped on store)
   long long estride, outer_stride;
-  int nx, n, outer, x_off, kind, promo;
-  bool operator<(const MapKey &o) const {
-    return std::tie(base, estride, outer_stride, nx, n, outer, x_off, kind, promo) <
-           std::tie(o.base, o.estride, o.outer_stride, o.nx, o.n, o.outer, o.x_off, o.kind, o.promo);
+  long long outer_extent;      // extent of coordinate 2
+  bool operator<(const TensorDesc &o) const {
+    return std::tie(base, dim0, estride, outer_stride, outer_extent) < std::tie(o.base, o.dim0, o.estride, o.outer_stride, o.outer_extent);
   }
+};
+struct MapKey {
+  TensorDesc in, out;
+  int n, kind, promo;
+  bool operator<(const MapKey &o) const { return std::tie(in, out, n, kind, promo) < std::tie(o.in, o.out, o.n, o.kind, o.promo); }
 };
 struct MapSet {
   CUtensorMap even, odd, natural, out;
@@ -687,20 +693,21 @@ struct Cache {
   bool attr1024[3] = {};
 };
 
-// kind: 0 plain output map, 1 swizzled output map
-inline const MapSet *maps_for(Cache &cache, double *base, int x_off, int nx, int n, int outer, long long estride,
-                              long long outer_stride, bool swizzle, int promo) {
-  const MapKey key{base, estride, outer_stride, nx, n, outer, x_off, swizzle ? 1 : 0, promo};
+// Tensor maps of one sweep: even rows / odd rows / natural rows of the input (boxes of 8 x kBoxRows), natural rows of the
+// output (boxes of 8 x kStoreRows, swizzled if the output stage is).  n = points per line.
+inline const MapSet *maps_for(Cache &cache, const TensorDesc &in, const TensorDesc &out, int n, bool swizzle, int promo) {
+  const MapKey key{in, out, n, swizzle ? 1 : 0, promo};
   auto it = cache.sets.find(key);
   if (it != cache.sets.end()) return it->second.ok ? &it->second : nullptr;
   MapSet set;
-  const uint64_t dim0 = (uint64_t)(x_off + nx), row = (uint64_t)estride * 8, outer_b = (uint64_t)outer_stride * 8;
+  const uint64_t row = (uint64_t)in.estride * 8, outer_b = (uint64_t)in.outer_stride * 8;
   const int half = (n - 1) / 2;
   const char *why = nullptr;
-  set.ok = tma::encode_map(&set.even, base, dim0, (uint64_t)half + 1, (uint64_t)outer, 2 * row, outer_b, kLines, kBoxRows, false, promo, &why) &&
-           tma::encode_map(&set.odd, base + estride, dim0, (uint64_t)half, (uint64_t)outer, 2 * row, outer_b, kLines, kBoxRows, false, promo, &why) &&
-           tma::encode_map(&set.natural, base, dim0, (uint64_t)n, (uint64_t)outer, row, outer_b, kLines, kBoxRows, false, promo, &why) &&
-           tma::encode_map(&set.out, base, dim0, (uint64_t)n, (uint64_t)outer, row, outer_b, kLines, kStoreRows, swizzle, 0, &why);
+  set.ok = tma::encode_map(&set.even, in.base, (uint64_t)in.dim0, (uint64_t)half + 1, (uint64_t)in.outer_extent, 2 * row, outer_b, kLines, kBoxRows, false, promo, &why) &&
+           tma::encode_map(&set.odd, in.base + in.estride, (uint64_t)in.dim0, (uint64_t)half, (uint64_t)in.outer_extent, 2 * row, outer_b, kLines, kBoxRows, false, promo, &why) &&
+           tma::encode_map(&set.natural, in.base, (uint64_t)in.dim0, (uint64_t)n, (uint64_t)in.outer_extent, row, outer_b, kLines, kBoxRows, false, promo, &why) &&
+           tma::encode_map(&set.out, out.base, (uint64_t)out.dim0, (uint64_t)n, (uint64_t)out.outer_extent, (uint64_t)out.estride * 8,
+                           (uint64_t)out.outer_stride * 8, kLines, kStoreRows, swizzle, 0, &why);
   if (!set.ok && getenv("MIFGPU_TMA_VERBOSE")) fprintf(stderr, "libmifgpu: no tensor map for this sweep: %s\n", why ? why : "?");
   auto ins = cache.sets.emplace(key, set);
   return set.ok ? &ins.first->second : nullptr;
