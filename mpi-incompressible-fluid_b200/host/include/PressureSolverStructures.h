@@ -7,6 +7,22 @@
 
 #include "Constants.h"
 
+// Sources written against the reference get <mpi.h>, <iostream>, <string> and `using namespace std` through this header
+// (include/PressureSolverStructures.h:9 pulls in deps/2Decomp_C/C2Decomp.hpp:4-14) and some rely on it
+// (test/pressure_test_mixed.cpp uses MPI_Init, std::cout and an unqualified chrono:: with none of them included).  The
+// build of the unchanged reference drivers (host/Makefile, bin/ref_*) defines MIF_REFERENCE_SOURCE_COMPAT to get the same
+// environment; the host layer's own code does not.
+#ifdef MIF_REFERENCE_SOURCE_COMPAT
+#include <mpi.h>  // host/compat/mpi.h
+#include <math.h>
+#include <memory.h>
+
+#include <cstdlib>
+#include <iostream>
+#include <string>
+using namespace ::std;
+#endif
+
 namespace mif {
 
 class PressureSolverStructures {

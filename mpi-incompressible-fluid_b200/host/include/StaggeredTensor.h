@@ -9,6 +9,9 @@
 
 #include "Constants.h"
 #include "Tensor.h"
+#ifdef MIF_REFERENCE_SOURCE_COMPAT
+#include <mpi.h>  // host/compat/mpi.h: the reference's StaggeredTensor.h:7 exposes MPI to its includers (test/velocity_test.cpp)
+#endif
 
 struct mifgpu_tensor;
 

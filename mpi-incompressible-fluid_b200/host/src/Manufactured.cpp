@@ -6,6 +6,11 @@
 #include "Manufactured.h"
 #include "ManufacturedPressure.h"
 
+// `Reynolds` is defined by the executables that use it (src/main.cpp:11, test/full_test.cpp:13); the reference's pressure
+// tests never define it because they link only the pressure artefact.  A weak definition here keeps those drivers
+// linkable against the single host library; any executable's own definition takes precedence.
+double Reynolds __attribute__((weak)) = 0.0;
+
 namespace {
 const double kA = M_PI / 4.0;  // Ethier-Steinman parameters a and d (generators/manufsol.py:31-32)
 const double kD = M_PI / 2.0;

@@ -95,3 +95,59 @@ def test_mif_driver_writes_the_reference_outputs(case, tmp_path):
         a, b = np.loadtxt(os.path.join(golden, name)), np.loadtxt(os.path.join(tmp_path, name))
         assert a.shape == b.shape
         assert np.allclose(a, b, rtol=1e-7, atol=1e-12), name
+
+
+# ---- the reference's own drivers, compiled unchanged against the host layer (host/Makefile: bin/ref_*) --------------------
+def ref_binary(name):
+    path = os.path.join(BIN, "ref_" + name)
+    if not os.path.exists(path):
+        pytest.skip("bin/ref_%s is built only where /root/reference is present (host/Makefile)" % name)
+    return "ref_" + name
+
+
+@pytest.mark.parametrize("n,steps", [(16, 1), (32, 2), (64, 4)])
+def test_unchanged_reference_full_test(n, steps, tmp_path):
+    """test/full_test.cpp of the reference, zero edits: host-side element access (pressure-gradient error through
+    VELOCITY_TENSOR_SET_FOR_ALL_POINTS), adjust_pressure, the nine norms, writeVTK / writeVTKFullMesh / writeDat."""
+    out = subprocess.run([os.path.join(BIN, ref_binary("full_test")), str(n), str(steps), "1"], cwd=tmp_path, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    got = [float(x) for l in out.stdout.splitlines() if l.strip() and not l.startswith("NCCL") for x in l.split()]
+    assert close(got, NORMS[f"full_test {n} {steps} 1"]), got
+    assert os.path.getsize(tmp_path / "solution.vtk") > 0 and os.path.getsize(tmp_path / "line1.dat") > 0
+
+
+@pytest.mark.parametrize("kind", ["hn", "mixed", "nhn"])
+@pytest.mark.parametrize("n", [8, 16, 32])
+def test_unchanged_reference_pressure_tests(kind, n):
+    out = run(ref_binary("pressure_test_" + kind), n, 1)
+    line = [l for l in out.splitlines() if l.startswith("Errors:")][0]
+    got = [float(x) for x in line.split()[1:]]
+    assert close(got, NORMS[f"pressure_test_{kind} {n} 1"]), got
+
+
+@pytest.mark.parametrize("mixed", [False, True])
+def test_unchanged_reference_velocity_tests(mixed):
+    name = "velocity_test_mixed" if mixed else "velocity_test"
+    got = [float(x) for x in run(ref_binary(name), 16, 1, 1).split()]
+    assert close(got, NORMS[f"{name} 16 1 1"]), got
+
+
+@pytest.mark.parametrize("case", ["mif_case1", "mif_case2"])
+def test_unchanged_reference_main_writes_the_reference_outputs(case, tmp_path):
+    """src/main.cpp of the reference, zero edits, on the reference's input-file format: profiles against the files the CPU
+    build of the same source wrote (tests/golden/mif_case*/)."""
+    import shutil
+
+    import numpy as np
+    golden = os.path.join(GOLDEN_DIR, case)
+    shutil.copy(os.path.join(golden, "input.txt"), tmp_path)
+    out = subprocess.run([os.path.join(BIN, ref_binary("mif")), "input.txt"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    profiles = [f for f in sorted(os.listdir(golden)) if f.startswith("profile")]
+    assert profiles and sorted(f for f in os.listdir(tmp_path) if f.startswith("profile")) == profiles
+    for name in profiles:
+        a, b = np.loadtxt(os.path.join(golden, name)), np.loadtxt(os.path.join(tmp_path, name))
+        assert a.shape == b.shape
+        assert np.allclose(a, b, rtol=1e-7, atol=1e-12), name
+    assert os.path.getsize(tmp_path / "solution.vtk") == os.path.getsize(os.path.join(golden, "solution.vtk"))
