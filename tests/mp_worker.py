@@ -30,6 +30,38 @@ def main():
     ids = [mif.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
 
+    if case.startswith("pz:"):
+        # Periodic z distributed over the ranks (neighbours wrap around, src/Constants.cpp:98-101): the pressure solve and the
+        # halo exchange that follows it (src/PressureTensor.cpp:30-33) against the oracle's single-rank solve, GHOST PLANES
+        # INCLUDED -- on two ranks both neighbours are the same peer and the two planes must not be swapped.
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import mif_oracle as mo
+        N = [int(v) for v in case[3:].split("x")]
+        periodic = (False, False, True)
+        grid = mo.Grid(N[0], N[1], N[2], 1.0, 1.0, 2.0, 0.0, 0.0, -1.0, 1e3, 1e-3, 4, periodic=periodic)
+        rng = np.random.default_rng(77)
+        host = [rng.uniform(-1, 1, grid.shape(c)) for c in range(3)]
+        want = grid.solve_pressure(*host, 0.37)  # single rank: planes 0 and -1 are the periodic ghosts
+        ctx = mif.Context(N[0], N[1], N[2], 1.0, 1.0, 2.0, 0.0, 0.0, -1.0, 1e3, 1e-3, 4, Py=1, Pz=world, rank=rank, periodic=periodic,
+                          device=local_rank, comm_id=ids[0])
+        first = mif.slab_plan(N[2] - 1, world)  # owner planes of the N_z - 1 periodic points
+        klo, khi = first[rank], first[rank + 1] + 2  # one ghost plane on each side, in the single-rank array's numbering
+        vel = ctx.velocity()
+        for c, (t, h) in enumerate(zip(vel, host)):
+            extra = 1 if (c == 2 and rank == world - 1) else 0  # the z-staggered component has one more plane on the last rank
+            assert t.shape == h[klo:khi + extra].shape[::-1], (c, t.shape, h[klo:khi].shape)
+            t.upload(np.ascontiguousarray(h[klo:khi + extra]))
+        p = ctx.tensor(mif.STAGGER_NONE)
+        ctx.solve_pressure(p, vel, 0.37)
+        got = p.download()
+        worst = float(np.max(np.abs(got - want[klo:khi]))) / float(np.max(np.abs(want)))
+        errs = [None] * world
+        dist.all_gather_object(errs, worst)
+        ctx.close()
+        if rank == 0:
+            print(json.dumps({"case": case, "world": world, "Py": 1, "Pz": world, "max_rel_err": max(errs)}))
+        dist.destroy_process_group()
+        return 0 if max(errs) <= 1e-11 else 1
     if case.startswith("es:"):
         # No golden file: the oracle (oracle/mif_oracle.c, pinned to the reference) computes the single-rank result
         # of one Ethier-Steinman step on the given grid; used for grids large enough to take the peer-memory path.

@@ -43,3 +43,17 @@ def test_peer_memory_and_nccl_transposes_agree(no_peer):
            "--master-port", "29533", os.path.join(ROOT, "tests", "mp_worker.py"), "es:9x257x257"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_periodic_z_distributed_over_the_ranks(world):
+    """Periodic z split over the ranks (src/Constants.cpp:98-101): the solve and its halo exchange against the oracle's
+    single-rank solve, ghost planes included (two ranks: both neighbours are the same peer)."""
+    if device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29540 + world), os.path.join(ROOT, "tests", "mp_worker.py"), "pz:12x10x33"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line)["max_rel_err"] <= 1e-11

@@ -105,6 +105,34 @@ def test_timestep_random_state(mif, N, periodic, kind):
     ctx.close()
 
 
+@pytest.mark.parametrize("N,kind", [
+    ((64, 64, 64), "ethier_steinman"),      # BASELINE configs[0] at its own size (full_test 64): generic sweep kernel, field level
+    ((257, 257, 257), "ethier_steinman"),   # a full 3-D grid with all three directions on the fast kernels (x sweeps from
+                                            # registers, TMA-staged y / fused z sweeps, persistent CTAs over many tiles)
+    ((513, 1025, 4), "test_case_1"),        # planes of more than 2.2 MB: the y-chunked stage launch (n_chunks > 1), 513- and
+                                            # 1025-point lines (16 x 32 transform, split 1024 transform) on one GPU
+])
+def test_timestep_full_grids(mif, N, kind):
+    """One projection step on grids the small cases above cannot reach, u v w p and the scratch tensors at 1e-11."""
+    periodic = (False, False, False)
+    ctx, grid = make_pair(mif, N, periodic)
+    rng = np.random.default_rng(7)
+    okind = {"ethier_steinman": mo.BC_ETHIER_STEINMAN, "test_case_1": mo.BC_TEST_CASE_1}[kind]
+    gkind = {"ethier_steinman": mif.BC_ETHIER_STEINMAN, "test_case_1": mif.BC_TEST_CASE_1}[kind]
+    h_vel = [0.3 * rng.uniform(-1, 1, grid.shape(c)) for c in range(3)]
+    h_p = rng.uniform(-1, 1, grid.shape(3))
+    h_buf, h_buf2, h_dp = [grid.zeros(c) for c in range(3)], [grid.zeros(c) for c in range(3)], grid.zeros(3)
+    vel, vb, vb2 = ctx.velocity(), ctx.velocity(), ctx.velocity()
+    p, dp = ctx.tensor(mif.STAGGER_NONE), ctx.tensor(mif.STAGGER_NONE)
+    for t, h in zip(vel + [p], h_vel + [h_p]):
+        t.upload(h)
+    ctx.timestep(vel, vb, vb2, ctx.make_bc(gkind, 1e3), 0.0, p, dp)
+    grid.timestep(okind, 0.0, h_vel, h_buf, h_buf2, h_p, h_dp)
+    for t, h, name in zip(vel + [p] + vb + vb2, h_vel + [h_p] + h_buf + h_buf2, ["u", "v", "w", "p", "ub", "vb", "wb", "ub2", "vb2", "wb2"]):
+        assert rel(t.download(), h) <= TOL, name
+    ctx.close()
+
+
 def test_timestep_nhn_matches_oracle(mif):
     N, periodic = (14, 11, 9), (False, False, False)
     ctx, grid = make_pair(mif, N, periodic, final_time=1e-4, steps=2)

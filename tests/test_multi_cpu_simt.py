@@ -47,6 +47,13 @@ def test_two_rank_slabs_with_peer_memory_transposes(simt_env):
     assert res["world"] == 2 and res["max_rel_err"] <= 1e-11
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_periodic_z_distributed_over_the_ranks(simt_env, world):
+    # two ranks: prev and next neighbour are the same peer (the halo planes pair in issue order); three ranks: a ring
+    res = run_worker(simt_env, "pz:6x6x13", world, 29717 + world)
+    assert res["world"] == world and res["max_rel_err"] <= 1e-11
+
+
 def test_four_rank_pencils(simt_env):
     # Py x Pz = 2 x 2 on 17^3 points (uneven blocks 9 + 8): y sheets then z planes as halos, the four 2Decomp transposes
     # as box exchanges, x / y / z sweeps on the sub-domain, the y pencil and the z pencil
