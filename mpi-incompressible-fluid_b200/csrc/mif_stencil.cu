@@ -16,159 +16,7 @@ namespace mifgpu {
 
 namespace {
 
-// ------------------------------------------------------------------------------------------------
-// RK stage kernel.  One thread per grid index (i, j, k); the three components share their loads
-// (9 u + 9 v + 9 w + 4 p values) and each component is stored only where (i, j, k) is interior to it
-// (STAGGERED_TENSOR_ITERATE_OVER_ALL_POINTS with include_border = false, include/StaggeredTensorMacros.h:6-37).
-// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_l2(const double *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
-
-#ifndef MIFGPU_STAGE_MIN_BLOCKS
-#define MIFGPU_STAGE_MIN_BLOCKS 4
-#endif
-template <int STAGE>
-__global__ void __launch_bounds__(256, MIFGPU_STAGE_MIN_BLOCKS)
-stage_kernel(const Geom g, const double *__restrict__ in_u, const double *__restrict__ in_v,
-             const double *__restrict__ in_w, const double *__restrict__ p, double *__restrict__ a_u,
-             double *__restrict__ a_v, double *__restrict__ a_w, double *__restrict__ b_u, double *__restrict__ b_v,
-             double *__restrict__ b_w, int prefetch_planes, int nk, int chunk_blocks_y) {
-  // blockIdx.z = y_chunk * nk + (k - 1): CTAs are scheduled x fastest, then y, then z, so the grid is walked one
-  // y chunk at a time, plane after plane.  The z neighbours of a plane are then still in L2 when they are needed
-  // even when a whole plane set (3 planes x 7 arrays) would not fit -- at 1025^2-point planes that set is 179 MB.
-  const int y_chunk = blockIdx.z / nk;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  const int j = (y_chunk * chunk_blocks_y + blockIdx.y) * blockDim.y + threadIdx.y + 1;
-  const int k = blockIdx.z - y_chunk * nk + 1;
-  // Each thread brings only 4-7 unique values in from HBM (everything else hits L1/L2), so the demand loads alone
-  // keep too few bytes in flight to cover the HBM latency.  The plane above (first touched by this plane's CTAs,
-  // which run in plane order) is therefore requested into L2 right away, one lane per 32-byte sector; measured on
-  // B200 at 513^3: 3.04/4.87/4.43 ms -> 2.56/3.46/3.19 ms for the three stages (distance 1 plane; 2+ is worse).
-  if (prefetch_planes > 0 && (threadIdx.x & 3) == 0 && k + prefetch_planes < g.PZ && i < g.PX && j < g.PY) {
-    const long long ahead = gidx(g, i - 1, j, k + prefetch_planes);
-    prefetch_l2(in_u + ahead);
-    prefetch_l2(in_v + ahead);
-    prefetch_l2(in_w + ahead);
-    prefetch_l2(p + ahead);
-    if (STAGE >= 2) {
-      prefetch_l2(a_u + ahead);
-      prefetch_l2(a_v + ahead);
-      prefetch_l2(a_w + ahead);
-    }
-  }
-  const bool in_i_u = i <= g.sx[0] - 2, in_i_o = i <= g.Nx - 2;  // v, w and p share the unstaggered x extent
-  if (!in_i_u && !in_i_o) return;
-  const bool in_j_v = j <= g.sy[1] - 2, in_j_o = j <= g.Ny - 2;
-  if (!in_j_v && !in_j_o) return;
-  const bool in_k_w = k <= g.sz[2] - 2, in_k_o = k <= g.Nz - 2;
-  const bool do_u = in_i_u && in_j_o && in_k_o;
-  const bool do_v = in_i_o && in_j_v && in_k_o;
-  const bool do_w = in_i_o && in_j_o && in_k_w;
-  if (!do_u && !do_v && !do_w) return;
-
-  const long long c = gidx(g, i, j, k);
-  const long long sj = g.PX, sk = g.plane;
-
-  // Neighbourhood (names: m = minus, p = plus along x/y/z).
-  const double u_c = in_u[c], u_xm = in_u[c - 1], u_xp = in_u[c + 1];
-  const double u_ym = in_u[c - sj], u_yp = in_u[c + sj], u_zm = in_u[c - sk], u_zp = in_u[c + sk];
-  const double u_xp_ym = in_u[c + 1 - sj], u_xp_zm = in_u[c + 1 - sk];
-  const double v_c = in_v[c], v_xm = in_v[c - 1], v_xp = in_v[c + 1];
-  const double v_ym = in_v[c - sj], v_yp = in_v[c + sj], v_zm = in_v[c - sk], v_zp = in_v[c + sk];
-  const double v_xm_yp = in_v[c - 1 + sj], v_yp_zm = in_v[c + sj - sk];
-  const double w_c = in_w[c], w_xm = in_w[c - 1], w_xp = in_w[c + 1];
-  const double w_ym = in_w[c - sj], w_yp = in_w[c + sj], w_zm = in_w[c - sk], w_zp = in_w[c + sk];
-  const double w_xm_zp = in_w[c - 1 + sk], w_ym_zp = in_w[c - sj + sk];
-  const double p_c = p[c], p_xm = p[c - 1], p_ym = p[c - sj], p_zm = p[c - sk];
-
-  const double dt = g.dt;
-  double a1, a2, a3, b;
-  if (STAGE == 1) {
-    a1 = 64.0 / 120.0 * dt;
-    a2 = 0.0;
-    a3 = 0.0;
-    b = a1;
-  } else if (STAGE == 2) {
-    a1 = -34.0 / 120.0 * dt;
-    a2 = 50.0 / 120.0 * dt;
-    a3 = 0.0;
-    b = a1 + a2;
-  } else {
-    a1 = 0.0;
-    a2 = -50.0 / 120.0 * dt;
-    a3 = 90.0 / 120.0 * dt;
-    b = a2 + a3;
-  }
-  (void)a1;
-  (void)a2;
-  (void)a3;
-
-  if (do_u) {
-    // include/MomentumEquation.h:50-96
-    const double convection = -u_c * (u_xp - u_xm) * g.one_over_2_dx -
-                              (v_yp + v_c + v_xm_yp + v_xm) * (u_yp - u_ym) * g.one_over_8_dy -
-                              (w_zp + w_c + w_xm_zp + w_xm) * (u_zp - u_zm) * g.one_over_8_dz;
-    const double diffusion = (u_xp - 2 * u_c + u_xm) * g.one_over_dx2_Re + (u_yp - 2 * u_c + u_ym) * g.one_over_dy2_Re +
-                             (u_zp - 2 * u_c + u_zm) * g.one_over_dz2_Re;
-    const double rhs = convection + diffusion;
-    const double p_grad = (p_c - p_xm) * g.one_over_dx;  // include/PressureGradient.h:9-12
-    if (STAGE == 1) {
-      a_u[c] = u_c + a1 * rhs - b * p_grad;  // src/Timestep.cpp:18
-      b_u[c] = rhs;                          // src/Timestep.cpp:19
-    } else if (STAGE == 2) {
-      const double rhs_1 = a_u[c];
-      const double rhs_2_scaled = a2 * rhs;
-      a_u[c] = u_c + a1 * rhs_1 + rhs_2_scaled - b * p_grad;  // src/Timestep.cpp:35-36
-      b_u[c] = rhs_2_scaled;                                  // src/Timestep.cpp:37
-    } else {
-      const double rhs_2_scaled = -a_u[c];
-      a_u[c] = u_c + rhs_2_scaled + a3 * rhs - b * p_grad;  // src/Timestep.cpp:51-52
-    }
-  }
-  if (do_v) {
-    // include/MomentumEquation.h:126-165
-    const double convection = -(u_xp + u_c + u_xp_ym + u_ym) * (v_xp - v_xm) * g.one_over_8_dx -
-                              v_c * (v_yp - v_ym) * g.one_over_2_dy -
-                              (w_zp + w_c + w_ym_zp + w_ym) * (v_zp - v_zm) * g.one_over_8_dz;
-    const double diffusion = (v_xp - 2 * v_c + v_xm) * g.one_over_dx2_Re + (v_yp - 2 * v_c + v_ym) * g.one_over_dy2_Re +
-                             (v_zp - 2 * v_c + v_zm) * g.one_over_dz2_Re;
-    const double rhs = convection + diffusion;
-    const double p_grad = (p_c - p_ym) * g.one_over_dy;  // include/PressureGradient.h:15-18
-    if (STAGE == 1) {
-      a_v[c] = v_c + a1 * rhs - b * p_grad;
-      b_v[c] = rhs;
-    } else if (STAGE == 2) {
-      const double rhs_1 = a_v[c];
-      const double rhs_2_scaled = a2 * rhs;
-      a_v[c] = v_c + a1 * rhs_1 + rhs_2_scaled - b * p_grad;
-      b_v[c] = rhs_2_scaled;
-    } else {
-      const double rhs_2_scaled = -a_v[c];
-      a_v[c] = v_c + rhs_2_scaled + a3 * rhs - b * p_grad;
-    }
-  }
-  if (do_w) {
-    // include/MomentumEquation.h:196-236
-    const double convection = -(u_xp + u_c + u_xp_zm + u_zm) * (w_xp - w_xm) * g.one_over_8_dx -
-                              (v_yp + v_c + v_yp_zm + v_zm) * (w_yp - w_ym) * g.one_over_8_dy -
-                              w_c * (w_zp - w_zm) * g.one_over_2_dz;
-    const double diffusion = (w_xp - 2 * w_c + w_xm) * g.one_over_dx2_Re + (w_yp - 2 * w_c + w_ym) * g.one_over_dy2_Re +
-                             (w_zp - 2 * w_c + w_zm) * g.one_over_dz2_Re;
-    const double rhs = convection + diffusion;
-    const double p_grad = (p_c - p_zm) * g.one_over_dz;  // include/PressureGradient.h:21-24
-    if (STAGE == 1) {
-      a_w[c] = w_c + a1 * rhs - b * p_grad;
-      b_w[c] = rhs;
-    } else if (STAGE == 2) {
-      const double rhs_1 = a_w[c];
-      const double rhs_2_scaled = a2 * rhs;
-      a_w[c] = w_c + a1 * rhs_1 + rhs_2_scaled - b * p_grad;
-      b_w[c] = rhs_2_scaled;
-    } else {
-      const double rhs_2_scaled = -a_w[c];
-      a_w[c] = w_c + rhs_2_scaled + a3 * rhs - b * p_grad;
-    }
-  }
-}
 
 
 // ------------------------------------------------------------------------------------------------
@@ -334,293 +182,6 @@ stage_kernel_pair(const Geom g, const double *__restrict__ in_u, const double *_
     store_pair(b_u + c, do_u[0], do_u[1], nb_u[0], nb_u[1]);
     store_pair(b_v + c, do_v[0], do_v[1], nb_v[0], nb_v[1]);
     store_pair(b_w + c, do_w[0], do_w[1], nb_w[0], nb_w[1]);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// RK stage kernel, z-marching: a thread owns a column (i, j) and walks kz planes, keeping the z neighbours of its
-// own point (and the diagonal neighbours that are in-plane neighbours one plane earlier or later) in registers, so
-// a plane costs 20 loads per point instead of 31 -- the kernel is bound by load-issue / L1 wavefronts and latency,
-// not by HBM traffic, which is already at the algorithmic minimum.  Arithmetic is identical to stage_kernel.
-// ------------------------------------------------------------------------------------------------
-template <int STAGE>
-__global__ void __launch_bounds__(256, 2)
-stage_kernel_march(const Geom g, const double *__restrict__ in_u, const double *__restrict__ in_v,
-                   const double *__restrict__ in_w, const double *__restrict__ p, double *__restrict__ a_u,
-                   double *__restrict__ a_v, double *__restrict__ a_w, double *__restrict__ b_u, double *__restrict__ b_v,
-                   double *__restrict__ b_w, int kz) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
-  const bool in_i_u = i <= g.sx[0] - 2, in_i_o = i <= g.Nx - 2;
-  const bool in_j_v = j <= g.sy[1] - 2, in_j_o = j <= g.Ny - 2;
-  if ((!in_i_u && !in_i_o) || (!in_j_v && !in_j_o)) return;
-  const int nk = max(g.sz[2], g.Nz) - 2;
-  const int k_first = blockIdx.z * kz + 1, k_last = min(k_first + kz - 1, nk);
-  if (k_first > k_last) return;
-  const long long sj = g.PX, sk = g.plane;
-  const double dt = g.dt;
-  double a1 = 0.0, a2 = 0.0, a3 = 0.0, b;
-  if (STAGE == 1) { a1 = 64.0 / 120.0 * dt; b = a1; }
-  else if (STAGE == 2) { a1 = -34.0 / 120.0 * dt; a2 = 50.0 / 120.0 * dt; b = a1 + a2; }
-  else { a2 = -50.0 / 120.0 * dt; a3 = 90.0 / 120.0 * dt; b = a2 + a3; }
-  (void)a1; (void)a2; (void)a3;
-
-  long long c = gidx(g, i, j, k_first);
-  // rolling registers: values at plane k-1 and k of this column, and the neighbours that roll with the planes
-  double u_zm = in_u[c - sk], u_c = in_u[c], u_xp_zm = in_u[c + 1 - sk];
-  double v_zm = in_v[c - sk], v_c = in_v[c], v_yp_zm = in_v[c + sj - sk];
-  double w_zm = in_w[c - sk], w_c = in_w[c], w_xm = in_w[c - 1], w_ym = in_w[c - sj];
-  double p_zm = p[c - sk], p_c = p[c];
-
-  for (int k = k_first; k <= k_last; k++, c += sk) {
-    // one lane per 32-byte sector asks L2 for the plane after next
-    if ((threadIdx.x & 3) == 0 && k + 2 < g.PZ) {
-      prefetch_l2(in_u + c - 1 + 2 * sk);
-      prefetch_l2(in_v + c - 1 + 2 * sk);
-      prefetch_l2(in_w + c - 1 + 2 * sk);
-      prefetch_l2(p + c - 1 + 2 * sk);
-    }
-    const double u_xm = in_u[c - 1], u_xp = in_u[c + 1], u_ym = in_u[c - sj], u_yp = in_u[c + sj], u_xp_ym = in_u[c + 1 - sj];
-    const double v_xm = in_v[c - 1], v_xp = in_v[c + 1], v_ym = in_v[c - sj], v_yp = in_v[c + sj], v_xm_yp = in_v[c - 1 + sj];
-    const double w_xp = in_w[c + 1], w_yp = in_w[c + sj];
-    const double u_zp = in_u[c + sk], v_zp = in_v[c + sk];
-    const double w_zp = in_w[c + sk], w_xm_zp = in_w[c - 1 + sk], w_ym_zp = in_w[c - sj + sk];
-    const double p_xm = p[c - 1], p_ym = p[c - sj];
-    const double p_zp = (k < k_last) ? p[c + sk] : 0.0;
-
-    const bool in_k_w = k <= g.sz[2] - 2, in_k_o = k <= g.Nz - 2;
-    if (in_i_u && in_j_o && in_k_o) {
-      const double convection = -u_c * (u_xp - u_xm) * g.one_over_2_dx -
-                                (v_yp + v_c + v_xm_yp + v_xm) * (u_yp - u_ym) * g.one_over_8_dy -
-                                (w_zp + w_c + w_xm_zp + w_xm) * (u_zp - u_zm) * g.one_over_8_dz;
-      const double diffusion = (u_xp - 2 * u_c + u_xm) * g.one_over_dx2_Re + (u_yp - 2 * u_c + u_ym) * g.one_over_dy2_Re +
-                               (u_zp - 2 * u_c + u_zm) * g.one_over_dz2_Re;
-      const double rhs = convection + diffusion;
-      const double p_grad = (p_c - p_xm) * g.one_over_dx;
-      if (STAGE == 1) {
-        a_u[c] = u_c + a1 * rhs - b * p_grad;
-        b_u[c] = rhs;
-      } else if (STAGE == 2) {
-        const double rhs_1 = a_u[c];
-        const double rhs_2_scaled = a2 * rhs;
-        a_u[c] = u_c + a1 * rhs_1 + rhs_2_scaled - b * p_grad;
-        b_u[c] = rhs_2_scaled;
-      } else {
-        const double rhs_2_scaled = -a_u[c];
-        a_u[c] = u_c + rhs_2_scaled + a3 * rhs - b * p_grad;
-      }
-    }
-    if (in_i_o && in_j_v && in_k_o) {
-      const double convection = -(u_xp + u_c + u_xp_ym + u_ym) * (v_xp - v_xm) * g.one_over_8_dx -
-                                v_c * (v_yp - v_ym) * g.one_over_2_dy -
-                                (w_zp + w_c + w_ym_zp + w_ym) * (v_zp - v_zm) * g.one_over_8_dz;
-      const double diffusion = (v_xp - 2 * v_c + v_xm) * g.one_over_dx2_Re + (v_yp - 2 * v_c + v_ym) * g.one_over_dy2_Re +
-                               (v_zp - 2 * v_c + v_zm) * g.one_over_dz2_Re;
-      const double rhs = convection + diffusion;
-      const double p_grad = (p_c - p_ym) * g.one_over_dy;
-      if (STAGE == 1) {
-        a_v[c] = v_c + a1 * rhs - b * p_grad;
-        b_v[c] = rhs;
-      } else if (STAGE == 2) {
-        const double rhs_1 = a_v[c];
-        const double rhs_2_scaled = a2 * rhs;
-        a_v[c] = v_c + a1 * rhs_1 + rhs_2_scaled - b * p_grad;
-        b_v[c] = rhs_2_scaled;
-      } else {
-        const double rhs_2_scaled = -a_v[c];
-        a_v[c] = v_c + rhs_2_scaled + a3 * rhs - b * p_grad;
-      }
-    }
-    if (in_i_o && in_j_o && in_k_w) {
-      const double convection = -(u_xp + u_c + u_xp_zm + u_zm) * (w_xp - w_xm) * g.one_over_8_dx -
-                                (v_yp + v_c + v_yp_zm + v_zm) * (w_yp - w_ym) * g.one_over_8_dy -
-                                w_c * (w_zp - w_zm) * g.one_over_2_dz;
-      const double diffusion = (w_xp - 2 * w_c + w_xm) * g.one_over_dx2_Re + (w_yp - 2 * w_c + w_ym) * g.one_over_dy2_Re +
-                               (w_zp - 2 * w_c + w_zm) * g.one_over_dz2_Re;
-      const double rhs = convection + diffusion;
-      const double p_grad = (p_c - p_zm) * g.one_over_dz;
-      if (STAGE == 1) {
-        a_w[c] = w_c + a1 * rhs - b * p_grad;
-        b_w[c] = rhs;
-      } else if (STAGE == 2) {
-        const double rhs_1 = a_w[c];
-        const double rhs_2_scaled = a2 * rhs;
-        a_w[c] = w_c + a1 * rhs_1 + rhs_2_scaled - b * p_grad;
-        b_w[c] = rhs_2_scaled;
-      } else {
-        const double rhs_2_scaled = -a_w[c];
-        a_w[c] = w_c + rhs_2_scaled + a3 * rhs - b * p_grad;
-      }
-    }
-    // roll the column one plane up
-    u_zm = u_c; u_c = u_zp; u_xp_zm = u_xp;
-    v_zm = v_c; v_c = v_zp; v_yp_zm = v_yp;
-    w_zm = w_c; w_c = w_zp; w_xm = w_xm_zp; w_ym = w_ym_zp;
-    p_zm = p_c; p_c = p_zp;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// RK stage kernel, 2.5-D blocked: a CTA owns a 64 x 8 tile in (x, y) and marches along z, keeping a ring of
-// three z planes of u, v, w, p (each with a one-cell halo in x and y) in shared memory, so every input is
-// fetched from L2/HBM about once instead of once per z neighbour.  The plane two steps ahead is prefetched into
-// registers while the current plane is being computed.  Arithmetic is identical to stage_kernel above.
-// ------------------------------------------------------------------------------------------------
-constexpr int kTX = 64, kTY = 8, kTileW = kTX + 2, kTileH = kTY + 2, kTileN = kTileW * kTileH;
-constexpr int kPerThread = (kTileN + kTX * kTY - 1) / (kTX * kTY);  // tile elements fetched per thread and field
-
-template <int STAGE>
-__global__ void __launch_bounds__(kTX * kTY, 2)
-stage_kernel_tiled(const Geom g, const double *__restrict__ in_u, const double *__restrict__ in_v,
-                   const double *__restrict__ in_w, const double *__restrict__ p, double *__restrict__ a_u,
-                   double *__restrict__ a_v, double *__restrict__ a_w, double *__restrict__ b_u, double *__restrict__ b_v,
-                   double *__restrict__ b_w, int kz) {
-  extern __shared__ double tile_smem[];  // [field 0..3][slot 0..2][kTileH][kTileW]
-  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kTX + tx;
-  const int i0 = blockIdx.x * kTX, j0 = blockIdx.y * kTY;  // global index of tile element (0, 0) (halo included)
-  const int i = i0 + tx + 1, j = j0 + ty + 1;
-  const int nk = max(g.sz[2], g.Nz) - 2;                   // last interior plane index of any component
-  const int k_first = blockIdx.z * kz + 1, k_last = min(k_first + kz - 1, nk);
-  const double *fields[4] = {in_u, in_v, in_w, p};
-
-  // tile element -> global offset within a plane (or -1 if outside the allocation)
-  long long src_off[kPerThread];
-  int dst_off[kPerThread];
-#pragma unroll
-  for (int r = 0; r < kPerThread; r++) {
-    const int e = tid + r * kTX * kTY;
-    const int row = e / kTileW, col = e - row * kTileW;
-    const int gi = i0 + col, gj = j0 + row;
-    dst_off[r] = (e < kTileN) ? e : -1;
-    src_off[r] = (e < kTileN && gi < g.PX && gj < g.PY) ? (long long)gi + (long long)gj * g.PX : -1;
-  }
-  auto fetch = [&](int plane, double (&regs)[4][kPerThread]) {
-#pragma unroll
-    for (int f = 0; f < 4; f++)
-#pragma unroll
-      for (int r = 0; r < kPerThread; r++)
-        regs[f][r] = (src_off[r] >= 0 && plane < g.PZ) ? fields[f][src_off[r] + (long long)plane * g.plane] : 0.0;
-  };
-  auto stash = [&](int plane, const double (&regs)[4][kPerThread]) {
-    const int slot = plane % 3;
-#pragma unroll
-    for (int f = 0; f < 4; f++)
-#pragma unroll
-      for (int r = 0; r < kPerThread; r++)
-        if (dst_off[r] >= 0) tile_smem[(f * 3 + slot) * kTileN + dst_off[r]] = regs[f][r];
-  };
-
-  double regs[4][kPerThread];
-  for (int plane = k_first - 1; plane <= k_first + 1; plane++) {
-    fetch(plane, regs);
-    stash(plane, regs);
-  }
-  __syncthreads();
-
-  const bool in_i_u = i <= g.sx[0] - 2, in_i_o = i <= g.Nx - 2;
-  const bool in_j_v = j <= g.sy[1] - 2, in_j_o = j <= g.Ny - 2;
-  const double dt = g.dt;
-  double a1 = 0.0, a2 = 0.0, a3 = 0.0, b;
-  if (STAGE == 1) { a1 = 64.0 / 120.0 * dt; b = a1; }
-  else if (STAGE == 2) { a1 = -34.0 / 120.0 * dt; a2 = 50.0 / 120.0 * dt; b = a1 + a2; }
-  else { a2 = -50.0 / 120.0 * dt; a3 = 90.0 / 120.0 * dt; b = a2 + a3; }
-  (void)a1; (void)a2; (void)a3;
-  const int cc = (ty + 1) * kTileW + tx + 1;  // this thread's point inside a tile
-
-  for (int k = k_first; k <= k_last; k++) {
-    const bool more = k + 1 <= k_last;
-    if (more) fetch(k + 2, regs);  // needed as plane k+1's upper neighbour in the next iteration
-
-    const double *Um = tile_smem + (0 * 3 + (k - 1) % 3) * kTileN, *Uc = tile_smem + (0 * 3 + k % 3) * kTileN,
-                 *Up = tile_smem + (0 * 3 + (k + 1) % 3) * kTileN;
-    const double *Vm = tile_smem + (1 * 3 + (k - 1) % 3) * kTileN, *Vc = tile_smem + (1 * 3 + k % 3) * kTileN,
-                 *Vp = tile_smem + (1 * 3 + (k + 1) % 3) * kTileN;
-    const double *Wm = tile_smem + (2 * 3 + (k - 1) % 3) * kTileN, *Wc = tile_smem + (2 * 3 + k % 3) * kTileN,
-                 *Wp = tile_smem + (2 * 3 + (k + 1) % 3) * kTileN;
-    const double *Pm = tile_smem + (3 * 3 + (k - 1) % 3) * kTileN, *Pc = tile_smem + (3 * 3 + k % 3) * kTileN;
-
-    const bool in_k_w = k <= g.sz[2] - 2, in_k_o = k <= g.Nz - 2;
-    const bool do_u = in_i_u && in_j_o && in_k_o;
-    const bool do_v = in_i_o && in_j_v && in_k_o;
-    const bool do_w = in_i_o && in_j_o && in_k_w;
-    const long long c = gidx(g, i, j, k);
-
-    const double u_c = Uc[cc], u_xm = Uc[cc - 1], u_xp = Uc[cc + 1], u_ym = Uc[cc - kTileW], u_yp = Uc[cc + kTileW];
-    const double u_zm = Um[cc], u_zp = Up[cc], u_xp_ym = Uc[cc + 1 - kTileW], u_xp_zm = Um[cc + 1];
-    const double v_c = Vc[cc], v_xm = Vc[cc - 1], v_xp = Vc[cc + 1], v_ym = Vc[cc - kTileW], v_yp = Vc[cc + kTileW];
-    const double v_zm = Vm[cc], v_zp = Vp[cc], v_xm_yp = Vc[cc - 1 + kTileW], v_yp_zm = Vm[cc + kTileW];
-    const double w_c = Wc[cc], w_xm = Wc[cc - 1], w_xp = Wc[cc + 1], w_ym = Wc[cc - kTileW], w_yp = Wc[cc + kTileW];
-    const double w_zm = Wm[cc], w_zp = Wp[cc], w_xm_zp = Wp[cc - 1], w_ym_zp = Wp[cc - kTileW];
-    const double p_c = Pc[cc], p_xm = Pc[cc - 1], p_ym = Pc[cc - kTileW], p_zm = Pm[cc];
-
-    if (do_u) {
-      const double convection = -u_c * (u_xp - u_xm) * g.one_over_2_dx -
-                                (v_yp + v_c + v_xm_yp + v_xm) * (u_yp - u_ym) * g.one_over_8_dy -
-                                (w_zp + w_c + w_xm_zp + w_xm) * (u_zp - u_zm) * g.one_over_8_dz;
-      const double diffusion = (u_xp - 2 * u_c + u_xm) * g.one_over_dx2_Re + (u_yp - 2 * u_c + u_ym) * g.one_over_dy2_Re +
-                               (u_zp - 2 * u_c + u_zm) * g.one_over_dz2_Re;
-      const double rhs = convection + diffusion;
-      const double p_grad = (p_c - p_xm) * g.one_over_dx;
-      if (STAGE == 1) {
-        a_u[c] = u_c + a1 * rhs - b * p_grad;
-        b_u[c] = rhs;
-      } else if (STAGE == 2) {
-        const double rhs_1 = a_u[c];
-        const double rhs_2_scaled = a2 * rhs;
-        a_u[c] = u_c + a1 * rhs_1 + rhs_2_scaled - b * p_grad;
-        b_u[c] = rhs_2_scaled;
-      } else {
-        const double rhs_2_scaled = -a_u[c];
-        a_u[c] = u_c + rhs_2_scaled + a3 * rhs - b * p_grad;
-      }
-    }
-    if (do_v) {
-      const double convection = -(u_xp + u_c + u_xp_ym + u_ym) * (v_xp - v_xm) * g.one_over_8_dx -
-                                v_c * (v_yp - v_ym) * g.one_over_2_dy -
-                                (w_zp + w_c + w_ym_zp + w_ym) * (v_zp - v_zm) * g.one_over_8_dz;
-      const double diffusion = (v_xp - 2 * v_c + v_xm) * g.one_over_dx2_Re + (v_yp - 2 * v_c + v_ym) * g.one_over_dy2_Re +
-                               (v_zp - 2 * v_c + v_zm) * g.one_over_dz2_Re;
-      const double rhs = convection + diffusion;
-      const double p_grad = (p_c - p_ym) * g.one_over_dy;
-      if (STAGE == 1) {
-        a_v[c] = v_c + a1 * rhs - b * p_grad;
-        b_v[c] = rhs;
-      } else if (STAGE == 2) {
-        const double rhs_1 = a_v[c];
-        const double rhs_2_scaled = a2 * rhs;
-        a_v[c] = v_c + a1 * rhs_1 + rhs_2_scaled - b * p_grad;
-        b_v[c] = rhs_2_scaled;
-      } else {
-        const double rhs_2_scaled = -a_v[c];
-        a_v[c] = v_c + rhs_2_scaled + a3 * rhs - b * p_grad;
-      }
-    }
-    if (do_w) {
-      const double convection = -(u_xp + u_c + u_xp_zm + u_zm) * (w_xp - w_xm) * g.one_over_8_dx -
-                                (v_yp + v_c + v_yp_zm + v_zm) * (w_yp - w_ym) * g.one_over_8_dy -
-                                w_c * (w_zp - w_zm) * g.one_over_2_dz;
-      const double diffusion = (w_xp - 2 * w_c + w_xm) * g.one_over_dx2_Re + (w_yp - 2 * w_c + w_ym) * g.one_over_dy2_Re +
-                               (w_zp - 2 * w_c + w_zm) * g.one_over_dz2_Re;
-      const double rhs = convection + diffusion;
-      const double p_grad = (p_c - p_zm) * g.one_over_dz;
-      if (STAGE == 1) {
-        a_w[c] = w_c + a1 * rhs - b * p_grad;
-        b_w[c] = rhs;
-      } else if (STAGE == 2) {
-        const double rhs_1 = a_w[c];
-        const double rhs_2_scaled = a2 * rhs;
-        a_w[c] = w_c + a1 * rhs_1 + rhs_2_scaled - b * p_grad;
-        b_w[c] = rhs_2_scaled;
-      } else {
-        const double rhs_2_scaled = -a_w[c];
-        a_w[c] = w_c + rhs_2_scaled + a3 * rhs - b * p_grad;
-      }
-    }
-    if (more) {
-      __syncthreads();       // every thread is done with plane k-1, whose slot receives plane k+2
-      stash(k + 2, regs);
-      __syncthreads();
-    }
   }
 }
 
@@ -1086,48 +647,7 @@ void launch_stage(cudaStream_t stream, const Geom &g, int stage, CVec3 in, const
                   uint64_t *launches) {
   const int ni = max(g.sx[0], g.Nx) - 2, nj = max(g.sy[1], g.Ny) - 2, nk = max(g.sz[2], g.Nz) - 2;
   if (ni <= 0 || nj <= 0 || nk <= 0) return;
-  static const bool use_tiled = getenv("MIFGPU_STAGE_TILED") != nullptr;  // A/B switch for profiling
   static const int prefetch_planes = getenv("MIFGPU_STAGE_PREFETCH") ? atoi(getenv("MIFGPU_STAGE_PREFETCH")) : 1;
-  static const int march_kz = getenv("MIFGPU_STAGE_MARCH") ? atoi(getenv("MIFGPU_STAGE_MARCH")) : 0;
-  if (march_kz > 0) {
-    const dim3 mblock(64, 4, 1);
-    const dim3 mgrid(cdiv(ni, mblock.x), cdiv(nj, mblock.y), cdiv(nk, march_kz));
-    if (stage == 1)
-      stage_kernel_march<1><<<mgrid, mblock, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
-                                                          b.c[1], b.c[2], march_kz);
-    else if (stage == 2)
-      stage_kernel_march<2><<<mgrid, mblock, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
-                                                          b.c[1], b.c[2], march_kz);
-    else
-      stage_kernel_march<3><<<mgrid, mblock, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
-                                                          b.c[1], b.c[2], march_kz);
-    ++*launches;
-    return;
-  }
-  if (use_tiled) {
-    const int kz = 64;  // planes marched by one CTA
-    const dim3 tblock(kTX, kTY, 1);
-    const dim3 tgrid(cdiv(ni, kTX), cdiv(nj, kTY), cdiv(nk, kz));
-    const size_t smem = sizeof(double) * 12 * kTileN;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(stage_kernel_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(stage_kernel_tiled<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(stage_kernel_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr_set = true;
-    }
-    if (stage == 1)
-      stage_kernel_tiled<1><<<tgrid, tblock, smem, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2],
-                                                             b.c[0], b.c[1], b.c[2], kz);
-    else if (stage == 2)
-      stage_kernel_tiled<2><<<tgrid, tblock, smem, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2],
-                                                             b.c[0], b.c[1], b.c[2], kz);
-    else
-      stage_kernel_tiled<3><<<tgrid, tblock, smem, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2],
-                                                             b.c[0], b.c[1], b.c[2], kz);
-    ++*launches;
-    return;
-  }
   const dim3 block(64, 4, 1);
   // y chunks of about 2.2 MB per array and plane (the plane size of the 513^3 case, where one launch reads every
   // input exactly once from HBM); MIFGPU_STAGE_CHUNK_MB overrides.
@@ -1141,32 +661,17 @@ void launch_stage(cudaStream_t stream, const Geom &g, int stage, CVec3 in, const
     n_chunks = (int)cdiv(blocks_y, chunk_blocks_y);
   }
   chunk_blocks_y = (int)cdiv(blocks_y, n_chunks);  // equal chunks
-  static const bool one_point = getenv("MIFGPU_STAGE_ONE_POINT") != nullptr;  // A/B switch for profiling
-  if (!one_point) {
-    const dim3 pblock(32, 4, 1);  // 64 x-points by 4 rows per CTA, as below
-    const dim3 pgrid(cdiv(ni + 1, 2 * pblock.x), chunk_blocks_y, nk * n_chunks);
-    if (stage == 1)
-      stage_kernel_pair<1><<<pgrid, pblock, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
-                                                         b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y);
-    else if (stage == 2)
-      stage_kernel_pair<2><<<pgrid, pblock, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
-                                                         b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y);
-    else
-      stage_kernel_pair<3><<<pgrid, pblock, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
-                                                         b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y);
-    ++*launches;
-    return;
-  }
-  const dim3 grid(cdiv(ni, block.x), chunk_blocks_y, nk * n_chunks);
+  const dim3 pblock(32, 4, 1);  // 64 x-points by 4 rows per CTA
+  const dim3 pgrid(cdiv(ni + 1, 2 * pblock.x), chunk_blocks_y, nk * n_chunks);
   if (stage == 1)
-    stage_kernel<1><<<grid, block, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
-                                                b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y);
+    stage_kernel_pair<1><<<pgrid, pblock, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
+                                                       b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y);
   else if (stage == 2)
-    stage_kernel<2><<<grid, block, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
-                                                b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y);
+    stage_kernel_pair<2><<<pgrid, pblock, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
+                                                       b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y);
   else
-    stage_kernel<3><<<grid, block, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
-                                                b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y);
+    stage_kernel_pair<3><<<pgrid, pblock, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
+                                                       b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y);
   ++*launches;
 }
 

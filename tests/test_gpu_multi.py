@@ -12,6 +12,12 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
+def failure_report(out):
+    """The ranks' own tracebacks / library errors first (torchrun's summary hides them at the end of a long stderr)."""
+    own = [l for l in out.stderr.splitlines() if l.startswith("[rank") or "libmifgpu" in l or "Error" in l]
+    return "\n".join(own[-60:]) + "\n--- stdout ---\n" + out.stdout[-1500:] + "\n--- stderr tail ---\n" + out.stderr[-1500:]
+
+
 def device_count():
     import torch
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
@@ -26,7 +32,7 @@ def test_slab_decomposition_matches_single_rank_reference(case, world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29500 + world), os.path.join(ROOT, "tests", "mp_worker.py"), case]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert out.returncode == 0, failure_report(out)
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     assert json.loads(line)["max_rel_err"] <= 1e-11
 
@@ -42,7 +48,7 @@ def test_peer_memory_and_nccl_transposes_agree(no_peer):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tests", "mp_worker.py"), "es:9x257x257"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
-    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert out.returncode == 0, failure_report(out)
 
 
 @pytest.mark.parametrize("world", [2, 4])
@@ -54,6 +60,6 @@ def test_periodic_z_distributed_over_the_ranks(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29540 + world), os.path.join(ROOT, "tests", "mp_worker.py"), "pz:12x10x33"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert out.returncode == 0, failure_report(out)
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     assert json.loads(line)["max_rel_err"] <= 1e-11

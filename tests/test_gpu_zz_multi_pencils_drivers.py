@@ -13,6 +13,12 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
+def failure_report(out):
+    """The ranks' own tracebacks / library errors first (torchrun's summary hides them at the end of a long stderr)."""
+    own = [l for l in out.stderr.splitlines() if l.startswith("[rank") or "libmifgpu" in l or "Error" in l]
+    return "\n".join(own[-60:]) + "\n--- stdout ---\n" + out.stdout[-1500:] + "\n--- stderr tail ---\n" + out.stderr[-1500:]
+
+
 def device_count():
     import torch
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
@@ -28,7 +34,7 @@ def test_pencil_decomposition_matches_single_rank_reference(case, world, py):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29560 + world + py), os.path.join(ROOT, "tests", "mp_worker.py"), case]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MIF_PY=str(py)))
-    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert out.returncode == 0, failure_report(out)
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     res = json.loads(line)
     assert res["Py"] == py and res["max_rel_err"] <= 1e-11
