@@ -1678,10 +1678,14 @@ bool launch_tma_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int
   return true;
 }
 
-void launch_tma_modes(cudaStream_t stream, tmasweep::Cache &cache, const tmasweep::MapSet &maps_ref, const tmasweep::Job &job, int logm,
+void launch_tma_modes(cudaStream_t stream, tmasweep::Cache &cache, const tmasweep::MapSet &maps_ref, const tmasweep::Job &job_in, int logm,
                       int mode) {
   static const bool radix8_fft = getenv("MIFGPU_FFT_RADIX8") != nullptr;  // A/B: 513-point lines on the radix-8 Stockham passes
+  static const int stagger_ns = getenv("MIFGPU_TMA_STAGGER_NS") ? atoi(getenv("MIFGPU_TMA_STAGGER_NS")) : 0;
   const tmasweep::MapSet *maps = &maps_ref;
+  tmasweep::Job job = job_in;
+  job.stagger_from = cache.sms;  // CTAs beyond the first wave of one per SM
+  job.stagger_ns = (logm == 10) ? 0u : (unsigned)stagger_ns;  // 1025-point lines: one CTA per SM
   if (logm == 10) {
     if (mode == 0) tmasweep::launch_1024<0>(stream, cache, *maps, job);
     else if (mode == 1) tmasweep::launch_1024<1>(stream, cache, *maps, job);
