@@ -637,10 +637,7 @@ int do_apply_bc(mifgpu_ctx *ctx, mifgpu_tensor *const vel[3], const mifgpu_bc *b
 // solve_pressure_equation_homogeneous_periodic / _non_homogeneous_neumann (src/PressureEquation.cpp:266-286).
 int do_solve(mifgpu_ctx *ctx, mifgpu_tensor *dp, mifgpu_tensor *const vel[3], double dt, const mifgpu_bc *nhn_bc,
              double t_new, double t_prev) {
-  // Without Neumann face terms the right-hand side is consumed only by the forward x sweep, which can compute it
-  // on the fly; otherwise it is materialised first (src/PressureEquation.cpp:59-61).
-  const bool fuse_rhs = !nhn_bc && ctx->nranks == 1 && poisson_can_fuse_divergence(ctx->plan);
-  if (!fuse_rhs) {
+  {  // rhs = div(velocity) / dt (src/PressureEquation.cpp:59-61)
     ProfScope prof(ctx, PROF_DIVERGENCE);
     launch_divergence(ctx->stream, ctx->g, cvec3(vel), 0.0, dt, dp->data, &ctx->launches);
   }
@@ -724,13 +721,7 @@ int do_solve(mifgpu_ctx *ctx, mifgpu_tensor *dp, mifgpu_tensor *const vel[3], do
     mifgpu_tensor *one_peer[1] = {dp};
     return exchange_z(ctx, one_peer, 1);
   }
-  if (fuse_rhs) {
-    ProfScope prof(ctx, PROF_SWEEP_X_FWD);
-    const double *velocity[3] = {vel[0]->data, vel[1]->data, vel[2]->data};
-    launch_poisson_sweep(ctx->stream, ctx->g, ctx->plan, dp->data, 0, 0, &ctx->launches, velocity, dt);
-  } else {
-    sweep(0, 0, PROF_SWEEP_X_FWD);
-  }
+  sweep(0, 0, PROF_SWEEP_X_FWD);
   sweep(1, 0, PROF_SWEEP_Y_FWD);
   if (ctx->nranks == 1) {
     sweep(2, 2, PROF_SWEEP_Z);

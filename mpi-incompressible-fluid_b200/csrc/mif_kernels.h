@@ -66,11 +66,8 @@ int poisson_plan_unsupported_direction(const PoissonPlan *plan);
 // One sweep of the in-place spectral solve on the owner region of `field` (src/PressureEquation.cpp:65-264):
 // dir = 0/1/2 (x/y/z); mode = 0 forward, 1 inverse + normalisation, 2 forward, eigenvalue division, inverse.
 // The solve is the sequence (0,0) (1,0) (2,2) (1,1) (0,1).
-// divergence_of (optional, forward x sweep only): {u, v, w}; the sweep then computes its input div(velocity)/dt on the
-// fly instead of reading `field` (only if poisson_can_fuse_divergence).
 void launch_poisson_sweep(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *field, int dir, int mode,
-                          uint64_t *launches, const double *const *divergence_of = nullptr, double dt = 1.0);
-bool poisson_can_fuse_divergence(const PoissonPlan *plan);
+                          uint64_t *launches);
 // The fused z sweep (mode 2) on a z pencil zbuf[z][y_local][x] (rows of g.PX doubles) that holds all z points of
 // the y rows [y_offset, y_offset + ny_local) of the transform domain (multi-GPU slab decomposition).
 void launch_poisson_zpencil(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *zbuf, int ny_local,

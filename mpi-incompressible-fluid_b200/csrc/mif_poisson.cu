@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <set>
 #include <vector>
 
 #include <algorithm>
@@ -30,6 +31,17 @@ namespace mifgpu {
 namespace {
 
 const double kPi = 3.14159265358979323846264338327950288;
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel AND per plan: the attribute belongs to the device
+// the plan's context runs on, so a process that drives several GPUs sets it on each of them.
+struct SmemAttrOnce {
+  std::set<const void *> done;
+  template <class K>
+  void ensure(K kernel, size_t bytes) {
+    if (done.insert(reinterpret_cast<const void *>(kernel)).second)
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  }
+};
 
 struct DirPlanDev {
   int periodic;   // 0: DCT-I, 1: halfcomplex real FFT
@@ -398,20 +410,6 @@ __device__ __forceinline__ double *seg_address(const SegMap &m, int e, int outer
          (long long)(e - m.lo[r]) * m.estride[r] + (x & 7);
 }
 
-// The same address with a segment cursor: `r` remembers the segment of the previous lookup, so a thread whose
-// elements ascend (UP) or descend (!UP) pays at most n - 1 search steps in total instead of up to n - 1 per element
-// (experiment MIFGPU_SEG_CARRY=1; the search reads the map arrays with indexed constant loads).
-template <bool UP>
-__device__ __forceinline__ double *seg_address_from(const SegMap &m, int &r, int e, int outer, int x) {
-  if (UP) {
-    while (r + 1 < m.n && e >= m.lo[r + 1]) r++;
-  } else {
-    while (r > 0 && e < m.lo[r]) r--;
-  }
-  return m.base[r] + (long long)(x >> 3) * m.xtile_stride[r] + (long long)outer * m.outer_stride[r] +
-         (long long)(e - m.lo[r]) * m.estride[r] + (x & 7);
-}
-
 struct FastJob {
   SegMap load_map, store_map;  // strided (y / z) sweeps of the warp-per-line kernel only
   long long origin, lstride, estride, tile_stride, outer_stride;
@@ -421,49 +419,7 @@ struct FastJob {
   const double *lam_x, *lam_y, *lam_z;
   double inv_norm;
   bool has_origin;  // the tile at (blockIdx.x, blockIdx.y) = (0, 0) contains the (0,0,0) mode
-  int prefetch_ctas;  // L2 prefetch distance in CTAs of the launch order (0 = off), see prefetch_next_tile
-  // Forward x sweep fused with the right-hand side (src/PressureEquation.cpp:59-61): when div_u != nullptr the
-  // input line is not read from `field` but computed as div(u, v, w) / dt from the velocity (same linear index).
-  const double *div_u, *div_v, *div_w;
-  double one_over_dx, one_over_dy, one_over_dz, dt;
-  long long stride_y, stride_z;
 };
-
-// Optional L2 prefetch (build with -DMIFGPU_SWEEP_PREFETCH_CTAS=296; MIFGPU_SWEEP_PREFETCH=<CTAs> then tunes it) of the tile that the CTA `job.prefetch_ctas`
-// positions further down the launch order will load (CTAs start in linear order, so with prefetch_ctas = resident
-// CTAs per GPU that tile is needed roughly when this CTA retires).  Motivation: each warp of the sweep kernels is a
-// serial load -> transform -> store chain and only 16 warps fit an SM, so about a fifth of the issue slots are lost
-// waiting for the first loads of a line (stall_long_sb in the ncu source view).  One request per 32-byte sector.
-// Measured: a net loss, see launch_sweep.
-__device__ __forceinline__ void prefetch_l2_sector(const double *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
-
-#ifndef MIFGPU_SWEEP_PREFETCH_CTAS
-#define MIFGPU_SWEEP_PREFETCH_CTAS 0  // compile-time switch: even a disabled run-time branch costs the x sweep a spill
-#endif
-template <bool CONTIG, int LINES, int THREADS>
-__device__ __forceinline__ void prefetch_next_tile(const FastJob &job, const double *field, int npts) {
-  if (MIFGPU_SWEEP_PREFETCH_CTAS == 0) return;
-  if (job.prefetch_ctas <= 0 || job.load_map.n != 0 || job.div_u != nullptr) return;
-  const long long id = (long long)blockIdx.x + (long long)gridDim.x * blockIdx.y + job.prefetch_ctas;
-  const int by = (int)(id / gridDim.x), bx = (int)(id - (long long)by * gridDim.x);
-  if (by >= (int)gridDim.y) return;
-  const int first_line = bx * LINES;
-  const int lines = min(LINES, job.n_tile_lines - first_line);
-  const double *base = field + job.origin + (long long)first_line * job.tile_stride + (long long)by * job.outer_stride;
-  if (CONTIG) {
-    const int per_line = (npts + 3) / 4;  // sectors per line
-    for (int idx = threadIdx.x; idx < lines * per_line; idx += THREADS) {
-      const int l = idx / per_line, t = idx - l * per_line;
-      prefetch_l2_sector(base + (long long)l * job.lstride + 4 * t);
-    }
-  } else {
-    const int per_row = (lines + 3) / 4;  // sectors per row of `lines` consecutive x
-    for (int idx = threadIdx.x; idx < npts * per_row; idx += THREADS) {
-      const int e = idx / per_row, t = idx - e * per_row;
-      prefetch_l2_sector(base + (long long)e * job.estride + 4 * t);
-    }
-  }
-}
 
 template <int LOGM, bool CONTIG>
 __global__ void __launch_bounds__(1 << LOGM, (LOGM <= 9 ? 2 : 1)) fast_dct_kernel(const FastJob job, double *__restrict__ field) {
@@ -552,15 +508,11 @@ __global__ void __launch_bounds__(1 << LOGM, (LOGM <= 9 ? 2 : 1)) fast_dct_kerne
 }
 
 template <int LOGM>
-void launch_fast(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid, double *field) {
+void launch_fast(cudaStream_t stream, SmemAttrOnce &attrs, const FastJob &job, bool contig, dim3 grid, double *field) {
   constexpr int M = 1 << LOGM;
   const size_t smem = (size_t)M * fast::kSlotPitch * sizeof(double2);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(fast_dct_kernel<LOGM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(fast_dct_kernel<LOGM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
+  attrs.ensure(fast_dct_kernel<LOGM, true>, smem);
+  attrs.ensure(fast_dct_kernel<LOGM, false>, smem);
   if (contig) fast_dct_kernel<LOGM, true><<<grid, M, smem, stream>>>(job, field);
   else fast_dct_kernel<LOGM, false><<<grid, M, smem, stream>>>(job, field);
 }
@@ -569,13 +521,10 @@ void launch_fast(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid
 // ------------------------------------------------------------------------------------------------
 // Warp-per-line path: DCT-I sweeps with M = 2^LOGM, 256 <= M <= 1024 (see mif_fft_warp.cuh).
 // ------------------------------------------------------------------------------------------------
-// FUSED_DIV (forward x sweep only): the input line is div(u, v, w) / dt formed in registers.  A separate instantiation,
-// so that the plain sweeps do not pay for its registers.
-// SEG (strided sweeps only): 0 = launches that use a segment map (multi-GPU fused transposes); 1 = launches that use
-// neither map (every single-GPU sweep): an instantiation without the map code -- no per-element map test, no indexed
-// constant loads of the map arrays, a third fewer instructions; 2 = experiment MIFGPU_SEG_CARRY=1, maps searched with
-// cursors (seg_address_from).
-template <int LOGM, bool CONTIG, bool FUSED_DIV = false, int SEG = 0>
+// SEG (strided sweeps only): 0 = launches that use a segment map (the LSU variant of the multi-GPU fused transposes); 1 =
+// launches that use neither map: an instantiation without the map code -- no per-element map test, no indexed constant
+// loads of the map arrays, a third fewer instructions.
+template <int LOGM, bool CONTIG, int SEG = 0>
 __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 : 2)) warp_dct_kernel(const FastJob job, double *__restrict__ field) {
   using namespace warpfft;
   using C = Cfg<LOGM>;
@@ -599,97 +548,12 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
     // slots q >= M/2 are the mirror images (x[2M-2q], x[2M-2q-1]).  No shared-memory staging, no CTA barrier.
     const double *src = base + (long long)line * job.lstride;
     const bool live = line < lines;
-    if constexpr (!FUSED_DIV && SEG == 1 && SHUFFLE) {
-      // Experiment MIFGPU_X_MIRROR_SHFL=1 (x sweeps, one warp per line): the mirrored slots q >= M/2 of the even
-      // extension, (x[2M-2q], x[2M-2q-1]), are not loaded a second time but fetched from the lanes that already hold
-      // those values (32 - j and 31 - j) -- 16 double shuffles instead of 16 strided 8-byte loads per lane (the x
-      // sweep is bound by the LSU data pipe, and a stride-2 warp load costs four wavefronts for two of payload).
-      double2 d[EPT / 2];
 #pragma unroll
-      for (int s = 0; s < EPT / 2; s++) {
-        d[s] = live ? *reinterpret_cast<const double2 *>(src + 2 * (j + s * TL)) : make_double2(0.0, 0.0);
-        v[s] = d[s];
-      }
-      const double x_last = live ? src[M] : 0.0;  // same address in all lanes: one broadcast request
-#pragma unroll
-      for (int sp = 1; sp <= EPT / 2; sp++) {
-        // slot q = j + 32 (EPT - sp):  2M - 2q = 64 sp - 2j
-        double x = __shfl_sync(0xffffffffu, d[sp - 1].x, (32 - j) & 31);
-        const double y = __shfl_sync(0xffffffffu, d[sp - 1].y, 31 - j);
-        if (j == 0) x = (sp < EPT / 2) ? d[sp < EPT / 2 ? sp : 0].x : x_last;
-        v[EPT - sp] = make_double2(x, y);
-      }
-    } else if (!FUSED_DIV && job.div_u == nullptr) {
-#pragma unroll
-      for (int s = 0; s < EPT; s++) {
-        const int q = j + s * TL;
-        if (!live) v[s] = make_double2(0.0, 0.0);
-        else if (s < EPT / 2) v[s] = *reinterpret_cast<const double2 *>(src + 2 * q);
-        else v[s] = make_double2(src[2 * M - 2 * q], src[2 * M - 2 * q - 1]);
-      }
-    } else if constexpr (!FUSED_DIV) {
-      // Shared-memory variant of the fused right-hand side (first version; 1.94 ms per launch at 513^3).  Never
-      // launched any more -- launch_warp sends fused sweeps to the FUSED_DIV instantiation -- but with this branch in
-      // place ptxas schedules the plain x sweep measurably better (0.585 ms per launch against 0.65 ms without it).
-      const long long off = src - field;
-      const double *pu = job.div_u + off, *pv = job.div_v + off, *pw = job.div_w + off;
-      constexpr int NIT = (NPTS + TL - 1) / TL;
-      double vals[NIT];
-#pragma unroll
-      for (int it = 0; it < NIT; it++) {
-        const int e = j + it * TL;
-        if (live && e < NPTS) {
-          const double du_dx = (pu[e + 1] - pu[e]) * job.one_over_dx;
-          const double dv_dy = (pv[e + job.stride_y] - pv[e]) * job.one_over_dy;
-          const double dw_dz = (pw[e + job.stride_z] - pw[e]) * job.one_over_dz;
-          vals[it] = (du_dx + dv_dy + dw_dz) / job.dt;
-        } else {
-          vals[it] = 0.0;
-        }
-      }
-#pragma unroll
-      for (int it = 0; it < NIT; it++) {
-        const int e = j + it * TL;
-        if (e < NPTS) put_packed(Sd, M, e, vals[it]);
-      }
-    } else if constexpr (!SHUFFLE) {
-      __trap();  // the fused right-hand side exists for one warp per line only (poisson_can_fuse_divergence)
-    } else {
-      // Fused right-hand side: rhs(e) = ((u[e+1]-u[e])/dx + (v[e+PX]-v[e])/dy + (w[e+plane]-w[e])/dz) / dt
-      // (include/VelocityDivergence.h:9-20, src/PressureEquation.cpp:59-61) computed in registers: lane j forms the
-      // pairs (rhs(2q), rhs(2q+1)), q = j + 32 s < M/2, from 128-bit loads of u, v, w (rows are 16-byte aligned), and
-      // the mirrored slots q >= M/2 of the even extension, (rhs(2M-2q), rhs(2M-2q-1)), come from the lanes that hold
-      // those values (32 - j and 31 - j) by shuffles -- the right-hand side never exists in memory.
-      const long long off = src - field;
-      const double *pu = job.div_u + off, *pv = job.div_v + off, *pw = job.div_w + off;
-      auto ld2 = [](const double *ptr) { return *reinterpret_cast<const double2 *>(ptr); };
-      double2 d[EPT / 2];
-#pragma unroll
-      for (int s = 0; s < EPT / 2; s++) {
-        const int e = 2 * (j + s * TL);
-        if (live) {
-          const double2 U = ld2(pu + e), V0 = ld2(pv + e), V1 = ld2(pv + e + job.stride_y);
-          const double2 W0 = ld2(pw + e), W1 = ld2(pw + e + job.stride_z);
-          const double u2 = pu[e + 2];
-          d[s].x = ((U.y - U.x) * job.one_over_dx + (V1.x - V0.x) * job.one_over_dy + (W1.x - W0.x) * job.one_over_dz) / job.dt;
-          d[s].y = ((u2 - U.y) * job.one_over_dx + (V1.y - V0.y) * job.one_over_dy + (W1.y - W0.y) * job.one_over_dz) / job.dt;
-        } else {
-          d[s] = make_double2(0.0, 0.0);
-        }
-        v[s] = d[s];
-      }
-      double rhs_last = 0.0;  // rhs(M), the last point of the line (same address in all lanes: one broadcast request)
-      if (live)
-        rhs_last = ((pu[M + 1] - pu[M]) * job.one_over_dx + (pv[M + job.stride_y] - pv[M]) * job.one_over_dy +
-                    (pw[M + job.stride_z] - pw[M]) * job.one_over_dz) / job.dt;
-#pragma unroll
-      for (int sp = 1; sp <= EPT / 2; sp++) {
-        // slot q = j + 32 (EPT - sp):  2M - 2q = 64 sp - 2j
-        double x = __shfl_sync(0xffffffffu, d[sp - 1].x, (32 - j) & 31);
-        const double y = __shfl_sync(0xffffffffu, d[sp - 1].y, 31 - j);
-        if (j == 0) x = (sp < EPT / 2) ? d[sp < EPT / 2 ? sp : 0].x : rhs_last;
-        v[EPT - sp] = make_double2(x, y);
-      }
+    for (int s = 0; s < EPT; s++) {
+      const int q = j + s * TL;
+      if (!live) v[s] = make_double2(0.0, 0.0);
+      else if (s < EPT / 2) v[s] = *reinterpret_cast<const double2 *>(src + 2 * q);
+      else v[s] = make_double2(src[2 * M - 2 * q], src[2 * M - 2 * q - 1]);
     }
     __syncthreads();  // twiddle tables are in place
   } else {
@@ -706,33 +570,7 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
       if constexpr (SEG == 1) return src[(long long)e * job.estride];
       else return job.load_map.n ? *seg_address(job.load_map, e, blockIdx.y, first_line + l) : src[(long long)e * job.estride];
     };
-    if (SEG == 2 && job.load_map.n > 0) {
-      // elements 2q, 2q+1 ascend with s, their mirror images 2M-2q, 2M-2q-1 descend: one cursor each
-      int r_up = 0, r_dn = job.load_map.n - 1;
-#pragma unroll
-      for (int s = 0; s < EPT; s++) {
-        const int q = b + s * TL;
-        if (!live) {
-          v[s] = make_double2(0.0, 0.0);
-        } else if (s < EPT / 2) {
-          const double x0 = *seg_address_from<true>(job.load_map, r_up, 2 * q, blockIdx.y, first_line + l);
-          const double x1 = *seg_address_from<true>(job.load_map, r_up, 2 * q + 1, blockIdx.y, first_line + l);
-          v[s] = make_double2(x0, x1);
-        } else {
-          const double x0 = *seg_address_from<false>(job.load_map, r_dn, 2 * M - 2 * q, blockIdx.y, first_line + l);
-          const double x1 = *seg_address_from<false>(job.load_map, r_dn, 2 * M - 2 * q - 1, blockIdx.y, first_line + l);
-          v[s] = make_double2(x0, x1);
-        }
-      }
-    } else if (SEG == 2) {
-#pragma unroll
-      for (int s = 0; s < EPT; s++) {
-        const int q = b + s * TL;
-        auto plain = [&](int e) { return live ? src[(long long)e * job.estride] : 0.0; };
-        if (s < EPT / 2) v[s] = make_double2(plain(2 * q), plain(2 * q + 1));
-        else v[s] = make_double2(plain(2 * M - 2 * q), plain(2 * M - 2 * q - 1));
-      }
-    } else {
+    {
 #pragma unroll
       for (int s = 0; s < EPT; s++) {
         const int q = b + s * TL;
@@ -747,8 +585,7 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
   double lo[PAIRS], hi[PAIRS], mid = 0.0, e_last = 0.0;
   double spec[EPT];  // shuffle path: spec[u + G t] = E_k, k = j + 32 u + NS t
   if (!CONTIG) fft_line<LOGM, false, SHUFFLE, true>(S, T, j, line, v);                     // first pass already done
-  else if (FUSED_DIV || SEG == 1 || job.div_u == nullptr) fft_line<LOGM, true, SHUFFLE>(S, T, j, line, v);  // first pass from registers
-  else fft_line<LOGM, false, SHUFFLE>(S, T, j, line, v);
+  else fft_line<LOGM, true, SHUFFLE>(S, T, j, line, v);  // first pass from registers
   if constexpr (SHUFFLE) unpack_regs<LOGM>(v, j, job.cs, spec, e_last);
   else unpack_line<LOGM>(S, j, job.cs, lo, hi, mid);
 
@@ -842,11 +679,6 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, (LOGM >= 10 ? 1 :
       double *out = base + (long long)l * job.lstride;
       if constexpr (SEG == 1) {
         for (int e = q0; e < NPTS; e += QSTEP) out[(long long)e * job.estride] = srcl[e];
-      } else if (SEG == 2 && job.store_map.n > 0) {
-        int r = 0;
-        for (int e = q0; e < NPTS; e += QSTEP) *seg_address_from<true>(job.store_map, r, e, blockIdx.y, first_line + l) = srcl[e];
-      } else if (SEG == 2) {
-        for (int e = q0; e < NPTS; e += QSTEP) out[(long long)e * job.estride] = srcl[e];
       } else if (job.store_map.n) {
         // Fused transpose: the results go straight into the pencil / slab buffers of the owning GPUs (peer stores
         // over NVLink for r != this rank), so no pack kernel and no separate all-to-all copy exist.
@@ -916,13 +748,10 @@ __global__ void __launch_bounds__(256, 2) x_dct512_kernel(const FastJob job, dou
   }
 }
 
-void launch_x512(cudaStream_t stream, const FastJob &job, int mode, int outer, double *field, bool *attr_set) {
+void launch_x512(cudaStream_t stream, SmemAttrOnce &attrs, const FastJob &job, int mode, int outer, double *field) {
   const size_t smem = (size_t)(warpfft::kLines * fft512::kLinePitch + fft512::kTwiddles) * sizeof(double2);
-  if (!*attr_set) {
-    cudaFuncSetAttribute(x_dct512_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(x_dct512_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    *attr_set = true;
-  }
+  attrs.ensure(x_dct512_kernel<0>, smem);
+  attrs.ensure(x_dct512_kernel<1>, smem);
   const dim3 grid((job.n_tile_lines + warpfft::kLines - 1) / warpfft::kLines, outer, 1);
   if (mode == 0) x_dct512_kernel<0><<<grid, 256, smem, stream>>>(job, field);
   else x_dct512_kernel<1><<<grid, 256, smem, stream>>>(job, field);
@@ -952,7 +781,6 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, 2) warp_rfft_kern
   double *base = field + job.origin + (long long)first_line * job.tile_stride + (long long)blockIdx.y * job.outer_stride;
   double2 v[EPT];
 
-  prefetch_next_tile<CONTIG, kLines, C::THREADS>(job, field, n);
   load_twiddles<LOGM>(T, job.tw);
   // loader thread: (line, j) along the line for x sweeps, line-fastest (l, b) for the strided sweeps
   const int ll = CONTIG ? line : (tid & 7), lb = CONTIG ? j : (tid >> 3);
@@ -1066,14 +894,10 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, 2) warp_rfft_kern
 }
 
 template <int LOGM>
-void launch_rfft(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid, double *field) {
+void launch_rfft(cudaStream_t stream, SmemAttrOnce &attrs, const FastJob &job, bool contig, dim3 grid, double *field) {
   using C = warpfft::Cfg<LOGM>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(warp_rfft_kernel<LOGM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    cudaFuncSetAttribute(warp_rfft_kernel<LOGM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    attr_set = true;
-  }
+  attrs.ensure(warp_rfft_kernel<LOGM, true>, C::SMEM);
+  attrs.ensure(warp_rfft_kernel<LOGM, false>, C::SMEM);
   if (contig) warp_rfft_kernel<LOGM, true><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
   else warp_rfft_kernel<LOGM, false><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
 }
@@ -1138,7 +962,7 @@ __device__ __forceinline__ void first_pass_both(double2 *even_region, double2 *o
 
 // LINES lines per CTA (64 threads each): 8 lines fill the register file with ONE CTA per SM, whose 16 warps then load,
 // transform and store in lockstep; 4 lines give two independent CTAs per SM that overlap each other's phases.
-// SEG as in warp_dct_kernel: 0 default, 1 no segment-map code (MIFGPU_PLAIN_STRIDED), 2 segment cursors (MIFGPU_SEG_CARRY)
+// SEG as in warp_dct_kernel: 0 = segment maps in use, 1 = instantiation without the map code
 template <bool CONTIG, int LINES, int SEG = 0>
 __global__ void __launch_bounds__(64 * LINES, 8 / LINES) warp_dct_split_kernel(const FastJob job, double *__restrict__ field) {
   using namespace warpfft;
@@ -1157,7 +981,6 @@ __global__ void __launch_bounds__(64 * LINES, 8 / LINES) warp_dct_split_kernel(c
   double *base = field + job.origin + (long long)first_line * job.tile_stride + (long long)blockIdx.y * job.outer_stride;
   double2 v[EPT];
 
-  prefetch_next_tile<CONTIG, LINES, kThreads>(job, field, NPTS);
   load_twiddles<9, 2, kThreads>(T, job.tw);
   {
     // loader thread: butterfly jj of line ll
@@ -1171,23 +994,7 @@ __global__ void __launch_bounds__(64 * LINES, 8 / LINES) warp_dct_split_kernel(c
       else return job.load_map.n ? *seg_address(job.load_map, e, blockIdx.y, first_line + ll) : src[(long long)e * job.estride];
     };
     double2 *a = v, *b = v + 8;
-    if (SEG == 2 && !CONTIG && job.load_map.n > 0) {
-      // segment cursors (MIFGPU_SEG_CARRY=1): 2q, 2q+1 ascend with t, the mirror images descend
-      int r_up = 0, r_dn = job.load_map.n - 1;
-#pragma unroll
-      for (int t = 0; t < 8; t++) {
-        const int q = jj + 64 * t;
-        double2 lo = make_double2(0.0, 0.0), hi = make_double2(0.0, 0.0);
-        if (live) {
-          lo.x = *seg_address_from<true>(job.load_map, r_up, 2 * q, blockIdx.y, first_line + ll);
-          lo.y = *seg_address_from<true>(job.load_map, r_up, 2 * q + 1, blockIdx.y, first_line + ll);
-          hi.x = *seg_address_from<false>(job.load_map, r_dn, kFull - 2 * q, blockIdx.y, first_line + ll);
-          hi.y = *seg_address_from<false>(job.load_map, r_dn, kFull - 1 - 2 * q, blockIdx.y, first_line + ll);
-        }
-        a[t] = cadd(lo, hi);
-        b[t] = csub(lo, hi);
-      }
-    } else {
+    {
 #pragma unroll
       for (int t = 0; t < 8; t++) {
         const int q = jj + 64 * t;
@@ -1270,9 +1077,6 @@ __global__ void __launch_bounds__(64 * LINES, 8 / LINES) warp_dct_split_kernel(c
       double *out = base + (long long)l * job.lstride;
       if constexpr (SEG == 1) {
         for (int e = q0; e < NPTS; e += 64) out[(long long)e * job.estride] = srcl[e];
-      } else if (SEG == 2 && job.store_map.n > 0) {
-        int r = 0;
-        for (int e = q0; e < NPTS; e += 64) *seg_address_from<true>(job.store_map, r, e, blockIdx.y, first_line + l) = srcl[e];
       } else if (job.store_map.n) {
         for (int e = q0; e < NPTS; e += 64) *seg_address(job.store_map, e, blockIdx.y, first_line + l) = srcl[e];
       } else {
@@ -1346,107 +1150,45 @@ __global__ void __launch_bounds__(256, 2) x_dct1024_kernel(const FastJob job, do
   }
 }
 
-void launch_x1024(cudaStream_t stream, const FastJob &job, int mode, int outer, double *field, bool *attr_set) {
+void launch_x1024(cudaStream_t stream, SmemAttrOnce &attrs, const FastJob &job, int mode, int outer, double *field) {
   const size_t smem = (size_t)(8 * fft512::kLinePitch + fft512::kTwiddles) * sizeof(double2);
-  if (!*attr_set) {
-    cudaFuncSetAttribute(x_dct1024_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(x_dct1024_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    *attr_set = true;
-  }
+  attrs.ensure(x_dct1024_kernel<0>, smem);
+  attrs.ensure(x_dct1024_kernel<1>, smem);
   const dim3 grid((job.n_tile_lines + 3) / 4, outer, 1);
   if (mode == 0) x_dct1024_kernel<0><<<grid, 256, smem, stream>>>(job, field);
   else x_dct1024_kernel<1><<<grid, 256, smem, stream>>>(job, field);
 }
 
 template <int LINES>
-void launch_split(cudaStream_t stream, const FastJob &job, bool contig, int outer, double *field) {
-  static bool attr_set = false;
+void launch_split(cudaStream_t stream, SmemAttrOnce &attrs, const FastJob &job, bool contig, int outer, double *field) {
   const size_t smem = split::smem_bytes(LINES);
-  if (!attr_set) {
-    cudaFuncSetAttribute(warp_dct_split_kernel<true, LINES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(warp_dct_split_kernel<false, LINES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
   const dim3 grid((job.n_tile_lines + LINES - 1) / LINES, outer, 1);
-  static const bool seg_carry = getenv("MIFGPU_SEG_CARRY") != nullptr;  // A/B switch, default off (not measured yet)
-  static const bool plain_strided = getenv("MIFGPU_NO_PLAIN_STRIDED") == nullptr;
   if (contig) {
+    attrs.ensure(warp_dct_split_kernel<true, LINES>, smem);
     warp_dct_split_kernel<true, LINES><<<grid, 64 * LINES, smem, stream>>>(job, field);
-  } else if (seg_carry && (job.load_map.n > 0 || job.store_map.n > 0)) {
-    static bool carry_attr_set = false;
-    if (!carry_attr_set) {
-      cudaFuncSetAttribute(warp_dct_split_kernel<false, LINES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      carry_attr_set = true;
-    }
-    warp_dct_split_kernel<false, LINES, 2><<<grid, 64 * LINES, smem, stream>>>(job, field);
-  } else if (plain_strided && job.load_map.n == 0 && job.store_map.n == 0) {
-    static bool plain_attr_set = false;
-    if (!plain_attr_set) {
-      cudaFuncSetAttribute(warp_dct_split_kernel<false, LINES, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      plain_attr_set = true;
-    }
+  } else if (job.load_map.n == 0 && job.store_map.n == 0) {
+    attrs.ensure(warp_dct_split_kernel<false, LINES, 1>, smem);
     warp_dct_split_kernel<false, LINES, 1><<<grid, 64 * LINES, smem, stream>>>(job, field);
   } else {
+    attrs.ensure(warp_dct_split_kernel<false, LINES>, smem);
     warp_dct_split_kernel<false, LINES><<<grid, 64 * LINES, smem, stream>>>(job, field);
   }
 }
 
 template <int LOGM>
-void launch_warp(cudaStream_t stream, const FastJob &job, bool contig, dim3 grid, double *field) {
+void launch_warp(cudaStream_t stream, SmemAttrOnce &attrs, const FastJob &job, bool contig, dim3 grid, double *field) {
   using C = warpfft::Cfg<LOGM>;
   grid.x = (job.n_tile_lines + C::LINES - 1) / C::LINES;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(warp_dct_kernel<LOGM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    cudaFuncSetAttribute(warp_dct_kernel<LOGM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    attr_set = true;
-  }
-  if (contig && job.div_u != nullptr) {
-    if constexpr (C::WPL == 1) {
-      static bool fused_attr_set = false;
-      if (!fused_attr_set) {
-        cudaFuncSetAttribute(warp_dct_kernel<LOGM, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        fused_attr_set = true;
-      }
-      warp_dct_kernel<LOGM, true, true><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
-    }
-  } else if (contig) {
-    static const bool mirror_shfl = getenv("MIFGPU_X_MIRROR_SHFL") != nullptr;  // A/B switch, default off (not measured yet)
-    if constexpr (C::WPL == 1) {
-      if (mirror_shfl) {
-        static bool mirror_attr_set = false;
-        if (!mirror_attr_set) {
-          cudaFuncSetAttribute(warp_dct_kernel<LOGM, true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-          mirror_attr_set = true;
-        }
-        warp_dct_kernel<LOGM, true, false, 1><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
-        return;
-      }
-    }
+  if (contig) {
+    attrs.ensure(warp_dct_kernel<LOGM, true>, C::SMEM);
     warp_dct_kernel<LOGM, true><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
+  } else if (job.load_map.n == 0 && job.store_map.n == 0) {
+    // strided sweeps without the segment-map code when no map is in use (profiles/r01_ab_plain_strided.json)
+    attrs.ensure(warp_dct_kernel<LOGM, false, 1>, C::SMEM);
+    warp_dct_kernel<LOGM, false, 1><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
   } else {
-    // Strided sweeps without the segment-map code when no map is in use.  Measured on B200 at 513^3: y sweeps 2.84 ->
-    // 2.62 ms, fused z sweep 5.56 -> 5.23 ms per step (profiles/r01_ab_plain_strided.json); MIFGPU_NO_PLAIN_STRIDED=1
-    // restores the common instantiation for A/B runs.
-    static const bool plain_strided = getenv("MIFGPU_NO_PLAIN_STRIDED") == nullptr;
-    static const bool seg_carry = getenv("MIFGPU_SEG_CARRY") != nullptr;
-    if (plain_strided && job.load_map.n == 0 && job.store_map.n == 0) {
-      static bool plain_attr_set = false;
-      if (!plain_attr_set) {
-        cudaFuncSetAttribute(warp_dct_kernel<LOGM, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        plain_attr_set = true;
-      }
-      warp_dct_kernel<LOGM, false, false, 1><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
-    } else if (seg_carry && (job.load_map.n > 0 || job.store_map.n > 0)) {
-      static bool carry_attr_set = false;
-      if (!carry_attr_set) {
-        cudaFuncSetAttribute(warp_dct_kernel<LOGM, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        carry_attr_set = true;
-      }
-      warp_dct_kernel<LOGM, false, false, 2><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
-    } else {
-      warp_dct_kernel<LOGM, false><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
-    }
+    attrs.ensure(warp_dct_kernel<LOGM, false>, C::SMEM);
+    warp_dct_kernel<LOGM, false><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
   }
 }
 
@@ -1495,7 +1237,7 @@ struct PoissonPlan {
   size_t smem[3];
   std::vector<void *> allocations;
   tmasweep::Cache tma;  // tensor maps of the TMA-staged strided sweeps, per field / direction
-  bool x512_attr = false, x1024_attr = false;
+  SmemAttrOnce attrs;   // dynamic shared-memory opt-in per kernel, for this plan's device
 };
 
 PoissonPlan *poisson_plan_create(const Geom &g, const int n_points[3], const int periodic[3], const double h[3],
@@ -1619,9 +1361,6 @@ struct SweepLayout {
   bool has_origin;   // this rank holds the (0,0,0) mode
   SegMap load_map, store_map;
   bool peer = false;  // peer-memory sweeps: tiles of exactly 8 lines (the x tiles of the blocked buffers)
-  const double *div_u = nullptr, *div_v = nullptr, *div_w = nullptr;  // fused right-hand side (forward x sweep only)
-  double one_over_dx = 0, one_over_dy = 0, one_over_dz = 0, dt = 1;
-  long long stride_y = 0, stride_z = 0;
 };
 
 void launch_tma_modes(cudaStream_t stream, tmasweep::Cache &cache, const tmasweep::MapSet &maps, const tmasweep::Job &job, int logm,
@@ -1681,11 +1420,8 @@ bool launch_tma_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int
 void launch_tma_modes(cudaStream_t stream, tmasweep::Cache &cache, const tmasweep::MapSet &maps_ref, const tmasweep::Job &job_in, int logm,
                       int mode) {
   static const bool radix8_fft = getenv("MIFGPU_FFT_RADIX8") != nullptr;  // A/B: 513-point lines on the radix-8 Stockham passes
-  static const int stagger_ns = getenv("MIFGPU_TMA_STAGGER_NS") ? atoi(getenv("MIFGPU_TMA_STAGGER_NS")) : 0;
   const tmasweep::MapSet *maps = &maps_ref;
-  tmasweep::Job job = job_in;
-  job.stagger_from = cache.sms;  // CTAs beyond the first wave of one per SM
-  job.stagger_ns = (logm == 10) ? 0u : (unsigned)stagger_ns;  // 1025-point lines: one CTA per SM
+  const tmasweep::Job &job = job_in;
   if (logm == 10) {
     if (mode == 0) tmasweep::launch_1024<0>(stream, cache, *maps, job);
     else if (mode == 1) tmasweep::launch_1024<1>(stream, cache, *maps, job);
@@ -1707,11 +1443,8 @@ void launch_tma_modes(cudaStream_t stream, tmasweep::Cache &cache, const tmaswee
 
 void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, int mode, const SweepLayout &lay,
                   uint64_t *launches) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
+  SmemAttrOnce &attrs = plan->attrs;
+  attrs.ensure(sweep_kernel, 200 * 1024);
   if (plan->fast_logm[d] > 0 || plan->rfft_logm[d] > 0) {
     FastJob fj;
     fj.origin = lay.origin; fj.lstride = lay.lstride; fj.estride = lay.estride;
@@ -1721,61 +1454,37 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
     fj.lam_x = plan->dir[0].lambda + lay.lam_x_offset; fj.lam_y = plan->dir[1].lambda + lay.lam_y_offset; fj.lam_z = plan->dir[2].lambda;
     fj.inv_norm = plan->dir[d].inv_norm;
     fj.has_origin = lay.has_origin;
-    // Off by default: measured on B200 at 513^3 with distances 148 / 296 / 592 the sweeps got 2-7 % SLOWER (x 1.76 ->
-    // 1.80 ms, y 2.72 -> 2.93 ms, fused z 5.40 -> 5.79 ms per step) -- the extra LSU requests cost more in these
-    // LSU-bound kernels than the shorter first-load wait gains.
-    static const int prefetch_ctas = getenv("MIFGPU_SWEEP_PREFETCH") ? atoi(getenv("MIFGPU_SWEEP_PREFETCH")) : MIFGPU_SWEEP_PREFETCH_CTAS;
-    fj.prefetch_ctas = prefetch_ctas;
     fj.load_map = lay.load_map; fj.store_map = lay.store_map;
-    fj.div_u = lay.div_u; fj.div_v = lay.div_v; fj.div_w = lay.div_w;
-    fj.one_over_dx = lay.one_over_dx; fj.one_over_dy = lay.one_over_dy; fj.one_over_dz = lay.one_over_dz;
-    fj.dt = lay.dt; fj.stride_y = lay.stride_y; fj.stride_z = lay.stride_z;
     const dim3 fgrid((lay.n_tile_lines + fast::kLines - 1) / fast::kLines, lay.outer, 1);
-    static const bool use_cta_sync_variant = getenv("MIFGPU_FFT_CTA_SYNC") != nullptr;  // A/B switch for profiling
     if (plan->rfft_logm[d] > 0) {
-      if (plan->rfft_logm[d] == 8) launch_rfft<8>(stream, fj, lay.contig, fgrid, field);
-      else launch_rfft<9>(stream, fj, lay.contig, fgrid, field);
+      if (plan->rfft_logm[d] == 8) launch_rfft<8>(stream, attrs, fj, lay.contig, fgrid, field);
+      else launch_rfft<9>(stream, attrs, fj, lay.contig, fgrid, field);
       ++*launches;
       return;
     }
-    if (launch_tma_sweep(stream, plan, field, d, mode, lay)) {
+    if (launch_tma_sweep(stream, plan, field, d, mode, lay)) {  // strided 257- / 513- / 1025-point lines
       ++*launches;
       return;
     }
+    // A/B switch: 513- and 1025-point lines on the radix-8 Stockham passes of mif_fft_warp.cuh instead of the 16 x 32 transform
+    static const bool radix8_fft = getenv("MIFGPU_FFT_RADIX8") != nullptr;
+    const bool aligned = ((lay.origin | lay.lstride | lay.tile_stride | lay.outer_stride) & 1) == 0;
     switch (plan->fast_logm[d]) {
-      case 6: launch_fast<6>(stream, fj, lay.contig, fgrid, field); break;
-      case 7: launch_fast<7>(stream, fj, lay.contig, fgrid, field); break;
-      case 8:
-        if (use_cta_sync_variant) launch_fast<8>(stream, fj, lay.contig, fgrid, field);
-        else launch_warp<8>(stream, fj, lay.contig, fgrid, field);
+      case 6: launch_fast<6>(stream, attrs, fj, lay.contig, fgrid, field); break;
+      case 7: launch_fast<7>(stream, attrs, fj, lay.contig, fgrid, field); break;
+      case 8: launch_warp<8>(stream, attrs, fj, lay.contig, fgrid, field); break;
+      case 9:
+        if (lay.contig && !radix8_fft && aligned && mode != 2) launch_x512(stream, attrs, fj, mode, lay.outer, field);
+        else launch_warp<9>(stream, attrs, fj, lay.contig, fgrid, field);
         break;
-      case 9: {
-        static const bool radix8_fft = getenv("MIFGPU_FFT_RADIX8") != nullptr;  // A/B: the radix-8 Stockham passes
-        const bool aligned = ((lay.origin | lay.lstride | lay.tile_stride | lay.outer_stride) & 1) == 0;
-        if (use_cta_sync_variant) launch_fast<9>(stream, fj, lay.contig, fgrid, field);
-        else if (lay.contig && !radix8_fft && aligned && lay.div_u == nullptr && mode != 2)
-          launch_x512(stream, fj, mode, lay.outer, field, &plan->x512_attr);
-        else launch_warp<9>(stream, fj, lay.contig, fgrid, field);
-        break;
-      }
       case 11:  // 2049-point lines (BASELINE configs[4]): four warps per line, 4-line CTAs
-        launch_warp<11>(stream, fj, lay.contig, fgrid, field);
+        launch_warp<11>(stream, attrs, fj, lay.contig, fgrid, field);
         break;
-      default: {
-        static const bool use_two_warp_variant = getenv("MIFGPU_FFT_NO_SPLIT") != nullptr;  // A/B switch for profiling
-        static const bool radix8_fft = getenv("MIFGPU_FFT_RADIX8") != nullptr;  // A/B: the radix-8 Stockham passes
-        const bool aligned = ((lay.origin | lay.lstride | lay.tile_stride | lay.outer_stride) & 1) == 0;
-        if (use_cta_sync_variant) launch_fast<10>(stream, fj, lay.contig, fgrid, field);
-        else if (lay.contig && !radix8_fft && aligned && mode != 2) launch_x1024(stream, fj, mode, lay.outer, field, &plan->x1024_attr);
-        else if (use_two_warp_variant) launch_warp<10>(stream, fj, lay.contig, fgrid, field);
-        else {
-          static const int lines_contig = getenv("MIFGPU_SPLIT_LINES_X") ? atoi(getenv("MIFGPU_SPLIT_LINES_X")) : 4;
-          static const int lines_strided = getenv("MIFGPU_SPLIT_LINES_YZ") ? atoi(getenv("MIFGPU_SPLIT_LINES_YZ")) : 4;
-          if (lay.peer || (lay.contig ? lines_contig : lines_strided) == 8) launch_split<8>(stream, fj, lay.contig, lay.outer, field);
-          else launch_split<4>(stream, fj, lay.contig, lay.outer, field);
-        }
+      default:  // 1025-point lines
+        if (lay.contig && !radix8_fft && aligned && mode != 2) launch_x1024(stream, attrs, fj, mode, lay.outer, field);
+        else if (lay.peer) launch_split<8>(stream, attrs, fj, lay.contig, lay.outer, field);  // 8-line tiles of the blocked buffers
+        else launch_split<4>(stream, attrs, fj, lay.contig, lay.outer, field);
         break;
-      }
     }
     ++*launches;
     return;
@@ -1799,19 +1508,8 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
 
 }  // namespace
 
-bool poisson_can_fuse_divergence(const PoissonPlan *plan) {
-  // The forward x sweep of the one-warp-per-line kernel (513- and 257-point lines) can form its input, div(u)/dt, in
-  // registers (128-bit loads of u, v, w; mirrored half of the even extension by shuffles).  Measured on B200 at 513^3:
-  // the fused launch takes 1.42 ms against 0.74 ms (divergence_kernel) + 0.65 ms (plain forward x sweep) -- it saves
-  // 16 B/point of HBM traffic but no time, because with 16 warps per SM the sweep cannot keep enough loads in flight
-  // to stream four arrays.  Kept as an experiment only (MIFGPU_FUSED_DIVERGENCE=1).
-  static const bool enabled = getenv("MIFGPU_FUSED_DIVERGENCE") && atoi(getenv("MIFGPU_FUSED_DIVERGENCE")) != 0 &&
-                              getenv("MIFGPU_FFT_CTA_SYNC") == nullptr;
-  return enabled && (plan->fast_logm[0] == 8 || plan->fast_logm[0] == 9);
-}
-
 void launch_poisson_sweep(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *field, int d, int mode,
-                          uint64_t *launches, const double *const *divergence_of, double dt) {
+                          uint64_t *launches) {
   const int nx = g.own_hi[0] - g.own_lo[0], ny = g.own_hi[1] - g.own_lo[1], nz = g.own_hi[2] - g.own_lo[2];
   SweepLayout lay;
   lay.origin = gidx(g, g.own_lo[0], g.own_lo[1], g.own_lo[2]);
@@ -1827,11 +1525,6 @@ void launch_poisson_sweep(cudaStream_t stream, const Geom &g, PoissonPlan *plan,
   } else {  // lines along z, tile over x, outer y
     lay.n_tile_lines = nx; lay.lstride = 1; lay.estride = g.plane;
     lay.tile_stride = 1; lay.outer_stride = g.PX; lay.outer = ny;
-  }
-  if (divergence_of && d == 0 && mode == 0) {
-    lay.div_u = divergence_of[0]; lay.div_v = divergence_of[1]; lay.div_w = divergence_of[2];
-    lay.one_over_dx = g.one_over_dx; lay.one_over_dy = g.one_over_dy; lay.one_over_dz = g.one_over_dz;
-    lay.dt = dt; lay.stride_y = g.PX; lay.stride_z = g.plane;
   }
   launch_sweep(stream, plan, field, d, mode, lay, launches);
 }

@@ -73,12 +73,6 @@ struct Job {
   double inv_norm;
   int has_origin;
   unsigned swz;  // 3: the output stage is swizzled (CU_TENSOR_MAP_SWIZZLE_64B), 0: plain
-  // The CTAs that share an SM run the same phases (FP64-heavy butterflies, then shared-memory traffic) for the same time
-  // per tile; started together they stay in step and the two pipes take turns.  The second CTA of every SM (blockIdx >=
-  // stagger_from) therefore starts stagger_ns later, about half a tile, so that one CTA's butterflies overlap the other's
-  // exchanges.
-  int stagger_from;
-  unsigned stagger_ns;
   // input side
   int outer_fastest;     // tile order: 0 = x tile fastest (plain arrays), 1 = outer index fastest (blocked buffers)
   int in_x_tiled;        // load coordinate 0 = x_off + 8 xt (plain arrays) or 0 (blocked buffers: x tile folded into coordinate 2)
@@ -209,9 +203,6 @@ __global__ void __launch_bounds__(kThreads, 2)
   int tile = blockIdx.x;
   if (tid == 0 && tile < n_tiles) issue_load(tile);
   unsigned parity = 0;
-  if (job.stagger_ns && (int)blockIdx.x >= job.stagger_from) {
-    for (unsigned waited = 0; waited < job.stagger_ns; waited += 500) tma::sleep_ns(500);
-  }
 
   for (; tile < n_tiles; tile += gridDim.x) {
     const Tile t = decode_tile(job, tile);
@@ -376,9 +367,6 @@ __global__ void __launch_bounds__(kThreads, 2)
   int tile = blockIdx.x;
   if (tid == 0 && tile < n_tiles) issue_load(tile);
   unsigned parity = 0;
-  if (job.stagger_ns && (int)blockIdx.x >= job.stagger_from) {
-    for (unsigned waited = 0; waited < job.stagger_ns; waited += 500) tma::sleep_ns(500);
-  }
 
   for (; tile < n_tiles; tile += gridDim.x) {
     const Tile t = decode_tile(job, tile);
@@ -573,9 +561,6 @@ __global__ void __launch_bounds__(Layout1024::kThreads, 1)
   int tile = blockIdx.x;
   if (tid == 0 && tile < n_tiles) issue_load(tile);
   unsigned parity = 0;
-  if (job.stagger_ns && (int)blockIdx.x >= job.stagger_from) {
-    for (unsigned waited = 0; waited < job.stagger_ns; waited += 500) tma::sleep_ns(500);
-  }
 
   for (; tile < n_tiles; tile += gridDim.x) {
     const Tile t = decode_tile(job, tile);

@@ -101,7 +101,6 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void prefetch_map(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
-__device__ __forceinline__ void sleep_ns(unsigned ns) { asm volatile("nanosleep.u32 %0;" ::"r"(ns)); }
 // Address bits the 128-byte swizzle mixes: shared-window address on the device.
 __device__ __forceinline__ uintptr_t swizzle_address(const void *p) { return (uintptr_t)smem_u32(p); }
 #else
@@ -125,7 +124,6 @@ __device__ __forceinline__ void wait_stores_read() { emu::tma_wait_group(0, true
 __device__ __forceinline__ void wait_stores_done() { emu::tma_wait_group(0, false); }
 __device__ __forceinline__ void fence_proxy_async() {}
 __device__ __forceinline__ void prefetch_map(const CUtensorMap *) {}
-__device__ __forceinline__ void sleep_ns(unsigned) {}
 __device__ __forceinline__ uintptr_t swizzle_address(const void *p) { return reinterpret_cast<uintptr_t>(p); }
 #endif
 
