@@ -556,14 +556,15 @@ def main():
         e2e_steps = max(6, min(steps, 9))
         # three sets: while set A computes, B uploads and C downloads (with two, the upload into a set would have to wait
         # for that set's own download and the two PCIe directions would take turns)
-        sets = [(vel, p)] + [(ctx.velocity(), ctx.tensor(mif.STAGGER_NONE)) for _ in range(2)]
+        n_sets = max(1, int(os.environ.get("MIF_BENCH_E2E_SETS", "3")))
+        sets = [(vel, p)] + [(ctx.velocity(), ctx.tensor(mif.STAGGER_NONE)) for _ in range(n_sets - 1)]
         out = [torch.zeros(tuple(a.shape), dtype=torch.float64).pin_memory() for a in host]
         for v2, p2 in sets[1:]:
             for t, arr in zip(v2 + [p2], host):
                 t.upload(arr.numpy())
 
         def one_job(i):
-            v_i, p_i = sets[i % 3]
+            v_i, p_i = sets[i % n_sets]
             for t, arr in zip(v_i + [p_i], host):
                 t.upload_async(arr.numpy())
             ctx.timestep(v_i, vb, vb2, bc, step_index[0] * dt, p_i, dp)
@@ -571,7 +572,7 @@ def main():
             for t, arr in zip(v_i + [p_i], out):
                 t.download_async(arr.numpy())
 
-        for i in range(3):
+        for i in range(n_sets):
             one_job(i)  # warm-up: copy streams, staging buffers
         barrier()
         t0 = time.perf_counter()
@@ -585,6 +586,7 @@ def main():
             e2e_s = float(tmax.item())
         e2e = {"value": world * cells * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": field_bytes,
                "d2h_bytes_per_step": field_bytes, "steps": e2e_steps, "ms_per_step": round(1e3 * e2e_s / e2e_steps, 3),
+               "device_field_sets": n_sets,
                "result_finite": bool(np.isfinite(out[1].numpy()).all()),
                "what": "per step (one job): async upload of u,v,w,p from pinned host memory, mifgpu_timestep, async download "
                        "of u,v,w,p; consecutive jobs are independent and rotate through three device field sets, so "
