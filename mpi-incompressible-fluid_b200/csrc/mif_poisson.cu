@@ -764,7 +764,9 @@ void launch_x512(cudaStream_t stream, SmemAttrOnce &attrs, const FastJob &job, i
 // registers: unpack, eigenvalue scaling in halfcomplex order, repack (the unpacked index k = j + 32 (u + G t) is
 // the first-pass slot of the next transform), inverse FFT as conj(FFT(conj .)), normalisation.
 // ------------------------------------------------------------------------------------------------
-template <int LOGM, bool CONTIG>
+// MODE as a template parameter: the three paths keep different arrays alive (the 1024-point instantiation spilled 400-600
+// bytes while the mode was a run-time value).
+template <int LOGM, bool CONTIG, int MODE>
 __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, 2) warp_rfft_kernel(const FastJob job, double *__restrict__ field) {
   using namespace warpfft;
   using C = Cfg<LOGM>;
@@ -787,7 +789,7 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, 2) warp_rfft_kern
   const bool live = ll < lines;
   const double *src = base + (long long)ll * job.lstride;
   auto element = [&](int e) -> double { return live ? src[(long long)e * job.estride] : 0.0; };
-  if (job.mode == 1) {
+  if (MODE == 1) {
     // halfcomplex input: X_k = (in[k], in[n-k]), partner X_{M-k} = (in[M-k], in[M+k]); X_0 and X_M are real
 #pragma unroll
     for (int s = 0; s < EPT; s++) {
@@ -814,9 +816,9 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, 2) warp_rfft_kern
   }
 
   double re[EPT], im[EPT], x_last = 0.0;
-  if (job.mode != 1) {
+  if (MODE != 1) {
     unpack_r2hc_regs<LOGM>(v, j, job.cs, re, im, x_last);
-    if (job.mode == 2) {
+    if (MODE == 2) {
       // pressure_hat *= 1 / (lambda_x + lambda_y + lambda_z) in FFTW output order; mode (0,0,0) := 0
       // (src/PressureEquation.cpp:158-163)
       const int ix = min(first_line + line, job.n_tile_lines - 1);
@@ -837,7 +839,7 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, 2) warp_rfft_kern
     }
   }
 
-  if (job.mode == 0) {
+  if (MODE == 0) {
     // halfcomplex output
     if (CONTIG) {
       if (line < lines) {
@@ -893,13 +895,22 @@ __global__ void __launch_bounds__(warpfft::Cfg<LOGM>::THREADS, 2) warp_rfft_kern
   }
 }
 
+template <int LOGM, int MODE>
+void launch_rfft_mode(cudaStream_t stream, SmemAttrOnce &attrs, const FastJob &job, bool contig, dim3 grid, double *field) {
+  using C = warpfft::Cfg<LOGM>;
+  if (contig) {
+    attrs.ensure(warp_rfft_kernel<LOGM, true, MODE>, C::SMEM);
+    warp_rfft_kernel<LOGM, true, MODE><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
+  } else {
+    attrs.ensure(warp_rfft_kernel<LOGM, false, MODE>, C::SMEM);
+    warp_rfft_kernel<LOGM, false, MODE><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
+  }
+}
 template <int LOGM>
 void launch_rfft(cudaStream_t stream, SmemAttrOnce &attrs, const FastJob &job, bool contig, dim3 grid, double *field) {
-  using C = warpfft::Cfg<LOGM>;
-  attrs.ensure(warp_rfft_kernel<LOGM, true>, C::SMEM);
-  attrs.ensure(warp_rfft_kernel<LOGM, false>, C::SMEM);
-  if (contig) warp_rfft_kernel<LOGM, true><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
-  else warp_rfft_kernel<LOGM, false><<<grid, C::THREADS, C::SMEM, stream>>>(job, field);
+  if (job.mode == 0) launch_rfft_mode<LOGM, 0>(stream, attrs, job, contig, grid, field);
+  else if (job.mode == 1) launch_rfft_mode<LOGM, 1>(stream, attrs, job, contig, grid, field);
+  else launch_rfft_mode<LOGM, 2>(stream, attrs, job, contig, grid, field);
 }
 
 // ------------------------------------------------------------------------------------------------
