@@ -25,6 +25,7 @@
 
 #include <map>
 #include <tuple>
+#include <vector>
 
 #include "mif_fft512.cuh"
 #include "mif_fft_warp.cuh"
@@ -80,7 +81,21 @@ struct Job {
   int in_perm_base;      // >= 0: the input rows left a swizzled output stage in which this tile's lines were row in_perm_base +
                          // outer, so the 16-byte pairs of its 8 columns arrive XOR-permuted by ((row >> 1) & 3); -1: in order
   PeerOut out;
+#ifdef MIFGPU_PHASE_TRACE
+  unsigned long long *trace;  // diagnostic build only (make trace): SM-clock stamps at the phase boundaries of two CTAs
+#endif
 };
+
+#ifdef MIFGPU_PHASE_TRACE
+constexpr int kTraceTiles = 24, kTraceSlots = 16;
+#define MIF_TRACE(id)                                                                                                          \
+  do {                                                                                                                          \
+    if (trace_cta >= 0 && j == 0 && n_traced < kTraceTiles)                                                                     \
+      job.trace[((size_t)(trace_cta * 8 + line) * kTraceTiles + n_traced) * kTraceSlots + (id)] = clock64();                    \
+  } while (0)
+#else
+#define MIF_TRACE(id)
+#endif
 
 struct Tile {
   int xt, outer, x_in, c2, perm;
@@ -367,6 +382,15 @@ __global__ void __launch_bounds__(kThreads, 2)
   int tile = blockIdx.x;
   if (tid == 0 && tile < n_tiles) issue_load(tile);
   unsigned parity = 0;
+#ifdef MIFGPU_PHASE_TRACE
+  const int trace_cta = (job.trace && blockIdx.x % 148 == 0 && blockIdx.x < 296) ? (int)(blockIdx.x / 148) : -1;
+  int n_traced = 0;
+  if (trace_cta >= 0 && tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    job.trace[(size_t)2 * 8 * kTraceTiles * kTraceSlots + trace_cta] = smid;
+  }
+#endif
 
   for (; tile < n_tiles; tile += gridDim.x) {
     const Tile t = decode_tile(job, tile);
@@ -374,8 +398,10 @@ __global__ void __launch_bounds__(kThreads, 2)
     double2 v[16];
 
     // ---- phase A by the stage threads: inputs c[b + 32 s] of line l -------------------------------------------------
+    MIF_TRACE(0);
     tma::mbar_wait(full, parity);
     parity ^= 1;
+    MIF_TRACE(1);
     if (MODE == 1) {
       const double *N = S + l;  // natural rows: element e of line l at N[8 e]
       const double2 base = __ldg(&job.cs[b]);
@@ -395,17 +421,24 @@ __global__ void __launch_bounds__(kThreads, 2)
         else v[s] = make_double2(Ev[8 * (M - q)], Od[8 * (M - q - 1)]);  // mirror image: e(2M-2q), e(2M-2q-1)
       }
     }
+    MIF_TRACE(2);
     fft512::phase_a(v, b, T);
+    MIF_TRACE(3);
     if (tid == 0) tma::wait_stores_read();  // the previous tile's output stage (in W) has been read out
     __syncthreads();                        // the stage has been consumed, W is free
+    MIF_TRACE(4);
     if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue_load(tile + gridDim.x);
     fft512::store_a(W + l * fft512::kLinePitch, b, v);
+    MIF_TRACE(5);
     __syncthreads();
+    MIF_TRACE(6);
 
     // ---- phase B by the line's warp ------------------------------------------------------------------------------------
     fft512::phase_b(Sline, j, v);
+    MIF_TRACE(7);
     double spec[16], e_last = 0.0;
     if (MODE != 1) fft512::unpack_dct(v, j, job.cs, spec, e_last);
+    MIF_TRACE(8);
     if (MODE == 2) {
       // pressure_hat *= 1 / (lambda_x + lambda_y + lambda_z); mode (0,0,0) := 0 (src/PressureEquation.cpp:158-163)
       const int ix = min(xt * kLines + col, job.n_lines - 1);
@@ -424,7 +457,9 @@ __global__ void __launch_bounds__(kThreads, 2)
       __syncwarp();
       fft512::phase_b(Sline, j, v);
     }
+    MIF_TRACE(9);
     __syncthreads();  // all warps are done with the work area: it becomes the output stage
+    MIF_TRACE(10);
 
     // ---- results into the swizzled output stage (see tma_dct_kernel): row e of the tile at 64 e, column `line` ----------
     const int k2 = j & 15, p = j >> 4;
@@ -450,9 +485,14 @@ __global__ void __launch_bounds__(kThreads, 2)
       }
       if (j == 0) *reinterpret_cast<double *>(O + tma::swizzle_offset((unsigned)(M * 64 + col * 8), job.swz)) = v[8].x * scale;
     }
+    MIF_TRACE(11);
     tma::fence_proxy_async();
     __syncthreads();
+    MIF_TRACE(12);
     if (tid == 0) store_tile<Y::kStoreBoxes>(job, &map_out, O, t);
+#ifdef MIFGPU_PHASE_TRACE
+    n_traced++;
+#endif
   }
   if (tid == 0) tma::wait_stores_done();
 }
@@ -737,7 +777,35 @@ void launch_512(cudaStream_t stream, Cache &cache, const MapSet &maps, const Job
   static const int per_sm = getenv("MIFGPU_TMA_CTAS_PER_SM") ? atoi(getenv("MIFGPU_TMA_CTAS_PER_SM")) : 2;
   const int n_tiles = job.n_xtiles * job.n_outer;
   const int grid = std::min(n_tiles, std::max(1, cache.sms * per_sm));
+#ifdef MIFGPU_PHASE_TRACE
+  // diagnostic build: the launch number MIFGPU_TRACE_LAUNCH of this mode writes its stamps to MIFGPU_TRACE_FILE
+  static int launch_no[3] = {0, 0, 0};
+  static unsigned long long *trace_dev = nullptr;
+  const size_t words = (size_t)2 * 8 * kTraceTiles * kTraceSlots + 2;
+  Job traced = job;
+  traced.trace = nullptr;
+  const char *file = getenv("MIFGPU_TRACE_FILE");
+  const int want_mode = getenv("MIFGPU_TRACE_MODE") ? atoi(getenv("MIFGPU_TRACE_MODE")) : 0;
+  const int want_launch = getenv("MIFGPU_TRACE_LAUNCH") ? atoi(getenv("MIFGPU_TRACE_LAUNCH")) : 12;
+  const bool dump = file && MODE == want_mode && launch_no[MODE]++ == want_launch;
+  if (dump) {
+    if (!trace_dev) cudaMalloc(&trace_dev, words * 8);
+    cudaMemsetAsync(trace_dev, 0, words * 8, stream);
+    traced.trace = trace_dev;
+  }
+  tma_dct512_kernel<MODE><<<grid, kThreads, Y::kSmem, stream>>>(MODE == 1 ? maps.natural : maps.even, maps.odd, maps.out, traced);
+  if (dump) {
+    std::vector<unsigned long long> host(words);
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(host.data(), trace_dev, words * 8, cudaMemcpyDeviceToHost);
+    if (FILE *f = fopen(file, "wb")) {
+      fwrite(host.data(), 8, words, f);
+      fclose(f);
+    }
+  }
+#else
   tma_dct512_kernel<MODE><<<grid, kThreads, Y::kSmem, stream>>>(MODE == 1 ? maps.natural : maps.even, maps.odd, maps.out, job);
+#endif
 }
 
 template <int MODE>
