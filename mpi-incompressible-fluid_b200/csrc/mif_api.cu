@@ -134,6 +134,7 @@ struct mifgpu_ctx {
   std::vector<int> zs, yzs;  // Pz + 1: owner z planes of z_rank r; y rows of the z pencil of z_rank r
   double *ypen = nullptr, *zpen = nullptr;           // pencil buffers, rows of pen_pitch doubles
   double *box_send = nullptr, *box_recv = nullptr;   // compact staging of the box exchanges
+  size_t box_capacity = 0;                           // doubles in each of them
   int pen_pitch = 0;
   double *staging = nullptr; // compact device copy of one tensor for host transfers
   size_t staging_bytes = 0;
@@ -500,6 +501,8 @@ int exchange_boxes(mifgpu_ctx *ctx, const std::vector<int> &peers, const std::ve
     stotal += send[i].count();
     rtotal += recv[i].count();
   }
+  if (stotal > ctx->box_capacity || rtotal > ctx->box_capacity)
+    return fail(MIFGPU_ERR_INVALID, "box exchange of %zu / %zu values exceeds the staging buffers (%zu)", stotal, rtotal, ctx->box_capacity);
   int rc;
   for (size_t i = 0; i < peers.size(); i++) {
     if (peers[i] == me) {
@@ -855,9 +858,12 @@ static int create_context(const mifgpu_params *params, const void *unique_id, mi
     const size_t nxl = ctx->xs[yr + 1] - ctx->xs[yr], nzl = ctx->zs[zr + 1] - ctx->zs[zr], nyz = ctx->yzs[zr + 1] - ctx->yzs[zr];
     ctx->pen_pitch = (int)((nxl + 7) / 8 * 8);
     const size_t ypen = (size_t)ctx->pen_pitch * n_points[1] * nzl, zpen = (size_t)ctx->pen_pitch * nyz * n_points[2];
-    // staging: the largest of one sub-domain (owner block or three halo sheets) and one pencil
+    // staging: the largest of one sub-domain, one pencil, and the y halo exchange of a velocity triple (three tensors, a
+    // sheet towards each neighbour: 6 x-z sheets -- more than the whole sub-domain when a rank holds fewer than 6 rows)
     const size_t sub = (size_t)g.PX * g.PY * g.PZ;
-    const size_t stage = std::max(std::max(ypen, zpen), sub);
+    const size_t sheets = (size_t)6 * g.PX * g.PZ;
+    const size_t stage = std::max(std::max(std::max(ypen, zpen), sub), sheets);
+    ctx->box_capacity = stage;
     if (cudaMalloc(&ctx->ypen, ypen * sizeof(double)) != cudaSuccess || cudaMalloc(&ctx->zpen, zpen * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&ctx->box_send, stage * sizeof(double)) != cudaSuccess || cudaMalloc(&ctx->box_recv, stage * sizeof(double)) != cudaSuccess) {
       mifgpu_destroy(ctx);

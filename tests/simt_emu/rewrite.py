@@ -93,12 +93,12 @@ def rewrite_launches(text):
 
 
 def drop_device_only_blocks(text):
-    """Remove the `#ifndef MIF_SIMT_EMU` branches (inline PTX the interpreter replaces by emu:: calls); the `#else`
-    branch, if any, stays."""
+    """Remove the `#ifndef MIF_SIMT_EMU` branches (inline PTX the interpreter replaces by emu:: calls) and the
+    `#ifdef MIFGPU_PHASE_TRACE` branches (diagnostic build only); the `#else` branch, if any, stays."""
     out, keep, depth_stack = [], True, []
     for line in text.split("\n"):
         stripped = line.strip()
-        if stripped.startswith("#ifndef MIF_SIMT_EMU"):
+        if stripped.startswith("#ifndef MIF_SIMT_EMU") or stripped.startswith("#ifdef MIFGPU_PHASE_TRACE"):
             depth_stack.append("emu")
             keep = False
             out.append("#if 1  // MIF_SIMT_EMU branch kept by rewrite.py")
