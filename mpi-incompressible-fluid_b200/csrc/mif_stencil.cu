@@ -58,8 +58,11 @@ __device__ __forceinline__ void store_pair(double *ptr, bool w0, bool w1, double
   else if (w1) ptr[1] = v1;
 }
 
+#ifndef MIFGPU_STAGE_CTAS
+#define MIFGPU_STAGE_CTAS 4  // resident CTAs per SM the register budget is set for (A/B: -DMIFGPU_STAGE_CTAS=5 / 6)
+#endif
 template <int STAGE>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, MIFGPU_STAGE_CTAS)
 stage_kernel_pair(const Geom g, const double *__restrict__ in_u, const double *__restrict__ in_v,
                   const double *__restrict__ in_w, const double *__restrict__ p, double *__restrict__ a_u,
                   double *__restrict__ a_v, double *__restrict__ a_w, double *__restrict__ b_u, double *__restrict__ b_v,
