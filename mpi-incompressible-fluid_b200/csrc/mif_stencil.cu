@@ -59,7 +59,8 @@ __device__ __forceinline__ void store_pair(double *ptr, bool w0, bool w1, double
 }
 
 #ifndef MIFGPU_STAGE_CTAS
-#define MIFGPU_STAGE_CTAS 4  // resident CTAs per SM the register budget is set for (A/B: -DMIFGPU_STAGE_CTAS=5 / 6)
+#define MIFGPU_STAGE_CTAS 4  // resident CTAs per SM the register budget is set for: 128 registers.  Measured with 5 (96
+                             // registers) and 6 (80): 7 % and 22 % slower (profiles/r02_s7_ab_stage_occupancy.jsonl)
 #endif
 template <int STAGE>
 __global__ void __launch_bounds__(128, MIFGPU_STAGE_CTAS)
