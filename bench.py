@@ -512,13 +512,13 @@ def main():
     ncu_summary = os.path.join(ROOT, "profiles", "r02_ncu_sweep_kernels.json")
     if world == 1 and dims == [513, 513, 513] and os.path.exists(ncu_summary):
         with open(ncu_summary) as f:
-            rows = [r for r in json.load(f) if "dct_kernel" in r["kernel"]]
+            rows = [r for r in json.load(f) if "dct" in r["kernel"]]
         if rows:
             traffic = round(sum(r["dram_read_GB"] + r["dram_write_GB"] for r in rows) / len(rows) * 1e9)
             traffic_src = ("profiles/r02_ncu_sweep_kernels.json (dram__bytes_read.sum + dram__bytes_write.sum, mean of the %d "
                            "sweep launches of one solve)" % len(rows))
-    sweep_kernel_names = ("tma_dct_kernel<9, 0|1|2> (y forward / y inverse / fused z, TMA-staged) and warp_dct_kernel<9, true> "
-                          "(x forward / inverse)") if dims[1] == 513 and dims[2] == 513 and world == 1 else \
+    sweep_kernel_names = ("tma_dct512_kernel<0|1|2> (y forward / y inverse / fused z, TMA-staged) and x_dct512_kernel<0|1> "
+                          "(x forward / inverse)") if dims == [513, 513, 513] and world == 1 else \
         "Poisson sweep kernels of this grid (csrc/mif_poisson.cu: launch_sweep picks them by line length)"
     roofline = {
         "bound": "hbm", "kernel": sweep_kernel_names + ", 15 launches per step",
