@@ -20,15 +20,17 @@ def main():
     F, T = False, True
     entry.smoke()                                                     # 16^3, generic sweeps, stage / bc / correct kernels
     solve = parity.test_pressure_solve_random_velocity
-    for N, periodic in [((513, 4, 9), (F, F, F)),                     # warp-per-line DCT-I, x sweep (M = 512)
-                        ((9, 257, 3), (F, F, F)),                     # ... strided y sweep (M = 256)
-                        ((11, 3, 513), (F, F, F)),                    # ... fused z sweep
-                        ((1025, 3, 4), (F, F, F)),                    # split kernel (two 512-point halves)
+    for N, periodic in [((513, 4, 9), (F, F, F)),                     # x sweeps on the 16 x 32 transform (M = 512)
+                        ((9, 257, 3), (F, F, F)),                     # TMA-staged strided y sweeps, radix-8 passes (M = 256)
+                        ((11, 3, 513), (F, F, F)),                    # TMA-staged fused z sweep on the 16 x 32 transform
+                        ((1025, 3, 4), (F, F, F)),                    # x sweeps of 1025-point lines (two 512-point halves)
                         ((20, 9, 513), (F, F, T)),                    # warp real-FFT path, fused z sweep
                         ((65, 9, 65), (F, F, F)),                     # CTA-synchronous fast path
                         ((12, 10, 14), (F, F, T))]:                   # Bluestein
         solve(mif, N, periodic)
         print("solve ok", N, periodic, flush=True)
+    solve(mif, (10, 1025, 3), (F, F, F))                              # TMA-staged 1025-point lines (split transform), two x tiles
+    parity.test_async_transfers_pipeline_matches_synchronous_calls(mif)  # asynchronous transfer API
     parity.test_timestep_random_state(mif, (9, 10, 12), (T, T, T), "test_case_2")
     parity.test_timestep_nhn_matches_oracle(mif)
     golden.test_timestep_velocity_matches_reference(mif, "vtest_12_2")
