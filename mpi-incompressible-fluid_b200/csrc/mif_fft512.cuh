@@ -116,26 +116,23 @@ __device__ __forceinline__ void load_twiddles(double2 *T, const double2 *__restr
 // Phase A on v[s] = c[n1 + 32 s]: leaves v[k2] = W_512^(n1 k2) sum_s v[s] W_16^(s k2).
 __device__ __forceinline__ void phase_a(double2 *v, int n1, const double2 *T) {
   dft16(v);
-  // W_512^(n1 k2), k2 = 1..15, as products of the four table values W^(1, 2, 4, 8): every product is formed from the base
-  // values and at most one running temporary and used at once, which keeps the live registers at the four base values
   const double2 w1 = T[n1], w2 = T[32 + n1], w4 = T[64 + n1], w8 = T[96 + n1];
-  double2 t;
+  const double2 w3 = cmul(w1, w2), w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
   v[1] = cmul(v[1], w1);
   v[2] = cmul(v[2], w2);
-  t = cmul(w1, w2);    v[3] = cmul(v[3], t);     // W^3
+  v[3] = cmul(v[3], w3);
   v[4] = cmul(v[4], w4);
-  t = cmul(w4, w1);    v[5] = cmul(v[5], t);     // W^5
-  t = cmul(w4, w2);    v[6] = cmul(v[6], t);     // W^6
-  t = cmul(t, w1);     v[7] = cmul(v[7], t);     // W^7
+  v[5] = cmul(v[5], w5);
+  v[6] = cmul(v[6], w6);
+  v[7] = cmul(v[7], w7);
   v[8] = cmul(v[8], w8);
-  t = cmul(w8, w1);    v[9] = cmul(v[9], t);     // W^9
-  t = cmul(w8, w2);    v[10] = cmul(v[10], t);   // W^10
-  t = cmul(t, w1);     v[11] = cmul(v[11], t);   // W^11
-  t = cmul(w8, w4);    v[12] = cmul(v[12], t);   // W^12
-  double2 t13 = cmul(t, w1);
-  v[13] = cmul(v[13], t13);                      // W^13
-  t = cmul(t, w2);     v[14] = cmul(v[14], t);   // W^14
-  t = cmul(t, w1);     v[15] = cmul(v[15], t);   // W^15
+  v[9] = cmul(v[9], cmul(w8, w1));
+  v[10] = cmul(v[10], cmul(w8, w2));
+  v[11] = cmul(v[11], cmul(w8, w3));
+  v[12] = cmul(v[12], cmul(w8, w4));
+  v[13] = cmul(v[13], cmul(w8, w5));
+  v[14] = cmul(v[14], cmul(w8, w6));
+  v[15] = cmul(v[15], cmul(w8, w7));
 }
 __device__ __forceinline__ void store_a(double2 *region, int n1, const double2 *v) {
 #pragma unroll
@@ -176,8 +173,8 @@ __device__ __forceinline__ double2 shuffle_from(double2 value, int src) {
 // HALF = 1 / 2: the warp holds the even (C_{2k}) / odd (C_{2k+1}) half of a radix-2 split 1024-point transform and
 // produces E_{2k} / E_{2k+1} of a 1025-point line; cs is then the table of the long transform, (cos, sin)(pi q / 1024).
 // Odd half: the partner of C_{2k+1} is C_{2(511-k)+1}, register 15 - r of lane 31 - L, with no special lanes.
-template <int HALF = 0, class Emit>
-__device__ __forceinline__ void unpack_dct_emit(const double2 *v, int L, const double2 *__restrict__ cs, Emit emit, double &e_last) {
+template <int HALF = 0>
+__device__ __forceinline__ void unpack_dct(const double2 *v, int L, const double2 *__restrict__ cs, double *out, double &e_last) {
   const int k2 = L & 15, p = L >> 4;
   const bool special = (HALF != 2) && (k2 == 0);
   const int src = (HALF == 2) ? 31 - L : (special ? (L ^ 16) : 32 - L);
@@ -196,14 +193,9 @@ __device__ __forceinline__ void unpack_dct_emit(const double2 *v, int L, const d
       wx = -wy;
       wy = t;
     }
-    emit(r, 0.5 * ((A.x + B.x) + wx * (A.y + B.y) - wy * (A.x - B.x)));
+    out[r] = 0.5 * ((A.x + B.x) + wx * (A.y + B.y) - wy * (A.x - B.x));
   }
   e_last = v[0].x - v[0].y;  // E_M = Re C_0 - Im C_0 (meaningful in lane 0)
-}
-// ... into an array: out[r] = E_k
-template <int HALF = 0>
-__device__ __forceinline__ void unpack_dct(const double2 *v, int L, const double2 *__restrict__ cs, double *out, double &e_last) {
-  unpack_dct_emit<HALF>(v, L, cs, [&](int r, double value) { out[r] = value; }, e_last);
 }
 
 // conj Z_k for a real spectrum (see mif_poisson_tma.cuh): X_k = xr, X_{M-k} = yr, (c, sn) = (cos, sin)(pi k / M).

@@ -1485,22 +1485,8 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
       case 7: launch_fast<7>(stream, attrs, fj, lay.contig, fgrid, field); break;
       case 8: launch_warp<8>(stream, attrs, fj, lay.contig, fgrid, field); break;
       case 9:
-        if (lay.contig && !radix8_fft && aligned && mode != 2) {
-          // per-warp TMA pipelines; MIFGPU_X_NO_TMA=1 (A/B) or a refused tensor map: inputs straight from global memory
-          static const bool x_tma = getenv("MIFGPU_X_NO_TMA") == nullptr && getenv("MIFGPU_NO_TMA") == nullptr;
-          static const int promo = getenv("MIFGPU_TMA_L2PROMO") ? atoi(getenv("MIFGPU_TMA_L2PROMO")) : 2;
-          tmasweep::Cache &cache = plan->tma;
-          if (cache.device < 0) {
-            cudaGetDevice(&cache.device);
-            cudaDeviceGetAttribute(&cache.sms, cudaDevAttrMultiProcessorCount, cache.device);
-          }
-          if (!(x_tma && lay.lstride == lay.tile_stride &&
-                tmasweep::launch_x512_tma(stream, cache, field + lay.origin, lay.lstride, lay.outer_stride, lay.n_tile_lines, lay.outer,
-                                          mode, fj.tw, fj.cs, fj.inv_norm, promo)))
-            launch_x512(stream, attrs, fj, mode, lay.outer, field);
-        } else {
-          launch_warp<9>(stream, attrs, fj, lay.contig, fgrid, field);
-        }
+        if (lay.contig && !radix8_fft && aligned && mode != 2) launch_x512(stream, attrs, fj, mode, lay.outer, field);
+        else launch_warp<9>(stream, attrs, fj, lay.contig, fgrid, field);
         break;
       case 11:  // 2049-point lines (BASELINE configs[4]): four warps per line, 4-line CTAs
         launch_warp<11>(stream, attrs, fj, lay.contig, fgrid, field);

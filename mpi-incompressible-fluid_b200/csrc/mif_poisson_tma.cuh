@@ -497,121 +497,6 @@ __global__ void __launch_bounds__(kThreads, 2)
   if (tid == 0) tma::wait_stores_done();
 }
 
-// ---- x sweeps of 513-point lines: one private TMA pipeline per warp ------------------------------------------------------
-// Lines along x are contiguous, so a line is its own tile: every warp of the persistent CTAs owns an mbarrier, a 5 KB
-// input stage and its FFT region, loads its next line (five boxes of 128 doubles) as soon as the current one sits in
-// registers, transforms (16 x 32, mif_fft512.cuh), writes the results into its region and stores them with five bulk
-// tensor stores.  No CTA-wide barrier after start-up: the 16 warps of an SM drift apart freely, and no warp waits for
-// HBM (the register-fed x sweep of mif_poisson.cu, x_dct512_kernel, spent a fifth of its time on that).
-struct LayoutX512 {
-  static constexpr int kBox = 128;                                    // doubles per box
-  static constexpr int kBoxes = (512 + 1 + kBox - 1) / kBox;          // 5
-  static constexpr size_t kStage = (size_t)kBoxes * kBox * 8;         // 5120 bytes
-  static constexpr size_t kRegion = ((size_t)fft512::kLinePitch * sizeof(double2) + 127) / 128 * 128;  // 8576 bytes
-  static constexpr size_t kTwBytes = (size_t)fft512::kTwiddles * sizeof(double2);
-  static constexpr size_t kSmem = 128 + kLines * (kStage + kRegion) + kTwBytes + 64;
-  static_assert(kRegion >= kStage, "the output stage fits the FFT region");
-};
-
-struct JobX {
-  int n_rows, n_outer;
-  const double2 *tw, *cs;
-  double inv_norm;
-};
-
-template <int MODE>  // 0 forward, 1 inverse + normalisation
-__global__ void __launch_bounds__(kThreads, 2) xtma_dct512_kernel(const __grid_constant__ CUtensorMap map, const JobX job) {
-  using Y = LayoutX512;
-  constexpr int M = 512;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char *smem = smem_raw + ((128 - (tma::swizzle_address(smem_raw) & 127)) & 127);
-  const int tid = threadIdx.x, warp = tid >> 5, L = tid & 31;
-  double *S = reinterpret_cast<double *>(smem + warp * Y::kStage);                                   // this warp's input stage
-  double2 *region = reinterpret_cast<double2 *>(smem + kLines * Y::kStage + warp * Y::kRegion);      // ... FFT region / output stage
-  double *O = reinterpret_cast<double *>(region);
-  double2 *T = reinterpret_cast<double2 *>(smem + kLines * (Y::kStage + Y::kRegion));
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + kLines * (Y::kStage + Y::kRegion) + Y::kTwBytes) + warp;
-  const int n_lines = job.n_rows * job.n_outer;
-
-  auto issue_load = [&](int ln) {
-    const int outer = ln / job.n_rows, row = ln - outer * job.n_rows;
-    tma::mbar_arrive_expect_tx(full, (unsigned)Y::kStage);
-#pragma unroll
-    for (int i = 0; i < Y::kBoxes; i++) tma::load_3d(S + i * Y::kBox, &map, full, i * Y::kBox, row, outer);
-  };
-
-  if (L == 0) {
-    if (warp == 0) tma::prefetch_map(&map);
-    tma::mbar_init(full, 1);
-    tma::fence_barrier_init();
-    tma::fence_proxy_async();
-  }
-  fft512::load_twiddles<kThreads>(T, job.tw);
-  __syncthreads();
-  const int stride = gridDim.x * kLines;
-  int ln = blockIdx.x * kLines + warp;
-  if (L == 0 && ln < n_lines) issue_load(ln);
-  unsigned parity = 0;
-
-  for (; ln < n_lines; ln += stride) {
-    const int outer = ln / job.n_rows, row = ln - outer * job.n_rows;
-    double2 v[16];
-    tma::mbar_wait(full, parity);
-    parity ^= 1;
-    if (MODE == 0) {
-      // packed even extension c_q = (e(2q), e(2q+1)), q = L + 32 s; slots q >= M/2 are the mirror images
-#pragma unroll
-      for (int s = 0; s < 16; s++) {
-        const int q = L + 32 * s;
-        if (s < 8) v[s] = *reinterpret_cast<const double2 *>(S + 2 * q);
-        else v[s] = make_double2(S[2 * M - 2 * q], S[2 * M - 2 * q - 1]);
-      }
-    } else {
-      // conj Z_k, k = L + 32 s, from E_k and its partner E_{M-k}: both straight from the stage (the partner as a second
-      // shared-memory read instead of a shuffle: same pipe, no register copy of the line)
-      const double2 base = __ldg(&job.cs[L]);
-#pragma unroll
-      for (int s = 0; s < 16; s++) {
-        const int k = L + 32 * s;
-        const double2 rt = fft512::rot16(s);
-        const double c = base.x * rt.x - base.y * rt.y, sn = base.x * rt.y + base.y * rt.x;
-        v[s] = fft512::pack_input(S[k], S[M - k], c, sn);
-      }
-    }
-    __syncwarp();  // every lane has its inputs: the stage is free for the next line
-    if (L == 0 && ln + stride < n_lines) issue_load(ln + stride);
-    fft512::phase_a(v, L, T);
-    if (L == 0) tma::wait_stores_read();  // the previous line's output stage (in the region) has been read out
-    __syncwarp();
-    fft512::store_a(region, L, v);
-    __syncwarp();
-    fft512::phase_b(region, L, v);
-    if (MODE == 0) {
-      // every result goes to the output stage as it is formed (the first shuffle of the unpack comes after every lane's
-      // reads of the region, which the stage aliases)
-      double e_last;
-      double *mine = O + (L & 15) + 128 * (L >> 4);
-      fft512::unpack_dct_emit<0>(v, L, job.cs, [&](int r, double value) { mine[16 * (r & 7) + 256 * (r >> 3)] = value; }, e_last);
-      if (L == 0) O[M] = e_last;
-    } else {
-      // register r < 8 holds z_q = conj(v[r]), q = k2 + 128 p + 16 r: x(2q) = Re z_q, x(2q+1) = Im z_q
-      const double scale = job.inv_norm;
-      const int q0 = (L & 15) + 128 * (L >> 4);
-#pragma unroll
-      for (int r = 0; r < 8; r++) *reinterpret_cast<double2 *>(O + 2 * (q0 + 16 * r)) = make_double2(v[r].x * scale, -v[r].y * scale);
-      if (L == 0) O[M] = v[8].x * scale;  // q = M/2
-    }
-    tma::fence_proxy_async();
-    __syncwarp();
-    if (L == 0) {
-#pragma unroll
-      for (int i = 0; i < Y::kBoxes; i++) tma::store_3d(&map, O + i * Y::kBox, i * Y::kBox, row, outer);
-      tma::commit_group();
-    }
-  }
-  if (L == 0) tma::wait_stores_done();
-}
-
 // ---- 1025-point lines: radix-2 split into two 16 x 32 transforms -----------------------------------------------------------
 // The 1024-point FFT of the packed even extension splits by one decimation-in-frequency step,
 //     a_q = c_q + c_{q+512}  ->  C_{2k},        b_q = (c_q - c_{q+512}) W_1024^q  ->  C_{2k+1},      q, k < 512,
@@ -840,23 +725,8 @@ struct MapSet {
   bool ok;
 };
 
-struct XKey {
-  const double *base;
-  long long lstride, outer_stride;
-  int n_rows, n_outer, promo;
-  bool operator<(const XKey &o) const {
-    return std::tie(base, lstride, outer_stride, n_rows, n_outer, promo) < std::tie(o.base, o.lstride, o.outer_stride, o.n_rows, o.n_outer, o.promo);
-  }
-};
-struct XMap {
-  CUtensorMap map;
-  bool ok;
-};
-
 struct Cache {
   std::map<MapKey, MapSet> sets;
-  std::map<XKey, XMap> xmaps;
-  bool attr_x512[2] = {};
   int device = -1, sms = 0;
   bool attr[2][3] = {};
   bool attr512[3] = {};
@@ -936,33 +806,6 @@ void launch_512(cudaStream_t stream, Cache &cache, const MapSet &maps, const Job
 #else
   tma_dct512_kernel<MODE><<<grid, kThreads, Y::kSmem, stream>>>(MODE == 1 ? maps.natural : maps.even, maps.odd, maps.out, job);
 #endif
-}
-
-// x sweep of 513-point lines through the per-warp pipelines; false when the geometry has no tensor map.
-inline bool launch_x512_tma(cudaStream_t stream, Cache &cache, double *base, long long lstride, long long outer_stride, int n_rows,
-                            int n_outer, int mode, const double2 *tw, const double2 *cs, double inv_norm, int promo) {
-  const XKey key{base, lstride, outer_stride, n_rows, n_outer, promo};
-  auto it = cache.xmaps.find(key);
-  if (it == cache.xmaps.end()) {
-    XMap m;
-    const char *why = nullptr;
-    m.ok = tma::encode_map(&m.map, base, 513, (uint64_t)n_rows, (uint64_t)n_outer, (uint64_t)lstride * 8, (uint64_t)outer_stride * 8,
-                           LayoutX512::kBox, 1, false, promo, &why);
-    if (!m.ok && getenv("MIFGPU_TMA_VERBOSE")) fprintf(stderr, "libmifgpu: no tensor map for this x sweep: %s\n", why ? why : "?");
-    it = cache.xmaps.emplace(key, m).first;
-  }
-  if (!it->second.ok) return false;
-  JobX job{n_rows, n_outer, tw, cs, inv_norm};
-  if (!cache.attr_x512[mode ? 1 : 0]) {
-    if (mode) cudaFuncSetAttribute(xtma_dct512_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LayoutX512::kSmem);
-    else cudaFuncSetAttribute(xtma_dct512_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LayoutX512::kSmem);
-    cache.attr_x512[mode ? 1 : 0] = true;
-  }
-  const int n_lines = n_rows * n_outer;
-  const int grid = std::min((n_lines + kLines - 1) / kLines, std::max(1, cache.sms * 2));
-  if (mode) xtma_dct512_kernel<1><<<grid, kThreads, LayoutX512::kSmem, stream>>>(it->second.map, job);
-  else xtma_dct512_kernel<0><<<grid, kThreads, LayoutX512::kSmem, stream>>>(it->second.map, job);
-  return true;
 }
 
 template <int MODE>
