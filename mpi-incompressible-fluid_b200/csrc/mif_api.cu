@@ -126,6 +126,13 @@ struct mifgpu_ctx {
   double *zbuf_peer[8] = {};
   double *xfer_peer[8] = {};
   int *barrier_word = nullptr;
+  // Halo exchanges overlapped with the interior planes of the kernel that consumes them (z slabs): the NCCL plane
+  // exchange runs on comm_stream after everything queued on the compute stream so far (ev_fork); the consumer kernel is
+  // launched for its interior planes, the compute stream then waits for ev_join and the boundary planes follow.
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap_halos = false;
+  bool halo_pending = false;
   // Py > 1: pencil decomposition in the 2Decomp layout (deps/2Decomp_C/C2Decomp.cpp:241-423): x pencil (this rank's
   // sub-domain) -> y pencil (x distributed over the Py ranks of the same z_rank) -> z pencil (y distributed over the
   // Pz ranks of the same y_rank).  Block distributions as in src/Constants.cpp:78-79 (bigger blocks on the low ranks).
@@ -229,16 +236,17 @@ struct ProfScope {
   mifgpu_ctx *ctx;
   ProfRecord rec;
   bool active;
-  ProfScope(mifgpu_ctx *c, int category) : ctx(c), active(c->profiling) {
+  cudaStream_t stream;
+  ProfScope(mifgpu_ctx *c, int category, cudaStream_t on = nullptr) : ctx(c), active(c->profiling), stream(on ? on : c->stream) {
     if (!active) return;
     rec.category = category;
     cudaEventCreate(&rec.start);
     cudaEventCreate(&rec.stop);
-    cudaEventRecord(rec.start, ctx->stream);
+    cudaEventRecord(rec.start, stream);
   }
   ~ProfScope() {
     if (!active) return;
-    cudaEventRecord(rec.stop, ctx->stream);
+    cudaEventRecord(rec.stop, stream);
     ctx->prof_records.push_back(rec);
   }
 };
@@ -325,10 +333,11 @@ int fill_face_tables(mifgpu_ctx *ctx, const mifgpu_bc *bc, int which, double tim
 
 // 1-cell halo exchange in z of whole (padded) planes: plane 1 -> prev rank's last plane, plane sz-2 -> next rank's
 // plane 0 (src/StaggeredTensor.cpp:60-135; tags and Isend/Recv become one NCCL group).
-int exchange_z(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count) {
+int exchange_z(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count, cudaStream_t on) {
   if (ctx->nranks == 1) return MIFGPU_OK;
   const Geom &g = ctx->g;
-  ProfScope prof(ctx, PROF_HALO);
+  cudaStream_t stream = on ? on : ctx->stream;
+  ProfScope prof(ctx, PROF_HALO, stream);
   const size_t plane = (size_t)g.plane;
   NCCL_TRY(g_nccl.GroupStart());
   for (int t = 0; t < count; t++) {
@@ -338,19 +347,19 @@ int exchange_z(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count) {
       // Periodic z on two ranks: both neighbours are the same peer.  NCCL pairs the operations between two ranks in
       // issue order (the reference tells them apart by tag, src/StaggeredTensor.cpp:60-135): the peer's first send is
       // its plane 1, which is this rank's TOP ghost, its second send (plane sz-2) the bottom ghost.
-      NCCL_TRY(g_nccl.Send(data + plane, plane, ncclDouble, g.prev_z, ctx->comm, ctx->stream));
-      NCCL_TRY(g_nccl.Send(data + plane * (sz - 2), plane, ncclDouble, g.next_z, ctx->comm, ctx->stream));
-      NCCL_TRY(g_nccl.Recv(data + plane * (sz - 1), plane, ncclDouble, g.next_z, ctx->comm, ctx->stream));
-      NCCL_TRY(g_nccl.Recv(data, plane, ncclDouble, g.prev_z, ctx->comm, ctx->stream));
+      NCCL_TRY(g_nccl.Send(data + plane, plane, ncclDouble, g.prev_z, ctx->comm, stream));
+      NCCL_TRY(g_nccl.Send(data + plane * (sz - 2), plane, ncclDouble, g.next_z, ctx->comm, stream));
+      NCCL_TRY(g_nccl.Recv(data + plane * (sz - 1), plane, ncclDouble, g.next_z, ctx->comm, stream));
+      NCCL_TRY(g_nccl.Recv(data, plane, ncclDouble, g.prev_z, ctx->comm, stream));
       continue;
     }
     if (g.prev_z != -1) {
-      NCCL_TRY(g_nccl.Send(data + plane, plane, ncclDouble, g.prev_z, ctx->comm, ctx->stream));
-      NCCL_TRY(g_nccl.Recv(data, plane, ncclDouble, g.prev_z, ctx->comm, ctx->stream));
+      NCCL_TRY(g_nccl.Send(data + plane, plane, ncclDouble, g.prev_z, ctx->comm, stream));
+      NCCL_TRY(g_nccl.Recv(data, plane, ncclDouble, g.prev_z, ctx->comm, stream));
     }
     if (g.next_z != -1) {
-      NCCL_TRY(g_nccl.Send(data + plane * (sz - 2), plane, ncclDouble, g.next_z, ctx->comm, ctx->stream));
-      NCCL_TRY(g_nccl.Recv(data + plane * (sz - 1), plane, ncclDouble, g.next_z, ctx->comm, ctx->stream));
+      NCCL_TRY(g_nccl.Send(data + plane * (sz - 2), plane, ncclDouble, g.next_z, ctx->comm, stream));
+      NCCL_TRY(g_nccl.Recv(data + plane * (sz - 1), plane, ncclDouble, g.next_z, ctx->comm, stream));
     }
   }
   NCCL_TRY(g_nccl.GroupEnd());
@@ -585,7 +594,7 @@ int transpose_pencil(mifgpu_ctx *ctx, double *field, int which) {
   return (which == 0 || which == 1) ? exchange_boxes(ctx, peers, a, b) : exchange_boxes(ctx, peers, b, a);
 }
 
-int exchange_z(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count);
+int exchange_z(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count, cudaStream_t on = nullptr);
 
 // Ghost refresh of `count` tensors in both split directions, y first (see exchange_y).
 int exchange_halos(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count) {
@@ -602,16 +611,59 @@ int exchange_halos(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count) {
 // divergence reads w one plane above every owner point, i.e. w's ghost plane towards the next rank.  The correction
 // touches owner planes only and its own exchange then refreshes every ghost plane of all three components, so the
 // tensors end up exactly as with the reference's full exchange -- at one sixth of the traffic of this exchange.
-int exchange_w_from_next(mifgpu_ctx *ctx, mifgpu_tensor *w) {
+int exchange_w_from_next(mifgpu_ctx *ctx, mifgpu_tensor *w, cudaStream_t on = nullptr) {
   if (ctx->nranks == 1) return MIFGPU_OK;
   const Geom &g = ctx->g;
-  ProfScope prof(ctx, PROF_HALO);
+  cudaStream_t stream = on ? on : ctx->stream;
+  ProfScope prof(ctx, PROF_HALO, stream);
   const size_t plane = (size_t)g.plane;
   const int sz = g.sz[2];
   NCCL_TRY(g_nccl.GroupStart());
-  if (g.prev_z != -1) NCCL_TRY(g_nccl.Send(w->data + plane, plane, ncclDouble, g.prev_z, ctx->comm, ctx->stream));
-  if (g.next_z != -1) NCCL_TRY(g_nccl.Recv(w->data + plane * (sz - 1), plane, ncclDouble, g.next_z, ctx->comm, ctx->stream));
+  if (g.prev_z != -1) NCCL_TRY(g_nccl.Send(w->data + plane, plane, ncclDouble, g.prev_z, ctx->comm, stream));
+  if (g.next_z != -1) NCCL_TRY(g_nccl.Recv(w->data + plane * (sz - 1), plane, ncclDouble, g.next_z, ctx->comm, stream));
   NCCL_TRY(g_nccl.GroupEnd());
+  return MIFGPU_OK;
+}
+
+// Start a z halo exchange behind everything queued on the compute stream so far and let the compute stream run on
+// (overlap_halos; otherwise the exchange is simply queued on the compute stream).  halo_wait() orders the compute stream
+// behind it.  w_top_only: the trimmed exchange that follows apply_bc inside the time step (exchange_w_from_next).
+int halo_begin(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count, bool w_top_only) {
+  if (ctx->nranks == 1) return MIFGPU_OK;
+  if (!ctx->overlap_halos) return w_top_only ? exchange_w_from_next(ctx, tensors[0]) : exchange_z(ctx, tensors, count);
+  CUDA_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  CUDA_TRY(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_fork, 0));
+  const int rc = w_top_only ? exchange_w_from_next(ctx, tensors[0], ctx->comm_stream) : exchange_z(ctx, tensors, count, ctx->comm_stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->comm_stream));
+  ctx->halo_pending = true;
+  return MIFGPU_OK;
+}
+int halo_wait(mifgpu_ctx *ctx) {
+  if (!ctx->halo_pending) return MIFGPU_OK;
+  ctx->halo_pending = false;
+  CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  return MIFGPU_OK;
+}
+// A stencil launch whose boundary planes read ghost planes that may still be in flight: interior planes [lo + inner_lo,
+// hi - inner_hi) first, then the wait, then the boundary planes.  n = number of planes of the launcher's own range.
+template <class Launch>
+int launch_around_halo(mifgpu_ctx *ctx, int n, int inner_lo, int inner_hi, Launch launch) {
+  if (!ctx->halo_pending || n - inner_lo - inner_hi <= 0) {
+    const int rc = halo_wait(ctx);
+    if (rc) return rc;
+    launch(PlaneRange());
+    return MIFGPU_OK;
+  }
+  PlaneRange interior, low, high;
+  interior.first = inner_lo; interior.count = n - inner_lo - inner_hi;
+  low.first = 0; low.count = inner_lo;
+  high.first = n - inner_hi; high.count = inner_hi;
+  launch(interior);
+  const int rc = halo_wait(ctx);
+  if (rc) return rc;
+  if (inner_lo > 0) launch(low);
+  if (inner_hi > 0) launch(high);
   return MIFGPU_OK;
 }
 
@@ -633,16 +685,19 @@ int do_apply_bc(mifgpu_ctx *ctx, mifgpu_tensor *const vel[3], const mifgpu_bc *b
     launch_apply_bc(ctx->stream, ctx->g, vec3(vel), dev, &ctx->launches);
   }
   static const bool full_exchange = getenv("MIFGPU_FULL_BC_EXCHANGE") != nullptr;  // A/B switch
-  if (inside_timestep && !full_exchange && ctx->Py == 1) return exchange_w_from_next(ctx, vel[2]);
+  if (inside_timestep && !full_exchange && ctx->Py == 1) return halo_begin(ctx, &vel[2], 1, true);  // the divergence waits for it
   return exchange_halos(ctx, vel, 3);  // send_mpi_data / receive_mpi_data of the three components (src/VelocityTensor.cpp:225-232)
 }
 
 // solve_pressure_equation_homogeneous_periodic / _non_homogeneous_neumann (src/PressureEquation.cpp:266-286).
 int do_solve(mifgpu_ctx *ctx, mifgpu_tensor *dp, mifgpu_tensor *const vel[3], double dt, const mifgpu_bc *nhn_bc,
-             double t_new, double t_prev) {
-  {  // rhs = div(velocity) / dt (src/PressureEquation.cpp:59-61)
+             double t_new, double t_prev, bool leave_dp_exchange_pending = false) {
+  {  // rhs = div(velocity) / dt (src/PressureEquation.cpp:59-61); only the top owner plane reads w's ghost plane
     ProfScope prof(ctx, PROF_DIVERGENCE);
-    launch_divergence(ctx->stream, ctx->g, cvec3(vel), 0.0, dt, dp->data, &ctx->launches);
+    const int rc = launch_around_halo(ctx, ctx->g.own_hi[2] - ctx->g.own_lo[2], 0, 1, [&](PlaneRange planes) {
+      launch_divergence(ctx->stream, ctx->g, cvec3(vel), 0.0, dt, dp->data, &ctx->launches, planes);
+    });
+    if (rc) return rc;
   }
   if (nhn_bc) {
     const Geom &g = ctx->g;
@@ -722,7 +777,8 @@ int do_solve(mifgpu_ctx *ctx, mifgpu_tensor *dp, mifgpu_tensor *const vel[3], do
       launch_periodic(ctx->stream, ctx->g, dp->data, 3, &ctx->launches);
     }
     mifgpu_tensor *one_peer[1] = {dp};
-    return exchange_z(ctx, one_peer, 1);
+    const int hrc = halo_begin(ctx, one_peer, 1, false);
+    return (hrc || leave_dp_exchange_pending) ? hrc : halo_wait(ctx);
   }
   sweep(0, 0, PROF_SWEEP_X_FWD);
   sweep(1, 0, PROF_SWEEP_Y_FWD);
@@ -747,7 +803,8 @@ int do_solve(mifgpu_ctx *ctx, mifgpu_tensor *dp, mifgpu_tensor *const vel[3], do
     launch_periodic(ctx->stream, ctx->g, dp->data, 3, &ctx->launches);  // copy_to_staggered, src/PressureTensor.cpp:21-34
   }
   mifgpu_tensor *one[1] = {dp};
-  return exchange_z(ctx, one, 1);  // other.send_mpi_data(base_tag) / receive_mpi_data (src/PressureTensor.cpp:30-33)
+  const int hrc = halo_begin(ctx, one, 1, false);  // other.send_mpi_data(base_tag) / receive_mpi_data (src/PressureTensor.cpp:30-33)
+  return (hrc || leave_dp_exchange_pending) ? hrc : halo_wait(ctx);
 }
 
 int check_launch(mifgpu_ctx *ctx) {
@@ -912,6 +969,18 @@ static int create_context(const mifgpu_params *params, const void *unique_id, mi
         return prc;
       }
     }
+    if (getenv("MIFGPU_NO_HALO_OVERLAP") == nullptr) {  // A/B switch
+      // highest priority: the exchange kernels get the first CTA slots the running stencil kernel frees
+      int least = 0, greatest = 0;
+      cudaDeviceGetStreamPriorityRange(&least, &greatest);
+      if (cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, greatest) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        mifgpu_destroy(ctx);
+        return fail(MIFGPU_ERR_CUDA, "creating the communication stream failed");
+      }
+      ctx->overlap_halos = true;
+    }
   }
   err = cudaDeviceSynchronize();
   if (err != cudaSuccess) {
@@ -953,6 +1022,12 @@ void mifgpu_destroy(mifgpu_ctx *ctx) {
   if (ctx->barrier_word) cudaFree(ctx->barrier_word);
   if (ctx->ylo_dev) cudaFree(ctx->ylo_dev);
   if (ctx->staging) cudaFree(ctx->staging);
+  if (ctx->comm_stream) {
+    cudaStreamSynchronize(ctx->comm_stream);
+    cudaStreamDestroy(ctx->comm_stream);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   for (int d = 0; d < 2; d++) {
     if (ctx->copy_stream[d]) {
       cudaStreamSynchronize(ctx->copy_stream[d]);
@@ -1202,44 +1277,51 @@ int mifgpu_timestep(mifgpu_ctx *ctx, mifgpu_tensor *const velocity[3], mifgpu_te
   const double dt_3 = 40.0 / 120.0 * g.dt, final_time = t_n + g.dt;
   const mifgpu_bc *nhn_bc = nhn ? bc : nullptr;
 
-  // Stage 1 (src/Timestep.cpp:107-117).
-  {
-    ProfScope prof(ctx, PROF_STAGE1);
-    launch_stage(s, g, 1, cvec3(velocity), pressure->data, vec3(velocity_buffer), vec3(velocity_buffer_2), &ctx->launches);
-  }
-  if ((rc = do_apply_bc(ctx, velocity_buffer, bc, time_1, true))) return rc;
-  if ((rc = do_solve(ctx, pressure_buffer, velocity_buffer, dt_1, nhn_bc, time_1, t_n))) return rc;
-  {
+  // The stencil kernels of a stage read ghost planes only in their first / last planes, so each of them starts on its
+  // interior planes while the halo exchange it depends on is still in flight (launch_around_halo); on one rank and with
+  // pencils every launch covers all planes at once.
+  const int nk_stage = std::max(g.sz[2], g.Nz) - 2;  // interior planes of the stage kernels: the lowest reads ghost plane 0,
+                                                     // the highest the top ghost plane
+  auto stage = [&](int category, int number, CVec3 in, Vec3 a, Vec3 b) {
+    ProfScope prof(ctx, category);
+    return launch_around_halo(ctx, nk_stage, 1, 1, [&](PlaneRange planes) {
+      launch_stage(s, g, number, in, pressure->data, a, b, &ctx->launches, planes);
+    });
+  };
+  // p += dp on all planes incl. ghosts and w -= dt grad_z(dp) at plane 1 read dp's ghost planes: planes 0, 1 and from Nz - 1
+  // up wait for the exchange of dp; the velocity planes 1 and Nz - 2 that the next exchange sends are complete afterwards
+  auto correct = [&](mifgpu_tensor *const vel[3], double dt_s) {
     ProfScope prof(ctx, PROF_CORRECT);
-    launch_correct(s, g, vec3(velocity_buffer), pressure->data, pressure_buffer->data, dt_1, &ctx->launches);
-  }
-  if ((rc = exchange_halos(ctx, velocity_buffer, 3))) return rc;  // src/Timestep.cpp:68-75
+    return launch_around_halo(ctx, g.sz[2], 2, g.sz[2] - (g.Nz - 1), [&](PlaneRange planes) {
+      launch_correct(s, g, vec3(vel), pressure->data, pressure_buffer->data, dt_s, &ctx->launches, planes);
+    });
+  };
+  auto exchange_velocity = [&](mifgpu_tensor *const vel[3]) {  // src/Timestep.cpp:68-75
+    if (ctx->Py > 1) return exchange_halos(ctx, vel, 3);
+    return halo_begin(ctx, vel, 3, false);
+  };
+
+  // Stage 1 (src/Timestep.cpp:107-117).
+  if ((rc = stage(PROF_STAGE1, 1, cvec3(velocity), vec3(velocity_buffer), vec3(velocity_buffer_2)))) return rc;
+  if ((rc = do_apply_bc(ctx, velocity_buffer, bc, time_1, true))) return rc;
+  if ((rc = do_solve(ctx, pressure_buffer, velocity_buffer, dt_1, nhn_bc, time_1, t_n, true))) return rc;
+  if ((rc = correct(velocity_buffer, dt_1))) return rc;
+  if ((rc = exchange_velocity(velocity_buffer))) return rc;
 
   // Stage 2 (src/Timestep.cpp:119-129).
-  {
-    ProfScope prof(ctx, PROF_STAGE2);
-    launch_stage(s, g, 2, cvec3(velocity_buffer), pressure->data, vec3(velocity_buffer_2), vec3(velocity), &ctx->launches);
-  }
+  if ((rc = stage(PROF_STAGE2, 2, cvec3(velocity_buffer), vec3(velocity_buffer_2), vec3(velocity)))) return rc;
   if ((rc = do_apply_bc(ctx, velocity_buffer_2, bc, time_2, true))) return rc;
-  if ((rc = do_solve(ctx, pressure_buffer, velocity_buffer_2, dt_2, nhn_bc, time_2, time_1))) return rc;
-  {
-    ProfScope prof(ctx, PROF_CORRECT);
-    launch_correct(s, g, vec3(velocity_buffer_2), pressure->data, pressure_buffer->data, dt_2, &ctx->launches);
-  }
-  if ((rc = exchange_halos(ctx, velocity_buffer_2, 3))) return rc;  // src/Timestep.cpp:68-75
+  if ((rc = do_solve(ctx, pressure_buffer, velocity_buffer_2, dt_2, nhn_bc, time_2, time_1, true))) return rc;
+  if ((rc = correct(velocity_buffer_2, dt_2))) return rc;
+  if ((rc = exchange_velocity(velocity_buffer_2))) return rc;
 
   // Stage 3 (src/Timestep.cpp:131-141).
-  {
-    ProfScope prof(ctx, PROF_STAGE3);
-    launch_stage(s, g, 3, cvec3(velocity_buffer_2), pressure->data, vec3(velocity), vec3(velocity), &ctx->launches);
-  }
+  if ((rc = stage(PROF_STAGE3, 3, cvec3(velocity_buffer_2), vec3(velocity), vec3(velocity)))) return rc;
   if ((rc = do_apply_bc(ctx, velocity, bc, final_time, true))) return rc;
-  if ((rc = do_solve(ctx, pressure_buffer, velocity, dt_3, nhn_bc, final_time, time_2))) return rc;
-  {
-    ProfScope prof(ctx, PROF_CORRECT);
-    launch_correct(s, g, vec3(velocity), pressure->data, pressure_buffer->data, dt_3, &ctx->launches);
-  }
-  if ((rc = exchange_halos(ctx, velocity, 3))) return rc;  // src/Timestep.cpp:68-75
+  if ((rc = do_solve(ctx, pressure_buffer, velocity, dt_3, nhn_bc, final_time, time_2, true))) return rc;
+  if ((rc = correct(velocity, dt_3))) return rc;
+  if ((rc = exchange_velocity(velocity))) return rc;
+  if ((rc = halo_wait(ctx))) return rc;  // the step ends with complete ghost planes
   return check_launch(ctx);
 }
 
@@ -1457,6 +1539,7 @@ int mifgpu_synchronize(mifgpu_ctx *ctx) {
   if (!ctx) return fail(MIFGPU_ERR_INVALID, "NULL context");
   CUDA_TRY(cudaSetDevice(ctx->params.device));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (ctx->comm_stream) CUDA_TRY(cudaStreamSynchronize(ctx->comm_stream));
   for (cudaStream_t s : ctx->copy_stream)
     if (s) CUDA_TRY(cudaStreamSynchronize(s));
   return MIFGPU_OK;

@@ -15,12 +15,18 @@ struct CVec3 {
 
 // ---- mif_stencil.cu ------------------------------------------------------------------------------
 
+// A sub-range of the planes a stencil launcher covers (0-based within that launcher's own plane range); count < 0: all.
+// Used to run the interior planes of a kernel while the halo exchange it depends on is still in flight (mif_api.cu).
+struct PlaneRange {
+  int first = 0, count = -1;
+};
+
 // RK stage kernels (src/Timestep.cpp:10-54).  stage = 1 (Y2), 2 (Y3), 3 (U*).
 //   stage 1: in = velocity,          a = velocity_buffer (write Y2),           b = velocity_buffer_2 (write R1)
 //   stage 2: in = velocity_buffer,   a = velocity_buffer_2 (read R1, write Y3), b = velocity (write a2*R2)
 //   stage 3: in = velocity_buffer_2, a = velocity (read a2*R2, write U*),       b unused
 void launch_stage(cudaStream_t stream, const Geom &g, int stage, CVec3 in, const double *pressure, Vec3 a, Vec3 b,
-                  uint64_t *launches);
+                  uint64_t *launches, PlaneRange planes = PlaneRange());
 
 // Dirichlet faces of all three components (src/VelocityTensor.cpp:36-218), then the single-rank
 // periodic ghost copies (src/StaggeredTensor.cpp:221-257).
@@ -29,13 +35,13 @@ void launch_periodic(cudaStream_t stream, const Geom &g, double *field, int comp
 
 // rhs = div(velocity)/dt on owner points (src/PressureEquation.cpp:59-61, include/VelocityDivergence.h:9-20).
 void launch_divergence(cudaStream_t stream, const Geom &g, CVec3 vel, double inv_dt_unused, double dt, double *rhs,
-                       uint64_t *launches);
+                       uint64_t *launches, PlaneRange planes = PlaneRange());
 // rhs(face) +-= 2 g / h on the six faces (src/PressureEquation.cpp:10-56); tables as in BcDev.
 void launch_nhn_rhs(cudaStream_t stream, const Geom &g, double *rhs, const BcDev &bc, uint64_t *launches);
 
 // p += dp on all points and vel -= dt_s * grad(dp) on interior points (src/Timestep.cpp:66-81).
 void launch_correct(cudaStream_t stream, const Geom &g, Vec3 vel, double *pressure, const double *dp, double dt_s,
-                    uint64_t *launches);
+                    uint64_t *launches, PlaneRange planes = PlaneRange());
 
 // Stages of the velocity-only integrator with the manufactured forcing (src/TimestepVelocity.cpp:20-50):
 //   stage 1: in = velocity,        rhs_buf written,       out = velocity_buffer

@@ -67,11 +67,11 @@ __global__ void __launch_bounds__(128, MIFGPU_STAGE_CTAS)
 stage_kernel_pair(const Geom g, const double *__restrict__ in_u, const double *__restrict__ in_v,
                   const double *__restrict__ in_w, const double *__restrict__ p, double *__restrict__ a_u,
                   double *__restrict__ a_v, double *__restrict__ a_w, double *__restrict__ b_u, double *__restrict__ b_v,
-                  double *__restrict__ b_w, int prefetch_planes, int nk, int chunk_blocks_y) {
-  const int y_chunk = blockIdx.z / nk;  // see stage_kernel
+                  double *__restrict__ b_w, int prefetch_planes, int nk, int chunk_blocks_y, int k_shift) {
+  const int y_chunk = blockIdx.z / nk;  // blockIdx.z = chunk * nk + plane: y chunks keep a plane's working set in L2
   const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int j = (y_chunk * chunk_blocks_y + blockIdx.y) * blockDim.y + threadIdx.y + 1;
-  const int k = blockIdx.z - y_chunk * nk + 1;
+  const int k = blockIdx.z - y_chunk * nk + 1 + k_shift;
   if (prefetch_planes > 0 && (threadIdx.x & 1) == 0 && k + prefetch_planes < g.PZ && i < g.PX && j < g.PY) {
     const long long ahead = gidx(g, i, j, k + prefetch_planes);
     prefetch_l2(in_u + ahead);
@@ -434,10 +434,10 @@ __global__ void __launch_bounds__(256) periodic_copy_kernel(const Geom g, double
 // Two x-adjacent points per thread, 128-bit accesses (see correct_kernel below).
 __global__ void __launch_bounds__(256)
 divergence_kernel(const Geom g, const double *__restrict__ u, const double *__restrict__ v,
-                  const double *__restrict__ w, double dt, double *__restrict__ rhs) {
+                  const double *__restrict__ w, double dt, double *__restrict__ rhs, int k_shift) {
   const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int j = blockIdx.y * blockDim.y + threadIdx.y + g.own_lo[1];
-  const int k = blockIdx.z + g.own_lo[2];
+  const int k = blockIdx.z + g.own_lo[2] + k_shift;
   if (i >= g.own_hi[0] || j >= g.own_hi[1]) return;
   const bool do0 = i >= g.own_lo[0], do1 = i + 1 < g.own_hi[0];
   const long long c = gidx(g, i, j, k);
@@ -465,10 +465,10 @@ divergence_kernel(const Geom g, const double *__restrict__ u, const double *__re
 // pair (i, i+1), i even, is 16-byte aligned in every array); arithmetic per point as in the reference.
 __global__ void __launch_bounds__(256)
 correct_kernel(const Geom g, double *__restrict__ u, double *__restrict__ v, double *__restrict__ w,
-               double *__restrict__ p, const double *__restrict__ dp, double dt_s) {
+               double *__restrict__ p, const double *__restrict__ dp, double dt_s, int k_shift) {
   const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int k = blockIdx.z;
+  const int k = blockIdx.z + k_shift;
   if (i >= g.sx[0] || j >= g.sy[1]) return;
   const long long c = gidx(g, i, j, k);
   const double2 raw = *reinterpret_cast<const double2 *>(dp + c);
@@ -648,8 +648,11 @@ inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) /
 }  // namespace
 
 void launch_stage(cudaStream_t stream, const Geom &g, int stage, CVec3 in, const double *pressure, Vec3 a, Vec3 b,
-                  uint64_t *launches) {
-  const int ni = max(g.sx[0], g.Nx) - 2, nj = max(g.sy[1], g.Ny) - 2, nk = max(g.sz[2], g.Nz) - 2;
+                  uint64_t *launches, PlaneRange planes) {
+  const int ni = max(g.sx[0], g.Nx) - 2, nj = max(g.sy[1], g.Ny) - 2, nk_all = max(g.sz[2], g.Nz) - 2;
+  // interior planes 1 .. nk_all, or the sub-range [planes.first, planes.first + planes.count) of them (0-based)
+  const int k_shift = planes.count < 0 ? 0 : planes.first;
+  const int nk = planes.count < 0 ? nk_all : min(planes.count, nk_all - planes.first);
   if (ni <= 0 || nj <= 0 || nk <= 0) return;
   static const int prefetch_planes = getenv("MIFGPU_STAGE_PREFETCH") ? atoi(getenv("MIFGPU_STAGE_PREFETCH")) : 1;
   const dim3 block(64, 4, 1);
@@ -669,13 +672,13 @@ void launch_stage(cudaStream_t stream, const Geom &g, int stage, CVec3 in, const
   const dim3 pgrid(cdiv(ni + 1, 2 * pblock.x), chunk_blocks_y, nk * n_chunks);
   if (stage == 1)
     stage_kernel_pair<1><<<pgrid, pblock, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
-                                                       b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y);
+                                                       b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y, k_shift);
   else if (stage == 2)
     stage_kernel_pair<2><<<pgrid, pblock, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
-                                                       b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y);
+                                                       b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y, k_shift);
   else
     stage_kernel_pair<3><<<pgrid, pblock, 0, stream>>>(g, in.c[0], in.c[1], in.c[2], pressure, a.c[0], a.c[1], a.c[2], b.c[0],
-                                                       b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y);
+                                                       b.c[1], b.c[2], prefetch_planes, nk, chunk_blocks_y, k_shift);
   ++*launches;
 }
 
@@ -711,11 +714,14 @@ void launch_apply_bc(cudaStream_t stream, const Geom &g, Vec3 vel, const BcDev &
 }
 
 void launch_divergence(cudaStream_t stream, const Geom &g, CVec3 vel, double, double dt, double *rhs,
-                       uint64_t *launches) {
-  const int nj = g.own_hi[1] - g.own_lo[1], nk = g.own_hi[2] - g.own_lo[2];
+                       uint64_t *launches, PlaneRange planes) {
+  const int nj = g.own_hi[1] - g.own_lo[1], nk_all = g.own_hi[2] - g.own_lo[2];
+  const int k_shift = planes.count < 0 ? 0 : planes.first;  // owner planes, 0-based
+  const int nk = planes.count < 0 ? nk_all : min(planes.count, nk_all - planes.first);
+  if (nk <= 0) return;
   const dim3 block(64, 4, 1);
   const dim3 grid(cdiv(g.own_hi[0], 2 * block.x), cdiv(nj, block.y), nk);  // pairs (i, i+1), i even, from i = 0
-  divergence_kernel<<<grid, block, 0, stream>>>(g, vel.c[0], vel.c[1], vel.c[2], dt, rhs);
+  divergence_kernel<<<grid, block, 0, stream>>>(g, vel.c[0], vel.c[1], vel.c[2], dt, rhs, k_shift);
   ++*launches;
 }
 
@@ -743,10 +749,13 @@ void launch_unpack_slab(cudaStream_t stream, const Geom &g, double *field, const
 }
 
 void launch_correct(cudaStream_t stream, const Geom &g, Vec3 vel, double *pressure, const double *dp, double dt_s,
-                    uint64_t *launches) {
+                    uint64_t *launches, PlaneRange planes) {
+  const int k_shift = planes.count < 0 ? 0 : planes.first;  // planes of the (ghosted) tensors, 0-based
+  const int nk = planes.count < 0 ? g.sz[2] : min(planes.count, g.sz[2] - planes.first);
+  if (nk <= 0) return;
   const dim3 block(64, 4, 1);
-  const dim3 grid(cdiv(g.sx[0], 2 * block.x), cdiv(g.sy[1], block.y), g.sz[2]);
-  correct_kernel<<<grid, block, 0, stream>>>(g, vel.c[0], vel.c[1], vel.c[2], pressure, dp, dt_s);
+  const dim3 grid(cdiv(g.sx[0], 2 * block.x), cdiv(g.sy[1], block.y), nk);
+  correct_kernel<<<grid, block, 0, stream>>>(g, vel.c[0], vel.c[1], vel.c[2], pressure, dp, dt_s, k_shift);
   ++*launches;
 }
 

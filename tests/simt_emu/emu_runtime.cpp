@@ -1,6 +1,7 @@
 // tests/simt_emu/emu_runtime.cpp -- TEST INFRASTRUCTURE ONLY: SIMT interpreter + CUDA runtime stand-ins (see
 // include/cuda_runtime.h).  One OS thread; the CUDA threads of one block are ucontext fibers that run until they reach
 // a scheduling point (block / warp / named barrier, shuffle) or return; blocks run one after the other.
+#include <dlfcn.h>
 #include <cuda_runtime.h>
 #include <mif_tma.cuh>
 #include <fcntl.h>
@@ -312,8 +313,21 @@ int &shuffle_parity() { return g_parity[g_current]; }
 }  // namespace emu
 
 // ---- CUDA runtime stand-ins: "device" memory is host memory --------------------------------------------------
-struct emu_stream { int unused; };
-struct emu_event { std::chrono::steady_clock::time_point when; };
+struct emu_stream { int side = 0; };  // 1: created with a priority; fake_nccl.cpp reads this int
+struct emu_event { std::chrono::steady_clock::time_point when; cudaStream_t recorded_on = nullptr; };
+
+// fake_nccl.cpp's fake_nccl_flush, if that library is loaded in this process (MIFGPU_NCCL_LIB)
+static void flush_late_exchanges(cudaStream_t stream) {
+  static int (*flush)(void *) = nullptr;
+  static bool looked = false;
+  if (!looked || !flush) {
+    const char *path = getenv("MIFGPU_NCCL_LIB");
+    void *handle = path ? dlopen(path, RTLD_NOW | RTLD_NOLOAD) : nullptr;
+    if (handle) flush = reinterpret_cast<int (*)(void *)>(dlsym(handle, "fake_nccl_flush"));
+    looked = true;
+  }
+  if (flush) flush(stream);
+}
 
 // With MIF_SIMT_IPC=1 (multi-process runs) every allocation is a shared-memory file, so that cudaIpcGetMemHandle /
 // cudaIpcOpenMemHandle can map a buffer of another rank's process: the handle carries the file name.
@@ -394,18 +408,25 @@ cudaError_t cudaDeviceGetAttribute(int *value, int attr, int) {
   *value = (attr == cudaDevAttrMultiProcessorCount) ? 3 : 0;  // few "SMs": persistent kernels loop over several tiles per CTA
   return cudaSuccess;
 }
-cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize() { flush_late_exchanges(nullptr); return cudaSuccess; }
 cudaError_t cudaGetLastError() { return cudaSuccess; }
 const char *cudaGetErrorString(cudaError_t err) { return err == cudaSuccess ? "no error" : "simt_emu: unsupported call"; }
 cudaError_t cudaStreamCreate(cudaStream_t *stream) { *stream = new emu_stream(); return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *stream, unsigned) { *stream = new emu_stream(); return cudaSuccess; }
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t *stream, unsigned, int) { *stream = new emu_stream(); (*stream)->side = 1; return cudaSuccess; }
+cudaError_t cudaDeviceGetStreamPriorityRange(int *least, int *greatest) { if (least) *least = 0; if (greatest) *greatest = -5; return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t stream) { delete stream; return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t s) { flush_late_exchanges(s); return cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t *event) { *event = new emu_event(); return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t *event, unsigned) { *event = new emu_event(); return cudaSuccess; }
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }  // everything is synchronous here
+// Kernels and copies are synchronous here; only the stand-in NCCL can defer the exchanges of a side stream
+// (MIF_FAKE_NCCL_LATE, fake_nccl.cpp) -- they complete when another stream waits for an event recorded behind them.
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t event, unsigned) {
+  if (event && event->recorded_on) flush_late_exchanges(event->recorded_on);
+  return cudaSuccess;
+}
 cudaError_t cudaEventDestroy(cudaEvent_t event) { delete event; return cudaSuccess; }
-cudaError_t cudaEventRecord(cudaEvent_t event, cudaStream_t) { event->when = std::chrono::steady_clock::now(); return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t event, cudaStream_t s) { event->when = std::chrono::steady_clock::now(); event->recorded_on = s; return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t start, cudaEvent_t stop) {
   *ms = std::chrono::duration<float, std::milli>(stop->when - start->when).count();
   return cudaSuccess;

@@ -8,6 +8,13 @@
 // the next sequence number of that pair.  Sends never block; receives issued between ncclGroupStart and ncclGroupEnd are
 // queued and carried out at ncclGroupEnd, after all sends of the group -- like NCCL, where nothing of a group runs before
 // it is closed -- so rings of three or more ranks (periodic z) cannot deadlock on a receive that precedes a send.
+//
+// MIF_FAKE_NCCL_LATE=1 models the other extreme of an exchange that runs on a second stream next to the compute stream
+// (the overlapped halo exchanges of mif_api.cu): every send / receive issued on a stream that was created with a priority
+// is carried out as LATE as stream order allows -- when the interpreter's runtime reports that another
+// stream waits for an event recorded behind it, or that the stream is synchronised (fake_nccl_flush, called from
+// emu_runtime.cpp).  A kernel that reads a ghost plane, or overwrites a plane still to be sent, before that wait then
+// fails the parity tests; the default mode (everything at once) covers the earliest possible completion.
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -16,7 +23,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
+#include <utility>
 #include <vector>
 
 extern "C" {
@@ -83,6 +92,28 @@ static int g_group_depth = 0;
 static std::vector<QueuedRecv> g_queued;
 static ncclResult_t recv_now(void *buf, size_t count, ncclDataType_t type, int peer, ncclComm_t c);
 
+static ncclResult_t send_now(const void *buf, size_t count, ncclDataType_t type, int peer, ncclComm_t c);
+
+// late mode: operations of side streams wait here, in issue order (sends before the receives of their group)
+struct LateOp { cudaStream_t stream; bool is_send; std::function<ncclResult_t()> run; };
+static std::vector<LateOp> g_late;
+static bool is_late(cudaStream_t s) {
+  static const bool enabled = getenv("MIF_FAKE_NCCL_LATE") != nullptr;
+  // emu_runtime.cpp's streams start with an int that is 1 for streams created with a priority (the side streams)
+  return enabled && s != nullptr && *static_cast<const int *>(s) == 1;
+}
+// carry out what was deferred on `stream` (nullptr: on every stream)
+int fake_nccl_flush(cudaStream_t stream) {
+  int rc = 0;
+  std::vector<LateOp> keep, run;
+  for (auto &op : g_late) (stream == nullptr || op.stream == stream ? run : keep).push_back(std::move(op));
+  g_late.swap(keep);
+  // all sends first, then the receives (each kind in issue order): ranks flushing at the same point cannot block
+  for (auto &op : run) if (op.is_send) rc |= op.run();
+  for (auto &op : run) if (!op.is_send) rc |= op.run();
+  return rc;
+}
+
 ncclResult_t ncclGroupStart() {
   g_group_depth++;
   return 0;
@@ -97,7 +128,15 @@ ncclResult_t ncclGroupEnd() {
   return rc;
 }
 
-ncclResult_t ncclSend(const void *buf, size_t count, ncclDataType_t type, int peer, ncclComm_t c, cudaStream_t) {
+ncclResult_t ncclSend(const void *buf, size_t count, ncclDataType_t type, int peer, ncclComm_t c, cudaStream_t s) {
+  if (is_late(s)) {
+    g_late.push_back(LateOp{s, true, [=] { return send_now(buf, count, type, peer, c); }});
+    return 0;
+  }
+  return send_now(buf, count, type, peer, c);
+}
+
+static ncclResult_t send_now(const void *buf, size_t count, ncclDataType_t type, int peer, ncclComm_t c) {
   const size_t bytes = count * type_size(type);
   const std::string final_name = mailbox(c, c->rank, peer, c->sent[peer]++);
   const std::string tmp = final_name + ".tmp";
@@ -109,7 +148,11 @@ ncclResult_t ncclSend(const void *buf, size_t count, ncclDataType_t type, int pe
   return 0;
 }
 
-ncclResult_t ncclRecv(void *buf, size_t count, ncclDataType_t type, int peer, ncclComm_t c, cudaStream_t) {
+ncclResult_t ncclRecv(void *buf, size_t count, ncclDataType_t type, int peer, ncclComm_t c, cudaStream_t s) {
+  if (is_late(s)) {
+    g_late.push_back(LateOp{s, false, [=] { return recv_now(buf, count, type, peer, c); }});
+    return 0;
+  }
   if (g_group_depth > 0) {
     g_queued.push_back(QueuedRecv{buf, count, type, peer, c});
     return 0;

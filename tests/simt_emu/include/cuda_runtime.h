@@ -84,6 +84,8 @@ cudaError_t cudaGetLastError();
 const char *cudaGetErrorString(cudaError_t err);
 cudaError_t cudaStreamCreate(cudaStream_t *stream);
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *stream, unsigned flags);
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t *stream, unsigned flags, int priority);
+cudaError_t cudaDeviceGetStreamPriorityRange(int *least, int *greatest);
 cudaError_t cudaStreamDestroy(cudaStream_t stream);
 cudaError_t cudaStreamSynchronize(cudaStream_t stream);
 cudaError_t cudaEventCreate(cudaEvent_t *event);

@@ -47,6 +47,22 @@ def test_two_rank_slabs_with_peer_memory_transposes(simt_env):
     assert res["world"] == 2 and res["max_rel_err"] <= 1e-11
 
 
+@pytest.mark.parametrize("case,world,port", [("full_16_2", 2, 29721), ("es:3x257x257", 2, 29722), ("pz:6x6x13", 3, 29723)])
+def test_overlapped_halo_exchanges_completing_as_late_as_stream_order_allows(simt_env, case, world, port):
+    """Inside the time step the plane exchanges run on a second stream while the consuming stencil kernel covers its
+    interior planes (mif_api.cu, launch_around_halo).  The interpreter runs kernels synchronously, so the default run is
+    the exchange finishing at once; MIF_FAKE_NCCL_LATE=1 defers every side-stream send / receive to the point where the
+    compute stream waits for it -- a kernel that touched a ghost plane (or a plane still to be sent) too early would
+    now compute with stale data and miss the single-rank result."""
+    res = run_worker(dict(simt_env, MIF_FAKE_NCCL_LATE="1"), case, world, port)
+    assert res["world"] == world and res["max_rel_err"] <= 1e-11
+
+
+def test_halo_overlap_can_be_switched_off(simt_env):
+    res = run_worker(dict(simt_env, MIFGPU_NO_HALO_OVERLAP="1"), "full_16_2", 2, 29724)
+    assert res["world"] == 2 and res["max_rel_err"] <= 1e-11
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_periodic_z_distributed_over_the_ranks(simt_env, world):
     # two ranks: prev and next neighbour are the same peer (the halo planes pair in issue order); three ranks: a ring
