@@ -42,6 +42,17 @@ typedef enum mifgpu_staggering {
   MIFGPU_STAGGER_NONE = 3 /* pressure */
 } mifgpu_staggering;
 
+/* The reference's `Real` (include/Real.h:9-17): the element type of every FIELD buffer that crosses this interface
+ * (tensor uploads / downloads, boundary face tables).  libmifgpu.so is the USE_DOUBLE=1 build; libmifgpu_f32.so is
+ * the USE_DOUBLE=0 build of the same sources and exports the same symbols -- compile the caller with -DMIFGPU_FP32
+ * and link that library instead (mifgpu_real_bytes() tells which one a process got).  Scalars -- times, dt, Re,
+ * domain sizes, norms, the values of mifgpu_allreduce / mifgpu_gather -- are double in both builds. */
+#ifdef MIFGPU_FP32
+typedef float mifgpu_real;
+#else
+typedef double mifgpu_real;
+#endif
+
 /* The 16 constructor arguments of mif::Constants (include/Constants.h:86-90, src/Constants.cpp:58-62),
  * plus the CUDA device ordinal.  All derived quantities are recomputed by the library with the same
  * formulas (src/Constants.cpp:63-101). */
@@ -85,7 +96,7 @@ typedef enum mifgpu_bc_kind {
  * exact_pressure_gradient.get_difference_over_time(t_new, t_old) = g(t_old) - g(t_new)
  * (src/Timestep.cpp:89-93 with src/VectorFunction.cpp:52-60: the difference is "second minus first"). */
 typedef void (*mifgpu_face_callback)(void *user, int which, double time, double time_prev, int component,
-                                     int face, double *values);
+                                     int face, mifgpu_real *values);
 
 typedef struct mifgpu_bc {
   int32_t kind; /* mifgpu_bc_kind */
@@ -119,6 +130,8 @@ int mifgpu_create_distributed(const mifgpu_params *params, const void *unique_id
  * deps/2Decomp_C/C2Decomp.cpp:273-324).  `first` has parts + 1 entries. */
 int mifgpu_slab_plan(uint64_t n_points, int32_t parts, int32_t *first);
 const char *mifgpu_last_error(void);
+/* sizeof(mifgpu_real) of the loaded library: 8 for libmifgpu.so, 4 for libmifgpu_f32.so. */
+int mifgpu_real_bytes(void);
 int mifgpu_abi_version(void);
 
 /* Local extents {sx, sy, sz} of a tensor with the given staggering on this rank
@@ -131,14 +144,14 @@ int mifgpu_tensor_extents(const mifgpu_ctx *ctx, int staggering, uint64_t extent
 int mifgpu_tensor_create(mifgpu_ctx *ctx, int staggering, mifgpu_tensor **tensor);
 void mifgpu_tensor_destroy(mifgpu_tensor *tensor);
 /* Host <-> device copies of a whole tensor in the reference layout (Tensor::raw_data(), include/Tensor.h:118). */
-int mifgpu_tensor_upload(mifgpu_tensor *tensor, const double *host);
-int mifgpu_tensor_download(const mifgpu_tensor *tensor, double *host);
+int mifgpu_tensor_upload(mifgpu_tensor *tensor, const mifgpu_real *host);
+int mifgpu_tensor_download(const mifgpu_tensor *tensor, mifgpu_real *host);
 /* The index box lo[d] <= index < hi[d] of a tensor as a compact array, x fastest:
  * host[(i - lo[0]) + (j - lo[1]) * bx + (k - lo[2]) * bx * by], bx = hi[0] - lo[0], by = hi[1] - lo[1].  This is what
  * the output path needs instead of whole fields: writeVTK reads three planes, writeDat one line with its
  * interpolation neighbours (src/VTKDatExport.cpp:115-312,342-583); the box is gathered on the device and crosses
  * PCIe as one contiguous block.  MIFGPU_ERR_INVALID if the box is empty or leaves the tensor. */
-int mifgpu_tensor_download_box(const mifgpu_tensor *tensor, const int32_t lo[3], const int32_t hi[3], double *host);
+int mifgpu_tensor_download_box(const mifgpu_tensor *tensor, const int32_t lo[3], const int32_t hi[3], mifgpu_real *host);
 /* Tensor::swap_data (include/Tensor.h:108-110) as used by VelocityTensor::swap_data (src/VelocityTensor.cpp:13-27). */
 int mifgpu_tensor_swap(mifgpu_tensor *a, mifgpu_tensor *b);
 
@@ -148,8 +161,8 @@ int mifgpu_tensor_swap(mifgpu_tensor *a, mifgpu_tensor *b);
  * the tensor's previous transfers, and compute calls that use the tensor afterwards wait for it on the device.  So
  * upload(A) | timestep(B) | download(C) of three different tensor sets overlap, and PCIe runs in both directions at
  * once.  `host` should be page-locked; it must not be touched until mifgpu_synchronize has returned. */
-int mifgpu_tensor_upload_async(mifgpu_tensor *tensor, const double *host);
-int mifgpu_tensor_download_async(mifgpu_tensor *tensor, double *host);
+int mifgpu_tensor_upload_async(mifgpu_tensor *tensor, const mifgpu_real *host);
+int mifgpu_tensor_download_async(mifgpu_tensor *tensor, mifgpu_real *host);
 
 /* ---- the hot path ------------------------------------------------------------------------------- */
 

@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "mifgpu_create_distributed", "mifgpu_slab_plan", "mifgpu_velocity_error_norms", "mifgpu_pressure_error_norms",
     "mifgpu_adjust_pressure", "mifgpu_timestep_velocity", "mifgpu_tensor_download_box",
     "mifgpu_allreduce", "mifgpu_gather", "mifgpu_rank_count", "mifgpu_tensor_upload_async", "mifgpu_tensor_download_async",
-    "mifgpu_transpose_path",
+    "mifgpu_transpose_path", "mifgpu_real_bytes",
 ]
 
 
@@ -53,7 +53,7 @@ class Params(ctypes.Structure):
     ]
 
 
-FACE_CALLBACK = ctypes.CFUNCTYPE(None, c_void_p, c_int, c_double, c_double, c_int, c_int, POINTER(c_double))
+FACE_CALLBACK = ctypes.CFUNCTYPE(None, c_void_p, c_int, c_double, c_double, c_int, c_int, c_void_p)  # values: mifgpu_real *
 
 
 class Bc(ctypes.Structure):
@@ -85,6 +85,7 @@ def lib() -> ctypes.CDLL:
                           "(there is no CPU fallback)")
     l = ctypes.CDLL(LIB_PATH)
     l.mifgpu_abi_version.restype = c_int
+    l.mifgpu_real_bytes.restype = c_int
     l.mifgpu_last_error.restype = ctypes.c_char_p
     l.mifgpu_create.argtypes = [POINTER(Params), POINTER(c_void_p)]
     l.mifgpu_destroy.argtypes = [c_void_p]
@@ -125,6 +126,12 @@ def lib() -> ctypes.CDLL:
     return l
 
 
+def real_dtype():
+    """numpy dtype of mifgpu_real in the loaded library: float64 for libmifgpu.so, float32 for libmifgpu_f32.so (the
+    reference's USE_DOUBLE=0 build, selected with MIFGPU_LIB=libmifgpu_f32.so)."""
+    return np.float64 if lib().mifgpu_real_bytes() == 8 else np.float32
+
+
 def _check(rc: int) -> None:
     if rc != 0:
         raise MifGpuError(f"libmifgpu error {rc}: {lib().mifgpu_last_error().decode()}")
@@ -161,20 +168,21 @@ class Tensor:
     def upload(self, host: np.ndarray) -> None:
         """host: array of shape (sz, sy, sx) C-order, i.e. the reference layout i + j*sx + k*sx*sy."""
         sx, sy, sz = self.shape
-        arr = np.ascontiguousarray(host, dtype=np.float64)
+        arr = np.ascontiguousarray(host, dtype=real_dtype())
         if arr.size != sx * sy * sz:
             raise ValueError(f"expected {sx * sy * sz} values, got {arr.size}")
         _check(lib().mifgpu_tensor_upload(self.handle, arr.ctypes.data_as(c_void_p)))
 
     def _check_host(self, arr: np.ndarray, what: str) -> None:
         sx, sy, sz = self.shape
-        if not isinstance(arr, np.ndarray) or arr.dtype != np.float64 or arr.size != sx * sy * sz or not arr.flags.c_contiguous:
-            raise ValueError(f"{what} must be a C-contiguous float64 array of {sx * sy * sz} values (shape ({sz}, {sy}, {sx}))")
+        if not isinstance(arr, np.ndarray) or arr.dtype != real_dtype() or arr.size != sx * sy * sz or not arr.flags.c_contiguous:
+            raise ValueError(f"{what} must be a C-contiguous {np.dtype(real_dtype()).name} array of {sx * sy * sz} values "
+                             f"(shape ({sz}, {sy}, {sx}))")
 
     def download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         sx, sy, sz = self.shape
         if out is None:
-            out = np.empty((sz, sy, sx), dtype=np.float64)
+            out = np.empty((sz, sy, sx), dtype=real_dtype())
         self._check_host(out, "out")
         _check(lib().mifgpu_tensor_download(self.handle, out.ctypes.data_as(c_void_p)))
         return out
@@ -192,7 +200,7 @@ class Tensor:
 
     def download_box(self, lo: Sequence[int], hi: Sequence[int]) -> np.ndarray:
         """The index box lo <= (i, j, k) < hi as an array of shape (hi[2]-lo[2], hi[1]-lo[1], hi[0]-lo[0])."""
-        out = np.empty((hi[2] - lo[2], hi[1] - lo[1], hi[0] - lo[0]), dtype=np.float64)
+        out = np.empty((hi[2] - lo[2], hi[1] - lo[1], hi[0] - lo[0]), dtype=real_dtype())
         _check(lib().mifgpu_tensor_download_box(self.handle, (c_int32 * 3)(*lo), (c_int32 * 3)(*hi),
                                                 out.ctypes.data_as(c_void_p)))
         return out
@@ -250,7 +258,8 @@ class Context:
             d = 2 - face // 2
             na = sy if d == 0 else sx
             nb = sy if d == 2 else sz
-            values = np.ctypeslib.as_array(ptr, shape=(nb, na))
+            ctype = c_double if real_dtype() == np.float64 else ctypes.c_float
+            values = np.ctypeslib.as_array((ctype * (na * nb)).from_address(ptr)).reshape(nb, na)
             callback(which, time, time_prev, comp, face, values)
 
         cb = FACE_CALLBACK(trampoline)

@@ -47,6 +47,7 @@ struct NcclApi {
   bool ok = false;
 };
 NcclApi g_nccl;
+constexpr ncclDataType_t kNcclReal = sizeof(real) == 8 ? ncclDouble : ncclFloat;  // MPI_MIF_REAL (include/Real.h:12,16)
 
 bool load_nccl() {
   if (g_nccl.ok) return true;
@@ -119,12 +120,12 @@ struct mifgpu_ctx {
   std::vector<int> ylo;      // nranks + 1: y rows [ylo[r], ylo[r+1]) of the transform domain belong to rank r's z pencil
   std::vector<int> zlo;      // nranks + 1: owner z points [zlo[r], zlo[r+1]) of rank r's slab
   int *ylo_dev = nullptr;
-  double *xfer = nullptr;    // send / receive staging, one local owner volume
-  double *zbuf = nullptr;    // z pencil: zbuf[z][y_local][x]
+  real *xfer = nullptr;    // send / receive staging, one local owner volume
+  real *zbuf = nullptr;    // z pencil: zbuf[z][y_local][x]
   // peer-memory transposes: zbuf / xfer of every rank mapped with CUDA IPC (index = rank; own entry = local pointer)
   bool peer_mode = false;
-  double *zbuf_peer[8] = {};
-  double *xfer_peer[8] = {};
+  real *zbuf_peer[8] = {};
+  real *xfer_peer[8] = {};
   int *barrier_word = nullptr;
   // Halo exchanges overlapped with the interior planes of the kernel that consumes them (z slabs): the NCCL plane
   // exchange runs on comm_stream after everything queued on the compute stream so far (ev_fork); the consumer kernel is
@@ -139,26 +140,26 @@ struct mifgpu_ctx {
   int Py = 1, Pz = 1, y_rank = 0, z_rank = 0;
   std::vector<int> ys, xs;   // Py + 1: owner y rows of y_rank r; x columns of the y / z pencils of y_rank r
   std::vector<int> zs, yzs;  // Pz + 1: owner z planes of z_rank r; y rows of the z pencil of z_rank r
-  double *ypen = nullptr, *zpen = nullptr;           // pencil buffers, rows of pen_pitch doubles
-  double *box_send = nullptr, *box_recv = nullptr;   // compact staging of the box exchanges
+  real *ypen = nullptr, *zpen = nullptr;           // pencil buffers, rows of pen_pitch doubles
+  real *box_send = nullptr, *box_recv = nullptr;   // compact staging of the box exchanges
   size_t box_capacity = 0;                           // doubles in each of them
   int pen_pitch = 0;
-  double *staging = nullptr; // compact device copy of one tensor for host transfers
+  real *staging = nullptr; // compact device copy of one tensor for host transfers
   size_t staging_bytes = 0;
   // asynchronous host transfers (mifgpu_tensor_upload_async / _download_async): one stream and one compact staging
   // buffer per direction, so that H2D, D2H and the kernels of independent tensors overlap
   cudaStream_t copy_stream[2] = {nullptr, nullptr};  // [0] host -> device, [1] device -> host
-  double *copy_staging[2] = {nullptr, nullptr};
+  real *copy_staging[2] = {nullptr, nullptr};
   size_t copy_staging_bytes[2] = {0, 0};
   // host-callback boundary faces: pinned staging + device copies, [which][component][face]
-  double *face_host[2][3][6] = {};
-  double *face_dev[2][3][6] = {};
+  real *face_host[2][3][6] = {};
+  real *face_dev[2][3][6] = {};
 };
 
 struct mifgpu_tensor {
   mifgpu_ctx *ctx;
   int staggering;
-  double *data;
+  real *data;
   // ordering between the three streams: last asynchronous upload into / download out of this tensor, last compute
   // call that used it (waiting on an event that was never recorded is a no-op)
   cudaEvent_t ev_uploaded = nullptr, ev_downloaded = nullptr, ev_computed = nullptr;
@@ -315,7 +316,7 @@ int fill_face_tables(mifgpu_ctx *ctx, const mifgpu_bc *bc, int which, double tim
       if (which == 0 && !face_is_active(g, face)) continue;
       const int t = (which == 1) ? 3 : comp;
       const size_t na = (dir == 0) ? g.sy[t] : g.sx[t], nb = (dir == 2) ? g.sy[t] : g.sz[t];
-      const size_t bytes = na * nb * sizeof(double);
+      const size_t bytes = na * nb * sizeof(real);
       if (!ctx->face_host[which][comp][face]) {
         CUDA_TRY(cudaMallocHost(&ctx->face_host[which][comp][face], bytes));
         CUDA_TRY(cudaMalloc(&ctx->face_dev[which][comp][face], bytes));
@@ -341,25 +342,25 @@ int exchange_z(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count, cudaSt
   const size_t plane = (size_t)g.plane;
   NCCL_TRY(g_nccl.GroupStart());
   for (int t = 0; t < count; t++) {
-    double *data = tensors[t]->data;
+    real *data = tensors[t]->data;
     const int sz = g.sz[tensors[t]->staggering];
     if (g.prev_z != -1 && g.prev_z == g.next_z) {
       // Periodic z on two ranks: both neighbours are the same peer.  NCCL pairs the operations between two ranks in
       // issue order (the reference tells them apart by tag, src/StaggeredTensor.cpp:60-135): the peer's first send is
       // its plane 1, which is this rank's TOP ghost, its second send (plane sz-2) the bottom ghost.
-      NCCL_TRY(g_nccl.Send(data + plane, plane, ncclDouble, g.prev_z, ctx->comm, stream));
-      NCCL_TRY(g_nccl.Send(data + plane * (sz - 2), plane, ncclDouble, g.next_z, ctx->comm, stream));
-      NCCL_TRY(g_nccl.Recv(data + plane * (sz - 1), plane, ncclDouble, g.next_z, ctx->comm, stream));
-      NCCL_TRY(g_nccl.Recv(data, plane, ncclDouble, g.prev_z, ctx->comm, stream));
+      NCCL_TRY(g_nccl.Send(data + plane, plane, kNcclReal, g.prev_z, ctx->comm, stream));
+      NCCL_TRY(g_nccl.Send(data + plane * (sz - 2), plane, kNcclReal, g.next_z, ctx->comm, stream));
+      NCCL_TRY(g_nccl.Recv(data + plane * (sz - 1), plane, kNcclReal, g.next_z, ctx->comm, stream));
+      NCCL_TRY(g_nccl.Recv(data, plane, kNcclReal, g.prev_z, ctx->comm, stream));
       continue;
     }
     if (g.prev_z != -1) {
-      NCCL_TRY(g_nccl.Send(data + plane, plane, ncclDouble, g.prev_z, ctx->comm, stream));
-      NCCL_TRY(g_nccl.Recv(data, plane, ncclDouble, g.prev_z, ctx->comm, stream));
+      NCCL_TRY(g_nccl.Send(data + plane, plane, kNcclReal, g.prev_z, ctx->comm, stream));
+      NCCL_TRY(g_nccl.Recv(data, plane, kNcclReal, g.prev_z, ctx->comm, stream));
     }
     if (g.next_z != -1) {
-      NCCL_TRY(g_nccl.Send(data + plane * (sz - 2), plane, ncclDouble, g.next_z, ctx->comm, stream));
-      NCCL_TRY(g_nccl.Recv(data + plane * (sz - 1), plane, ncclDouble, g.next_z, ctx->comm, stream));
+      NCCL_TRY(g_nccl.Send(data + plane * (sz - 2), plane, kNcclReal, g.next_z, ctx->comm, stream));
+      NCCL_TRY(g_nccl.Recv(data + plane * (sz - 1), plane, kNcclReal, g.next_z, ctx->comm, stream));
     }
   }
   NCCL_TRY(g_nccl.GroupEnd());
@@ -408,8 +409,8 @@ int setup_peer_memory(mifgpu_ctx *ctx) {
       ok = false;
       break;
     }
-    ctx->zbuf_peer[r] = static_cast<double *>(pz);
-    ctx->xfer_peer[r] = static_cast<double *>(px);
+    ctx->zbuf_peer[r] = static_cast<real *>(pz);
+    ctx->xfer_peer[r] = static_cast<real *>(px);
   }
   // All ranks must agree, otherwise one side would wait at a barrier the other never reaches.
   int flags[2] = {ok ? 0 : 1, 0};
@@ -443,7 +444,7 @@ PeerLayout peer_layout(const mifgpu_ctx *ctx) {
 // TransposeZ2Y.cpp:18-46) as one grouped NCCL send/recv all-to-all.  Forward: pack rows per destination, receive
 // straight into zbuf (the planes of one source are contiguous there).  Backward: send straight out of zbuf,
 // receive into the staging buffer, unpack.
-int transpose_slab(mifgpu_ctx *ctx, double *field, bool forward) {
+int transpose_slab(mifgpu_ctx *ctx, real *field, bool forward) {
   const Geom &g = ctx->g;
   ProfScope prof(ctx, PROF_TRANSPOSE);
   const int me = ctx->params.rank, P = ctx->nranks;
@@ -452,15 +453,15 @@ int transpose_slab(mifgpu_ctx *ctx, double *field, bool forward) {
   NCCL_TRY(g_nccl.GroupStart());
   for (int r = 0; r < P; r++) {
     const long long ny_r = ctx->ylo[r + 1] - ctx->ylo[r], nz_r = ctx->zlo[r + 1] - ctx->zlo[r];
-    double *slab_block = ctx->xfer + nz_me * g.PX * ctx->ylo[r];            // [z_local][y in r's range][x]
-    double *pencil_block = ctx->zbuf + (long long)ctx->zlo[r] * ny_me * g.PX;  // planes z in r's slab
+    real *slab_block = ctx->xfer + nz_me * g.PX * ctx->ylo[r];            // [z_local][y in r's range][x]
+    real *pencil_block = ctx->zbuf + (long long)ctx->zlo[r] * ny_me * g.PX;  // planes z in r's slab
     const size_t slab_count = (size_t)(nz_me * ny_r * g.PX), pencil_count = (size_t)(nz_r * ny_me * g.PX);
     if (forward) {
-      NCCL_TRY(g_nccl.Send(slab_block, slab_count, ncclDouble, r, ctx->comm, ctx->stream));
-      NCCL_TRY(g_nccl.Recv(pencil_block, pencil_count, ncclDouble, r, ctx->comm, ctx->stream));
+      NCCL_TRY(g_nccl.Send(slab_block, slab_count, kNcclReal, r, ctx->comm, ctx->stream));
+      NCCL_TRY(g_nccl.Recv(pencil_block, pencil_count, kNcclReal, r, ctx->comm, ctx->stream));
     } else {
-      NCCL_TRY(g_nccl.Send(pencil_block, pencil_count, ncclDouble, r, ctx->comm, ctx->stream));
-      NCCL_TRY(g_nccl.Recv(slab_block, slab_count, ncclDouble, r, ctx->comm, ctx->stream));
+      NCCL_TRY(g_nccl.Send(pencil_block, pencil_count, kNcclReal, r, ctx->comm, ctx->stream));
+      NCCL_TRY(g_nccl.Recv(slab_block, slab_count, kNcclReal, r, ctx->comm, ctx->stream));
     }
   }
   NCCL_TRY(g_nccl.GroupEnd());
@@ -471,7 +472,7 @@ int transpose_slab(mifgpu_ctx *ctx, double *field, bool forward) {
 // ---- Py > 1: box exchanges ---------------------------------------------------------------------------------------
 // A sub-box of a pitched 3-D array (x fastest): element (x, y, z) at base[x + pitch * (y + ysize * z)].
 struct Box {
-  double *base;
+  real *base;
   size_t pitch, ysize;
   int x0, y0, z0, nx, ny, nz;
   size_t count() const { return (size_t)nx * ny * nz; }
@@ -481,17 +482,17 @@ int copy_box(mifgpu_ctx *ctx, const Box &dst, const Box &src) {
   if (src.count() == 0) return MIFGPU_OK;
   cudaMemcpy3DParms parms;
   std::memset(&parms, 0, sizeof(parms));
-  parms.srcPtr = make_cudaPitchedPtr(src.base, src.pitch * sizeof(double), src.pitch, src.ysize);
-  parms.srcPos = make_cudaPos((size_t)src.x0 * sizeof(double), (size_t)src.y0, (size_t)src.z0);
-  parms.dstPtr = make_cudaPitchedPtr(dst.base, dst.pitch * sizeof(double), dst.pitch, dst.ysize);
-  parms.dstPos = make_cudaPos((size_t)dst.x0 * sizeof(double), (size_t)dst.y0, (size_t)dst.z0);
-  parms.extent = make_cudaExtent((size_t)src.nx * sizeof(double), (size_t)src.ny, (size_t)src.nz);
+  parms.srcPtr = make_cudaPitchedPtr(src.base, src.pitch * sizeof(real), src.pitch, src.ysize);
+  parms.srcPos = make_cudaPos((size_t)src.x0 * sizeof(real), (size_t)src.y0, (size_t)src.z0);
+  parms.dstPtr = make_cudaPitchedPtr(dst.base, dst.pitch * sizeof(real), dst.pitch, dst.ysize);
+  parms.dstPos = make_cudaPos((size_t)dst.x0 * sizeof(real), (size_t)dst.y0, (size_t)dst.z0);
+  parms.extent = make_cudaExtent((size_t)src.nx * sizeof(real), (size_t)src.ny, (size_t)src.nz);
   parms.kind = cudaMemcpyDeviceToDevice;
   CUDA_TRY(cudaMemcpy3DAsync(&parms, ctx->stream));
   return MIFGPU_OK;
 }
 
-Box compact_box(double *base, const Box &like) {
+Box compact_box(real *base, const Box &like) {
   return Box{base, (size_t)like.nx, (size_t)like.ny, 0, 0, 0, like.nx, like.ny, like.nz};
 }
 
@@ -523,8 +524,8 @@ int exchange_boxes(mifgpu_ctx *ctx, const std::vector<int> &peers, const std::ve
   NCCL_TRY(g_nccl.GroupStart());
   for (size_t i = 0; i < peers.size(); i++) {
     if (peers[i] == me) continue;
-    if (send[i].count()) NCCL_TRY(g_nccl.Send(ctx->box_send + soff[i], send[i].count(), ncclDouble, peers[i], ctx->comm, ctx->stream));
-    if (recv[i].count()) NCCL_TRY(g_nccl.Recv(ctx->box_recv + roff[i], recv[i].count(), ncclDouble, peers[i], ctx->comm, ctx->stream));
+    if (send[i].count()) NCCL_TRY(g_nccl.Send(ctx->box_send + soff[i], send[i].count(), kNcclReal, peers[i], ctx->comm, ctx->stream));
+    if (recv[i].count()) NCCL_TRY(g_nccl.Recv(ctx->box_recv + roff[i], recv[i].count(), kNcclReal, peers[i], ctx->comm, ctx->stream));
   }
   NCCL_TRY(g_nccl.GroupEnd());
   for (size_t i = 0; i < peers.size(); i++) {
@@ -563,7 +564,7 @@ int exchange_y(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count) {
 
 // The four 2Decomp transposes of the pencil decomposition as box exchanges.  which = 0: x pencil (owner region of
 // `field`) -> y pencil; 1: y pencil -> z pencil; 2: z pencil -> y pencil; 3: y pencil -> x pencil.
-int transpose_pencil(mifgpu_ctx *ctx, double *field, int which) {
+int transpose_pencil(mifgpu_ctx *ctx, real *field, int which) {
   const Geom &g = ctx->g;
   ProfScope prof(ctx, PROF_TRANSPOSE);
   const int yr = ctx->y_rank, zr = ctx->z_rank, Py = ctx->Py, Pz = ctx->Pz;
@@ -619,8 +620,8 @@ int exchange_w_from_next(mifgpu_ctx *ctx, mifgpu_tensor *w, cudaStream_t on = nu
   const size_t plane = (size_t)g.plane;
   const int sz = g.sz[2];
   NCCL_TRY(g_nccl.GroupStart());
-  if (g.prev_z != -1) NCCL_TRY(g_nccl.Send(w->data + plane, plane, ncclDouble, g.prev_z, ctx->comm, stream));
-  if (g.next_z != -1) NCCL_TRY(g_nccl.Recv(w->data + plane * (sz - 1), plane, ncclDouble, g.next_z, ctx->comm, stream));
+  if (g.prev_z != -1) NCCL_TRY(g_nccl.Send(w->data + plane, plane, kNcclReal, g.prev_z, ctx->comm, stream));
+  if (g.next_z != -1) NCCL_TRY(g_nccl.Recv(w->data + plane * (sz - 1), plane, kNcclReal, g.next_z, ctx->comm, stream));
   NCCL_TRY(g_nccl.GroupEnd());
   return MIFGPU_OK;
 }
@@ -821,6 +822,7 @@ extern "C" {
 int mifgpu_abi_version(void) { return MIFGPU_ABI_VERSION; }
 
 const char *mifgpu_last_error(void) { return g_last_error.c_str(); }
+int mifgpu_real_bytes(void) { return (int)sizeof(real); }
 
 static int create_context(const mifgpu_params *params, const void *unique_id, mifgpu_ctx **out);
 
@@ -921,13 +923,13 @@ static int create_context(const mifgpu_params *params, const void *unique_id, mi
     const size_t sheets = (size_t)6 * g.PX * g.PZ;
     const size_t stage = std::max(std::max(std::max(ypen, zpen), sub), sheets);
     ctx->box_capacity = stage;
-    if (cudaMalloc(&ctx->ypen, ypen * sizeof(double)) != cudaSuccess || cudaMalloc(&ctx->zpen, zpen * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&ctx->box_send, stage * sizeof(double)) != cudaSuccess || cudaMalloc(&ctx->box_recv, stage * sizeof(double)) != cudaSuccess) {
+    if (cudaMalloc(&ctx->ypen, ypen * sizeof(real)) != cudaSuccess || cudaMalloc(&ctx->zpen, zpen * sizeof(real)) != cudaSuccess ||
+        cudaMalloc(&ctx->box_send, stage * sizeof(real)) != cudaSuccess || cudaMalloc(&ctx->box_recv, stage * sizeof(real)) != cudaSuccess) {
       mifgpu_destroy(ctx);
       return fail(MIFGPU_ERR_CUDA, "allocating the pencil buffers failed");
     }
-    cudaMemset(ctx->ypen, 0, ypen * sizeof(double));
-    cudaMemset(ctx->zpen, 0, zpen * sizeof(double));
+    cudaMemset(ctx->ypen, 0, ypen * sizeof(real));
+    cudaMemset(ctx->zpen, 0, zpen * sizeof(real));
   } else if (ctx->nranks > 1) {
     // MIF block distribution: the first (n mod P) ranks own one more point (src/Constants.cpp:78-79,
     // deps/2Decomp_C/C2Decomp.cpp:273-324).
@@ -952,7 +954,7 @@ static int create_context(const mifgpu_params *params, const void *unique_id, mi
     const int me = params->rank;
     const size_t slab = (size_t)(ctx->zlo[me + 1] - ctx->zlo[me]) * n_points[1] * g.PX;
     const size_t pencil = (size_t)n_points[2] * (ctx->ylo[me + 1] - ctx->ylo[me]) * g.PX;
-    if (cudaMalloc(&ctx->xfer, slab * sizeof(double)) != cudaSuccess || cudaMalloc(&ctx->zbuf, pencil * sizeof(double)) != cudaSuccess ||
+    if (cudaMalloc(&ctx->xfer, slab * sizeof(real)) != cudaSuccess || cudaMalloc(&ctx->zbuf, pencil * sizeof(real)) != cudaSuccess ||
         cudaMalloc(&ctx->ylo_dev, (P + 1) * sizeof(int)) != cudaSuccess) {
       mifgpu_destroy(ctx);
       return fail(MIFGPU_ERR_CUDA, "allocating the transpose buffers failed");
@@ -1052,8 +1054,8 @@ int mifgpu_tensor_create(mifgpu_ctx *ctx, int staggering, mifgpu_tensor **out) {
   if (!ctx || !out || staggering < 0 || staggering > 3) return fail(MIFGPU_ERR_INVALID, "bad argument");
   *out = nullptr;
   CUDA_TRY(cudaSetDevice(ctx->params.device));
-  double *data = nullptr;
-  const size_t bytes = (size_t)ctx->g.volume * sizeof(double);
+  real *data = nullptr;
+  const size_t bytes = (size_t)ctx->g.volume * sizeof(real);
   CUDA_TRY(cudaMalloc(&data, bytes));
   cudaError_t err = cudaMemsetAsync(data, 0, bytes, ctx->stream);
   if (err != cudaSuccess) {
@@ -1090,13 +1092,13 @@ void mifgpu_tensor_destroy(mifgpu_tensor *t) {
 // Host (compact reference extents) <-> device (padded pitches).  The PCIe transfer is one contiguous copy to or
 // from a compact device staging buffer (row-pitched DMA over PCIe is several times slower); the re-pitching is a
 // device-to-device 3-D copy.
-static int copy_tensor(const mifgpu_tensor *t, double *host, bool to_device) {
+static int copy_tensor(const mifgpu_tensor *t, real *host, bool to_device) {
   if (!t || !host) return fail(MIFGPU_ERR_INVALID, "NULL argument");
   mifgpu_ctx *ctx = t->ctx;
   const Geom &g = ctx->g;
   CUDA_TRY(cudaSetDevice(ctx->params.device));
   const int s = t->staggering;
-  const size_t bytes = (size_t)g.sx[s] * g.sy[s] * g.sz[s] * sizeof(double);
+  const size_t bytes = (size_t)g.sx[s] * g.sy[s] * g.sz[s] * sizeof(real);
   if (ctx->staging_bytes < bytes) {
     if (ctx->staging) cudaFree(ctx->staging);
     ctx->staging = nullptr;
@@ -1106,11 +1108,11 @@ static int copy_tensor(const mifgpu_tensor *t, double *host, bool to_device) {
   }
   cudaMemcpy3DParms parms;
   std::memset(&parms, 0, sizeof(parms));
-  const cudaPitchedPtr compact = make_cudaPitchedPtr(ctx->staging, (size_t)g.sx[s] * sizeof(double), g.sx[s], g.sy[s]);
-  const cudaPitchedPtr padded = make_cudaPitchedPtr(t->data, (size_t)g.PX * sizeof(double), g.PX, g.PY);
+  const cudaPitchedPtr compact = make_cudaPitchedPtr(ctx->staging, (size_t)g.sx[s] * sizeof(real), g.sx[s], g.sy[s]);
+  const cudaPitchedPtr padded = make_cudaPitchedPtr(t->data, (size_t)g.PX * sizeof(real), g.PX, g.PY);
   parms.srcPtr = to_device ? compact : padded;
   parms.dstPtr = to_device ? padded : compact;
-  parms.extent = make_cudaExtent((size_t)g.sx[s] * sizeof(double), g.sy[s], g.sz[s]);
+  parms.extent = make_cudaExtent((size_t)g.sx[s] * sizeof(real), g.sy[s], g.sz[s]);
   parms.kind = cudaMemcpyDeviceToDevice;
   // asynchronous transfers of this tensor that are still in flight come first
   CUDA_TRY(cudaStreamWaitEvent(ctx->stream, t->ev_uploaded, 0));
@@ -1131,7 +1133,7 @@ static int copy_tensor(const mifgpu_tensor *t, double *host, bool to_device) {
 // used the tensor and after its previous transfers; compute calls that use the tensor later wait for it (UseScope).
 // Nothing blocks the host; `host` (pinned memory, or the copy degrades to a synchronous one) must stay untouched
 // until mifgpu_synchronize.
-static int copy_tensor_async(mifgpu_tensor *t, double *host, bool to_device) {
+static int copy_tensor_async(mifgpu_tensor *t, real *host, bool to_device) {
   if (!t || !host) return fail(MIFGPU_ERR_INVALID, "NULL argument");
   mifgpu_ctx *ctx = t->ctx;
   const Geom &g = ctx->g;
@@ -1139,24 +1141,24 @@ static int copy_tensor_async(mifgpu_tensor *t, double *host, bool to_device) {
   const int dir = to_device ? 0 : 1, s = t->staggering;
   if (!ctx->copy_stream[dir]) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream[dir], cudaStreamNonBlocking));
   cudaStream_t cs = ctx->copy_stream[dir];
-  const size_t bytes = (size_t)g.sx[s] * g.sy[s] * g.sz[s] * sizeof(double);
+  const size_t bytes = (size_t)g.sx[s] * g.sy[s] * g.sz[s] * sizeof(real);
   if (ctx->copy_staging_bytes[dir] < bytes) {
     CUDA_TRY(cudaStreamSynchronize(cs));
     if (ctx->copy_staging[dir]) cudaFree(ctx->copy_staging[dir]);
     ctx->copy_staging[dir] = nullptr;
     ctx->copy_staging_bytes[dir] = 0;
     // one size for all staggerings, so that the buffer is allocated once
-    const size_t most = (size_t)(g.sx[0]) * (size_t)(g.sy[1]) * (size_t)(g.sz[2]) * sizeof(double);
+    const size_t most = (size_t)(g.sx[0]) * (size_t)(g.sy[1]) * (size_t)(g.sz[2]) * sizeof(real);
     CUDA_TRY(cudaMalloc(&ctx->copy_staging[dir], std::max(bytes, most)));
     ctx->copy_staging_bytes[dir] = std::max(bytes, most);
   }
   cudaMemcpy3DParms parms;
   std::memset(&parms, 0, sizeof(parms));
-  const cudaPitchedPtr compact = make_cudaPitchedPtr(ctx->copy_staging[dir], (size_t)g.sx[s] * sizeof(double), g.sx[s], g.sy[s]);
-  const cudaPitchedPtr padded = make_cudaPitchedPtr(t->data, (size_t)g.PX * sizeof(double), g.PX, g.PY);
+  const cudaPitchedPtr compact = make_cudaPitchedPtr(ctx->copy_staging[dir], (size_t)g.sx[s] * sizeof(real), g.sx[s], g.sy[s]);
+  const cudaPitchedPtr padded = make_cudaPitchedPtr(t->data, (size_t)g.PX * sizeof(real), g.PX, g.PY);
   parms.srcPtr = to_device ? compact : padded;
   parms.dstPtr = to_device ? padded : compact;
-  parms.extent = make_cudaExtent((size_t)g.sx[s] * sizeof(double), g.sy[s], g.sz[s]);
+  parms.extent = make_cudaExtent((size_t)g.sx[s] * sizeof(real), g.sy[s], g.sz[s]);
   parms.kind = cudaMemcpyDeviceToDevice;
   CUDA_TRY(cudaStreamWaitEvent(cs, t->ev_computed, 0));
   CUDA_TRY(cudaStreamWaitEvent(cs, to_device ? t->ev_downloaded : t->ev_uploaded, 0));
@@ -1172,15 +1174,15 @@ static int copy_tensor_async(mifgpu_tensor *t, double *host, bool to_device) {
   return MIFGPU_OK;
 }
 
-int mifgpu_tensor_upload_async(mifgpu_tensor *t, const double *host) { return copy_tensor_async(t, const_cast<double *>(host), true); }
-int mifgpu_tensor_download_async(mifgpu_tensor *t, double *host) { return copy_tensor_async(t, host, false); }
+int mifgpu_tensor_upload_async(mifgpu_tensor *t, const mifgpu_real *host) { return copy_tensor_async(t, const_cast<real *>(host), true); }
+int mifgpu_tensor_download_async(mifgpu_tensor *t, mifgpu_real *host) { return copy_tensor_async(t, host, false); }
 
-int mifgpu_tensor_upload(mifgpu_tensor *t, const double *host) { return copy_tensor(t, const_cast<double *>(host), true); }
-int mifgpu_tensor_download(const mifgpu_tensor *t, double *host) { return copy_tensor(t, host, false); }
+int mifgpu_tensor_upload(mifgpu_tensor *t, const mifgpu_real *host) { return copy_tensor(t, const_cast<real *>(host), true); }
+int mifgpu_tensor_download(const mifgpu_tensor *t, mifgpu_real *host) { return copy_tensor(t, host, false); }
 
 // Sub-box [lo, hi) of a tensor as one compact array: a device-to-device 3-D copy gathers the box from the padded
 // tensor into the staging buffer (srcPos.x is in bytes, y / z in rows / slices), one contiguous copy crosses PCIe.
-int mifgpu_tensor_download_box(const mifgpu_tensor *t, const int32_t lo[3], const int32_t hi[3], double *host) {
+int mifgpu_tensor_download_box(const mifgpu_tensor *t, const int32_t lo[3], const int32_t hi[3], mifgpu_real *host) {
   if (!t || !lo || !hi || !host) return fail(MIFGPU_ERR_INVALID, "NULL argument");
   mifgpu_ctx *ctx = t->ctx;
   const Geom &g = ctx->g;
@@ -1191,7 +1193,7 @@ int mifgpu_tensor_download_box(const mifgpu_tensor *t, const int32_t lo[3], cons
       return fail(MIFGPU_ERR_INVALID, "box [%d, %d) outside the tensor extent %d in direction %d", lo[d], hi[d], ext[d], d);
   CUDA_TRY(cudaSetDevice(ctx->params.device));
   const size_t bx = (size_t)(hi[0] - lo[0]), by = (size_t)(hi[1] - lo[1]), bz = (size_t)(hi[2] - lo[2]);
-  const size_t bytes = bx * by * bz * sizeof(double);
+  const size_t bytes = bx * by * bz * sizeof(real);
   if (ctx->staging_bytes < bytes) {
     if (ctx->staging) cudaFree(ctx->staging);
     ctx->staging = nullptr;
@@ -1201,11 +1203,11 @@ int mifgpu_tensor_download_box(const mifgpu_tensor *t, const int32_t lo[3], cons
   }
   cudaMemcpy3DParms parms;
   std::memset(&parms, 0, sizeof(parms));
-  parms.srcPtr = make_cudaPitchedPtr(t->data, (size_t)g.PX * sizeof(double), g.PX, g.PY);
-  parms.srcPos = make_cudaPos((size_t)lo[0] * sizeof(double), (size_t)lo[1], (size_t)lo[2]);
-  parms.dstPtr = make_cudaPitchedPtr(ctx->staging, bx * sizeof(double), bx, by);
+  parms.srcPtr = make_cudaPitchedPtr(t->data, (size_t)g.PX * sizeof(real), g.PX, g.PY);
+  parms.srcPos = make_cudaPos((size_t)lo[0] * sizeof(real), (size_t)lo[1], (size_t)lo[2]);
+  parms.dstPtr = make_cudaPitchedPtr(ctx->staging, bx * sizeof(real), bx, by);
   parms.dstPos = make_cudaPos(0, 0, 0);
-  parms.extent = make_cudaExtent(bx * sizeof(double), by, bz);
+  parms.extent = make_cudaExtent(bx * sizeof(real), by, bz);
   parms.kind = cudaMemcpyDeviceToDevice;
   CUDA_TRY(cudaStreamWaitEvent(ctx->stream, t->ev_uploaded, 0));
   CUDA_TRY(cudaMemcpy3DAsync(&parms, ctx->stream));
@@ -1375,23 +1377,23 @@ static int analytic_family(const mifgpu_bc *exact, double time, BcDev &dev) {
 }
 
 // Runs one of the error kernels and adds the per-CTA partial results up in CTA order: sums[0..3].
-static int run_error_kernel(mifgpu_ctx *ctx, bool velocity, CVec3 vel, const double *p, const BcDev &dev, double sums[4]) {
+static int run_error_kernel(mifgpu_ctx *ctx, bool velocity, CVec3 vel, const real *p, const BcDev &dev, double sums[4]) {
   sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
   const int blocks = diag_blocks(ctx->g, velocity);
   if (blocks == 0) return MIFGPU_OK;
-  double *partial = nullptr;
-  CUDA_TRY(cudaMalloc(&partial, sizeof(double) * 4 * blocks));
+  real *partial = nullptr;
+  CUDA_TRY(cudaMalloc(&partial, sizeof(real) * 4 * blocks));
   if (velocity) launch_velocity_error(ctx->stream, ctx->g, vel, dev, partial, &ctx->launches);
   else launch_pressure_error(ctx->stream, ctx->g, p, dev, partial, &ctx->launches);
-  std::vector<double> host(4 * (size_t)blocks);
-  cudaError_t err = cudaMemcpyAsync(host.data(), partial, sizeof(double) * host.size(), cudaMemcpyDeviceToHost, ctx->stream);
+  std::vector<real> host(4 * (size_t)blocks);
+  cudaError_t err = cudaMemcpyAsync(host.data(), partial, sizeof(real) * host.size(), cudaMemcpyDeviceToHost, ctx->stream);
   if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
   cudaFree(partial);
   if (err != cudaSuccess) return fail(MIFGPU_ERR_CUDA, "error kernel failed: %s", cudaGetErrorString(err));
   for (int b = 0; b < blocks; b++) {
     sums[0] += host[4 * b];
     sums[1] += host[4 * b + 1];
-    sums[2] = std::max(sums[2], host[4 * b + 2]);
+    sums[2] = std::max(sums[2], (double)host[4 * b + 2]);
     sums[3] += host[4 * b + 3];
   }
   return MIFGPU_OK;

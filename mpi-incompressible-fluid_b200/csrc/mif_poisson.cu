@@ -20,11 +20,13 @@
 
 #include <algorithm>
 
+#include "mif_kernels.h"
+#ifndef MIFGPU_FP32  // the tuned transform kernels are FP64 (tile geometry, register FFTs); the float build runs sweep_kernel
 #include "mif_fft512.cuh"
 #include "mif_fft_fast.cuh"
 #include "mif_fft_warp.cuh"
-#include "mif_kernels.h"
 #include "mif_poisson_tma.cuh"
+#endif
 
 namespace mifgpu {
 
@@ -49,13 +51,13 @@ struct DirPlanDev {
   int m;          // complex DFT length
   int P, logP;    // executed power-of-two FFT size
   int bluestein;  // m is not a power of two
-  const double2 *tw;      // P/2: exp(-2 pi i q / P)
-  const double2 *tw_full; // P:   exp(-2 pi i q / P), all q (fast path)
-  const double2 *chirp;   // m:   exp(-i pi j^2 / m)                         (Bluestein)
-  const double2 *filt;    // P:   FFT_P(wrapped conj chirp) / P, bit-reversed (Bluestein)
-  const double2 *unpack;  // (cos, sin)(pi k / m) for DCT-I, (cos, sin)(2 pi k / n) for real FFTs
-  const double *lambda;   // n eigenvalues of the 1-D second difference in FFTW output order
-  double inv_norm;        // 1 / (2 (N_global - 1)) or 1 / (N_global - 1)
+  const real2 *tw;      // P/2: exp(-2 pi i q / P)
+  const real2 *tw_full; // P:   exp(-2 pi i q / P), all q (fast path)
+  const real2 *chirp;   // m:   exp(-i pi j^2 / m)                         (Bluestein)
+  const real2 *filt;    // P:   FFT_P(wrapped conj chirp) / P, bit-reversed (Bluestein)
+  const real2 *unpack;  // (cos, sin)(pi k / m) for DCT-I, (cos, sin)(2 pi k / n) for real FFTs
+  const real *lambda;   // n eigenvalues of the 1-D second difference in FFTW output order
+  real inv_norm;        // 1 / (2 (N_global - 1)) or 1 / (N_global - 1)
 };
 
 struct SweepJob {
@@ -67,21 +69,18 @@ struct SweepJob {
   long long estride;   // element offset between consecutive points of a line
   int r_pitch;         // shared-memory pitch of one real line
   int mode;            // 0 forward, 1 inverse (+normalise), 2 forward * eigen, inverse (+normalise)
-  const double *lam_a, *lam_b;  // eigenvalues of the two other directions (mode 2)
+  const real *lam_a, *lam_b;  // eigenvalues of the two other directions (mode 2)
   bool has_origin;              // this launch holds the (0,0,0) mode at tile line 0, outer index 0
 };
 
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
-  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ double2 cmul_conj(double2 a, double2 b) {  // a * conj(b)
-  return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+__device__ __forceinline__ real2 cmul(real2 a, real2 b) {
+  return make_real2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
 // Radix-2 decimation-in-frequency stages, natural order in, bit-reversed order out -- executed two stages per pass
 // over shared memory (a radix-4 butterfly on w[i0 + {0, 1, 2, 3} q]): the same butterflies and table twiddles as two
 // single-stage passes, half the shared-memory round trips and barriers.  A last single stage remains when logP is odd.
-__device__ void fft_dif(double2 *W, int L, int P, int logP, const double2 *__restrict__ tw, bool conj_tw) {
+__device__ void fft_dif(real2 *W, int L, int P, int logP, const real2 *__restrict__ tw, bool conj_tw) {
   const int halfP = P >> 1, quarterP = P >> 2;
   int s = logP - 1;
   for (; s >= 1; s -= 2) {
@@ -91,39 +90,39 @@ __device__ void fft_dif(double2 *W, int L, int P, int logP, const double2 *__res
       const int l = item / quarterP, g = item - l * quarterP;
       const int k = g & (q - 1);
       const int i0 = ((g >> (s - 1)) << (s + 1)) + k;
-      double2 *w = W + (size_t)l * P;
-      const double2 a = w[i0], b = w[i0 + q], c = w[i0 + 2 * q], d = w[i0 + 3 * q];
-      double2 t0 = __ldg(&tw[k * tstride]), t1 = __ldg(&tw[(k + q) * tstride]), t2 = __ldg(&tw[2 * k * tstride]);
+      real2 *w = W + (size_t)l * P;
+      const real2 a = w[i0], b = w[i0 + q], c = w[i0 + 2 * q], d = w[i0 + 3 * q];
+      real2 t0 = __ldg(&tw[k * tstride]), t1 = __ldg(&tw[(k + q) * tstride]), t2 = __ldg(&tw[2 * k * tstride]);
       if (conj_tw) {
         t0.y = -t0.y;
         t1.y = -t1.y;
         t2.y = -t2.y;
       }
-      const double2 a1 = make_double2(a.x + c.x, a.y + c.y), c1 = cmul(make_double2(a.x - c.x, a.y - c.y), t0);
-      const double2 b1 = make_double2(b.x + d.x, b.y + d.y), d1 = cmul(make_double2(b.x - d.x, b.y - d.y), t1);
-      w[i0] = make_double2(a1.x + b1.x, a1.y + b1.y);
-      w[i0 + q] = cmul(make_double2(a1.x - b1.x, a1.y - b1.y), t2);
-      w[i0 + 2 * q] = make_double2(c1.x + d1.x, c1.y + d1.y);
-      w[i0 + 3 * q] = cmul(make_double2(c1.x - d1.x, c1.y - d1.y), t2);
+      const real2 a1 = make_real2(a.x + c.x, a.y + c.y), c1 = cmul(make_real2(a.x - c.x, a.y - c.y), t0);
+      const real2 b1 = make_real2(b.x + d.x, b.y + d.y), d1 = cmul(make_real2(b.x - d.x, b.y - d.y), t1);
+      w[i0] = make_real2(a1.x + b1.x, a1.y + b1.y);
+      w[i0 + q] = cmul(make_real2(a1.x - b1.x, a1.y - b1.y), t2);
+      w[i0 + 2 * q] = make_real2(c1.x + d1.x, c1.y + d1.y);
+      w[i0 + 3 * q] = cmul(make_real2(c1.x - d1.x, c1.y - d1.y), t2);
     }
     __syncthreads();
   }
   if (s == 0) {  // half = 1, twiddle 1
     for (int item = threadIdx.x; item < L * halfP; item += blockDim.x) {
       const int l = item / halfP, i0 = (item - l * halfP) << 1;
-      double2 *w = W + (size_t)l * P;
-      const double2 a = w[i0], b = w[i0 + 1];
-      double2 t = __ldg(&tw[0]);
+      real2 *w = W + (size_t)l * P;
+      const real2 a = w[i0], b = w[i0 + 1];
+      real2 t = __ldg(&tw[0]);
       if (conj_tw) t.y = -t.y;
-      w[i0] = make_double2(a.x + b.x, a.y + b.y);
-      w[i0 + 1] = cmul(make_double2(a.x - b.x, a.y - b.y), t);
+      w[i0] = make_real2(a.x + b.x, a.y + b.y);
+      w[i0 + 1] = cmul(make_real2(a.x - b.x, a.y - b.y), t);
     }
     __syncthreads();
   }
 }
 
 // Radix-2 decimation-in-time stages, bit-reversed order in, natural order out, two stages per pass like fft_dif.
-__device__ void fft_dit(double2 *W, int L, int P, int logP, const double2 *__restrict__ tw, bool conj_tw) {
+__device__ void fft_dit(real2 *W, int L, int P, int logP, const real2 *__restrict__ tw, bool conj_tw) {
   const int halfP = P >> 1, quarterP = P >> 2;
   int s = 0;
   for (; s + 1 < logP; s += 2) {
@@ -133,20 +132,20 @@ __device__ void fft_dit(double2 *W, int L, int P, int logP, const double2 *__res
       const int l = item / quarterP, g = item - l * quarterP;
       const int k = g & (h - 1);
       const int i0 = ((g >> s) << (s + 2)) + k;
-      double2 *w = W + (size_t)l * P;
-      double2 t0 = __ldg(&tw[2 * k * tstride]), t1 = __ldg(&tw[k * tstride]), t2 = __ldg(&tw[(k + h) * tstride]);
+      real2 *w = W + (size_t)l * P;
+      real2 t0 = __ldg(&tw[2 * k * tstride]), t1 = __ldg(&tw[k * tstride]), t2 = __ldg(&tw[(k + h) * tstride]);
       if (conj_tw) {
         t0.y = -t0.y;
         t1.y = -t1.y;
         t2.y = -t2.y;
       }
-      const double2 a = w[i0], b = cmul(w[i0 + h], t0), c = w[i0 + 2 * h], d = cmul(w[i0 + 3 * h], t0);
-      const double2 a1 = make_double2(a.x + b.x, a.y + b.y), b1 = make_double2(a.x - b.x, a.y - b.y);
-      const double2 c1 = cmul(make_double2(c.x + d.x, c.y + d.y), t1), d1 = cmul(make_double2(c.x - d.x, c.y - d.y), t2);
-      w[i0] = make_double2(a1.x + c1.x, a1.y + c1.y);
-      w[i0 + 2 * h] = make_double2(a1.x - c1.x, a1.y - c1.y);
-      w[i0 + h] = make_double2(b1.x + d1.x, b1.y + d1.y);
-      w[i0 + 3 * h] = make_double2(b1.x - d1.x, b1.y - d1.y);
+      const real2 a = w[i0], b = cmul(w[i0 + h], t0), c = w[i0 + 2 * h], d = cmul(w[i0 + 3 * h], t0);
+      const real2 a1 = make_real2(a.x + b.x, a.y + b.y), b1 = make_real2(a.x - b.x, a.y - b.y);
+      const real2 c1 = cmul(make_real2(c.x + d.x, c.y + d.y), t1), d1 = cmul(make_real2(c.x - d.x, c.y - d.y), t2);
+      w[i0] = make_real2(a1.x + c1.x, a1.y + c1.y);
+      w[i0 + 2 * h] = make_real2(a1.x - c1.x, a1.y - c1.y);
+      w[i0 + h] = make_real2(b1.x + d1.x, b1.y + d1.y);
+      w[i0 + 3 * h] = make_real2(b1.x - d1.x, b1.y - d1.y);
     }
     __syncthreads();
   }
@@ -157,12 +156,12 @@ __device__ void fft_dit(double2 *W, int L, int P, int logP, const double2 *__res
       const int l = item / halfP, bfly = item - l * halfP;
       const int k = bfly & (half - 1);
       const int i0 = ((bfly >> s) << (s + 1)) + k;
-      double2 *w = W + (size_t)l * P;
-      double2 t = __ldg(&tw[k * tstride]);
+      real2 *w = W + (size_t)l * P;
+      real2 t = __ldg(&tw[k * tstride]);
       if (conj_tw) t.y = -t.y;
-      const double2 a = w[i0], b = cmul(w[i0 + half], t);
-      w[i0] = make_double2(a.x + b.x, a.y + b.y);
-      w[i0 + half] = make_double2(a.x - b.x, a.y - b.y);
+      const real2 a = w[i0], b = cmul(w[i0 + half], t);
+      w[i0] = make_real2(a.x + b.x, a.y + b.y);
+      w[i0 + half] = make_real2(a.x - b.x, a.y - b.y);
     }
     __syncthreads();
   }
@@ -170,7 +169,7 @@ __device__ void fft_dit(double2 *W, int L, int P, int logP, const double2 *__res
 
 // Complex DFT of length m of every line of the tile.  Input: W[l][0..m) in natural order.
 // Output: element k of the spectrum is at W[l][spec_pos(k)].  inverse = unnormalised exp(+...).
-__device__ void cdft_tile(double2 *W, int L, const DirPlanDev &pl, bool inverse) {
+__device__ void cdft_tile(real2 *W, int L, const DirPlanDev &pl, bool inverse) {
   const int P = pl.P, m = pl.m;
   if (!pl.bluestein) {
     fft_dif(W, L, P, pl.logP, pl.tw, inverse);
@@ -180,28 +179,28 @@ __device__ void cdft_tile(double2 *W, int L, const DirPlanDev &pl, bool inverse)
   // conj(DFT(conj x)).
   for (int item = threadIdx.x; item < L * P; item += blockDim.x) {
     const int l = item / P, j = item - l * P;
-    double2 *w = W + (size_t)l * P;
+    real2 *w = W + (size_t)l * P;
     if (j < m) {
-      double2 x = w[j];
+      real2 x = w[j];
       if (inverse) x.y = -x.y;
       w[j] = cmul(x, __ldg(&pl.chirp[j]));
     } else {
-      w[j] = make_double2(0.0, 0.0);
+      w[j] = make_real2(RC(0.0), RC(0.0));
     }
   }
   __syncthreads();
   fft_dif(W, L, P, pl.logP, pl.tw, false);
   for (int item = threadIdx.x; item < L * P; item += blockDim.x) {
     const int l = item / P, j = item - l * P;
-    double2 *w = W + (size_t)l * P;
+    real2 *w = W + (size_t)l * P;
     w[j] = cmul(w[j], __ldg(&pl.filt[j]));
   }
   __syncthreads();
   fft_dit(W, L, P, pl.logP, pl.tw, true);
   for (int item = threadIdx.x; item < L * m; item += blockDim.x) {
     const int l = item / m, k = item - l * m;
-    double2 *w = W + (size_t)l * P;
-    double2 x = cmul(w[k], __ldg(&pl.chirp[k]));
+    real2 *w = W + (size_t)l * P;
+    real2 x = cmul(w[k], __ldg(&pl.chirp[k]));
     if (inverse) x.y = -x.y;
     w[k] = x;
   }
@@ -214,20 +213,20 @@ __device__ __forceinline__ int spec_pos(const DirPlanDev &pl, int k) {
 }
 
 // Forward real transform of every line: R (n reals, natural order) -> R (FFTW output order).
-__device__ void real_forward(double *R, double2 *W, int L, int r_pitch, const DirPlanDev &pl) {
+__device__ void real_forward(real *R, real2 *W, int L, int r_pitch, const DirPlanDev &pl) {
   const int n = pl.n, m = pl.m, P = pl.P;
   // pack
   for (int item = threadIdx.x; item < L * m; item += blockDim.x) {
     const int l = item / m, j = item - l * m;
-    const double *r = R + (size_t)l * r_pitch;
-    double2 c;
+    const real *r = R + (size_t)l * r_pitch;
+    real2 c;
     if (!pl.periodic) {
       const int q0 = 2 * j, q1 = 2 * j + 1;  // even extension of period 2m
-      c = make_double2(r[q0 <= m ? q0 : 2 * m - q0], r[q1 <= m ? q1 : 2 * m - q1]);
+      c = make_real2(r[q0 <= m ? q0 : 2 * m - q0], r[q1 <= m ? q1 : 2 * m - q1]);
     } else if ((n & 1) == 0) {
-      c = make_double2(r[2 * j], r[2 * j + 1]);
+      c = make_real2(r[2 * j], r[2 * j + 1]);
     } else {
-      c = make_double2(r[j], 0.0);
+      c = make_real2(r[j], RC(0.0));
     }
     W[(size_t)l * P + j] = c;
   }
@@ -237,30 +236,30 @@ __device__ void real_forward(double *R, double2 *W, int L, int r_pitch, const Di
   if (!pl.periodic) {
     for (int item = threadIdx.x; item < L * n; item += blockDim.x) {
       const int l = item / n, k = item - l * n;
-      const double2 *w = W + (size_t)l * P;
+      const real2 *w = W + (size_t)l * P;
       const int k0 = (k == m) ? 0 : k, k1 = (k == 0) ? 0 : m - k;
-      const double2 A = w[spec_pos(pl, k0)], B = w[spec_pos(pl, k1)];
-      const double2 cs = __ldg(&pl.unpack[k]);
-      R[(size_t)l * r_pitch + k] = 0.5 * ((A.x + B.x) + cs.x * (A.y + B.y) - cs.y * (A.x - B.x));
+      const real2 A = w[spec_pos(pl, k0)], B = w[spec_pos(pl, k1)];
+      const real2 cs = __ldg(&pl.unpack[k]);
+      R[(size_t)l * r_pitch + k] = RC(0.5) * ((A.x + B.x) + cs.x * (A.y + B.y) - cs.y * (A.x - B.x));
     }
   } else if ((n & 1) == 0) {
     const int h = m;
     for (int item = threadIdx.x; item < L * (h + 1); item += blockDim.x) {
       const int l = item / (h + 1), k = item - l * (h + 1);
-      const double2 *w = W + (size_t)l * P;
+      const real2 *w = W + (size_t)l * P;
       const int k0 = (k == h) ? 0 : k, k1 = (k == 0) ? 0 : h - k;
-      const double2 A = w[spec_pos(pl, k0)], B = w[spec_pos(pl, k1)];
-      const double2 cs = __ldg(&pl.unpack[k]);
-      double *r = R + (size_t)l * r_pitch;
-      r[k] = 0.5 * ((A.x + B.x) + cs.x * (A.y + B.y) - cs.y * (A.x - B.x));
-      if (k > 0 && k < h) r[n - k] = 0.5 * ((A.y - B.y) - cs.x * (A.x - B.x) - cs.y * (A.y + B.y));
+      const real2 A = w[spec_pos(pl, k0)], B = w[spec_pos(pl, k1)];
+      const real2 cs = __ldg(&pl.unpack[k]);
+      real *r = R + (size_t)l * r_pitch;
+      r[k] = RC(0.5) * ((A.x + B.x) + cs.x * (A.y + B.y) - cs.y * (A.x - B.x));
+      if (k > 0 && k < h) r[n - k] = RC(0.5) * ((A.y - B.y) - cs.x * (A.x - B.x) - cs.y * (A.y + B.y));
     }
   } else {
     const int h = n / 2;
     for (int item = threadIdx.x; item < L * (h + 1); item += blockDim.x) {
       const int l = item / (h + 1), k = item - l * (h + 1);
-      const double2 A = W[(size_t)l * P + spec_pos(pl, k)];
-      double *r = R + (size_t)l * r_pitch;
+      const real2 A = W[(size_t)l * P + spec_pos(pl, k)];
+      real *r = R + (size_t)l * r_pitch;
       r[k] = A.x;
       if (k > 0) r[n - k] = A.y;
     }
@@ -270,7 +269,7 @@ __device__ void real_forward(double *R, double2 *W, int L, int r_pitch, const Di
 
 // Inverse real transform of every line (unnormalised): for DCT-I the same transform, for periodic
 // directions FFTW_HC2R.  R (FFTW order) -> R (natural order).
-__device__ void real_inverse(double *R, double2 *W, int L, int r_pitch, const DirPlanDev &pl) {
+__device__ void real_inverse(real *R, real2 *W, int L, int r_pitch, const DirPlanDev &pl) {
   if (!pl.periodic) {
     real_forward(R, W, L, r_pitch, pl);
     return;
@@ -280,20 +279,20 @@ __device__ void real_inverse(double *R, double2 *W, int L, int r_pitch, const Di
     const int h = m;
     for (int item = threadIdx.x; item < L * h; item += blockDim.x) {
       const int l = item / h, k = item - l * h;
-      const double *r = R + (size_t)l * r_pitch;
+      const real *r = R + (size_t)l * r_pitch;
       const int kk = h - k;
-      const double xr = r[k], xi = (k == 0) ? 0.0 : r[n - k];
-      const double yr = r[kk], yi = (kk == h) ? 0.0 : r[n - kk];
-      const double pr = xr + yr, pi = xi - yi, dr = xr - yr, di = xi + yi;
-      const double2 cs = __ldg(&pl.unpack[k]);
-      W[(size_t)l * P + k] = make_double2(pr - cs.y * dr - cs.x * di, pi + cs.x * dr - cs.y * di);
+      const real xr = r[k], xi = (k == 0) ? RC(0.0) : r[n - k];
+      const real yr = r[kk], yi = (kk == h) ? RC(0.0) : r[n - kk];
+      const real pr = xr + yr, pi = xi - yi, dr = xr - yr, di = xi + yi;
+      const real2 cs = __ldg(&pl.unpack[k]);
+      W[(size_t)l * P + k] = make_real2(pr - cs.y * dr - cs.x * di, pi + cs.x * dr - cs.y * di);
     }
     __syncthreads();
     cdft_tile(W, L, pl, true);
     for (int item = threadIdx.x; item < L * h; item += blockDim.x) {
       const int l = item / h, j = item - l * h;
-      const double2 A = W[(size_t)l * P + spec_pos(pl, j)];
-      double *r = R + (size_t)l * r_pitch;
+      const real2 A = W[(size_t)l * P + spec_pos(pl, j)];
+      real *r = R + (size_t)l * r_pitch;
       r[2 * j] = A.x;
       r[2 * j + 1] = A.y;
     }
@@ -301,13 +300,13 @@ __device__ void real_inverse(double *R, double2 *W, int L, int r_pitch, const Di
     const int h = n / 2;
     for (int item = threadIdx.x; item < L * (h + 1); item += blockDim.x) {
       const int l = item / (h + 1), k = item - l * (h + 1);
-      const double *r = R + (size_t)l * r_pitch;
-      double2 *w = W + (size_t)l * P;
+      const real *r = R + (size_t)l * r_pitch;
+      real2 *w = W + (size_t)l * P;
       if (k == 0) {
-        w[0] = make_double2(r[0], 0.0);
+        w[0] = make_real2(r[0], RC(0.0));
       } else {
-        w[k] = make_double2(r[k], r[n - k]);
-        w[n - k] = make_double2(r[k], -r[n - k]);
+        w[k] = make_real2(r[k], r[n - k]);
+        w[n - k] = make_real2(r[k], -r[n - k]);
       }
     }
     __syncthreads();
@@ -320,27 +319,27 @@ __device__ void real_inverse(double *R, double2 *W, int L, int r_pitch, const Di
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) sweep_kernel(const SweepJob job, double *__restrict__ field, long long origin,
+__global__ void __launch_bounds__(256) sweep_kernel(const SweepJob job, real *__restrict__ field, long long origin,
                                                     long long tile_stride, long long outer_stride) {
-  extern __shared__ double2 smem2[];
+  extern __shared__ real2 smem2[];
   const DirPlanDev &pl = job.plan;
   const int L = job.L, n = pl.n, r_pitch = job.r_pitch;
-  double2 *W = smem2;
-  double *R = reinterpret_cast<double *>(W + (size_t)L * pl.P);
+  real2 *W = smem2;
+  real *R = reinterpret_cast<real *>(W + (size_t)L * pl.P);
   const int first_line = blockIdx.x * L;
   const int lines = min(L, job.n_tile_lines - first_line);
-  double *base = field + origin + (long long)first_line * tile_stride + (long long)blockIdx.y * outer_stride;
+  real *base = field + origin + (long long)first_line * tile_stride + (long long)blockIdx.y * outer_stride;
 
   // load: element-fastest when points of a line are contiguous (x sweeps), line-fastest otherwise
   if (job.estride == 1) {
     for (int item = threadIdx.x; item < L * n; item += blockDim.x) {
       const int l = item / n, e = item - l * n;
-      R[(size_t)l * r_pitch + e] = (l < lines) ? base[(long long)l * job.lstride + e] : 0.0;
+      R[(size_t)l * r_pitch + e] = (l < lines) ? base[(long long)l * job.lstride + e] : RC(0.0);
     }
   } else {
     for (int item = threadIdx.x; item < L * n; item += blockDim.x) {
       const int e = item / L, l = item - e * L;
-      R[(size_t)l * r_pitch + e] = (l < lines) ? base[(long long)l * job.lstride + (long long)e * job.estride] : 0.0;
+      R[(size_t)l * r_pitch + e] = (l < lines) ? base[(long long)l * job.lstride + (long long)e * job.estride] : RC(0.0);
     }
   }
   __syncthreads();
@@ -350,14 +349,14 @@ __global__ void __launch_bounds__(256) sweep_kernel(const SweepJob job, double *
     // pressure_hat *= 1 / (lambda_x + lambda_y + lambda_z); mode (0,0,0) := 0  (src/PressureEquation.cpp:158-163,
     // table of src/PressureSolverStructures.cpp:52-69).  For the z sweep a tile line is x index
     // first_line + l and blockIdx.y is the y index.
-    const double lam_y = job.lam_b[blockIdx.y];
+    const real lam_y = job.lam_b[blockIdx.y];
     for (int item = threadIdx.x; item < L * n; item += blockDim.x) {
       const int l = item / n, e = item - l * n;
       if (l < lines) {
         const int ix = first_line + l;
-        const double lam_x = job.lam_a[ix];
-        double scale = 1.0 / (lam_x + lam_y + pl.lambda[e]);
-        if (job.has_origin && ix == 0 && blockIdx.y == 0 && e == 0) scale = 0.0;
+        const real lam_x = job.lam_a[ix];
+        real scale = RC(1.0) / (lam_x + lam_y + pl.lambda[e]);
+        if (job.has_origin && ix == 0 && blockIdx.y == 0 && e == 0) scale = RC(0.0);
         R[(size_t)l * r_pitch + e] *= scale;
       }
     }
@@ -400,9 +399,10 @@ constexpr int kMaxRanks = 8;
 struct SegMap {
   int n = 0;  // 0: plain strided addressing
   int lo[kMaxRanks + 1];
-  double *base[kMaxRanks];
+  real *base[kMaxRanks];
   long long estride[kMaxRanks], outer_stride[kMaxRanks], xtile_stride[kMaxRanks];
 };
+#ifndef MIFGPU_FP32
 __device__ __forceinline__ double *seg_address(const SegMap &m, int e, int outer, int x) {
   int r = 0;
   while (r + 1 < m.n && e >= m.lo[r + 1]) r++;
@@ -1203,6 +1203,8 @@ void launch_warp(cudaStream_t stream, SmemAttrOnce &attrs, const FastJob &job, b
   }
 }
 
+#endif  // !MIFGPU_FP32
+
 template <typename T>
 T *to_device(const std::vector<T> &host) {
   if (host.empty()) return nullptr;
@@ -1211,6 +1213,18 @@ T *to_device(const std::vector<T> &host) {
   cudaMemcpy(dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice);
   return dev;
 }
+// The plan tables are computed in double and stored in the build's scalar type.
+#ifdef MIFGPU_FP32
+real2 *to_device(const std::vector<double2> &host) {
+  std::vector<real2> narrow(host.size());
+  for (size_t i = 0; i < host.size(); i++) narrow[i] = make_real2((real)host[i].x, (real)host[i].y);
+  return to_device(narrow);
+}
+real *to_device(const std::vector<double> &host) {
+  std::vector<real> narrow(host.begin(), host.end());
+  return to_device(narrow);
+}
+#endif
 
 // exp(-2 pi i num / den) with the argument reduced in integers.
 double2 unit_root(long long num, long long den) {
@@ -1247,7 +1261,9 @@ struct PoissonPlan {
   int L[3];
   size_t smem[3];
   std::vector<void *> allocations;
+#ifndef MIFGPU_FP32
   tmasweep::Cache tma;  // tensor maps of the TMA-staged strided sweeps, per field / direction
+#endif
   SmemAttrOnce attrs;   // dynamic shared-memory opt-in per kernel, for this plan's device
 };
 
@@ -1331,13 +1347,17 @@ PoissonPlan *poisson_plan_create(const Geom &g, const int n_points[3], const int
     pl.lambda = to_device(lambda);
     plan->allocations.push_back((void *)pl.lambda);
     // src/PressureEquation.cpp:167,200,234: N_domains_global * (periodic ? 1 : 2)
-    pl.inv_norm = 1.0 / ((double)(n_global[d] - 1) * (periodic[d] ? 1.0 : 2.0));
+    pl.inv_norm = (real)(1.0 / ((double)(n_global[d] - 1) * (periodic[d] ? 1.0 : 2.0)));
 
+#ifdef MIFGPU_FP32
+    plan->fast_logm[d] = plan->rfft_logm[d] = 0;  // every line length on sweep_kernel
+#else
     plan->fast_logm[d] = (!periodic[d] && pow2 && pl.logP >= 6 && pl.logP <= 11) ? pl.logP : 0;
     static const bool no_rfft = getenv("MIFGPU_NO_WARP_RFFT") != nullptr;  // A/B switch for profiling
     plan->rfft_logm[d] = (periodic[d] && n % 2 == 0 && pow2 && (pl.logP == 8 || pl.logP == 9) && !no_rfft) ? pl.logP : 0;
+#endif
     // lines per CTA: the largest power of two <= 8 that fits a ~100 KB shared-memory budget (two CTAs per SM)
-    const size_t per_line = (size_t)P * sizeof(double2) + (size_t)(n | 1) * sizeof(double);
+    const size_t per_line = (size_t)P * sizeof(real2) + (size_t)(n | 1) * sizeof(real);
     int L = 8;
     while (L > 1 && per_line * L > 100 * 1024) L >>= 1;
     plan->L[d] = L;
@@ -1374,6 +1394,7 @@ struct SweepLayout {
   bool peer = false;  // peer-memory sweeps: tiles of exactly 8 lines (the x tiles of the blocked buffers)
 };
 
+#ifndef MIFGPU_FP32
 void launch_tma_modes(cudaStream_t stream, tmasweep::Cache &cache, const tmasweep::MapSet &maps, const tmasweep::Job &job, int logm,
                       int mode);
 
@@ -1452,10 +1473,13 @@ void launch_tma_modes(cudaStream_t stream, tmasweep::Cache &cache, const tmaswee
   }
 }
 
-void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, int mode, const SweepLayout &lay,
+#endif  // !MIFGPU_FP32
+
+void launch_sweep(cudaStream_t stream, PoissonPlan *plan, real *field, int d, int mode, const SweepLayout &lay,
                   uint64_t *launches) {
   SmemAttrOnce &attrs = plan->attrs;
   attrs.ensure(sweep_kernel, 200 * 1024);
+#ifndef MIFGPU_FP32
   if (plan->fast_logm[d] > 0 || plan->rfft_logm[d] > 0) {
     FastJob fj;
     fj.origin = lay.origin; fj.lstride = lay.lstride; fj.estride = lay.estride;
@@ -1500,6 +1524,7 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
     ++*launches;
     return;
   }
+#endif
   SweepJob job;
   job.plan = plan->dir[d];
   job.dir = d;
@@ -1519,7 +1544,7 @@ void launch_sweep(cudaStream_t stream, PoissonPlan *plan, double *field, int d, 
 
 }  // namespace
 
-void launch_poisson_sweep(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *field, int d, int mode,
+void launch_poisson_sweep(cudaStream_t stream, const Geom &g, PoissonPlan *plan, real *field, int d, int mode,
                           uint64_t *launches) {
   const int nx = g.own_hi[0] - g.own_lo[0], ny = g.own_hi[1] - g.own_lo[1], nz = g.own_hi[2] - g.own_lo[2];
   SweepLayout lay;
@@ -1541,9 +1566,14 @@ void launch_poisson_sweep(cudaStream_t stream, const Geom &g, PoissonPlan *plan,
 }
 
 bool poisson_peer_capable(const PoissonPlan *plan) {
+#ifdef MIFGPU_FP32
+  (void)plan;
+  return false;  // multi-GPU float runs take the pack -> all-to-all -> unpack transposes
+#endif
   return plan->fast_logm[1] >= 8 && plan->fast_logm[1] <= 10 && plan->fast_logm[2] >= 8 && plan->fast_logm[2] <= 10;
 }
 
+#ifndef MIFGPU_FP32
 // Blocked buffer layouts of the peer path (nxt = PX / 8 x tiles; all extents in doubles):
 //   zbuf[r]  z pencil of rank r:          [z (all N_z)][x tile][y in r's range][8]
 //   xfer[r]  slab staging of rank r:      [x tile][y (all N_y)][z in r's slab][8]
@@ -1676,8 +1706,15 @@ static bool launch_tma_peer(cudaStream_t stream, const Geom &g, PoissonPlan *pla
   return true;
 }
 
-void launch_poisson_sweep_peer(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *field, const PeerLayout &peer,
+#endif  // !MIFGPU_FP32
+
+void launch_poisson_sweep_peer(cudaStream_t stream, const Geom &g, PoissonPlan *plan, real *field, const PeerLayout &peer,
                                int which, uint64_t *launches) {
+#ifdef MIFGPU_FP32
+  (void)stream; (void)g; (void)plan; (void)field; (void)peer; (void)which; (void)launches;
+  fprintf(stderr, "libmifgpu_f32: the peer-memory sweeps are FP64 only (poisson_peer_capable is false in this build)\n");
+  abort();
+#else
   if (launch_tma_peer(stream, g, plan, field, peer, which)) {
     ++*launches;
     return;
@@ -1715,9 +1752,10 @@ void launch_poisson_sweep_peer(cudaStream_t stream, const Geom &g, PoissonPlan *
     fill_map(lay.store_map, peer, 1, g);
     launch_sweep(stream, plan, peer.zbuf[me], 2, 2, lay, launches);
   }
+#endif
 }
 
-void launch_poisson_zpencil(cudaStream_t stream, const Geom &g, PoissonPlan *plan, double *zbuf, int ny_local,
+void launch_poisson_zpencil(cudaStream_t stream, const Geom &g, PoissonPlan *plan, real *zbuf, int ny_local,
                             int y_offset, bool has_origin, uint64_t *launches) {
   // zbuf[z][y_local][x]: x rows of PX doubles, ny_local rows per z plane, all N_z transform points.
   SweepLayout lay;
@@ -1738,7 +1776,7 @@ void launch_poisson_zpencil(cudaStream_t stream, const Geom &g, PoissonPlan *pla
 //   dir = 1: y pencil buf[z_local][y (all points)][x_local], n_outer = local z planes: lines along y;
 //   dir = 2: z pencil buf[z (all points)][y_local][x_local], n_outer = local y rows: lines along z (mode 2: fused).
 // x_offset / y_offset: global transform indices of local x = 0 and (dir = 2) local y = 0, for the eigenvalues.
-void launch_poisson_pencil(cudaStream_t stream, PoissonPlan *plan, double *buf, int dir, int mode, int nx_local, int pitch,
+void launch_poisson_pencil(cudaStream_t stream, PoissonPlan *plan, real *buf, int dir, int mode, int nx_local, int pitch,
                            int n_outer, int x_offset, int y_offset, bool has_origin, uint64_t *launches) {
   if (nx_local <= 0 || n_outer <= 0) return;  // this rank holds no line of the pencil (fewer rows than ranks)
   SweepLayout lay;

@@ -30,22 +30,22 @@ def run(cmd, np_ranks=1, cwd=None):
     return out.stdout
 
 
-def load_dump(outdir, rank=0):
+def load_dump(outdir, rank=0, dtype=np.float64):
     fields = {}
     with open(os.path.join(outdir, f"manifest_r{rank}.txt")) as f:
         for line in f:
             name, r, sx, sy, sz = line.split()
-            data = np.fromfile(os.path.join(outdir, f"{name}_r{r}.f64"), dtype=np.float64)
+            data = np.fromfile(os.path.join(outdir, f"{name}_r{r}.f64"), dtype=dtype)  # the dumper writes sizeof(Real)
             fields[name] = data.reshape(int(sz), int(sy), int(sx))
     return fields
 
 
-def dump_case(name, args, meta, np_ranks=1):
+def dump_case(name, args, meta, np_ranks=1, f32=False):
     tmp = tempfile.mkdtemp(prefix="mifgolden_")
     try:
-        cmd = [os.path.join(REF, "ref_dump")] + [str(a).replace("{out}", tmp) for a in args]
+        cmd = [os.path.join(REF, "f32" if f32 else "", "ref_dump")] + [str(a).replace("{out}", tmp) for a in args]
         stdout = run(cmd, np_ranks)
-        fields = load_dump(tmp)
+        fields = load_dump(tmp, dtype=np.float32 if f32 else np.float64)
         meta = dict(meta, command="ref_dump " + " ".join(str(a) for a in args), stdout=stdout.strip())
         np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), meta=json.dumps(meta), **fields)
         print(f"{name}: {len(fields)} arrays, stdout={stdout.strip()!r}")
@@ -64,10 +64,42 @@ def velocity_cases():
         dump_case("vtest_mixed_12_2" if mixed else "vtest_12_2", args, meta)
 
 
+def f32_cases():
+    """The reference's USE_DOUBLE=0 build (oracle/_ref/f32, `make -C oracle f32`): float32 fields of three of the cases
+    above plus the numbers its full_test prints -- the pins of libmifgpu_f32.so (tests/fp32_cases.py)."""
+    full = dict(kind="full", x_size=1.0, y_size=1.0, z_size=2.0, min=[0.0, 0.0, -1.0], Re=1e3, final_time=1e-4,
+                periodic=[0, 0, 0], bc="ethier_steinman", real="float32")
+    dump_case("f32_full_16_2", ["full", 16, 2, 1, "{out}"], dict(full, N=[16, 16, 16], steps=2, nhn=0), f32=True)
+    lid1 = dict(kind="lid", x_size=1.0, y_size=1.0, z_size=2.0, min=[0.0, 0.0, -1.0], Re=1e3, periodic=[0, 0, 0],
+                bc="test_case_1", real="float32")
+    dump_case("f32_lid1_12x10x14_2", ["lid", 12, 10, 14, 1e-3, 2, 0, 1, "{out}"],
+              dict(lid1, N=[12, 10, 14], steps=2, dt=1e-3, final_time=2e-3), f32=True)
+    lid2 = dict(kind="lid", x_size=1.0, y_size=1.0, z_size=1.0, min=[-0.5, -0.5, -0.5], Re=1e3, periodic=[0, 0, 1],
+                bc="test_case_2", real="float32")
+    dump_case("f32_lid2_10x12x9_2", ["lid", 10, 12, 9, 1e-3, 2, 1, 1, "{out}"],
+              dict(lid2, N=[10, 12, 9], steps=2, dt=1e-3, final_time=2e-3), f32=True)
+    norms = {}
+    tmp = tempfile.mkdtemp(prefix="mifgolden_")
+    try:
+        for n, steps in ((16, 1), (32, 2)):
+            out = run([os.path.join(REF, "f32", "full_test"), str(n), str(steps), "1"], cwd=tmp)
+            norms[f"full_test {n} {steps} 1"] = [float(x) for x in out.split()]
+    finally:
+        shutil.rmtree(tmp)
+    with open(os.path.join(GOLDEN, "f32_norms.json"), "w") as f:
+        json.dump(norms, f, indent=1)
+    print("f32 norms", norms)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     if not os.path.exists(os.path.join(REF, "ref_dump")):
         sys.exit("oracle/_ref/ref_dump missing: run `make -C oracle ref` first")
+    if len(sys.argv) > 1 and sys.argv[1] == "--f32":  # add the single-precision cases without touching the others
+        if not os.path.exists(os.path.join(REF, "f32", "ref_dump")):
+            sys.exit("oracle/_ref/f32/ref_dump missing: run `make -C oracle f32` first")
+        f32_cases()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "--only-velocity":  # add the velocity cases without touching the others
         velocity_cases()
         return

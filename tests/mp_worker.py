@@ -134,7 +134,7 @@ def main():
     if rank == 0:
         print(json.dumps({"case": case, "world": world, "Py": Py, "Pz": Pz, "max_rel_err": max(errs)}))
     dist.destroy_process_group()
-    return 0 if max(errs) <= 1e-11 else 1
+    return 0 if max(errs) <= float(os.environ.get("MIF_WORKER_TOL", "1e-11")) else 1  # the float build's cases pass their own bound
 
 
 if __name__ == "__main__":

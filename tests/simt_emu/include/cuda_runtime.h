@@ -37,6 +37,8 @@ struct dim3 {
   dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+static inline void sincos(float a, float *s, float *c) { sincosf(a, s, c); }
 static inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }
 
 extern uint3 threadIdx, blockIdx;
@@ -164,5 +166,6 @@ static inline long long max(long long a, int b) { return a > b ? a : b; }
 static inline long long max(int a, long long b) { return a > b ? a : b; }
 static inline double min(double a, double b) { return fmin(a, b); }
 static inline double max(double a, double b) { return fmax(a, b); }
+static inline float max(float a, float b) { return fmaxf(a, b); }
 
 #endif  // MIF_SIMT_EMU_CUDA_RUNTIME_H
