@@ -77,13 +77,15 @@ void prefetch(const VelocityTensor &velocity, const StaggeredTensor &pressure, c
   prefetch(pressure, lo, hi, reach_all);
 }
 
+const char *const kTypeName = (sizeof(Real) == 8) ? "double" : "float";  // src/VTKDatExport.cpp:123
+
 void append_big_endian(std::string &out, const std::vector<Real> &values) {
-  for (Real value : values) {
-    uint64_t bits;
-    std::memcpy(&bits, &value, sizeof(bits));
-    char bytes[8];
-    for (int b = 0; b < 8; b++) bytes[b] = static_cast<char>((bits >> (56 - 8 * b)) & 0xff);
-    out.append(bytes, 8);
+  for (Real value : values) {  // sizeof(Real) bytes per value, as the reference writes them (src/VTKDatExport.cpp:123)
+    unsigned char raw[sizeof(Real)];
+    std::memcpy(raw, &value, sizeof(Real));
+    char bytes[sizeof(Real)];
+    for (size_t b = 0; b < sizeof(Real); b++) bytes[b] = static_cast<char>(raw[sizeof(Real) - 1 - b]);  // little-endian host
+    out.append(bytes, sizeof(Real));
   }
 }
 
@@ -107,11 +109,12 @@ bool gather_to_root(const Constants &c, std::vector<Real> &values) {
   if (mifgpu_allreduce(c.gpu(), sizes.data(), c.P, 0) != MIFGPU_OK) throw std::runtime_error(std::string("mifgpu_allreduce: ") + mifgpu_last_error());
   size_t total = 0;
   for (double n : sizes) total += static_cast<size_t>(n);
-  std::vector<Real> all(c.rank == 0 ? total : 0);
-  if (mifgpu_gather(c.gpu(), values.data(), values.size(), all.data(), counts.data()) != MIFGPU_OK)
+  // mifgpu_gather moves doubles in both builds of the library: a float build widens its values for the trip
+  std::vector<double> mine(values.begin(), values.end()), all(c.rank == 0 ? total : 0);
+  if (mifgpu_gather(c.gpu(), mine.data(), mine.size(), all.data(), counts.data()) != MIFGPU_OK)
     throw std::runtime_error(std::string("mifgpu_gather: ") + mifgpu_last_error());
   if (c.rank != 0) return false;
-  values.swap(all);
+  values.assign(all.begin(), all.end());
   return true;
 }
 
@@ -162,16 +165,16 @@ void writeVTK(const std::string &filename, const VelocityTensor &velocity, const
   char text[256];
   std::string out;
   std::snprintf(text, sizeof(text), "# vtk DataFile Version 2.0\nvtk output\nBINARY\nDATASET UNSTRUCTURED_GRID \nPOINTS %d %s\n",
-                points, "double");
+                points, kTypeName);
   out += text;
   append_big_endian(out, xyz);
-  std::snprintf(text, sizeof(text), "\nPOINT_DATA %d\nSCALARS u %s 1\nLOOKUP_TABLE default\n", points, "double");
+  std::snprintf(text, sizeof(text), "\nPOINT_DATA %d\nSCALARS u %s 1\nLOOKUP_TABLE default\n", points, kTypeName);
   out += text;
   append_big_endian(out, su);
   const char *names[3] = {"v", "w", "p"};
   const std::vector<Real> *fields[3] = {&sv, &sw, &sp};
   for (int f = 0; f < 3; f++) {
-    std::snprintf(text, sizeof(text), "\nSCALARS %s %s 1\nLOOKUP_TABLE default\n", names[f], "double");
+    std::snprintf(text, sizeof(text), "\nSCALARS %s %s 1\nLOOKUP_TABLE default\n", names[f], kTypeName);
     out += text;
     append_big_endian(out, *fields[f]);
   }

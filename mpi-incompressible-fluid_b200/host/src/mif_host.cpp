@@ -343,10 +343,13 @@ VectorFunction TimeVectorFunction::get_difference_over_time(Real time_1, Real ti
 // ---- boundary data for the C ABI ----------------------------------------------------------------------
 namespace {
 
-typedef Real (*TimeFn)(Real, Real, Real, Real);
+// The generated exact solutions are double functions whatever Real is (include/Manufactured.h), the lid-driven cases
+// of TestCaseBoundaries.h are Real functions: the wrapped pointer is looked up with the type it was wrapped with.
+typedef double (*TimeFn)(double, double, double, double);
 
-bool is_function(const TimeVectorFunction::Component &f, TimeFn fn) {
-  const TimeFn *target = f.target<TimeFn>();
+template <class Fn>
+bool is_function(const TimeVectorFunction::Component &f, Fn fn) {
+  const Fn *target = f.template target<Fn>();
   return target && *target == fn;
 }
 
@@ -372,7 +375,7 @@ struct FaceSource {
 // One face of one velocity component, i.e. what VelocityTensor::apply_bc stores there
 // (src/VelocityTensor.cpp:47-217): the analytic value at the staggered point for tangential components; for the
 // wall-normal component the wall value plus/minus half a cell of the tangential divergence of the analytic field.
-void fill_velocity_face(const VelocityTensor &vt, const VectorFunction &f, int component, int face, double *values) {
+void fill_velocity_face(const VelocityTensor &vt, const VectorFunction &f, int component, int face, mifgpu_real *values) {
   const Constants &c = vt.constants;
   const StaggeredTensor &tensor = *vt.components[component];
   const auto &s = tensor.sizes();
@@ -409,7 +412,7 @@ void fill_velocity_face(const VelocityTensor &vt, const VectorFunction &f, int c
 }
 
 // Neumann data on one face of the pressure tensor (src/PressureEquation.cpp:15-55): g_n at unstaggered points.
-void fill_gradient_face(const Constants &c, const VectorFunction &g, int face, double *values) {
+void fill_gradient_face(const Constants &c, const VectorFunction &g, int face, mifgpu_real *values) {
   const int dir = 2 - face / 2;
   const bool upper = face & 1;
   const size_t n[3] = {c.Nx, c.Ny, c.Nz};
@@ -428,7 +431,7 @@ void fill_gradient_face(const Constants &c, const VectorFunction &g, int face, d
     }
 }
 
-void face_callback(void *user, int which, double time, double time_prev, int component, int face, double *values) {
+void face_callback(void *user, int which, double time, double time_prev, int component, int face, mifgpu_real *values) {
   const FaceSource &src = *static_cast<const FaceSource *>(user);
   if (which == 0) {
     if (src.velocity_fixed) fill_velocity_face(*src.shape, *src.velocity_fixed, component, face, values);

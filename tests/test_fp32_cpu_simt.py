@@ -67,3 +67,27 @@ def test_float_library_on_two_ranks_matches_one_rank():
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert res["world"] == 2 and res["max_rel_err"] <= 2e-5, res
+
+
+def test_float_host_layer_prints_the_float_reference_numbers():
+    """host/bin_f32: the ported full_test and the reference's own test/full_test.cpp compiled UNCHANGED, both with
+    -DUSE_DOUBLE=0 (Real = float, include/Real.h:9-17) against the float host layer and libmifgpu_f32.so; the nine numbers
+    are those of the float build of the reference (tests/golden/f32_norms.json; the error norms are sums of float
+    round-off sized terms, hence 2e-3)."""
+    build = subprocess.run(["make", "-C", EMU, "-j8"], capture_output=True, text=True)
+    assert build.returncode == 0, build.stdout[-2000:] + build.stderr[-2000:]
+    want = json.load(open(os.path.join(GOLDEN_DIR, "f32_norms.json")))["full_test 16 1 1"]
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(EMU, "build", "as_libmifgpu"))
+    ran = 0
+    for name in ("full_test", "ref_full_test"):
+        exe = os.path.join(PKG, "host", "bin_f32", name)
+        if name == "ref_full_test" and not os.path.exists(exe):
+            continue  # built only where the reference tree is present
+        out = subprocess.run([exe, "16", "1", "1"], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout[-1000:] + out.stderr[-2000:]
+        got = [float(x) for x in out.stdout.split()]
+        assert len(got) == 9
+        for a, b in zip(got, want):
+            assert abs(a - b) <= 2e-3 * abs(b), (name, got, want)
+        ran += 1
+    assert ran >= 1

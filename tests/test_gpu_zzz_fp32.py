@@ -23,3 +23,20 @@ def test_float_library_passes_the_parity_cases_on_the_device():
     out = json.loads([l for l in run.stdout.splitlines() if l.startswith("{")][-1])
     assert len(out) >= 16
     fp32_cases.check(out)
+
+
+def test_float_host_layer_prints_the_float_reference_numbers_on_the_device():
+    """host/bin_f32/full_test and the reference's unchanged full_test.cpp (-DUSE_DOUBLE=0) on libmifgpu_f32.so."""
+    from conftest import GOLDEN_DIR
+    want = json.load(open(os.path.join(GOLDEN_DIR, "f32_norms.json")))
+    for name in ("full_test", "ref_full_test"):
+        exe = os.path.join(ROOT, "mpi-incompressible-fluid_b200", "host", "bin_f32", name)
+        if name == "ref_full_test" and not os.path.exists(exe):
+            continue
+        for args in (("16", "1", "1"), ("32", "2", "1")):
+            out = subprocess.run([exe, *args], capture_output=True, text=True, timeout=600)
+            assert out.returncode == 0, out.stdout[-1000:] + out.stderr[-2000:]
+            got = [float(x) for x in out.stdout.split()]
+            assert len(got) == 9
+            for a, b in zip(got, want["full_test " + " ".join(args)]):
+                assert abs(a - b) <= 5e-3 * abs(b), (name, args, got)  # error norms of ~4e-4 carry float round-off of ~3e-7
