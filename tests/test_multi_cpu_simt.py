@@ -47,7 +47,7 @@ def test_two_rank_slabs_with_peer_memory_transposes(simt_env):
     assert res["world"] == 2 and res["max_rel_err"] <= 1e-11
 
 
-@pytest.mark.parametrize("case,world,port", [("full_16_2", 2, 29721), ("es:3x257x257", 2, 29722), ("pz:6x6x13", 3, 29723)])
+@pytest.mark.parametrize("case,world,port", [("full_16_2", 2, 29721), ("full_17_1", 3, 29722), ("pz:6x6x13", 3, 29723)])
 def test_overlapped_halo_exchanges_completing_as_late_as_stream_order_allows(simt_env, case, world, port):
     """Inside the time step the plane exchanges run on a second stream while the consuming stencil kernel covers its
     interior planes (mif_api.cu, launch_around_halo).  The interpreter runs kernels synchronously, so the default run is
