@@ -115,6 +115,52 @@ def oracle_timestep(mif, mo, N, periodic, kind):
     return worst
 
 
+def velocity_only_case(mif, case):
+    """mif::timestep_velocity with the manufactured forcing (src/TimestepVelocity.cpp) against the DOUBLE reference's fields
+    of the velocity tests, inputs rounded to float: the forcing is evaluated in double in both builds."""
+    from conftest import load_golden
+    meta, f = load_golden(case)
+    N = meta["N"]
+    ctx = mif.Context(N[0], N[1], N[2], meta["x_size"], meta["y_size"], meta["z_size"], *meta["min"], meta["Re"],
+                      meta["final_time"], meta["steps"], periodic=[bool(p) for p in meta["periodic"]])
+    vel, vb, rb = ctx.velocity(), ctx.velocity(), ctx.velocity()
+    for t, name in zip(vel, "uvw"):
+        t.upload(f[name + "_s0"])
+    bc = ctx.make_bc(mif.BC_VELOCITY_TEST, meta["Re"])
+    dt = meta["final_time"] / meta["steps"]
+    worst = 0.0
+    for step in range(meta["steps"]):
+        ctx.timestep_velocity(vel, vb, rb, bc, step * dt)
+        vmax = max(float(np.max(np.abs(f[f"{c}_s{step + 1}"]))) for c in "uvw")
+        for t, name in zip(vel, "uvw"):
+            worst = max(worst, rel(t.download(), f[f"{name}_s{step + 1}"], floor=1e-3 * vmax))
+    ctx.close()
+    return worst
+
+
+def nhn_solve_case(mif):
+    """Pressure solve with non-homogeneous Neumann data through the host callback (float face tables) against the DOUBLE
+    reference's ptest_nhn golden (test/pressure_test_nhn.cpp)."""
+    from conftest import load_golden
+    import test_gpu_golden as g64
+    meta, f = load_golden("ptest_nhn_8x24x40")
+    ctx = g64.make_ctx(mif, meta)
+    vel = ctx.velocity()
+    for t, name in zip(vel, ("u_in", "v_in", "w_in")):
+        t.upload(f[name])
+    p = ctx.tensor(mif.STAGGER_NONE)
+
+    def cb(which, time, time_prev, comp, face, values):
+        assert which == 1 and comp == 2 - face // 2 and values.dtype == np.float32
+        x, y, z = g64.face_points(meta, face)
+        values[...] = g64.ptest_gradient(comp, time, x, y, z)
+
+    ctx.solve_pressure(p, vel, ctx.dt, ctx.make_bc(mif.BC_HOST_CALLBACK, 1.0, cb), meta["time"])
+    err = rel(p.download(), f["p_out"])
+    ctx.close()
+    return err
+
+
 def norms_case(mif):
     """The nine numbers `full_test 16 1 1` prints (test/full_test.cpp:36-187) from the float library, started from the
     t = 0 fields of the float reference's own run: returns the largest relative deviation of the six velocity /
@@ -159,6 +205,9 @@ def main():
         steps += [((33, 17, 65), (F, F, F), "ethier_steinman")]
     for N, periodic, kind in steps:
         out[f"timestep {N} {periodic} {kind}"] = oracle_timestep(mif, mo, N, periodic, kind)
+    out["velocity-only vtest_12_2"] = velocity_only_case(mif, "vtest_12_2")
+    out["velocity-only vtest_mixed_12_2"] = velocity_only_case(mif, "vtest_mixed_12_2")
+    out["solve nhn callback 8x24x40"] = nhn_solve_case(mif)
     out["norms full_test 16 1 1"] = norms_case(mif)
     print(json.dumps(out))
     return out
