@@ -397,6 +397,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     mif.lib()  # fails loudly if libmifgpu.so is missing
+    if mif.lib().mifgpu_real_bytes() != 8:
+        sys.exit("bench.py measures BASELINE.json's FP64 metric: MIFGPU_LIB names the float build of the library, unset it")
 
     N = args.size
     steps, warmup = args.steps, max(args.warmup, 3)
