@@ -8,4 +8,4 @@ for py in 4 2; do
   MIF_PY=$py timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 2965$py tests/mp_worker.py lid1_12x10x14_2 > $out/${tag}_pencil_py$py.log 2>&1
   grep -E "^\{|\[rank[0-9]\]:.*(Error|error|assert)|libmifgpu" $out/${tag}_pencil_py$py.log | head -8
 done
-bash scripts/gpu_multi.sh 4 r02m4 "4"
+bash scripts/sessions/gpu_multi.sh 4 r02m4 "4"

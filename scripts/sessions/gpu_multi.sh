@@ -1,6 +1,6 @@
 #!/bin/bash
 # Multi-GPU session on N GPUs: parity tests selected by $3 (pytest -k), weak / strong 1025^3 / aniso bench lines.
-#   gpurun --gpus N -- 'bash scripts/gpu_multi.sh N tag "<pytest -k expression>"'
+#   gpurun --gpus N -- 'bash scripts/sessions/gpu_multi.sh N tag "<pytest -k expression>"'
 cd "${GRAFT_REPO_ROOT:-.}" || exit 1
 N=${1:-4}; tag=${2:-r02m$N}; sel=${3:-}
 out=gpurun_out
