@@ -120,7 +120,8 @@ void mifgpu_destroy(mifgpu_ctx *ctx);
  * library over NCCL.  Py = 1 (z slabs, Pz = number of GPUs) is the fast configuration on one NVSwitch box: its Y<->Z
  * transposes are fused into the sweep kernels over peer memory.  Py > 1 gives the reference's Py x Pz pencils
  * (rank = y_rank * Pz + z_rank, src/Constants.cpp:68): two-phase halos (y sheets, then whole z planes) and the four
- * 2Decomp transposes as grouped send/recv box exchanges; a periodic y direction cannot be distributed. */
+ * 2Decomp transposes as grouped send/recv box exchanges.  Periodic y and z directions may be distributed: the neighbours
+ * wrap around (src/Constants.cpp:98-101). */
 #define MIFGPU_UNIQUE_ID_BYTES 128
 int mifgpu_comm_unique_id(void *unique_id);
 int mifgpu_create_distributed(const mifgpu_params *params, const void *unique_id, mifgpu_ctx **ctx);

@@ -548,6 +548,17 @@ int exchange_y(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count) {
     const int s = tensors[t]->staggering;
     const int sy = g.sy[s];
     auto row = [&](int j) { return Box{tensors[t]->data, (size_t)g.PX, (size_t)g.PY, 0, j, 0, g.sx[s], 1, g.sz[s]}; };
+    if (g.prev_y != -1 && g.prev_y == g.next_y) {
+      // periodic y on two y ranks: both neighbours are the same peer, and NCCL pairs the operations with one peer in issue
+      // order (the reference tells them apart by tag): my row 1 is the peer's top ghost, my row sy - 2 its bottom ghost
+      peers.push_back(g.prev_y);
+      send.push_back(row(1));
+      recv.push_back(row(sy - 1));
+      peers.push_back(g.next_y);
+      send.push_back(row(sy - 2));
+      recv.push_back(row(0));
+      continue;
+    }
     if (g.prev_y != -1) {
       peers.push_back(g.prev_y);
       send.push_back(row(1));
@@ -856,8 +867,6 @@ static int create_context(const mifgpu_params *params, const void *unique_id, mi
   int n_points[3];
   int rc = build_geometry(*params, g, n_points);
   if (rc) return rc;
-  if (params->Py > 1 && params->periodic_bc[1])
-    return fail(MIFGPU_ERR_UNSUPPORTED, "a periodic y direction cannot be distributed (Py = %d) in this build", params->Py);
   if (params->Pz > 1 && (params->Nz_global - (params->periodic_bc[2] ? 1 : 0)) / params->Pz < 2)
     return fail(MIFGPU_ERR_INVALID, "fewer than 2 owner planes per rank");
   if (params->Py > 1 && (params->Ny_global / params->Py < 2 || (params->Nx_global - (params->periodic_bc[0] ? 1 : 0)) / params->Py < 1))

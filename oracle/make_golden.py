@@ -64,6 +64,43 @@ def velocity_cases():
         dump_case("vtest_mixed_12_2" if mixed else "vtest_12_2", args, meta)
 
 
+def multi_rank_cases():
+    """The reference ITSELF on several ranks (threads of the MPI stand-in), every rank's local arrays kept: the pins of
+    the distributed periodic directions (neighbours wrap around, src/Constants.cpp:98-101; halos of the staggered
+    component, src/StaggeredTensor.cpp:60-165), which cannot be checked by cutting a single-rank result -- the
+    reference's one-rank periodic ghost copy has its own one-cell quirk.  Keys: <field>_s<step>_r<rank>."""
+    def dump(name, args, meta, ranks):
+        tmp = tempfile.mkdtemp(prefix="mifgolden_")
+        try:
+            run([os.path.join(REF, "ref_dump")] + [str(a).replace("{out}", tmp) for a in args], ranks)
+            fields = {}
+            for r in range(ranks):
+                for key, arr in load_dump(tmp, rank=r).items():
+                    fields[f"{key}_r{r}"] = arr
+            meta = dict(meta, ranks=ranks, command=f"MIF_SHIM_NP={ranks} ref_dump " + " ".join(str(a) for a in args))
+            np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), meta=json.dumps(meta), **fields)
+            print(f"{name}: {len(fields)} arrays on {ranks} ranks")
+        finally:
+            shutil.rmtree(tmp)
+
+    lid2 = dict(kind="lid", x_size=1.0, y_size=1.0, z_size=1.0, min=[-0.5, -0.5, -0.5], Re=1e3, periodic=[0, 0, 1],
+                bc="test_case_2", steps=2, dt=1e-3, final_time=2e-3)
+    dump("mr_lid2_10x12x9_pz2", ["lid", 10, 12, 9, 1e-3, 2, 1, 2, "{out}"], dict(lid2, N=[10, 12, 9], Py=1, Pz=2), 2)
+    dump("mr_lid2_10x12x14_pz3", ["lid", 10, 12, 14, 1e-3, 2, 1, 3, "{out}"], dict(lid2, N=[10, 12, 14], Py=1, Pz=3), 3)
+    full = dict(kind="full", x_size=1.0, y_size=1.0, z_size=2.0, min=[0.0, 0.0, -1.0], Re=1e3, final_time=1e-4, steps=1,
+                bc="ethier_steinman")
+    dump("mr_full_p010_9x12x10_py2", ["full", 9, 1, 1, "{out}", "hn", 12, 10, "010"],
+         dict(full, N=[9, 12, 10], periodic=[0, 1, 0], Py=2, Pz=1), 2)
+    dump("mr_full_p011_9x13x11_py2pz2", ["full", 9, 1, 2, "{out}", "hn", 13, 11, "011"],
+         dict(full, N=[9, 13, 11], periodic=[0, 1, 1], Py=2, Pz=2), 4)
+    dump("mr_full_p010_9x13x10_py3", ["full", 9, 1, 1, "{out}", "hn", 13, 10, "010"],
+         dict(full, N=[9, 13, 10], periodic=[0, 1, 0], Py=3, Pz=1), 3)
+    ln = 2 * np.pi
+    vt = dict(kind="vtest", N=[12, 12, 12], x_size=ln, y_size=ln, z_size=1.0, min=[0.0, 0.0, 0.0], Re=1e4, final_time=1e-4,
+              steps=2, periodic=[1, 1, 0], bc="velocity_test")
+    dump("mr_vtest_mixed_12_py2", ["vtest", 12, 2, 1, "{out}", "mixed"], dict(vt, Py=2, Pz=1), 2)
+
+
 def f32_cases():
     """The reference's USE_DOUBLE=0 build (oracle/_ref/f32, `make -C oracle f32`): float32 fields of three of the cases
     above plus the numbers its full_test prints -- the pins of libmifgpu_f32.so (tests/fp32_cases.py)."""
@@ -95,6 +132,9 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     if not os.path.exists(os.path.join(REF, "ref_dump")):
         sys.exit("oracle/_ref/ref_dump missing: run `make -C oracle ref` first")
+    if len(sys.argv) > 1 and sys.argv[1] == "--multi-rank":  # add the several-rank cases without touching the others
+        multi_rank_cases()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "--f32":  # add the single-precision cases without touching the others
         if not os.path.exists(os.path.join(REF, "f32", "ref_dump")):
             sys.exit("oracle/_ref/f32/ref_dump missing: run `make -C oracle f32` first")

@@ -5,7 +5,9 @@
 // reference's own tests only print error norms (test/full_test.cpp:171-175), which are far too
 // coarse for a 1e-11 parity contract.  The set-ups replicate the reference's mains:
 //
-//   full  N steps Pz out [nhn|hn [Ny Nz]]  test/full_test.cpp:36-76,118-126 (Ethier-Steinman, all walls)
+//   full  N steps Pz out [nhn|hn [Ny Nz [pxyz]]]  test/full_test.cpp:36-76,118-126 (Ethier-Steinman; all walls unless the
+//                                     optional mask, e.g. 010, makes directions periodic -- a parity set-up for the
+//                                     periodic code paths on several ranks, not a physical one)
 //   lid   Nx Ny Nz dt steps tc2 Pz out  src/main.cpp:121-156               (test case 1 / 2)
 //   ptest kind Nx Ny Nz Pz out        test/pressure_test_{hn,mixed,nhn}.cpp:20-59 (any grid, kind = hn|mixed|nhn)
 //   vtest N steps Pz out [mixed]      test/velocity_test{,_mixed}.cpp
@@ -80,7 +82,8 @@ static int run_full(int argc, char **argv, int size) {
   reset_manifest();
   const int Py = size / Pz;
   constexpr Real Re = 1e3;
-  const std::array<bool, 3> periodic{false, false, false};
+  const char *mask = argc > 9 ? argv[9] : "000";
+  const std::array<bool, 3> periodic{mask[0] == '1', mask[1] == '1', mask[2] == '1'};
   const Constants constants(N, Ny, Nz, 1.0, 1.0, 2.0, 0.0, 0.0, -1.0, Re, 1e-4, steps, Py, Pz, g_rank, periodic);
   PressureSolverStructures structures(constants);
   Reynolds = Re;

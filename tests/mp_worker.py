@@ -62,6 +62,64 @@ def main():
             print(json.dumps({"case": case, "world": world, "Py": 1, "Pz": world, "max_rel_err": max(errs)}))
         dist.destroy_process_group()
         return 0 if max(errs) <= 1e-11 else 1
+    if case.startswith("mr:"):
+        # A run of the reference itself on this many ranks (oracle/make_golden.py --multi-rank): every rank uploads ITS local
+        # arrays of the reference's run and must reproduce the reference's local arrays after every step, ghosts included.
+        data = np.load(os.path.join(ROOT, "tests", "golden", case[3:] + ".npz"))
+        meta = json.loads(str(data["meta"]))
+        assert meta["ranks"] == world, (meta["ranks"], world)
+        N, Py, Pz = meta["N"], meta["Py"], meta["Pz"]
+        periodic = [bool(p) for p in meta["periodic"]]
+        ctx = mif.Context(N[0], N[1], N[2], meta["x_size"], meta["y_size"], meta["z_size"], *meta["min"], meta["Re"],
+                          meta["final_time"], meta["steps"], Py=Py, Pz=Pz, rank=rank, periodic=periodic, device=local_rank,
+                          comm_id=ids[0])
+        velocity_only = meta["kind"] == "vtest"
+        names = "uvw" if velocity_only else "uvwp"
+        y_rank = rank // Pz
+        ctx_prev_y = Py > 1 and (y_rank > 0 or periodic[1])      # this rank has a y neighbour below / above
+        ctx_next_y = Py > 1 and (y_rank < Py - 1 or periodic[1])
+        vel, vb, vb2 = ctx.velocity(), ctx.velocity(), ctx.velocity()
+        p, dp = ctx.tensor(mif.STAGGER_NONE), ctx.tensor(mif.STAGGER_NONE)
+        tensors = vel if velocity_only else vel + [p]
+        for t, name in zip(tensors, names):
+            host = data[f"{name}_s0_r{rank}"]
+            assert t.shape == host.shape[::-1], (name, t.shape, host.shape)
+            t.upload(host)
+        kind = {"ethier_steinman": mif.BC_ETHIER_STEINMAN, "test_case_1": mif.BC_TEST_CASE_1,
+                "test_case_2": mif.BC_TEST_CASE_2, "velocity_test": mif.BC_VELOCITY_TEST}[meta["bc"]]
+        bc = ctx.make_bc(kind, meta["Re"])
+        dt = meta["final_time"] / meta["steps"]
+        worst = 0.0
+        for step in range(meta["steps"]):
+            if velocity_only:
+                ctx.timestep_velocity(vel, vb, vb2, bc, step * dt)
+            else:
+                ctx.timestep(vel, vb, vb2, bc, step * dt, p, dp)
+            ctx.synchronize()
+            # scales: the largest value of the field over ALL ranks; a velocity component that is zero in exact arithmetic
+            # is normalised by the largest component (see tests/test_gpu_golden.py)
+            def field_max(name):
+                return max(float(np.max(np.abs(data[f"{name}_s{step + 1}_r{r}"]))) for r in range(world))
+            vmax = max(field_max(c) for c in "uvw")
+            for t, name in zip(tensors, names):
+                ref = data[f"{name}_s{step + 1}_r{rank}"]
+                scale = max(field_max(name), 1e-6 * vmax if name in "uvw" else 0.0)
+                err = np.abs(t.download() - ref)
+                if Py > 1:
+                    # The reference unpacks a received y sheet into the interior of the ghost row only, i and k borders
+                    # keep what they held (src/StaggeredTensor.cpp:145-149,158-162); the library refreshes whole rows
+                    # (equality with the single-rank result).  No stencil reads those points.
+                    for j in ([0] if ctx_prev_y else []) + ([ref.shape[1] - 1] if ctx_next_y else []):
+                        err[0, j, :] = err[-1, j, :] = 0.0
+                        err[:, j, 0] = err[:, j, -1] = 0.0
+                worst = max(worst, float(np.max(err)) / scale)
+        errs = [None] * world
+        dist.all_gather_object(errs, worst)
+        ctx.close()
+        if rank == 0:
+            print(json.dumps({"case": case, "world": world, "Py": Py, "Pz": Pz, "max_rel_err": max(errs)}))
+        dist.destroy_process_group()
+        return 0 if max(errs) <= float(os.environ.get("MIF_WORKER_TOL", "1e-11")) else 1
     if case.startswith("es:"):
         # No golden file: the oracle (oracle/mif_oracle.c, pinned to the reference) computes the single-rank result
         # of one Ethier-Steinman step on the given grid; used for grids large enough to take the peer-memory path.

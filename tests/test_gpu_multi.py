@@ -63,3 +63,21 @@ def test_periodic_z_distributed_over_the_ranks(world):
     assert out.returncode == 0, failure_report(out)
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     assert json.loads(line)["max_rel_err"] <= 1e-11
+
+
+@pytest.mark.parametrize("case,world,py,tol", [
+    ("mr_lid2_10x12x9_pz2", 2, 1, 1e-11), ("mr_lid2_10x12x14_pz3", 3, 1, 1e-11), ("mr_full_p010_9x12x10_py2", 2, 2, 1e-11),
+    ("mr_full_p010_9x13x10_py3", 3, 3, 1e-11), ("mr_vtest_mixed_12_py2", 2, 2, 1e-10), ("mr_full_p011_9x13x11_py2pz2", 4, 2, 1e-6),
+])
+def test_distributed_periodic_directions_match_the_reference_on_the_same_ranks(case, world, py, tol):
+    """Time steps with a periodic z and / or y direction split over the ranks against the reference ITSELF run on the same
+    number of ranks, every rank's arrays, ghosts included (tests/test_multi_cpu_simt.py explains the tolerances)."""
+    if device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ, MIF_PY=str(py), MIF_WORKER_TOL=str(tol))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29560 + world + py), os.path.join(ROOT, "tests", "mp_worker.py"), "mr:" + case]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, failure_report(out)
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line)["max_rel_err"] <= tol

@@ -70,6 +70,26 @@ def test_periodic_z_distributed_over_the_ranks(simt_env, world):
     assert res["world"] == world and res["max_rel_err"] <= 1e-11
 
 
+@pytest.mark.parametrize("case,world,tol", [
+    ("mr_lid2_10x12x9_pz2", 2, 1e-11),          # periodic z over two slabs, lid-driven case, two projection steps
+    ("mr_full_p010_9x12x10_py2", 2, 1e-11),     # periodic y over two y ranks (same-peer sheets in issue order)
+    ("mr_full_p010_9x13x10_py3", 3, 1e-11),     # ... over a ring of three
+    ("mr_vtest_mixed_12_py2", 2, 1e-10),        # periodic x on the rank + periodic y over two ranks, velocity-only integrator
+    ("mr_full_p011_9x13x11_py2pz2", 4, 1e-6),   # periodic y AND z distributed (2 x 2)
+])
+def test_distributed_periodic_directions_match_the_reference_on_the_same_ranks(simt_env, case, world, tol):
+    """The reference ITSELF run on `world` ranks (oracle/make_golden.py --multi-rank keeps every rank's arrays): each rank
+    uploads its local arrays of that run and must reproduce the reference's local arrays after every step, ghost planes
+    and rows included.  A single-rank result cannot be the target here -- with a distributed periodic direction the
+    reference's own runs differ between decompositions (its one-rank ghost copy of the staggered component is shifted by
+    one cell).  Two known differences, both in points / effects the reference leaves one exchange
+    stale: the x-periodic corners of received y sheets (1.2e-11 on the velocity-only case) and, with Py > 1 AND Pz > 1,
+    the y-ghost / z-ghost edges (2e-7 on the 2 x 2 case, where the library keeps them fresh)."""
+    py = {"mr_full_p010_9x12x10_py2": 2, "mr_full_p010_9x13x10_py3": 3, "mr_vtest_mixed_12_py2": 2, "mr_full_p011_9x13x11_py2pz2": 2}.get(case, 1)
+    res = run_worker(dict(simt_env, MIF_WORKER_TOL=str(tol)), "mr:" + case, world, 29740 + world + 7 * py, py=py)
+    assert res["world"] == world and res["max_rel_err"] <= tol, res
+
+
 def test_four_rank_pencils(simt_env):
     # Py x Pz = 2 x 2 on 17^3 points (uneven blocks 9 + 8): y sheets then z planes as halos, the four 2Decomp transposes
     # as box exchanges, x / y / z sweeps on the sub-domain, the y pencil and the z pencil
