@@ -134,6 +134,9 @@ struct mifgpu_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap_halos = false;
   bool halo_pending = false;
+  // MIFGPU_REFERENCE_HALOS=1: the y / z exchanges of a Py x Pz run exactly as the reference orders them, stale edge
+  // ghosts included (exchange_halos)
+  bool reference_halos = false;
   // Py > 1: pencil decomposition in the 2Decomp layout (deps/2Decomp_C/C2Decomp.cpp:241-423): x pencil (this rank's
   // sub-domain) -> y pencil (x distributed over the Py ranks of the same z_rank) -> z pencil (y distributed over the
   // Pz ranks of the same y_rank).  Block distributions as in src/Constants.cpp:78-79 (bigger blocks on the low ranks).
@@ -538,7 +541,7 @@ int exchange_boxes(mifgpu_ctx *ctx, const std::vector<int> &peers, const std::ve
 // 1-cell halo exchange in y of whole x-z sheets (src/StaggeredTensor.cpp:137-165): row 1 -> prev rank's last row, row
 // sy-2 -> next rank's row 0.  Run BEFORE exchange_z, whose whole planes then carry the fresh y ghosts into the edge
 // regions (SURVEY.md section 8a "edge ghosts": the result equals the single-rank one).
-int exchange_y(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count) {
+int exchange_y(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count, bool interior_only = false) {
   const Geom &g = ctx->g;
   if (g.prev_y == -1 && g.next_y == -1) return MIFGPU_OK;
   ProfScope prof(ctx, PROF_HALO);
@@ -547,7 +550,10 @@ int exchange_y(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count) {
   for (int t = 0; t < count; t++) {
     const int s = tensors[t]->staggering;
     const int sy = g.sy[s];
-    auto row = [&](int j) { return Box{tensors[t]->data, (size_t)g.PX, (size_t)g.PY, 0, j, 0, g.sx[s], 1, g.sz[s]}; };
+    // interior_only: the part of a sheet the reference unpacks, 1 <= i <= sx - 2 and 1 <= k <= sz - 2
+    // (src/StaggeredTensor.cpp:145-149,158-162)
+    const int lo = interior_only ? 1 : 0, nx = g.sx[s] - 2 * lo, nz = g.sz[s] - 2 * lo;
+    auto row = [&](int j) { return Box{tensors[t]->data, (size_t)g.PX, (size_t)g.PY, lo, j, lo, nx, 1, nz}; };
     if (g.prev_y != -1 && g.prev_y == g.next_y) {
       // periodic y on two y ranks: both neighbours are the same peer, and NCCL pairs the operations with one peer in issue
       // order (the reference tells them apart by tag): my row 1 is the peer's top ghost, my row sy - 2 its bottom ghost
@@ -611,6 +617,15 @@ int exchange_z(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count, cudaSt
 // Ghost refresh of `count` tensors in both split directions, y first (see exchange_y).
 int exchange_halos(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count) {
   if (ctx->nranks == 1) return MIFGPU_OK;
+  if (ctx->Py > 1 && ctx->reference_halos) {
+    // The reference's own order and extents (src/StaggeredTensor.cpp:60-165): whole z planes are sent while their y
+    // ghost rows still hold the previous exchange's values, and a received y sheet is unpacked without its i and k
+    // borders -- so the y-ghost / z-ghost edges lag one exchange behind and a Py x Pz run differs from the one-rank run
+    // (2e-5 after one step on 17^3).  With this switch a Py x Pz run reproduces the reference's Py x Pz run instead.
+    const int rc = exchange_z(ctx, tensors, count);
+    if (rc) return rc;
+    return exchange_y(ctx, tensors, count, true);
+  }
   if (ctx->Py > 1) {
     const int rc = exchange_y(ctx, tensors, count);
     if (rc) return rc;
@@ -899,6 +914,7 @@ static int create_context(const mifgpu_params *params, const void *unique_id, mi
   ctx->Pz = params->Pz;
   ctx->y_rank = params->rank / params->Pz;
   ctx->z_rank = params->rank % params->Pz;
+  ctx->reference_halos = getenv("MIFGPU_REFERENCE_HALOS") != nullptr;
   if (ctx->Py > 1) {
     // Pencil decomposition: block distributions of the transform points (src/Constants.cpp:78-79), NCCL communicator
     // over all Py * Pz ranks, pencil buffers and compact staging for the box exchanges.

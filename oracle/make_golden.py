@@ -93,6 +93,7 @@ def multi_rank_cases():
          dict(full, N=[9, 12, 10], periodic=[0, 1, 0], Py=2, Pz=1), 2)
     dump("mr_full_p011_9x13x11_py2pz2", ["full", 9, 1, 2, "{out}", "hn", 13, 11, "011"],
          dict(full, N=[9, 13, 11], periodic=[0, 1, 1], Py=2, Pz=2), 4)
+    dump("mr_full_17_py2pz2", ["full", 17, 1, 2, "{out}"], dict(full, N=[17, 17, 17], periodic=[0, 0, 0], Py=2, Pz=2), 4)
     dump("mr_full_p010_9x13x10_py3", ["full", 9, 1, 1, "{out}", "hn", 13, 10, "010"],
          dict(full, N=[9, 13, 10], periodic=[0, 1, 0], Py=3, Pz=1), 3)
     ln = 2 * np.pi

@@ -105,7 +105,7 @@ def main():
                 ref = data[f"{name}_s{step + 1}_r{rank}"]
                 scale = max(field_max(name), 1e-6 * vmax if name in "uvw" else 0.0)
                 err = np.abs(t.download() - ref)
-                if Py > 1:
+                if Py > 1 and "MIFGPU_REFERENCE_HALOS" not in os.environ:
                     # The reference unpacks a received y sheet into the interior of the ghost row only, i and k borders
                     # keep what they held (src/StaggeredTensor.cpp:145-149,158-162); the library refreshes whole rows
                     # (equality with the single-rank result).  No stencil reads those points.

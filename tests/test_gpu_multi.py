@@ -81,3 +81,18 @@ def test_distributed_periodic_directions_match_the_reference_on_the_same_ranks(c
     assert out.returncode == 0, failure_report(out)
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     assert json.loads(line)["max_rel_err"] <= tol
+
+
+@pytest.mark.parametrize("case,world,py", [("mr_full_17_py2pz2", 4, 2), ("mr_full_p011_9x13x11_py2pz2", 4, 2), ("mr_vtest_mixed_12_py2", 2, 2)])
+def test_reference_halo_mode_reproduces_the_reference_pencil_runs_point_for_point(case, world, py):
+    """MIFGPU_REFERENCE_HALOS=1 (the reference's exchange order and extents, stale edge ghosts included): a Py x Pz run
+    equals the reference's own Py x Pz run at every point of every rank's arrays."""
+    if device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ, MIF_PY=str(py), MIFGPU_REFERENCE_HALOS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29580 + world + py), os.path.join(ROOT, "tests", "mp_worker.py"), "mr:" + case]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, failure_report(out)
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line)["max_rel_err"] <= 1e-11

@@ -90,6 +90,16 @@ def test_distributed_periodic_directions_match_the_reference_on_the_same_ranks(s
     assert res["world"] == world and res["max_rel_err"] <= tol, res
 
 
+@pytest.mark.parametrize("case,world,py", [("mr_full_17_py2pz2", 4, 2), ("mr_full_p011_9x13x11_py2pz2", 4, 2), ("mr_vtest_mixed_12_py2", 2, 2)])
+def test_reference_halo_mode_reproduces_the_reference_pencil_runs_point_for_point(simt_env, case, world, py):
+    """MIFGPU_REFERENCE_HALOS=1: z planes first, y sheets unpacked without their borders -- the reference's order and
+    extents (src/StaggeredTensor.cpp:60-165), stale edge ghosts included.  A Py x Pz run then equals the reference's
+    Py x Pz run at every point of every rank's arrays, with no point left out of the comparison (the default keeps the
+    edges fresh and equals the ONE-rank run instead: test_four_rank_pencils; on 17^3 the two differ by 4e-8)."""
+    res = run_worker(dict(simt_env, MIFGPU_REFERENCE_HALOS="1"), "mr:" + case, world, 29770 + world + py, py=py)
+    assert res["world"] == world and res["max_rel_err"] <= 1e-11, res
+
+
 def test_four_rank_pencils(simt_env):
     # Py x Pz = 2 x 2 on 17^3 points (uneven blocks 9 + 8): y sheets then z planes as halos, the four 2Decomp transposes
     # as box exchanges, x / y / z sweeps on the sub-domain, the y pencil and the z pencil
