@@ -621,7 +621,7 @@ int exchange_halos(mifgpu_ctx *ctx, mifgpu_tensor *const *tensors, int count) {
     // The reference's own order and extents (src/StaggeredTensor.cpp:60-165): whole z planes are sent while their y
     // ghost rows still hold the previous exchange's values, and a received y sheet is unpacked without its i and k
     // borders -- so the y-ghost / z-ghost edges lag one exchange behind and a Py x Pz run differs from the one-rank run
-    // (2e-5 after one step on 17^3).  With this switch a Py x Pz run reproduces the reference's Py x Pz run instead.
+    // (4e-8 in p after one step on 17^3, and the never-unpacked borders keep old values).  With this switch a Py x Pz run reproduces the reference's Py x Pz run instead.
     const int rc = exchange_z(ctx, tensors, count);
     if (rc) return rc;
     return exchange_y(ctx, tensors, count, true);
