@@ -18,22 +18,29 @@ def main():
     import test_gpu_vs_oracle as parity
 
     F, T = False, True
-    entry.smoke()                                                     # 16^3, generic sweeps, stage / bc / correct kernels
+    # `--shard i/n` runs every n-th case starting at i, so that the caller can spread the list over processes
+    shard, shards = (int(v) for v in sys.argv[sys.argv.index("--shard") + 1].split("/")) if "--shard" in sys.argv else (0, 1)
     solve = parity.test_pressure_solve_random_velocity
+    cases = [lambda: entry.smoke()]                                   # 16^3, generic sweeps, stage / bc / correct kernels
     for N, periodic in [((513, 4, 9), (F, F, F)),                     # x sweeps on the 16 x 32 transform (M = 512)
                         ((9, 257, 3), (F, F, F)),                     # TMA-staged strided y sweeps, radix-8 passes (M = 256)
                         ((11, 3, 513), (F, F, F)),                    # TMA-staged fused z sweep on the 16 x 32 transform
                         ((1025, 3, 4), (F, F, F)),                    # x sweeps of 1025-point lines (two 512-point halves)
                         ((20, 9, 513), (F, F, T)),                    # warp real-FFT path, fused z sweep
                         ((65, 9, 65), (F, F, F)),                     # CTA-synchronous fast path
-                        ((12, 10, 14), (F, F, T))]:                   # Bluestein
-        solve(mif, N, periodic)
-        print("solve ok", N, periodic, flush=True)
-    solve(mif, (10, 1025, 3), (F, F, F))                              # TMA-staged 1025-point lines (split transform), two x tiles
-    parity.test_async_transfers_pipeline_matches_synchronous_calls(mif)  # asynchronous transfer API
-    parity.test_timestep_random_state(mif, (9, 10, 12), (T, T, T), "test_case_2")
-    parity.test_timestep_nhn_matches_oracle(mif)
-    golden.test_timestep_velocity_matches_reference(mif, "vtest_12_2")
+                        ((12, 10, 14), (F, F, T)),                    # Bluestein
+                        ((10, 1025, 3), (F, F, F))]:                  # TMA-staged 1025-point lines (split transform), two x tiles
+        cases.append(lambda N=N, periodic=periodic: solve(mif, N, periodic))
+    cases.append(lambda: parity.test_async_transfers_pipeline_matches_synchronous_calls(mif))  # asynchronous transfer API
+    cases.append(lambda: parity.test_timestep_random_state(mif, (9, 10, 12), (T, T, T), "test_case_2"))
+    cases.append(lambda: parity.test_timestep_nhn_matches_oracle(mif))
+    cases.append(lambda: golden.test_timestep_velocity_matches_reference(mif, "vtest_12_2"))
+    for index, case in enumerate(cases):
+        # smoke() alone takes as long as all other cases together (its 513 x 513 x 3 solve): it gets shard 0 to itself
+        mine = (index == 0) == (shard == 0) and (index == 0 or index % (shards - 1) == shard - 1) if shards > 1 else True
+        if mine:
+            case()
+            print("case", index, "ok", flush=True)
     print("simt cases ok")
 
 

@@ -15,10 +15,16 @@ def test_kernel_sources_pass_parity_cases_under_the_simt_interpreter():
     build = subprocess.run(["make", "-C", EMU, "-j8"], capture_output=True, text=True)
     assert build.returncode == 0, build.stdout[-2000:] + build.stderr[-2000:]
     env = dict(os.environ, MIFGPU_LIB=os.path.join(EMU, "build", "libmifgpu_simt.so"))
-    run = subprocess.run([sys.executable, os.path.join(EMU, "run_cases.py")], env=env, capture_output=True, text=True,
-                         timeout=900)
-    assert run.returncode == 0, run.stdout[-3000:] + run.stderr[-3000:]
-    assert "simt cases ok" in run.stdout
+    shards = 4  # the cases are independent: spread them over a few processes (the interpreter is single-threaded)
+    runs = [subprocess.Popen([sys.executable, os.path.join(EMU, "run_cases.py"), "--shard", f"{i}/{shards}"], env=env,
+                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for i in range(shards)]
+    seen = 0
+    for run in runs:
+        out, err = run.communicate(timeout=900)
+        assert run.returncode == 0, out[-3000:] + err[-3000:]
+        assert "simt cases ok" in out
+        seen += out.count(" ok\n") - 1
+    assert seen == 13, seen  # every case of run_cases.py ran in exactly one shard
 
 
 def test_bench_line_carries_the_contract_keys_in_a_dry_run():
