@@ -40,6 +40,57 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+class GpuLocalCpus:
+    """Context manager: while pinned host buffers are allocated, run the calling thread on the CPUs of the NUMA node the
+    GPU hangs off (sysfs `local_cpulist` of its PCI function), so that the pages land on that node and the copy engines
+    do not pull them across the socket interconnect; the previous affinity is restored on exit.  Best effort: without
+    the sysfs entry, or in a cpuset that excludes those CPUs, nothing changes.  `info` goes into the JSON line."""
+
+    def __init__(self, device_index):
+        self.info = {"bound": False}
+        self.cpus = None
+        try:
+            prop = torch.cuda.get_device_properties(device_index)
+            address = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+            base = "/sys/bus/pci/devices/" + address
+            with open(base + "/local_cpulist") as f:
+                text = f.read().strip()
+            cpus = set()
+            for part in text.split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            self.previous = os.sched_getaffinity(0)
+            usable = cpus & self.previous
+            node = None
+            try:
+                with open(base + "/numa_node") as f:
+                    node = int(f.read())
+            except (OSError, ValueError):
+                pass
+            self.info = {"bound": False, "pci": address, "numa_node": node, "local_cpus": text}
+            if usable and usable != self.previous:
+                self.cpus = usable
+        except Exception as err:  # no sysfs, no such property, ...: leave the affinity alone
+            self.info = {"bound": False, "why": type(err).__name__}
+
+    def __enter__(self):
+        if self.cpus:
+            try:
+                os.sched_setaffinity(0, self.cpus)
+                self.info["bound"] = True
+            except OSError:
+                self.cpus = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.cpus:
+            try:
+                os.sched_setaffinity(0, self.previous)
+            except OSError:
+                pass
+        return False
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The sampler is started before the
     warm-up (nvidia-smi needs up to a second to produce its first row, longer on an 8-GPU box) and only the rows
@@ -443,10 +494,12 @@ def main():
     # selected by index here; the library's boundary data finds it by coordinate, like
     # include/TestCaseBoundaries.h:18-35, and both agree because the domain ends at x = 1 exactly (checked below).
     host = []
-    for t in vel + [p]:
-        sx, sy, sz = t.shape
-        arr = torch.zeros((sz, sy, sx), dtype=torch.float64).pin_memory()
-        host.append(arr)
+    gpu_local = GpuLocalCpus(local_rank)  # pinned host buffers on the GPU's own NUMA node (e2e moves 8.65 GB per job)
+    with gpu_local:
+        for t in vel + [p]:
+            sx, sy, sz = t.shape
+            arr = torch.zeros((sz, sy, sx), dtype=torch.float64).pin_memory()
+            host.append(arr)
     host[1][:, :, dims[0] - 1] = 1.0
     for t, arr in zip(vel + [p], host):
         t.upload(arr.numpy())
@@ -560,7 +613,8 @@ def main():
         # for that set's own download and the two PCIe directions would take turns)
         n_sets = max(1, int(os.environ.get("MIF_BENCH_E2E_SETS", "3")))
         sets = [(vel, p)] + [(ctx.velocity(), ctx.tensor(mif.STAGGER_NONE)) for _ in range(n_sets - 1)]
-        out = [torch.zeros(tuple(a.shape), dtype=torch.float64).pin_memory() for a in host]
+        with gpu_local:
+            out = [torch.zeros(tuple(a.shape), dtype=torch.float64).pin_memory() for a in host]
         for v2, p2 in sets[1:]:
             for t, arr in zip(v2 + [p2], host):
                 t.upload(arr.numpy())
@@ -588,7 +642,7 @@ def main():
             e2e_s = float(tmax.item())
         e2e = {"value": world * cells * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": field_bytes,
                "d2h_bytes_per_step": field_bytes, "steps": e2e_steps, "ms_per_step": round(1e3 * e2e_s / e2e_steps, 3),
-               "device_field_sets": n_sets,
+               "device_field_sets": n_sets, "host_buffers": gpu_local.info,
                "result_finite": bool(np.isfinite(out[1].numpy()).all()),
                "what": "per step (one job): async upload of u,v,w,p from pinned host memory, mifgpu_timestep, async download "
                        "of u,v,w,p; consecutive jobs are independent and rotate through three device field sets, so "

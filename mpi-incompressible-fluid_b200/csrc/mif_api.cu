@@ -151,9 +151,15 @@ struct mifgpu_ctx {
   size_t staging_bytes = 0;
   // asynchronous host transfers (mifgpu_tensor_upload_async / _download_async): one stream and one compact staging
   // buffer per direction, so that H2D, D2H and the kernels of independent tensors overlap
-  cudaStream_t copy_stream[2] = {nullptr, nullptr};  // [0] host -> device, [1] device -> host
-  real *copy_staging[2] = {nullptr, nullptr};
+  // Asynchronous transfers: [0] host -> device and [1] device -> host over PCIe, [2] / [3] the re-pitching copies on the
+  // device behind / ahead of them.  Two compact staging buffers per direction, so that the link moves tensor n + 1 while
+  // tensor n is re-pitched; ev_stage_filled / ev_stage_free hand a buffer from one stream to the other and back.
+  cudaStream_t copy_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+  real *copy_staging[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   size_t copy_staging_bytes[2] = {0, 0};
+  cudaEvent_t ev_stage_filled[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  cudaEvent_t ev_stage_free[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  int copy_next[2] = {0, 0};
   // host-callback boundary faces: pinned staging + device copies, [which][component][face]
   real *face_host[2][3][6] = {};
   real *face_dev[2][3][6] = {};
@@ -1055,13 +1061,18 @@ void mifgpu_destroy(mifgpu_ctx *ctx) {
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-  for (int d = 0; d < 2; d++) {
+  for (int d = 0; d < 4; d++) {
     if (ctx->copy_stream[d]) {
       cudaStreamSynchronize(ctx->copy_stream[d]);
       cudaStreamDestroy(ctx->copy_stream[d]);
     }
-    if (ctx->copy_staging[d]) cudaFree(ctx->copy_staging[d]);
   }
+  for (int d = 0; d < 2; d++)
+    for (int b = 0; b < 2; b++) {
+      if (ctx->copy_staging[d][b]) cudaFree(ctx->copy_staging[d][b]);
+      if (ctx->ev_stage_filled[d][b]) cudaEventDestroy(ctx->ev_stage_filled[d][b]);
+      if (ctx->ev_stage_free[d][b]) cudaEventDestroy(ctx->ev_stage_free[d][b]);
+    }
   if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -1096,6 +1107,12 @@ int mifgpu_tensor_create(mifgpu_ctx *ctx, int staggering, mifgpu_tensor **out) {
       cudaEventCreateWithFlags(&t->ev_computed, cudaEventDisableTiming) != cudaSuccess) {
     mifgpu_tensor_destroy(t);
     return fail(MIFGPU_ERR_CUDA, "creating the tensor's events failed");
+  }
+  // the zero fill counts as the tensor's first "compute" use: an asynchronous transfer issued right after the creation
+  // runs on another stream and must not overtake it
+  if (cudaEventRecord(t->ev_computed, ctx->stream) != cudaSuccess) {
+    mifgpu_tensor_destroy(t);
+    return fail(MIFGPU_ERR_CUDA, "recording the tensor's creation failed");
   }
   *out = t;
   return MIFGPU_OK;
@@ -1164,37 +1181,61 @@ static int copy_tensor_async(mifgpu_tensor *t, real *host, bool to_device) {
   const Geom &g = ctx->g;
   CUDA_TRY(cudaSetDevice(ctx->params.device));
   const int dir = to_device ? 0 : 1, s = t->staggering;
-  if (!ctx->copy_stream[dir]) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream[dir], cudaStreamNonBlocking));
-  cudaStream_t cs = ctx->copy_stream[dir];
+  for (int which : {dir, dir + 2})
+    if (!ctx->copy_stream[which]) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream[which], cudaStreamNonBlocking));
+  cudaStream_t link = ctx->copy_stream[dir], repack = ctx->copy_stream[dir + 2];
   const size_t bytes = (size_t)g.sx[s] * g.sy[s] * g.sz[s] * sizeof(real);
   if (ctx->copy_staging_bytes[dir] < bytes) {
-    CUDA_TRY(cudaStreamSynchronize(cs));
-    if (ctx->copy_staging[dir]) cudaFree(ctx->copy_staging[dir]);
-    ctx->copy_staging[dir] = nullptr;
-    ctx->copy_staging_bytes[dir] = 0;
-    // one size for all staggerings, so that the buffer is allocated once
-    const size_t most = (size_t)(g.sx[0]) * (size_t)(g.sy[1]) * (size_t)(g.sz[2]) * sizeof(real);
-    CUDA_TRY(cudaMalloc(&ctx->copy_staging[dir], std::max(bytes, most)));
-    ctx->copy_staging_bytes[dir] = std::max(bytes, most);
+    CUDA_TRY(cudaStreamSynchronize(link));
+    CUDA_TRY(cudaStreamSynchronize(repack));
+    // one size for all staggerings, so that the buffers are allocated once
+    const size_t most = std::max(bytes, (size_t)(g.sx[0]) * (size_t)(g.sy[1]) * (size_t)(g.sz[2]) * sizeof(real));
+    for (int b = 0; b < 2; b++) {
+      if (ctx->copy_staging[dir][b]) cudaFree(ctx->copy_staging[dir][b]);
+      ctx->copy_staging[dir][b] = nullptr;
+      ctx->copy_staging_bytes[dir] = 0;
+      CUDA_TRY(cudaMalloc(&ctx->copy_staging[dir][b], most));
+      if (!ctx->ev_stage_filled[dir][b]) CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_stage_filled[dir][b], cudaEventDisableTiming));
+      if (!ctx->ev_stage_free[dir][b]) CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_stage_free[dir][b], cudaEventDisableTiming));
+    }
+    ctx->copy_staging_bytes[dir] = most;
   }
+  const int b = ctx->copy_next[dir];
+  ctx->copy_next[dir] ^= 1;
+  real *stage = ctx->copy_staging[dir][b];
   cudaMemcpy3DParms parms;
   std::memset(&parms, 0, sizeof(parms));
-  const cudaPitchedPtr compact = make_cudaPitchedPtr(ctx->copy_staging[dir], (size_t)g.sx[s] * sizeof(real), g.sx[s], g.sy[s]);
+  const cudaPitchedPtr compact = make_cudaPitchedPtr(stage, (size_t)g.sx[s] * sizeof(real), g.sx[s], g.sy[s]);
   const cudaPitchedPtr padded = make_cudaPitchedPtr(t->data, (size_t)g.PX * sizeof(real), g.PX, g.PY);
   parms.srcPtr = to_device ? compact : padded;
   parms.dstPtr = to_device ? padded : compact;
   parms.extent = make_cudaExtent((size_t)g.sx[s] * sizeof(real), g.sy[s], g.sz[s]);
   parms.kind = cudaMemcpyDeviceToDevice;
-  CUDA_TRY(cudaStreamWaitEvent(cs, t->ev_computed, 0));
-  CUDA_TRY(cudaStreamWaitEvent(cs, to_device ? t->ev_downloaded : t->ev_uploaded, 0));
   if (to_device) {
-    CUDA_TRY(cudaMemcpyAsync(ctx->copy_staging[dir], host, bytes, cudaMemcpyHostToDevice, cs));
-    CUDA_TRY(cudaMemcpy3DAsync(&parms, cs));
-    CUDA_TRY(cudaEventRecord(t->ev_uploaded, cs));
+    // link: host -> stage b, once the re-pitching copy that last read stage b is done
+    CUDA_TRY(cudaStreamWaitEvent(link, ctx->ev_stage_free[dir][b], 0));
+    CUDA_TRY(cudaMemcpyAsync(stage, host, bytes, cudaMemcpyHostToDevice, link));
+    CUDA_TRY(cudaEventRecord(ctx->ev_stage_filled[dir][b], link));
+    // repack: stage b -> tensor, once the tensor is free (last compute call, last download of it)
+    CUDA_TRY(cudaStreamWaitEvent(repack, ctx->ev_stage_filled[dir][b], 0));
+    CUDA_TRY(cudaStreamWaitEvent(repack, t->ev_computed, 0));
+    CUDA_TRY(cudaStreamWaitEvent(repack, t->ev_downloaded, 0));
+    CUDA_TRY(cudaMemcpy3DAsync(&parms, repack));
+    CUDA_TRY(cudaEventRecord(t->ev_uploaded, repack));
+    CUDA_TRY(cudaEventRecord(ctx->ev_stage_free[dir][b], repack));
   } else {
-    CUDA_TRY(cudaMemcpy3DAsync(&parms, cs));
-    CUDA_TRY(cudaMemcpyAsync(host, ctx->copy_staging[dir], bytes, cudaMemcpyDeviceToHost, cs));
-    CUDA_TRY(cudaEventRecord(t->ev_downloaded, cs));
+    // repack: tensor -> stage b, once the tensor holds its values (last compute call, last upload) and the transfer
+    // that last read stage b is done; the tensor may be overwritten as soon as this copy is done
+    CUDA_TRY(cudaStreamWaitEvent(repack, t->ev_computed, 0));
+    CUDA_TRY(cudaStreamWaitEvent(repack, t->ev_uploaded, 0));
+    CUDA_TRY(cudaStreamWaitEvent(repack, ctx->ev_stage_free[dir][b], 0));
+    CUDA_TRY(cudaMemcpy3DAsync(&parms, repack));
+    CUDA_TRY(cudaEventRecord(ctx->ev_stage_filled[dir][b], repack));
+    CUDA_TRY(cudaEventRecord(t->ev_downloaded, repack));
+    // link: stage b -> host
+    CUDA_TRY(cudaStreamWaitEvent(link, ctx->ev_stage_filled[dir][b], 0));
+    CUDA_TRY(cudaMemcpyAsync(host, stage, bytes, cudaMemcpyDeviceToHost, link));
+    CUDA_TRY(cudaEventRecord(ctx->ev_stage_free[dir][b], link));
   }
   return MIFGPU_OK;
 }

@@ -2,6 +2,7 @@
 // include/cuda_runtime.h).  One OS thread; the CUDA threads of one block are ucontext fibers that run until they reach
 // a scheduling point (block / warp / named barrier, shuffle) or return; blocks run one after the other.
 #include <dlfcn.h>
+#include <deque>
 #include <cuda_runtime.h>
 #include <mif_tma.cuh>
 #include <fcntl.h>
@@ -125,9 +126,12 @@ void run_block() {
 
 }  // namespace
 
+extern "C" void emu_flush_stream_for_nccl(void *stream);  // defined with the stream queues below
+
 namespace emu {
 
-void launch(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::function<void()> &thread_body) {
+void launch(dim3 grid, dim3 block, size_t dynamic_smem_bytes, cudaStream_t stream, const std::function<void()> &thread_body) {
+  emu_flush_stream_for_nccl(stream);  // a kernel runs behind everything queued on its stream (MIF_EMU_LAZY_COPIES)
   const size_t n = (size_t)block.x * block.y * block.z;
   if (n == 0 || n > kMaxThreads) {
     std::fprintf(stderr, "simt_emu: block of %zu threads\n", n);
@@ -313,8 +317,85 @@ int &shuffle_parity() { return g_parity[g_current]; }
 }  // namespace emu
 
 // ---- CUDA runtime stand-ins: "device" memory is host memory --------------------------------------------------
-struct emu_stream { int side = 0; };  // 1: created with a priority; fake_nccl.cpp reads this int
-struct emu_event { std::chrono::steady_clock::time_point when; cudaStream_t recorded_on = nullptr; };
+// Streams.  By default everything is carried out at once, in program order.  MIF_EMU_LAZY_COPIES=1 models the freedom a
+// device has with ASYNCHRONOUS COPIES: cudaMemcpyAsync / cudaMemcpy3DAsync / cudaMemsetAsync, event records and
+// cudaStreamWaitEvent are queued per stream and carried out as LATE as the programming model allows -- when the host
+// synchronises with the stream (or the device), when an event recorded behind them is waited for (by the host, or by
+// another stream at the moment THAT stream's wait is carried out), or when a kernel / an NCCL operation is issued on
+// the same stream (those run at once, after the stream's own queue).  A missing event dependency then shows: the
+// consumer computes with data the copy has not delivered yet, or a late copy reads a buffer that was reused too early.
+struct StreamOp {
+  std::function<void()> run;
+  uint64_t marker;  // != 0: the record of an event
+};
+struct emu_stream {
+  int side = 0;  // 1: created with a priority; fake_nccl.cpp reads this int (must stay the first member)
+  int index = -1;  // creation order within the process (the legacy default stream: -1)
+  std::deque<StreamOp> pending;
+};
+struct emu_event {
+  std::chrono::steady_clock::time_point when;
+  cudaStream_t recorded_on = nullptr;
+  uint64_t marker = 0;
+};
+
+namespace {
+emu_stream g_null_stream;
+std::vector<emu_stream *> g_streams;  // live streams (cudaDeviceSynchronize, cudaFree)
+uint64_t g_next_marker = 1;
+// MIF_EMU_LAZY_COPIES: unset = everything at once; "1" / "all" = every stream as late as possible; "odd" / "even" = the
+// streams with an odd / even creation index run at once and the others as late as possible -- one stream racing ahead
+// of another is what exposes a buffer that is refilled before its previous contents were consumed.
+int lazy_mode() {
+  static const int mode = [] {
+    const char *v = getenv("MIF_EMU_LAZY_COPIES");
+    if (!v) return 0;
+    if (!strcmp(v, "odd")) return 2;
+    if (!strcmp(v, "even")) return 3;
+    return 1;
+  }();
+  return mode;
+}
+bool lazy_copies() { return lazy_mode() != 0; }
+bool trace_streams() {  // MIF_EMU_TRACE=1: log the queueing and the carrying out of stream operations
+  static const bool on = getenv("MIF_EMU_TRACE") != nullptr;
+  return on;
+}
+int g_stream_count = 0;
+emu_stream *queue_of(cudaStream_t s) { return s ? s : &g_null_stream; }
+// Carry out the queued operations of a stream in order: all of them, or up to and including the record with this marker
+// (nothing if that record has been carried out already).
+void flush_stream(cudaStream_t stream, uint64_t up_to_marker = 0) {
+  emu_stream *q = queue_of(stream);
+  if (up_to_marker) {
+    bool found = false;
+    for (const StreamOp &op : q->pending) found = found || op.marker == up_to_marker;
+    if (!found) return;
+  }
+  while (!q->pending.empty()) {
+    StreamOp op = std::move(q->pending.front());
+    q->pending.pop_front();
+    if (trace_streams()) std::fprintf(stderr, "simt_emu:   carry out an operation of stream %d (event record %llu)\n", q->index, (unsigned long long)op.marker);
+    op.run();  // may flush other streams (a queued cudaStreamWaitEvent)
+    if (up_to_marker && op.marker == up_to_marker) return;
+  }
+}
+void flush_all_streams() {
+  flush_stream(nullptr);
+  for (size_t i = 0; i < g_streams.size(); i++) flush_stream(g_streams[i]);
+}
+void enqueue(cudaStream_t stream, std::function<void()> run, uint64_t marker = 0) {
+  emu_stream *q = queue_of(stream);
+  if (trace_streams()) std::fprintf(stderr, "simt_emu: queue on stream %d (event record %llu), %zu pending\n", q->index, (unsigned long long)marker, q->pending.size());
+  q->pending.push_back(StreamOp{std::move(run), marker});
+  const bool eager = (lazy_mode() == 2 && q->index >= 0 && (q->index & 1)) || (lazy_mode() == 3 && q->index >= 0 && !(q->index & 1));
+  if (eager) flush_stream(stream);
+}
+}  // namespace
+// for fake_nccl.cpp: an NCCL operation issued on `stream` runs behind everything queued on that stream
+extern "C" void emu_flush_stream_for_nccl(void *stream) {
+  if (lazy_copies()) flush_stream(static_cast<cudaStream_t>(stream));
+}
 
 // fake_nccl.cpp's fake_nccl_flush, if that library is loaded in this process (MIFGPU_NCCL_LIB)
 static void flush_late_exchanges(cudaStream_t stream) {
@@ -324,6 +405,9 @@ static void flush_late_exchanges(cudaStream_t stream) {
     const char *path = getenv("MIFGPU_NCCL_LIB");
     void *handle = path ? dlopen(path, RTLD_NOW | RTLD_NOLOAD) : nullptr;
     if (handle) flush = reinterpret_cast<int (*)(void *)>(dlsym(handle, "fake_nccl_flush"));
+    if (handle)
+      if (auto set = reinterpret_cast<void (*)(void (*)(void *))>(dlsym(handle, "fake_nccl_set_stream_flush")))
+        set(emu_flush_stream_for_nccl);
     looked = true;
   }
   if (flush) flush(stream);
@@ -374,6 +458,7 @@ cudaError_t emu_malloc(void **ptr, size_t bytes) {
 }
 cudaError_t cudaFree(void *ptr) {
   if (!ptr) return cudaSuccess;
+  flush_all_streams();  // cudaFree synchronises the device
   for (size_t i = 0; i < g_allocations.size(); i++)
     if (g_allocations[i].ptr == ptr) {
       if (g_allocations[i].shm_name.empty()) free(ptr);
@@ -388,10 +473,18 @@ cudaError_t cudaFree(void *ptr) {
 }
 cudaError_t cudaFreeHost(void *ptr) { return cudaFree(ptr); }
 cudaError_t cudaMemcpy(void *dst, const void *src, size_t bytes, cudaMemcpyKind) { memmove(dst, src, bytes); return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t bytes, cudaMemcpyKind, cudaStream_t) { memmove(dst, src, bytes); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t bytes, cudaMemcpyKind, cudaStream_t stream) {
+  if (lazy_copies()) enqueue(stream, [=] { memmove(dst, src, bytes); });
+  else memmove(dst, src, bytes);
+  return cudaSuccess;
+}
 cudaError_t cudaMemset(void *dst, int value, size_t bytes) { memset(dst, value, bytes); return cudaSuccess; }
-cudaError_t cudaMemsetAsync(void *dst, int value, size_t bytes, cudaStream_t) { memset(dst, value, bytes); return cudaSuccess; }
-cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms *p, cudaStream_t) {
+cudaError_t cudaMemsetAsync(void *dst, int value, size_t bytes, cudaStream_t stream) {
+  if (lazy_copies()) enqueue(stream, [=] { memset(dst, value, bytes); });
+  else memset(dst, value, bytes);
+  return cudaSuccess;
+}
+static void copy_3d(const cudaMemcpy3DParms *p) {
   const cudaPitchedPtr &s = p->srcPtr, &d = p->dstPtr;
   for (size_t z = 0; z < p->extent.depth; z++)
     for (size_t y = 0; y < p->extent.height; y++) {
@@ -399,6 +492,14 @@ cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms *p, cudaStream_t) {
       char *dst = static_cast<char *>(d.ptr) + ((p->dstPos.z + z) * d.ysize + p->dstPos.y + y) * d.pitch + p->dstPos.x;
       memmove(dst, src, p->extent.width);
     }
+}
+cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms *p, cudaStream_t stream) {
+  if (lazy_copies()) {
+    const cudaMemcpy3DParms parms = *p;
+    enqueue(stream, [parms] { copy_3d(&parms); });
+  } else {
+    copy_3d(p);
+  }
   return cudaSuccess;
 }
 cudaError_t cudaGetDeviceCount(int *count) { *count = 64; return cudaSuccess; }  // any ordinal a rank asks for exists
@@ -408,26 +509,65 @@ cudaError_t cudaDeviceGetAttribute(int *value, int attr, int) {
   *value = (attr == cudaDevAttrMultiProcessorCount) ? 3 : 0;  // few "SMs": persistent kernels loop over several tiles per CTA
   return cudaSuccess;
 }
-cudaError_t cudaDeviceSynchronize() { flush_late_exchanges(nullptr); return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize() {
+  flush_all_streams();
+  flush_late_exchanges(nullptr);
+  return cudaSuccess;
+}
 cudaError_t cudaGetLastError() { return cudaSuccess; }
 const char *cudaGetErrorString(cudaError_t err) { return err == cudaSuccess ? "no error" : "simt_emu: unsupported call"; }
-cudaError_t cudaStreamCreate(cudaStream_t *stream) { *stream = new emu_stream(); return cudaSuccess; }
-cudaError_t cudaStreamCreateWithFlags(cudaStream_t *stream, unsigned) { *stream = new emu_stream(); return cudaSuccess; }
-cudaError_t cudaStreamCreateWithPriority(cudaStream_t *stream, unsigned, int) { *stream = new emu_stream(); (*stream)->side = 1; return cudaSuccess; }
+cudaError_t cudaStreamCreate(cudaStream_t *stream) {
+  *stream = new emu_stream();
+  (*stream)->index = g_stream_count++;
+  g_streams.push_back(*stream);
+  return cudaSuccess;
+}
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *stream, unsigned) { return cudaStreamCreate(stream); }
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t *stream, unsigned, int) { cudaStreamCreate(stream); (*stream)->side = 1; return cudaSuccess; }
 cudaError_t cudaDeviceGetStreamPriorityRange(int *least, int *greatest) { if (least) *least = 0; if (greatest) *greatest = -5; return cudaSuccess; }
-cudaError_t cudaStreamDestroy(cudaStream_t stream) { delete stream; return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t s) { flush_late_exchanges(s); return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t stream) {
+  flush_stream(stream);  // work already issued completes
+  for (size_t i = 0; i < g_streams.size(); i++)
+    if (g_streams[i] == stream) g_streams.erase(g_streams.begin() + i);
+  delete stream;
+  return cudaSuccess;
+}
+cudaError_t cudaStreamSynchronize(cudaStream_t s) {
+  flush_stream(s);
+  flush_late_exchanges(s);
+  return cudaSuccess;
+}
 cudaError_t cudaEventCreate(cudaEvent_t *event) { *event = new emu_event(); return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t *event, unsigned) { *event = new emu_event(); return cudaSuccess; }
 // Kernels and copies are synchronous here; only the stand-in NCCL can defer the exchanges of a side stream
 // (MIF_FAKE_NCCL_LATE, fake_nccl.cpp) -- they complete when another stream waits for an event recorded behind them.
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t event, unsigned) {
-  if (event && event->recorded_on) flush_late_exchanges(event->recorded_on);
+cudaError_t cudaStreamWaitEvent(cudaStream_t stream, cudaEvent_t event, unsigned) {
+  if (!event || !event->marker) return cudaSuccess;  // never recorded: nothing to wait for
+  const cudaStream_t source = event->recorded_on;
+  const uint64_t marker = event->marker;  // the record the wait refers to is the one made so far
+  auto wait = [source, marker] {
+    flush_stream(source, marker);
+    if (source) flush_late_exchanges(source);
+  };
+  if (lazy_copies()) enqueue(stream, wait);
+  else wait();
   return cudaSuccess;
 }
 cudaError_t cudaEventDestroy(cudaEvent_t event) { delete event; return cudaSuccess; }
-cudaError_t cudaEventRecord(cudaEvent_t event, cudaStream_t s) { event->when = std::chrono::steady_clock::now(); event->recorded_on = s; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t event, cudaStream_t s) {
+  event->recorded_on = s;
+  event->marker = g_next_marker++;
+  if (lazy_copies()) enqueue(s, [event] { event->when = std::chrono::steady_clock::now(); }, event->marker);
+  else event->when = std::chrono::steady_clock::now();
+  return cudaSuccess;
+}
+cudaError_t cudaEventSynchronize(cudaEvent_t event) {
+  if (event && event->marker) flush_stream(event->recorded_on, event->marker);
+  return cudaSuccess;
+}
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t start, cudaEvent_t stop) {
+  cudaEventSynchronize(start);
+  cudaEventSynchronize(stop);
   *ms = std::chrono::duration<float, std::milli>(stop->when - start->when).count();
   return cudaSuccess;
 }

@@ -94,6 +94,14 @@ static ncclResult_t recv_now(void *buf, size_t count, ncclDataType_t type, int p
 
 static ncclResult_t send_now(const void *buf, size_t count, ncclDataType_t type, int peer, ncclComm_t c);
 
+// The interpreter's runtime registers its "carry out what is queued on this stream" here (MIF_EMU_LAZY_COPIES): an
+// operation issued on a stream runs behind the asynchronous copies queued on that stream before it.
+static void (*g_stream_flush)(void *) = nullptr;
+void fake_nccl_set_stream_flush(void (*flush)(void *)) { g_stream_flush = flush; }
+static void behind_stream(cudaStream_t s) {
+  if (g_stream_flush) g_stream_flush(s);
+}
+
 // late mode: operations of side streams wait here, in issue order (sends before the receives of their group)
 struct LateOp { cudaStream_t stream; bool is_send; std::function<ncclResult_t()> run; };
 static std::vector<LateOp> g_late;
@@ -129,6 +137,7 @@ ncclResult_t ncclGroupEnd() {
 }
 
 ncclResult_t ncclSend(const void *buf, size_t count, ncclDataType_t type, int peer, ncclComm_t c, cudaStream_t s) {
+  behind_stream(s);
   if (is_late(s)) {
     g_late.push_back(LateOp{s, true, [=] { return send_now(buf, count, type, peer, c); }});
     return 0;
@@ -149,6 +158,7 @@ static ncclResult_t send_now(const void *buf, size_t count, ncclDataType_t type,
 }
 
 ncclResult_t ncclRecv(void *buf, size_t count, ncclDataType_t type, int peer, ncclComm_t c, cudaStream_t s) {
+  behind_stream(s);
   if (is_late(s)) {
     g_late.push_back(LateOp{s, false, [=] { return recv_now(buf, count, type, peer, c); }});
     return 0;

@@ -94,6 +94,7 @@ cudaError_t cudaEventCreate(cudaEvent_t *event);
 enum { cudaEventDisableTiming = 2 };
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t *event, unsigned flags);
 cudaError_t cudaStreamWaitEvent(cudaStream_t stream, cudaEvent_t event, unsigned flags = 0);
+cudaError_t cudaEventSynchronize(cudaEvent_t event);
 cudaError_t cudaEventDestroy(cudaEvent_t event);
 cudaError_t cudaEventRecord(cudaEvent_t event, cudaStream_t stream = nullptr);
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t start, cudaEvent_t stop);
@@ -104,7 +105,7 @@ template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) {
 
 // ---- SIMT interpreter ----------------------------------------------------------------------------------------
 namespace emu {
-void launch(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::function<void()> &thread_body);
+void launch(dim3 grid, dim3 block, size_t dynamic_smem_bytes, cudaStream_t stream, const std::function<void()> &thread_body);
 void *dynamic_smem();
 void tma_block_end();
 void block_barrier();

@@ -4,7 +4,7 @@
 Turns the three CUDA-only constructs g++ cannot parse into calls of the SIMT interpreter; everything else in the kernel
 sources is compiled unchanged against include/cuda_runtime.h:
 
-  kernel<T...><<<grid, block, smem, stream>>>(args);   ->  emu::launch(grid, block, smem, [&] { kernel<T...>(args); });
+  kernel<T...><<<grid, block, smem, stream>>>(args);   ->  emu::launch(grid, block, smem, stream, [&] { kernel<T...>(args); });
   extern __shared__ T name[];                          ->  T *name = reinterpret_cast<T *>(emu::dynamic_smem());
   asm volatile("bar.sync ...") / ("prefetch...")       ->  emu::named_barrier(id, count) / nothing
 
@@ -87,7 +87,7 @@ def rewrite_launches(text):
         semi = text.index(";", paren_end)
         args = text[paren + 1:paren_end]
         out += text[pos:k]
-        out += "emu::launch(%s, %s, %s, [&] { %s(%s); })" % (config[0], config[1], config[2], kernel, args)
+        out += "emu::launch(%s, %s, %s, %s, [&] { %s(%s); })" % (config[0], config[1], config[2], config[3], kernel, args)
         out += text[paren_end + 1:semi + 1]
         pos = semi + 1
 

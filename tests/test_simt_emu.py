@@ -6,6 +6,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 from conftest import ROOT
 
 EMU = os.path.join(ROOT, "tests", "simt_emu")
@@ -25,6 +27,23 @@ def test_kernel_sources_pass_parity_cases_under_the_simt_interpreter():
         assert "simt cases ok" in out
         seen += out.count(" ok\n") - 1
     assert seen == 13, seen  # every case of run_cases.py ran in exactly one shard
+
+
+@pytest.mark.parametrize("policy", ["all", "odd", "even"])
+def test_asynchronous_transfers_with_copies_carried_out_as_late_as_allowed(policy):
+    """mifgpu_tensor_upload_async / _download_async (link and re-pitching streams, two staging buffers per direction,
+    per-tensor events) with the interpreter's asynchronous copies queued per stream and carried out as late as the
+    programming model allows ("all"), or with every second stream racing ahead ("odd" / "even"): a missing dependency
+    or a staging buffer refilled before it was consumed changes the fields.  (Removing either of the two staging
+    hand-over waits fails exactly one of the policies; this model also found the one real ordering bug of the API --
+    a new tensor's zero fill could be overtaken by an asynchronous upload.)"""
+    build = subprocess.run(["make", "-C", EMU, "-j8"], capture_output=True, text=True)
+    assert build.returncode == 0, build.stdout[-2000:] + build.stderr[-2000:]
+    env = dict(os.environ, MIFGPU_LIB=os.path.join(EMU, "build", "libmifgpu_simt.so"), MIF_EMU_LAZY_COPIES=policy)
+    run = subprocess.run([sys.executable, os.path.join(EMU, "run_async_cases.py")], env=env, capture_output=True, text=True,
+                         timeout=900)
+    assert run.returncode == 0, run.stdout[-2000:] + run.stderr[-3000:]
+    assert "async cases ok" in run.stdout
 
 
 def test_bench_line_carries_the_contract_keys_in_a_dry_run():
