@@ -157,8 +157,9 @@ int mifgpu_tensor_download_box(const mifgpu_tensor *tensor, const int32_t lo[3],
 int mifgpu_tensor_swap(mifgpu_tensor *a, mifgpu_tensor *b);
 
 /* The same transfers without blocking the host, for callers that stream independent jobs through the device (the
- * reference has no counterpart: its tensors live in host memory).  Each direction has its own copy stream and staging
- * buffer; ordering is by events only: a transfer starts after the last compute call that used the tensor and after
+ * reference has no counterpart: its tensors live in host memory).  Each direction has its own link stream, its own
+ * stream for the re-pitching copy on the device and two staging buffers (the link moves the next tensor while the last
+ * one is re-pitched); ordering is by events only: a transfer starts after the last compute call that used the tensor and after
  * the tensor's previous transfers, and compute calls that use the tensor afterwards wait for it on the device.  So
  * upload(A) | timestep(B) | download(C) of three different tensor sets overlap, and PCIe runs in both directions at
  * once.  `host` should be page-locked; it must not be touched until mifgpu_synchronize has returned. */
