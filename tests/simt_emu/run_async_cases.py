@@ -30,8 +30,9 @@ def main():
     ctx.synchronize()
     assert all(np.array_equal(a, b) for a, b in zip(got, fields))
     ctx.close()
-    # three jobs rotated through two device field sets against the blocking calls (the GPU test's own body)
-    parity.test_async_transfers_pipeline_matches_synchronous_calls(mif)
+    # three jobs rotated through two device field sets against the blocking calls (the GPU test's own body, on a grid the
+    # interpreter steps through in seconds)
+    parity.test_async_transfers_pipeline_matches_synchronous_calls(mif, N=(12, 9, 8))
     parity.test_timestep_random_state(mif, (9, 7, 6), (False, False, False), "ethier_steinman")
     print("async cases ok")
 

@@ -36,9 +36,7 @@ def main():
     cases.append(lambda: parity.test_timestep_nhn_matches_oracle(mif))
     cases.append(lambda: golden.test_timestep_velocity_matches_reference(mif, "vtest_12_2"))
     for index, case in enumerate(cases):
-        # smoke() alone takes as long as all other cases together (its 513 x 513 x 3 solve): it gets shard 0 to itself
-        mine = (index == 0) == (shard == 0) and (index == 0 or index % (shards - 1) == shard - 1) if shards > 1 else True
-        if mine:
+        if index % shards == shard:
             case()
             print("case", index, "ok", flush=True)
     print("simt cases ok")

@@ -265,12 +265,12 @@ def test_upload_download_roundtrip_and_swap(mif):
     ctx.close()
 
 
-def test_async_transfers_pipeline_matches_synchronous_calls(mif):
+def test_async_transfers_pipeline_matches_synchronous_calls(mif, N=(33, 20, 17)):
     """mifgpu_tensor_upload_async / _download_async (per-direction copy streams, event ordered against the compute
     stream): three independent single-step jobs rotated through two device field sets give exactly the fields of the
     same jobs run one after the other with the blocking transfers -- including the re-use of a set whose previous
     download is still in flight when the next upload is enqueued."""
-    N, periodic = (33, 20, 17), (False, False, False)
+    periodic = (False, False, False)
     ctx, grid = make_pair(mif, N, periodic)
     rng = np.random.default_rng(2024)
     jobs = [[0.3 * rng.uniform(-1, 1, grid.shape(c)) for c in range(3)] + [rng.uniform(-1, 1, grid.shape(3))] for _ in range(3)]
