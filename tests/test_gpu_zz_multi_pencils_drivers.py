@@ -79,3 +79,21 @@ def test_ported_full_test_on_several_gpus_prints_the_reference_numbers(ranks, pz
     assert len(got) == 9
     for a, b in zip(got, want):
         assert abs(a - b) <= 2e-5 * abs(b), (got, want)
+
+
+def test_velocity_test_mixed_with_periodic_y_split_over_two_gpus():
+    """`mifrun -n 2 velocity_test_mixed 16 1 1` (Py = 2: the periodic y direction is distributed): the ported driver and
+    the reference's unchanged test/velocity_test_mixed.cpp print the reference's numbers."""
+    if device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    want = json.load(open(os.path.join(GOLDEN_DIR, "norms.json")))["velocity_test_mixed 16 1 1"]
+    bins = os.path.join(ROOT, "mpi-incompressible-fluid_b200", "host", "bin")
+    runs = [[os.path.join(bins, "velocity_test"), "16", "1", "1", "mixed"]]
+    if os.path.exists(os.path.join(bins, "ref_velocity_test_mixed")):
+        runs.append([os.path.join(bins, "ref_velocity_test_mixed"), "16", "1", "1"])
+    for cmd in runs:
+        out = subprocess.run([os.path.join(ROOT, "scripts", "mifrun"), "-n", "2"] + cmd, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+        got = [float(x) for x in out.stdout.split()[-3:]]
+        for a, b in zip(got, want):
+            assert abs(a - b) <= 2e-5 * abs(b), (cmd, got, want)

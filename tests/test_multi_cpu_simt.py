@@ -183,3 +183,23 @@ def test_bench_line_on_two_ranks_in_a_dry_run(simt_env):
     assert line["e2e"]["result_finite"] is True
     assert line["nvlink"]["bytes_sent_per_gpu_per_step"] == 6 * 8 * (9 * 9 * 17 / 2) * 0.5
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["gpu_launches"] > 0 and "halo_exchange" in line["kernels"]
+
+
+def test_velocity_test_mixed_with_periodic_y_split_over_two_ranks(simt_env):
+    """`mifrun -n 2 velocity_test_mixed 16 1 1` (Pz = 1, so Py = 2: the periodic y direction is distributed, its neighbours
+    wrap around) -- the ported driver and, where it was built, the reference's own test/velocity_test_mixed.cpp compiled
+    unchanged print the numbers of the reference (which prints the same on one and on two ranks)."""
+    from conftest import GOLDEN_DIR
+    want = json.load(open(os.path.join(GOLDEN_DIR, "norms.json")))["velocity_test_mixed 16 1 1"]
+    env = dict(simt_env, LD_LIBRARY_PATH=os.path.join(EMU, "build", "as_libmifgpu"))
+    bins = os.path.join(ROOT, "mpi-incompressible-fluid_b200", "host", "bin")
+    runs = [[os.path.join(bins, "velocity_test"), "16", "1", "1", "mixed"]]
+    if os.path.exists(os.path.join(bins, "ref_velocity_test_mixed")):
+        runs.append([os.path.join(bins, "ref_velocity_test_mixed"), "16", "1", "1"])
+    for cmd in runs:
+        out = subprocess.run([os.path.join(ROOT, "scripts", "mifrun"), "-n", "2"] + cmd, env=env, capture_output=True, text=True,
+                             timeout=600)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+        got = [float(x) for x in out.stdout.split()[-3:]]
+        for a, b in zip(got, want):
+            assert abs(a - b) <= 2e-5 * abs(b), (cmd, got, want)
