@@ -86,6 +86,7 @@ def test_velocity_test_mixed_with_periodic_y_split_over_two_gpus():
     the reference's unchanged test/velocity_test_mixed.cpp print the reference's numbers."""
     if device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    from conftest import GOLDEN_DIR
     want = json.load(open(os.path.join(GOLDEN_DIR, "norms.json")))["velocity_test_mixed 16 1 1"]
     bins = os.path.join(ROOT, "mpi-incompressible-fluid_b200", "host", "bin")
     runs = [[os.path.join(bins, "velocity_test"), "16", "1", "1", "mixed"]]
