@@ -50,6 +50,7 @@ class GpuLocalCpus:
         self.info = {"bound": False}
         self.cpus = None
         try:
+            import torch
             prop = torch.cuda.get_device_properties(device_index)
             address = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
             base = "/sys/bus/pci/devices/" + address
