@@ -54,7 +54,7 @@ def test_overlapped_halo_exchanges_completing_as_late_as_stream_order_allows(sim
     the exchange finishing at once; MIF_FAKE_NCCL_LATE=1 defers every side-stream send / receive to the point where the
     compute stream waits for it -- a kernel that touched a ghost plane (or a plane still to be sent) too early would
     now compute with stale data and miss the single-rank result."""
-    res = run_worker(dict(simt_env, MIF_FAKE_NCCL_LATE="1"), case, world, port)
+    res = run_worker(dict(simt_env, MIF_FAKE_NCCL_LATE="1", MIF_EMU_LAZY_COPIES="all"), case, world, port)  # copies as late as allowed, too
     assert res["world"] == world and res["max_rel_err"] <= 1e-11
 
 
@@ -102,8 +102,9 @@ def test_reference_halo_mode_reproduces_the_reference_pencil_runs_point_for_poin
 
 def test_four_rank_pencils(simt_env):
     # Py x Pz = 2 x 2 on 17^3 points (uneven blocks 9 + 8): y sheets then z planes as halos, the four 2Decomp transposes
-    # as box exchanges, x / y / z sweeps on the sub-domain, the y pencil and the z pencil
-    res = run_worker(simt_env, "full_17_1", 4, 29714, py=2)
+    # as box exchanges, x / y / z sweeps on the sub-domain, the y pencil and the z pencil; the staging copies of the box
+    # exchanges are asynchronous 3-D copies: run with every second stream racing ahead of the lazily served others
+    res = run_worker(dict(simt_env, MIF_EMU_LAZY_COPIES="odd"), "full_17_1", 4, 29714, py=2)
     assert res["world"] == 4 and res["Py"] == 2 and res["Pz"] == 2 and res["max_rel_err"] <= 1e-11
 
 
