@@ -175,27 +175,39 @@ __device__ __forceinline__ double2 shuffle_from(double2 value, int src) {
 // Odd half: the partner of C_{2k+1} is C_{2(511-k)+1}, register 15 - r of lane 31 - L, with no special lanes.
 template <int HALF = 0>
 __device__ __forceinline__ void unpack_dct(const double2 *v, int L, const double2 *__restrict__ cs, double *out, double &e_last) {
+  // E_k and E_{M-k} come from the same pair (A, B) = (C_k, C_{M-k}): with (wx, wy) = (cos, sin)(pi k / M),
+  //   S = A.x + B.x,  T = wx (A.y + B.y) - wy (A.x - B.x),  E_k = (S + T) / 2,  E_{M-k} = (S - T) / 2
+  // (the twiddle of M - k is (-wx, wy)).  Every lane therefore unpacks only its registers r < 8, for which it fetches the
+  // partner's register 15 - r (>= 8), and hands the second result back to the partner, whose register 15 - r it is:
+  // half the twiddle rotations and products of unpacking all sixteen registers, and 24 shuffles instead of 32.
+  // Lanes 0 and 16 (k2 = 0) pair with each other, register r with register 16 - r; their register 0 pairs inside the lane:
+  // lane 0 has k = 0 (partner itself, second result E_M) and k = 256 in register 8 (its own partner, E_256 = Re C_256),
+  // lane 16 has k = 128 with partner k = 384 in its own register 8.
   const int k2 = L & 15, p = L >> 4;
   const bool special = (HALF != 2) && (k2 == 0);
   const int src = (HALF == 2) ? 31 - L : (special ? (L ^ 16) : 32 - L);
   const double2 base = __ldg(&cs[HALF == 0 ? k2 + 128 * p : 2 * (k2 + 128 * p) + (HALF == 2 ? 1 : 0)]);
+  double back[8];
 #pragma unroll
-  for (int r = 0; r < 16; r++) {
+  for (int r = 0; r < 8; r++) {
     const double2 send = special ? v[(16 - r) & 15] : v[15 - r];
     double2 B = shuffle_from(send, src);
     if (special && r == 0) B = p ? v[8] : v[0];
-    if (special && r == 8) B = p ? v[0] : v[8];
     const double2 A = v[r];
-    const double2 rt = rot32(r & 7);
-    double wx = base.x * rt.x - base.y * rt.y, wy = base.x * rt.y + base.y * rt.x;
-    if (r >= 8) {  // + pi / 2
-      const double t = wx;
-      wx = -wy;
-      wy = t;
-    }
-    out[r] = 0.5 * ((A.x + B.x) + wx * (A.y + B.y) - wy * (A.x - B.x));
+    const double2 rt = rot32(r);
+    const double wx = (r == 0) ? base.x : base.x * rt.x - base.y * rt.y, wy = (r == 0) ? base.y : base.x * rt.y + base.y * rt.x;
+    const double half_s = 0.5 * (A.x + B.x);
+    const double t = wx * (A.y + B.y) - wy * (A.x - B.x);
+    out[r] = 0.5 * t + half_s;
+    const double image = half_s - 0.5 * t;  // E_{M-k}: register 15 - r (special lanes: 16 - r) of lane src
+    back[r] = __shfl_sync(0xffffffffu, image, src);
+    if (r == 0) e_last = image;  // lane 0: E_M = Re C_0 - Im C_0 (meaningful in lane 0 only)
   }
-  e_last = v[0].x - v[0].y;  // E_M = Re C_0 - Im C_0 (meaningful in lane 0)
+  // what the partner computed for this lane's upper registers
+#pragma unroll
+  for (int r = 0; r < 7; r++) out[15 - r] = special ? back[r + 1] : back[r];
+  // register 8: general lanes the partner's last image; lane 16 its own pair (k = 128, 384); lane 0 the self-paired k = 256
+  out[8] = special ? (p ? e_last : v[8].x) : back[7];
 }
 
 // conj Z_k for a real spectrum (see mif_poisson_tma.cuh): X_k = xr, X_{M-k} = yr, (c, sn) = (cos, sin)(pi k / M).
