@@ -334,6 +334,35 @@ struct Layout512 {
   static constexpr size_t kSmem = 1024 + kWorkArea + (kTwBytes + 127) / 128 * 128 + kStageBytes + 64;
 };
 
+// Scale the 16 spectrum values of a lane by 1 / (lam_xy + lam_z[k]) (src/PressureEquation.cpp:158-163) with ONE division
+// per four values: prefix products, one reciprocal, back-substitution -- 9 multiplications replace three of the four
+// divisions (each a MUFU.RCP64H plus two Newton steps and a guarded slow path).  The products stay far from the FP64
+// range (|lambda sums| <= 12 / h^2); the (0,0,0) mode, whose sum is zero, takes the divisor 1 and the factor 0.
+template <class KOf>
+__device__ __forceinline__ void scale_by_inverse_eigenvalues(double *spec, double lam_xy, const double *__restrict__ lam_z,
+                                                             bool origin_line, KOf k_of_register) {
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    double d[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int k = k_of_register(4 * q + e);
+      d[e] = (origin_line && k == 0) ? 1.0 : lam_xy + lam_z[k];
+    }
+    const double p01 = d[0] * d[1], p012 = p01 * d[2];
+    double inv = 1.0 / (p012 * d[3]);
+    const double r3 = inv * p012;
+    inv *= d[3];
+    const double r2 = inv * p01;
+    inv *= d[2];
+    const double r1 = inv * d[0], r0 = inv * d[1];
+    spec[4 * q] *= (origin_line && k_of_register(4 * q) == 0) ? 0.0 : r0;
+    spec[4 * q + 1] *= r1;
+    spec[4 * q + 2] *= r2;
+    spec[4 * q + 3] *= r3;
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 2)
     tma_dct512_kernel(const __grid_constant__ CUtensorMap map_in_a, const __grid_constant__ CUtensorMap map_in_b,
@@ -444,11 +473,7 @@ __global__ void __launch_bounds__(kThreads, 2)
       const int ix = min(xt * kLines + col, job.n_lines - 1);
       const double lam_xy = job.lam_x[ix] + job.lam_y[outer];
       const bool origin_line = job.has_origin && (xt * kLines + col == 0) && (outer == 0);
-#pragma unroll
-      for (int r = 0; r < 16; r++) {
-        const int k = fft512::k_of(j, r);
-        spec[r] *= (origin_line && k == 0) ? 0.0 : 1.0 / (lam_xy + job.lam_z[k]);
-      }
+      scale_by_inverse_eigenvalues(spec, lam_xy, job.lam_z, origin_line, [j](int r) { return fft512::k_of(j, r); });
       e_last *= 1.0 / (lam_xy + job.lam_z[M]);
       fft512::repack_for_inverse(spec, e_last, j, job.cs, v);
       fft512::phase_a(v, j, T);
@@ -647,11 +672,7 @@ __global__ void __launch_bounds__(Layout1024::kThreads, 1)
       const int ix = min(xt * kLines + col, job.n_lines - 1);
       const double lam_xy = job.lam_x[ix] + job.lam_y[outer];
       const bool origin_line = job.has_origin && (xt * kLines + col == 0) && (outer == 0);
-#pragma unroll
-      for (int r = 0; r < 16; r++) {
-        const int k = 2 * fft512::k_of(j, r) + half;
-        spec[r] *= (origin_line && k == 0) ? 0.0 : 1.0 / (lam_xy + job.lam_z[k]);
-      }
+      scale_by_inverse_eigenvalues(spec, lam_xy, job.lam_z, origin_line, [j, half](int r) { return 2 * fft512::k_of(j, r) + half; });
       e_last *= 1.0 / (lam_xy + job.lam_z[M]);
       line_pair_sync(line);  // both warps of the line are done with their regions
 #pragma unroll
